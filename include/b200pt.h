@@ -1,0 +1,181 @@
+/* libb200pt -- C ABI of the B200-native (sm_100a) path-tracing hot path.
+ *
+ * This is the drop-in boundary for the Taichi hot path of fakhirsh/path-tracer-python.  The seam is
+ * the compiled-array boundary between the reference's host compile step (L2) and its device
+ * state + kernels (L1/L0), i.e. what `TaichiRenderer.__init__` hands to `_upload_to_gpu`
+ * (reference: src/render_server/taichi_renderer/renderer.py:84-98).  Every entry point names the
+ * reference interface it replaces (paths relative to src/render_server/taichi_renderer/).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types.  Pointers documented "device" must be
+ *     CUDA device pointers on the context's GPU (the Python host owns them as torch tensors);
+ *     pointers documented "host" are ordinary host memory.  The library never frees either.
+ *   - every function returns PT_OK (0) or a negative PT_ERR_* code; pt_last_error() gives the
+ *     message of the calling thread's last failure.  (The reference prints and continues,
+ *     scene_compiler.py:353; kernels never report.)
+ *   - all launches go to the caller's `stream` (a cudaStream_t passed as void*; NULL = default
+ *     stream); no hidden synchronisation except where stated.
+ *   - one context per GPU / host thread (thread-compatible, not thread-safe).
+ *   - arithmetic: PT-F32 contract (strict IEEE binary32, contract-defined elementary functions
+ *     and per-path random stream) -- see DESIGN.md section 3 and oracle/oracle_math.h.
+ */
+#ifndef B200PT_H
+#define B200PT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PT_OK 0
+#define PT_ERR_INVALID_ARG (-1)
+#define PT_ERR_CUDA (-2)
+#define PT_ERR_NO_SCENE (-3)
+#define PT_ERR_WORKSPACE (-4)
+#define PT_ERR_CAPACITY (-5)
+
+#define PT_MAX_IMAGES 16 /* fields.py:117 MAX_IMAGE_TEXTURES */
+
+/* Primitive / material / texture codes: scene_compiler.py:9-25 */
+#define PT_PRIM_SPHERE 0
+#define PT_PRIM_TRIANGLE 1
+#define PT_PRIM_QUAD 2
+
+typedef struct PtContext PtContext;
+
+/* Per-primitive-type material/texture/medium arrays exactly as compile_materials returns them
+ * (scene_compiler.py:254-439; fields.py:70-138).  All host pointers, n entries each. */
+typedef struct PtHostMaterials {
+    const int32_t* material_type;   /* 0 Lambert 1 Metal 2 Dielectric 3 Emissive 4 Isotropic */
+    const float* albedo;            /* [n][3] */
+    const float* fuzz;
+    const float* ir;
+    const float* emit;              /* [n][3] */
+    const int32_t* texture_type;    /* 0 solid 1 checker 2 image 3 noise */
+    const float* texture_scale;
+    const float* color1;            /* [n][3] */
+    const float* color2;            /* [n][3] */
+    const int32_t* image_idx;
+    const int32_t* is_medium;
+    const float* medium_density;
+    const float* medium_albedo;     /* [n][3] */
+} PtHostMaterials;
+
+/* The reference-layout scene: output of compile_scene (scene_compiler.py:931-965) and compile_bvh
+ * (bvh_compiler.py:132-168) plus the Perlin tables (fields.py:145-153) and image textures
+ * (renderer.py:202-214; 8-bit RGB, texel = u8/255.0f as util/rtw_image.py:66). Host pointers. */
+typedef struct PtHostScene {
+    int32_t num_spheres, num_quads, num_triangles, num_nodes, num_images;
+    const float* sphere_data;                                   /* [n][4] cx cy cz r */
+    const float *quad_Q, *quad_u, *quad_v, *quad_normal, *quad_D, *quad_w;
+    const float *tri_v0, *tri_edge1, *tri_edge2, *tri_normal;
+    PtHostMaterials mat[3];                                     /* by prim type: sphere, triangle, quad */
+    const float *bvh_bbox_min, *bvh_bbox_max;                   /* [nodes][3] */
+    const int32_t *bvh_left, *bvh_right, *bvh_prim_type, *bvh_prim_idx;
+    const float* perlin_randvec;                                /* [256][3] */
+    const int32_t *perm_x, *perm_y, *perm_z;                    /* [256] */
+    const uint8_t* images[PT_MAX_IMAGES];                       /* [h][w][3] */
+    int32_t image_w[PT_MAX_IMAGES], image_h[PT_MAX_IMAGES];
+} PtHostScene;
+
+/* Layout of the packed device blob.  Offsets are bytes from blob start,
+ * every section 256-byte aligned. */
+typedef struct PtPackedInfo {
+    uint64_t total_bytes;
+    uint64_t off_nodes;      /* num_inner * 64 B : two child boxes + two child refs per node */
+    uint64_t off_spheres;    /* num_spheres * 16 B */
+    uint64_t off_quads;      /* num_quads * 64 B */
+    uint64_t off_tris;       /* num_triangles * 48 B */
+    uint64_t off_prim_mat;   /* (num_spheres+num_triangles+num_quads) * 4 B material ids */
+    uint64_t off_materials;  /* num_materials * 48 B de-duplicated records */
+    uint64_t off_perlin;     /* 256*16 B vectors + 768 B permutations */
+    uint64_t off_images;     /* RGBA8 texels, image after image */
+    uint64_t image_off[PT_MAX_IMAGES]; /* from off_images */
+    int32_t image_w[PT_MAX_IMAGES], image_h[PT_MAX_IMAGES];
+    int32_t num_inner, num_spheres, num_quads, num_triangles, num_materials, num_images;
+    int32_t max_depth_tree;  /* depth of the tree (stack bound check) */
+    int32_t has_media;       /* any is_medium flag set */
+} PtPackedInfo;
+
+/* Camera + render settings: what _upload_camera writes (renderer.py:230-247; fields.py:159-172) */
+typedef struct PtCamera {
+    float center[3], pixel00[3], delta_u[3], delta_v[3], defocus_disk_u[3], defocus_disk_v[3];
+    float defocus_angle;
+    float background[3];
+    int32_t max_depth;
+} PtCamera;
+
+typedef struct PtCounters {
+    uint64_t rays;        /* BVH traversals (primary + bounce + medium-exit searches) */
+    uint64_t box_tests;   /* child-box slab tests (32 B of node data each) */
+    uint64_t sphere_tests, triangle_tests, quad_tests;
+    uint64_t paths;
+    uint64_t bounces;     /* path segments */
+} PtCounters;
+
+const char* pt_last_error(void);
+const char* pt_version(void);
+
+/* ---- host side of the seam: replaces _upload_to_gpu's per-element field writes
+ *      (renderer.py:102-228) with one packed blob that the caller copies to the device. */
+int pt_pack_scene_info(const PtHostScene* scene, PtPackedInfo* info);
+int pt_pack_scene(const PtHostScene* scene, const PtPackedInfo* info, void* host_blob);
+
+/* ---- native binned-SAH builder: replaces SAHBVHBuilder.build + flatten
+ *      (sah_bvh_builder.py:167-418) and produces bit-identical arrays.  Inputs are per-primitive
+ *      float32 boxes/centroids as add_sphere/add_quad/add_triangle compute them (:104-165).
+ *      Outputs must hold 2*n-1 nodes.  Returns the node count (>= 0) or an error code. */
+int pt_bvh_build_sah(int32_t n_prims, const float* prim_bbox_min, const float* prim_bbox_max,
+                     const float* prim_centroid, const int32_t* prim_type, const int32_t* prim_idx,
+                     float* out_bbox_min, float* out_bbox_max, int32_t* out_left, int32_t* out_right,
+                     int32_t* out_parent, int32_t* out_prim_type, int32_t* out_prim_idx);
+
+/* ---- context */
+int pt_create(int device_ordinal, PtContext** out_ctx);   /* replaces ti.init (renderer.py:16) */
+int pt_destroy(PtContext* ctx);
+/* tuning knobs: "block_threads", "smem_nodes" (inner nodes staged in shared memory; -1 = auto),
+ * "wavefront_sort" (0/1) */
+int pt_set_option(PtContext* ctx, const char* name, int64_t value);
+
+/* `device_blob` (device, info->total_bytes) stays owned by the caller and must outlive its use. */
+int pt_set_scene(PtContext* ctx, const void* device_blob, const PtPackedInfo* info);
+int pt_set_camera(PtContext* ctx, const PtCamera* cam);  /* replaces _upload_camera, renderer.py:230 */
+
+/* ---- megakernel: replaces `render_sample` (kernels.py:1177-1187) launched once per sample by
+ *      render() (renderer.py:405-409).  Adds samples [sample_begin, sample_begin+sample_count) of
+ *      rows [y0,y1) to accum (device, H*W*3 f32, row-major like fields.accum_buffer). */
+int pt_render_megakernel(PtContext* ctx, float* accum, int W, int H, int y0, int y1, int sample_begin,
+                         int sample_count, uint32_t seed, void* stream);
+
+/* ---- wavefront: replaces generate_camera_rays / intersect_rays / shade_miss_rays /
+ *      reset_next_ray_count / shade_and_scatter / swap_ray_buffers (kernels.py:1219-1418) and
+ *      their host loop (renderer.py:305-334).  workspace: device, >= pt_wavefront_workspace_bytes. */
+size_t pt_wavefront_workspace_bytes(int W, int rows);
+int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int y1, int sample_begin,
+                        int sample_count, uint32_t seed, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- stage-level probes used by the parity tests */
+/* get_ray for one sample of every pixel (kernels.py:176-201, :1219-1239); o,d: device [H*W][3] */
+int pt_generate_camera_rays(PtContext* ctx, int W, int H, uint32_t seed, int sample, float* o, float* d, void* stream);
+/* traverse_bvh over a ray list (intersect_rays, kernels.py:1242-1263): out_t = closest t (t_max on a
+ * miss); out_prim = (prim_type << 28) | prim_idx, or -1 on a miss; out_p/out_n may be NULL. */
+int pt_first_hit(PtContext* ctx, const float* o, const float* d, int n, float t_min, float t_max, float* out_t,
+                 int32_t* out_prim, float* out_p, float* out_n, void* stream);
+/* the contract's elementary functions: fn 0 sin 1 cos 2 log 3 acos 4 atan2(a,b) 5 pow(a,5);
+ * fn 6: a/b unused, out[i] = i-th draw of the random stream with state seed (uint32 bits of a[0]) */
+int pt_math_eval(PtContext* ctx, int fn, int n, const float* a, const float* b, float* out, void* stream);
+
+/* ---- output: replaces LivePreview.buffer_to_image (preview.py:117-132) on the device */
+int pt_tonemap(PtContext* ctx, const float* accum, int n_floats, int sample_count, uint8_t* out_rgb, void* stream);
+
+/* ---- statistics (synchronises the context's device).  Counting is off unless enabled; the
+ *      counting kernels are separate instantiations so the timed path carries no atomics. */
+int pt_enable_counters(PtContext* ctx, int enable);
+int pt_get_counters(PtContext* ctx, PtCounters* out, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200PT_H */

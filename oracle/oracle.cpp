@@ -1,0 +1,826 @@
+/* TEST INFRASTRUCTURE ONLY -- the CPU parity oracle.  Not part of the product: only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this.
+ *
+ * A restatement, in plain scalar C++, of the reference's Taichi hot path
+ *   /root/reference/src/render_server/taichi_renderer/kernels.py   (all @ti.func / @ti.kernel)
+ * over the reference's own device layout
+ *   /root/reference/src/render_server/taichi_renderer/fields.py:25-222
+ * i.e. the arrays `compile_scene` (scene_compiler.py:931) and `compile_bvh` (bvh_compiler.py:132)
+ * produce.  Control flow, constants, traversal order and evaluation order follow kernels.py
+ * statement by statement; every function cites the lines it restates.  Arithmetic follows the
+ * PT-F32 contract (oracle_math.h): strict IEEE binary32, no contraction (build with
+ * -ffp-contract=off), contract-defined elementary functions and random stream.
+ *
+ * Pinning: tests/test_oracle_golden.py checks this file bit-for-bit against fixtures produced by
+ * executing the reference's unmodified renderer.py/kernels.py/fields.py under oracle/taichi_shim
+ * (a pure-Python stand-in for the absent `taichi` module); see oracle/gen_golden.py.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+#include "oracle_math.h"
+
+extern "C" {
+
+typedef struct {
+    const int32_t* material_type;   /* 0 Lambert 1 Metal 2 Dielectric 3 Emissive 4 Isotropic */
+    const float* albedo;            /* [n][3] */
+    const float* fuzz;
+    const float* ir;
+    const float* emit;              /* [n][3] */
+    const int32_t* texture_type;    /* 0 solid 1 checker 2 image 3 noise */
+    const float* texture_scale;
+    const float* color1;            /* [n][3] */
+    const float* color2;            /* [n][3] */
+    const int32_t* image_idx;
+    const int32_t* is_medium;
+    const float* medium_density;
+    const float* medium_albedo;     /* [n][3] */
+} OMaterials;
+
+typedef struct {
+    int32_t num_spheres, num_quads, num_triangles, num_nodes, num_images;
+    const float* sphere_data;       /* [n][4] cx cy cz r                 fields.py:25 */
+    const float *quad_Q, *quad_u, *quad_v, *quad_normal, *quad_D, *quad_w;   /* fields.py:38-43 */
+    const float *tri_v0, *tri_edge1, *tri_edge2, *tri_normal;                /* fields.py:29-34 */
+    OMaterials mat[3];              /* indexed by prim_type: 0 sphere, 1 triangle, 2 quad */
+    const float *bvh_bbox_min, *bvh_bbox_max;                                /* fields.py:52-63 */
+    const int32_t *bvh_left, *bvh_right, *bvh_prim_type, *bvh_prim_idx;
+    const float* perlin_randvec;    /* [256][3] */
+    const int32_t *perm_x, *perm_y, *perm_z;
+    const uint8_t* images[16];      /* [h][w][3] u8; texel value = u8 / 255.0f (rtw_image.py:66) */
+    int32_t image_w[16], image_h[16];
+} OScene;
+
+typedef struct {
+    float center[3], pixel00[3], delta_u[3], delta_v[3], disk_u[3], disk_v[3];
+    float defocus_angle;
+    float bg[3];
+    int32_t max_depth;
+} OCamera;
+
+typedef struct {
+    uint64_t rays;          /* traverse_bvh invocations */
+    uint64_t node_tests;    /* hit_aabb_optimized evaluations */
+    uint64_t sphere_tests, triangle_tests, quad_tests;
+    uint64_t paths;
+    uint64_t bounces;       /* trace_ray loop iterations / wavefront ray-waves */
+} OCounters;
+
+} /* extern "C" */
+
+namespace {
+
+struct V3 {
+    float x, y, z;
+};
+inline V3 v3(float x, float y, float z) { return V3{x, y, z}; }
+inline V3 ld3(const float* p) { return V3{p[0], p[1], p[2]}; }
+inline V3 operator+(V3 a, V3 b) { return V3{a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline V3 operator-(V3 a, V3 b) { return V3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline V3 operator-(V3 a) { return V3{-a.x, -a.y, -a.z}; }
+inline V3 operator*(V3 a, V3 b) { return V3{a.x * b.x, a.y * b.y, a.z * b.z}; }
+inline V3 operator*(float s, V3 a) { return V3{s * a.x, s * a.y, s * a.z}; }
+inline V3 operator*(V3 a, float s) { return V3{a.x * s, a.y * s, a.z * s}; }
+inline V3 operator/(V3 a, float s) { return V3{a.x / s, a.y / s, a.z / s}; }
+/* Taichi Vector.dot = sum of elementwise products, accumulated left to right */
+inline float dot(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+inline V3 cross(V3 a, V3 b) {
+    return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+/* Taichi Vector.normalized(): invlen = 1 / (norm() + eps), eps = 0; return invlen * v */
+inline V3 normalized(V3 a) {
+    float invlen = 1.0f / (sqrtf(dot(a, a)) + 0.0f);
+    return invlen * a;
+}
+inline float fmin2(float a, float b) { return a < b ? a : b; }   /* ti.min / ti.max on f32 */
+inline float fmax2(float a, float b) { return a > b ? a : b; }
+
+struct Rng {
+    uint32_t s;
+    float next() { return o_rng_next(&s); }
+};
+
+struct Hit {
+    bool hit;
+    float t;
+    V3 p, n;
+    int prim_type, prim_idx;
+};
+
+struct Ctx {
+    const OScene* sc;
+    const OCamera* cam;
+    OCounters cnt;
+};
+
+/* kernels.py:16-25 */
+V3 random_in_unit_disk(Rng& rng) {
+    for (;;) {
+        float px = rng.next() * 2.0f - 1.0f;
+        float py = rng.next() * 2.0f - 1.0f;
+        V3 p = v3(px, py, 0.0f);
+        if (dot(p, p) < 1.0f) return p;
+    }
+}
+
+/* kernels.py:28-38 */
+V3 random_unit_vector(Rng& rng) {
+    for (;;) {
+        float px = rng.next() * 2.0f - 1.0f;
+        float py = rng.next() * 2.0f - 1.0f;
+        float pz = rng.next() * 2.0f - 1.0f;
+        V3 p = v3(px, py, pz);
+        float lensq = dot(p, p);
+        if (lensq < 1.0f && lensq > 1e-20f) return normalized(p);
+    }
+}
+
+/* kernels.py:41-71 */
+V3 random_cosine_direction(V3 normal, Rng& rng) {
+    float r1 = rng.next();
+    float r2 = rng.next();
+    float z = sqrtf(1.0f - r2);
+    float phi = 6.283185307179586f * r1; /* 2.0 * math.pi folded in Python, narrowed to f32 */
+    float sin_theta = sqrtf(r2);
+    float x = o_cosf(phi) * sin_theta;
+    float y = o_sinf(phi) * sin_theta;
+    V3 w = normalized(normal);
+    V3 a;
+    if (fabsf(w.x) < 0.9f) a = v3(1.0f, 0.0f, 0.0f);
+    else if (fabsf(w.y) < 0.9f) a = v3(0.0f, 1.0f, 0.0f);
+    else a = v3(0.0f, 0.0f, 1.0f);
+    V3 v = normalized(cross(a, w));
+    V3 u = cross(v, w);
+    return normalized((x * u + y * v) + z * w);
+}
+
+/* kernels.py:78-102 */
+void get_sphere_uv(V3 p, V3 center, float* u, float* v) {
+    V3 on = normalized(p - center);
+    float phi = o_acosf(-on.y);
+    float theta = o_atan2f(-on.z, on.x) + 3.141592653589793f;
+    *u = theta / 6.283185307179586f;
+    *v = phi / 3.141592653589793f;
+}
+
+/* kernels.py:109-151 */
+float perlin_noise(const OScene* sc, V3 p) {
+    float fx = floorf(p.x), fy = floorf(p.y), fz = floorf(p.z);
+    float u = p.x - fx, v = p.y - fy, w = p.z - fz;
+    int i = (int)fx, j = (int)fy, k = (int)fz;
+    float uu = u * u * (3.0f - 2.0f * u);
+    float vv = v * v * (3.0f - 2.0f * v);
+    float ww = w * w * (3.0f - 2.0f * w);
+    float accum = 0.0f;
+    for (int di = 0; di < 2; di++)
+        for (int dj = 0; dj < 2; dj++)
+            for (int dk = 0; dk < 2; dk++) {
+                int idx = sc->perm_x[(i + di) & 255] ^ sc->perm_y[(j + dj) & 255] ^ sc->perm_z[(k + dk) & 255];
+                V3 g = ld3(sc->perlin_randvec + 3 * idx);
+                float fi = (float)di, fj = (float)dj, fk = (float)dk;
+                V3 weight = v3(u - fi, v - fj, w - fk);
+                accum = accum + (fi * uu + (1.0f - fi) * (1.0f - uu)) *
+                                    (fj * vv + (1.0f - fj) * (1.0f - vv)) *
+                                    (fk * ww + (1.0f - fk) * (1.0f - ww)) * dot(g, weight);
+            }
+    return accum;
+}
+
+/* kernels.py:154-169 */
+float perlin_turb(const OScene* sc, V3 p, int depth) {
+    float accum = 0.0f;
+    V3 temp_p = p;
+    float weight = 1.0f;
+    for (int i = 0; i < depth; i++) {
+        accum = accum + weight * perlin_noise(sc, temp_p);
+        weight = weight * 0.5f;
+        temp_p = temp_p * 2.0f;
+    }
+    return fabsf(accum);
+}
+
+/* kernels.py:176-201 */
+void get_ray(const OCamera* cam, int px, int py, Rng& rng, V3* o, V3* d) {
+    float offset_x = rng.next() - 0.5f;
+    float offset_y = rng.next() - 0.5f;
+    V3 pixel_sample = (ld3(cam->pixel00) + ((float)px + offset_x) * ld3(cam->delta_u)) +
+                      ((float)py + offset_y) * ld3(cam->delta_v);
+    V3 origin = ld3(cam->center);
+    if (cam->defocus_angle > 0.0f) {
+        V3 p = random_in_unit_disk(rng);
+        origin = (ld3(cam->center) + p.x * ld3(cam->disk_u)) + p.y * ld3(cam->disk_v);
+    }
+    *o = origin;
+    *d = pixel_sample - origin;
+}
+
+/* kernels.py:208-248 */
+bool hit_sphere(Ctx& c, int idx, V3 o, V3 d, float t_min, float t_max, float* t, V3* p, V3* n) {
+    c.cnt.sphere_tests++;
+    const float* s = c.sc->sphere_data + 4 * idx;
+    V3 center = v3(s[0], s[1], s[2]);
+    float radius = s[3];
+    V3 oc = center - o;
+    float a = dot(d, d);
+    float h = dot(d, oc);
+    float cc = dot(oc, oc) - radius * radius;
+    float disc = h * h - a * cc;
+    if (disc >= 0.0f) {
+        float sqrtd = sqrtf(disc);
+        float root = (h - sqrtd) / a;
+        if (root < t_min || root > t_max) root = (h + sqrtd) / a;
+        if (root >= t_min && root <= t_max) {
+            *t = root;
+            *p = o + root * d;
+            *n = (*p - center) / radius;
+            return true;
+        }
+    }
+    return false;
+}
+
+/* kernels.py:251-307 */
+bool hit_triangle(Ctx& c, int idx, V3 o, V3 d, float t_min, float t_max, float* t, V3* p, V3* n) {
+    c.cnt.triangle_tests++;
+    const OScene* sc = c.sc;
+    V3 v0 = ld3(sc->tri_v0 + 3 * idx), e1 = ld3(sc->tri_edge1 + 3 * idx), e2 = ld3(sc->tri_edge2 + 3 * idx);
+    V3 normal = ld3(sc->tri_normal + 3 * idx);
+    V3 h = cross(d, e2);
+    float det = dot(e1, h);
+    if (fabsf(det) >= 1e-8f) {
+        float inv_det = 1.0f / det;
+        V3 s = o - v0;
+        float u = inv_det * dot(s, h);
+        if (u >= 0.0f && u <= 1.0f) {
+            V3 q = cross(s, e1);
+            float v = inv_det * dot(d, q);
+            if (v >= 0.0f && u + v <= 1.0f) {
+                float tt = inv_det * dot(e2, q);
+                if (tt >= t_min && tt <= t_max) {
+                    *t = tt;
+                    *p = o + tt * d;
+                    *n = dot(d, normal) > 0.0f ? -normal : normal;
+                    return true;
+                }
+            }
+        }
+    }
+    return false;
+}
+
+/* kernels.py:310-362 */
+bool hit_quad(Ctx& c, int idx, V3 o, V3 d, float t_min, float t_max, float* t, V3* p, V3* n) {
+    c.cnt.quad_tests++;
+    const OScene* sc = c.sc;
+    V3 Q = ld3(sc->quad_Q + 3 * idx), u = ld3(sc->quad_u + 3 * idx), v = ld3(sc->quad_v + 3 * idx);
+    V3 normal = ld3(sc->quad_normal + 3 * idx), w = ld3(sc->quad_w + 3 * idx);
+    float D = sc->quad_D[idx];
+    float denom = dot(normal, d);
+    if (fabsf(denom) >= 1e-8f) {
+        float tt = (D - dot(normal, o)) / denom;
+        if (tt >= t_min && tt <= t_max) {
+            V3 isect = o + tt * d;
+            V3 ph = isect - Q;
+            float alpha = dot(w, cross(ph, v));
+            float beta = dot(w, cross(u, ph));
+            if (alpha >= 0.0f && alpha <= 1.0f && beta >= 0.0f && beta <= 1.0f) {
+                *t = tt;
+                *p = isect;
+                *n = denom < 0.0f ? normal : -normal;
+                return true;
+            }
+        }
+    }
+    return false;
+}
+
+/* kernels.py:600-621 */
+bool hit_aabb_optimized(V3 bmin, V3 bmax, V3 o, V3 inv, float t_min, float t_max) {
+    V3 t0 = (bmin - o) * inv;
+    V3 t1 = (bmax - o) * inv;
+    V3 lo = v3(fmin2(t0.x, t1.x), fmin2(t0.y, t1.y), fmin2(t0.z, t1.z));
+    V3 hi = v3(fmax2(t0.x, t1.x), fmax2(t0.y, t1.y), fmax2(t0.z, t1.z));
+    float tmin = fmax2(fmax2(lo.x, lo.y), fmax2(lo.z, t_min));
+    float tmax = fmin2(fmin2(hi.x, hi.y), fmin2(hi.z, t_max));
+    return tmax >= tmin;
+}
+
+/* kernels.py:624-742 (traverse_bvh_legacy; the active branch of traverse_bvh, :749-759) */
+Hit traverse_bvh(Ctx& c, V3 o, V3 d, float t_min, float t_max) {
+    const OScene* sc = c.sc;
+    c.cnt.rays++;
+    Hit best;
+    best.hit = false;
+    best.t = t_max; /* closest_t */
+    best.p = v3(0, 0, 0);
+    best.n = v3(0, 0, 0);
+    best.prim_type = 0;
+    best.prim_idx = 0;
+    V3 inv = v3(fabsf(d.x) > 1e-8f ? 1.0f / d.x : 1e8f, fabsf(d.y) > 1e-8f ? 1.0f / d.y : 1e8f,
+                fabsf(d.z) > 1e-8f ? 1.0f / d.z : 1e8f);
+    int stack[64];
+    int sp = 0;
+    stack[sp++] = 0;
+    while (sp > 0) {
+        int ni = stack[--sp];
+        if (ni < 0 || ni >= sc->num_nodes) continue;
+        V3 bmin = ld3(sc->bvh_bbox_min + 3 * ni), bmax = ld3(sc->bvh_bbox_max + 3 * ni);
+        c.cnt.node_tests++;
+        if (!hit_aabb_optimized(bmin, bmax, o, inv, t_min, best.t)) continue;
+        int prim_idx = sc->bvh_prim_idx[ni];
+        if (prim_idx >= 0) {
+            int prim_type = sc->bvh_prim_type[ni];
+            bool hit = false;
+            float t = 0.0f;
+            V3 p = v3(0, 0, 0), n = v3(0, 0, 0);
+            if (prim_type == 0) hit = hit_sphere(c, prim_idx, o, d, t_min, best.t, &t, &p, &n);
+            else if (prim_type == 1) hit = hit_triangle(c, prim_idx, o, d, t_min, best.t, &t, &p, &n);
+            else if (prim_type == 2) hit = hit_quad(c, prim_idx, o, d, t_min, best.t, &t, &p, &n);
+            if (hit && t < best.t) {
+                best.hit = true;
+                best.t = t;
+                best.p = p;
+                best.n = n;
+                best.prim_type = prim_type;
+                best.prim_idx = prim_idx;
+            }
+        } else {
+            int l = sc->bvh_left[ni], r = sc->bvh_right[ni];
+            if (l >= 0 && r >= 0) {
+                V3 lc = (ld3(sc->bvh_bbox_min + 3 * l) + ld3(sc->bvh_bbox_max + 3 * l)) * 0.5f;
+                V3 rc = (ld3(sc->bvh_bbox_min + 3 * r) + ld3(sc->bvh_bbox_max + 3 * r)) * 0.5f;
+                float ld = dot(lc - o, d);
+                float rd = dot(rc - o, d);
+                if (ld < rd) {
+                    if (sp < 64) stack[sp++] = r;
+                    if (sp < 64) stack[sp++] = l;
+                } else {
+                    if (sp < 64) stack[sp++] = l;
+                    if (sp < 64) stack[sp++] = r;
+                }
+            } else {
+                if (r >= 0 && sp < 64) stack[sp++] = r;
+                if (l >= 0 && sp < 64) stack[sp++] = l;
+            }
+        }
+    }
+    return best;
+}
+
+/* kernels.py:766-786 */
+V3 reflect(V3 v, V3 n) { return v - (2.0f * dot(v, n)) * n; }
+V3 refract(V3 uv, V3 n, float eta) {
+    float cos_theta = fmin2(-dot(uv, n), 1.0f);
+    V3 perp = eta * (uv + cos_theta * n);
+    V3 par = (-sqrtf(fabsf(1.0f - dot(perp, perp)))) * n;
+    return perp + par;
+}
+float reflectance(float cosine, float ref_idx) {
+    float r0 = (1.0f - ref_idx) / (1.0f + ref_idx);
+    r0 = r0 * r0;
+    return r0 + (1.0f - r0) * o_pow5f(1.0f - cosine);
+}
+
+/* kernels.py:789-814 */
+V3 emitted(const OScene* sc, int prim_type, int prim_idx) {
+    const OMaterials& m = sc->mat[prim_type];
+    if (m.material_type[prim_idx] == 3) return ld3(m.emit + 3 * prim_idx);
+    return v3(0, 0, 0);
+}
+
+/* kernels.py:924-1017 */
+V3 eval_texture(const OScene* sc, int prim_type, int prim_idx, V3 hp) {
+    const OMaterials& m = sc->mat[prim_type];
+    int tex_type = m.texture_type[prim_idx];
+    V3 color1 = ld3(m.color1 + 3 * prim_idx), color2 = ld3(m.color2 + 3 * prim_idx);
+    float scale = m.texture_scale[prim_idx];
+    int img_idx = m.image_idx[prim_idx];
+    V3 result = v3(1, 1, 1);
+    if (tex_type == 0) {
+        result = color1;
+    } else if (tex_type == 1) {
+        float inv_scale = 1.0f / scale;
+        int xi = (int)floorf(inv_scale * hp.x), yi = (int)floorf(inv_scale * hp.y), zi = (int)floorf(inv_scale * hp.z);
+        int s = xi + yi + zi;
+        bool is_even = (((s % 2) + 2) % 2) == 0; /* Python-style modulo */
+        result = is_even ? color1 : color2;
+    } else if (tex_type == 2) {
+        if (prim_type == 0) {
+            const float* sd = sc->sphere_data + 4 * prim_idx;
+            float u, v;
+            get_sphere_uv(hp, v3(sd[0], sd[1], sd[2]), &u, &v);
+            if (img_idx >= 0 && img_idx < sc->num_images) {
+                int iw = sc->image_w[img_idx], ih = sc->image_h[img_idx];
+                u = fmax2(0.0f, fmin2(1.0f, u));
+                v = 1.0f - fmax2(0.0f, fmin2(1.0f, v));
+                int i = (int)(u * (float)iw);
+                int j = (int)(v * (float)ih);
+                i = i > iw - 1 ? iw - 1 : i; i = i < 0 ? 0 : i;   /* max(0, min(w-1, i)) */
+                j = j > ih - 1 ? ih - 1 : j; j = j < 0 ? 0 : j;
+                const uint8_t* px = sc->images[img_idx] + 3 * ((size_t)j * iw + i);
+                result = v3((float)px[0] / 255.0f, (float)px[1] / 255.0f, (float)px[2] / 255.0f);
+            }
+        } else {
+            result = v3(1.0f, 0.0f, 1.0f);
+        }
+    } else if (tex_type == 3) {
+        float noise_val = o_sinf(scale * hp.z + 10.0f * perlin_turb(sc, hp, 3));
+        result = (color1 * 0.5f) * (1.0f + noise_val);
+    }
+    return result;
+}
+
+/* kernels.py:817-917 */
+bool scatter(const OScene* sc, V3 ray_dir, V3 hp, V3 normal, int prim_type, int prim_idx, Rng& rng,
+             V3* scatter_dir, V3* attenuation) {
+    const OMaterials& m = sc->mat[prim_type];
+    int mat_type = m.material_type[prim_idx];
+    *scatter_dir = v3(0, 0, 0);
+    *attenuation = v3(1, 1, 1);
+    bool scattered = false;
+    if (mat_type == 0) {
+        V3 albedo = eval_texture(sc, prim_type, prim_idx, hp);
+        *scatter_dir = random_cosine_direction(normal, rng);
+        *attenuation = albedo;
+        scattered = true;
+    } else if (mat_type == 1) {
+        V3 albedo = ld3(m.albedo + 3 * prim_idx);
+        float fuzz = m.fuzz[prim_idx];
+        V3 reflected = reflect(normalized(ray_dir), normal);
+        *scatter_dir = reflected + fuzz * random_unit_vector(rng);
+        if (dot(*scatter_dir, normal) > 0.0f) {
+            *attenuation = albedo;
+            scattered = true;
+        }
+    } else if (mat_type == 2) {
+        float ir = m.ir[prim_idx];
+        bool front_face = dot(ray_dir, normal) < 0.0f;
+        V3 nf = front_face ? normal : -normal;
+        float ratio = front_face ? (1.0f / ir) : ir;
+        V3 unit_dir = normalized(ray_dir);
+        float cos_theta = fmin2(-dot(unit_dir, nf), 1.0f);
+        float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
+        bool cannot_refract = ratio * sin_theta > 1.0f;
+        /* `a or b` short-circuits: the random number is drawn only when refraction is possible */
+        if (cannot_refract || reflectance(cos_theta, ratio) > rng.next()) *scatter_dir = reflect(unit_dir, nf);
+        else *scatter_dir = refract(unit_dir, nf, ratio);
+        *attenuation = v3(1, 1, 1);
+        scattered = true;
+    } else if (mat_type == 3) {
+        scattered = false;
+    } else if (mat_type == 4) {
+        *scatter_dir = random_unit_vector(rng);
+        *attenuation = eval_texture(sc, prim_type, prim_idx, hp);
+        scattered = true;
+    }
+    return scattered;
+}
+
+struct MediumResult {
+    bool is_medium_hit;
+    float t_scatter;
+    V3 scatter_point;
+    float t_exit;
+};
+
+/* kernels.py:365-450 */
+MediumResult apply_constant_medium(Ctx& c, int prim_type, int prim_idx, V3 o, V3 d, float t_min, float t_max,
+                                   float t_entry, Rng& rng) {
+    MediumResult r;
+    r.is_medium_hit = false;
+    r.t_scatter = 0.0f;
+    r.scatter_point = v3(0, 0, 0);
+    r.t_exit = 0.0f;
+    const OMaterials& m = c.sc->mat[prim_type];
+    int is_medium = m.is_medium[prim_idx];
+    float density = m.medium_density[prim_idx];
+    if (is_medium > 0) {
+        Hit ex = traverse_bvh(c, o, d, t_entry + 0.0001f, 1e10f);
+        if (ex.hit) {
+            r.t_exit = ex.t;
+            float t1 = fmax2(t_entry, t_min);
+            float t2 = fmin2(r.t_exit, t_max);
+            if (t1 < t2) {
+                if (t1 < 0.0f) t1 = 0.0f;
+                float ray_length = sqrtf(dot(d, d));
+                float distance_inside = (t2 - t1) * ray_length;
+                float hit_distance = -o_logf(fmax2(rng.next(), 1e-10f)) / density;
+                if (hit_distance < distance_inside) {
+                    r.t_scatter = t1 + hit_distance / ray_length;
+                    r.scatter_point = o + r.t_scatter * d;
+                    r.is_medium_hit = true;
+                }
+            }
+        }
+    }
+    return r;
+}
+
+/* kernels.py:1024-1170 */
+V3 trace_ray(Ctx& c, V3 ray_origin, V3 ray_dir, Rng& rng) {
+    const OScene* sc = c.sc;
+    const int max_depth = c.cam->max_depth;
+    V3 color = v3(0, 0, 0);
+    V3 throughput = v3(1, 1, 1);
+    V3 cur_o = ray_origin;
+    V3 cur_d = normalized(ray_dir);
+    for (int depth = 0; depth < max_depth; depth++) {
+        c.cnt.bounces++;
+        Hit h = traverse_bvh(c, cur_o, cur_d, 0.001f, 1e10f);
+        if (h.hit) {
+            int is_cm = sc->mat[h.prim_type].is_medium[h.prim_idx];
+            bool scattered = false;
+            V3 scatter_dir = v3(0, 0, 0), attenuation = v3(1, 1, 1);
+            bool volume_passthrough = false;
+            V3 hit_point = h.p, normal = h.n;
+            if (is_cm > 0) {
+                MediumResult mr = apply_constant_medium(c, h.prim_type, h.prim_idx, cur_o, cur_d, 0.001f, 1e10f, h.t, rng);
+                if (mr.is_medium_hit) {
+                    hit_point = mr.scatter_point;
+                    normal = v3(1, 0, 0);
+                    scatter_dir = random_unit_vector(rng);
+                    attenuation = ld3(sc->mat[h.prim_type].medium_albedo + 3 * h.prim_idx);
+                    scattered = true;
+                } else if (mr.t_exit > 0.0f) {
+                    volume_passthrough = true;
+                    float ray_length = sqrtf(dot(cur_d, cur_d));
+                    float epsilon_t = 0.001f / ray_length;
+                    cur_o = cur_o + cur_d * (mr.t_exit + epsilon_t);
+                } else {
+                    V3 emit = emitted(sc, h.prim_type, h.prim_idx);
+                    color = color + throughput * emit;
+                    scattered = scatter(sc, cur_d, hit_point, normal, h.prim_type, h.prim_idx, rng, &scatter_dir, &attenuation);
+                }
+            } else {
+                V3 emit = emitted(sc, h.prim_type, h.prim_idx);
+                color = color + throughput * emit;
+                scattered = scatter(sc, cur_d, hit_point, normal, h.prim_type, h.prim_idx, rng, &scatter_dir, &attenuation);
+            }
+            if (scattered) {
+                cur_o = hit_point;
+                cur_d = scatter_dir;
+                throughput = throughput * attenuation;
+                if (depth + 1 >= max_depth) break;
+                if (depth + 1 >= 5) {
+                    float survival = fmin2(fmax2(fmax2(throughput.x, throughput.y), throughput.z), 0.95f);
+                    if (rng.next() > survival) break;
+                    throughput = throughput / survival;
+                }
+            } else if (!volume_passthrough) {
+                break;
+            }
+        } else {
+            color = color + throughput * ld3(c.cam->bg);
+            break;
+        }
+    }
+    return color;
+}
+
+void add_counters(OCounters* dst, const OCounters& s) {
+    dst->rays += s.rays; dst->node_tests += s.node_tests; dst->sphere_tests += s.sphere_tests;
+    dst->triangle_tests += s.triangle_tests; dst->quad_tests += s.quad_tests; dst->paths += s.paths;
+    dst->bounces += s.bounces;
+}
+
+} /* namespace */
+
+extern "C" {
+
+/* Elementary functions, vectorised, for tests/test_gpu_math.py and oracle/taichi_shim */
+void o_math_eval(int fn, int n, const float* a, const float* b, float* out) {
+    for (int i = 0; i < n; i++) {
+        switch (fn) {
+            case 0: out[i] = o_sinf(a[i]); break;
+            case 1: out[i] = o_cosf(a[i]); break;
+            case 2: out[i] = o_logf(a[i]); break;
+            case 3: out[i] = o_acosf(a[i]); break;
+            case 4: out[i] = o_atan2f(a[i], b[i]); break;
+            case 5: out[i] = o_pow5f(a[i]); break;
+            default: out[i] = 0.0f;
+        }
+    }
+}
+
+uint32_t o_rng_seed_state(uint32_t seed, uint32_t pixel, uint32_t sample) { return o_rng_seed(seed, pixel, sample); }
+void o_rng_draw(uint32_t* state, int n, float* out) {
+    for (int i = 0; i < n; i++) out[i] = o_rng_next(state);
+}
+
+/* get_ray for sample `sample` of every pixel (kernels.py:176-201; generate_camera_rays :1219-1239).
+ * Also returns the per-path RNG state after ray generation. */
+void o_generate_camera_rays(const OCamera* cam, int W, int H, uint32_t seed, int sample, float* out_o, float* out_d,
+                            uint32_t* out_rng) {
+    for (int py = 0; py < H; py++)
+        for (int px = 0; px < W; px++) {
+            int idx = py * W + px;
+            Rng rng{o_rng_seed(seed, (uint32_t)idx, (uint32_t)sample)};
+            V3 o, d;
+            get_ray(cam, px, py, rng, &o, &d);
+            out_o[3 * idx] = o.x; out_o[3 * idx + 1] = o.y; out_o[3 * idx + 2] = o.z;
+            out_d[3 * idx] = d.x; out_d[3 * idx + 1] = d.y; out_d[3 * idx + 2] = d.z;
+            if (out_rng) out_rng[idx] = rng.s;
+        }
+}
+
+/* traverse_bvh over an arbitrary ray list (intersect_rays, kernels.py:1242-1263) */
+void o_first_hit(const OScene* sc, int n, const float* o, const float* d, float t_min, float t_max, int32_t* out_valid,
+                 float* out_t, int32_t* out_type, int32_t* out_idx, float* out_p, float* out_n, OCounters* counters,
+                 int nthreads) {
+    OCounters total;
+    memset(&total, 0, sizeof total);
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel
+    {
+        Ctx c;
+        c.sc = sc;
+        c.cam = nullptr;
+        memset(&c.cnt, 0, sizeof c.cnt);
+#pragma omp for schedule(dynamic, 256)
+        for (int i = 0; i < n; i++) {
+            Hit h = traverse_bvh(c, ld3(o + 3 * i), ld3(d + 3 * i), t_min, t_max);
+            out_valid[i] = h.hit ? 1 : 0;
+            out_t[i] = h.t; /* traverse_bvh returns closest_t (kernels.py:742): t_max on a miss */
+            out_type[i] = h.prim_type;
+            out_idx[i] = h.prim_idx;
+            if (out_p) { out_p[3 * i] = h.p.x; out_p[3 * i + 1] = h.p.y; out_p[3 * i + 2] = h.p.z; }
+            if (out_n) { out_n[3 * i] = h.n.x; out_n[3 * i + 1] = h.n.y; out_n[3 * i + 2] = h.n.z; }
+        }
+#pragma omp critical
+        add_counters(&total, c.cnt);
+    }
+    if (counters) add_counters(counters, total);
+}
+
+/* render_sample (kernels.py:1177-1187) for samples [sample_begin, sample_begin+sample_count) and
+ * rows [y0, y1): accum[py,px] += trace_ray(get_ray(px,py)), one sample after the other. */
+void o_render_megakernel(const OScene* sc, const OCamera* cam, int W, int H, int y0, int y1, int sample_begin,
+                         int sample_count, uint32_t seed, float* accum, OCounters* counters, int nthreads) {
+    OCounters total;
+    memset(&total, 0, sizeof total);
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel
+    {
+        Ctx c;
+        c.sc = sc;
+        c.cam = cam;
+        memset(&c.cnt, 0, sizeof c.cnt);
+#pragma omp for schedule(dynamic, 1)
+        for (int py = y0; py < y1; py++)
+            for (int px = 0; px < W; px++) {
+                int idx = py * W + px;
+                V3 acc = ld3(accum + 3 * (size_t)idx);
+                for (int s = sample_begin; s < sample_begin + sample_count; s++) {
+                    Rng rng{o_rng_seed(seed, (uint32_t)idx, (uint32_t)s)};
+                    V3 o, d;
+                    get_ray(cam, px, py, rng, &o, &d);
+                    V3 col = trace_ray(c, o, d, rng);
+                    acc = acc + col;
+                    c.cnt.paths++;
+                }
+                accum[3 * (size_t)idx] = acc.x; accum[3 * (size_t)idx + 1] = acc.y; accum[3 * (size_t)idx + 2] = acc.z;
+            }
+#pragma omp critical
+        add_counters(&total, c.cnt);
+    }
+    if (counters) add_counters(counters, total);
+}
+
+/* The wavefront pipeline (kernels.py:1219-1418 driven by renderer.py:305-334), one sample at a
+ * time: generate_camera_rays; then per bounce intersect_rays, shade_miss_rays,
+ * reset_next_ray_count, shade_and_scatter, swap_ray_buffers, for at most max_depth waves.
+ * A path never forks, so each pixel owns at most one ray per wave and the queue order chosen by
+ * the atomic append (kernels.py:1345, :1394) cannot change any pixel's result; the restatement
+ * therefore processes paths one after the other, wave by wave, with the per-path random stream
+ * carried in the ray record. */
+void o_render_wavefront(const OScene* sc, const OCamera* cam, int W, int H, int y0, int y1, int sample_begin,
+                        int sample_count, uint32_t seed, float* accum, OCounters* counters, int nthreads) {
+    OCounters total;
+    memset(&total, 0, sizeof total);
+    const int max_depth = cam->max_depth;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel
+    {
+        Ctx c;
+        c.sc = sc;
+        c.cam = cam;
+        memset(&c.cnt, 0, sizeof c.cnt);
+#pragma omp for schedule(dynamic, 1)
+        for (int py = y0; py < y1; py++)
+            for (int px = 0; px < W; px++) {
+                int idx = py * W + px;
+                float* A = accum + 3 * (size_t)idx;
+                for (int s = sample_begin; s < sample_begin + sample_count; s++) {
+                    c.cnt.paths++;
+                    Rng rng{o_rng_seed(seed, (uint32_t)idx, (uint32_t)s)};
+                    /* generate_camera_rays: direction NOT normalised (kernels.py:1229-1233) */
+                    V3 ro, rd;
+                    get_ray(cam, px, py, rng, &ro, &rd);
+                    V3 thr = v3(1, 1, 1);
+                    int depth = 0;
+                    bool active = true;
+                    for (int bounce = 0; bounce < max_depth && active; bounce++) { /* renderer.py:313 */
+                        c.cnt.bounces++;
+                        /* intersect_rays */
+                        Hit h = traverse_bvh(c, ro, rd, 0.001f, 1e10f);
+                        if (!h.hit) { /* shade_miss_rays, kernels.py:1266-1280 */
+                            V3 add = thr * ld3(cam->bg);
+                            A[0] = A[0] + add.x; A[1] = A[1] + add.y; A[2] = A[2] + add.z;
+                            active = false;
+                            break;
+                        }
+                        /* shade_and_scatter, kernels.py:1289-1399 */
+                        V3 hit_point = h.p, normal = h.n;
+                        int is_cm = sc->mat[h.prim_type].is_medium[h.prim_idx];
+                        bool scattered = false, passthrough = false;
+                        V3 scatter_dir = v3(0, 0, 0), attenuation = v3(1, 1, 1), emit = v3(0, 0, 0);
+                        V3 next_o = ro;
+                        if (is_cm > 0) {
+                            MediumResult mr = apply_constant_medium(c, h.prim_type, h.prim_idx, ro, rd, 0.001f, 1e10f, h.t, rng);
+                            if (mr.is_medium_hit) {
+                                hit_point = mr.scatter_point;
+                                scatter_dir = random_unit_vector(rng);
+                                attenuation = ld3(sc->mat[h.prim_type].medium_albedo + 3 * h.prim_idx);
+                                scattered = true;
+                            } else if (mr.t_exit > 0.0f) {
+                                float epsilon_t = 0.001f / sqrtf(dot(rd, rd));
+                                next_o = ro + rd * (mr.t_exit + epsilon_t);
+                                passthrough = true; /* re-enqueued with unchanged depth/throughput */
+                            } else {
+                                emit = emitted(sc, h.prim_type, h.prim_idx);
+                                scattered = scatter(sc, rd, hit_point, normal, h.prim_type, h.prim_idx, rng, &scatter_dir, &attenuation);
+                            }
+                        } else {
+                            emit = emitted(sc, h.prim_type, h.prim_idx);
+                            scattered = scatter(sc, rd, hit_point, normal, h.prim_type, h.prim_idx, rng, &scatter_dir, &attenuation);
+                        }
+                        if (emit.x > 0.0f || emit.y > 0.0f || emit.z > 0.0f) {
+                            V3 add = thr * emit;
+                            A[0] = A[0] + add.x; A[1] = A[1] + add.y; A[2] = A[2] + add.z;
+                        }
+                        active = false;
+                        if (passthrough) {
+                            ro = next_o;
+                            active = true;
+                        }
+                        if (scattered) {
+                            V3 new_thr = thr * attenuation;
+                            int new_depth = depth + 1;
+                            if (new_depth < max_depth) {
+                                bool cont = true;
+                                if (new_depth >= 5) {
+                                    float survival = fmin2(fmax2(fmax2(new_thr.x, new_thr.y), new_thr.z), 0.95f);
+                                    if (rng.next() > survival) cont = false;
+                                    else new_thr = new_thr / survival;
+                                }
+                                if (cont) {
+                                    ro = hit_point;
+                                    rd = scatter_dir;
+                                    thr = new_thr;
+                                    depth = new_depth;
+                                    active = true;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+#pragma omp critical
+        add_counters(&total, c.cnt);
+    }
+    if (counters) add_counters(counters, total);
+}
+
+/* preview.py:117-132 buffer_to_image */
+void o_buffer_to_image(const float* accum, int n_floats, int sample_count, uint8_t* out) {
+    float scale = 1.0f / (float)(sample_count > 1 ? sample_count : 1);
+    for (int i = 0; i < n_floats; i++) {
+        float v = accum[i] * scale;
+        v = v > 0.0f ? v : 0.0f;
+        float g = sqrtf(v) * 255.999f;
+        g = g < 0.0f ? 0.0f : (g > 255.0f ? 255.0f : g);
+        out[i] = (uint8_t)g;
+    }
+}
+
+int o_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+} /* extern "C" */
