@@ -1,0 +1,208 @@
+"""ctypes binding of libb200pt.so (include/b200pt.h).  No CPU fallback: if the CUDA library is
+missing or fails to load, importing the renderer raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200pt.so")
+
+PT_MAX_IMAGES = 16
+PRIM_SPHERE, PRIM_TRIANGLE, PRIM_QUAD = 0, 1, 2
+PRIM_PREFIX = {PRIM_SPHERE: "sphere", PRIM_TRIANGLE: "triangle", PRIM_QUAD: "quad"}
+
+
+class PtHostMaterials(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "material_type", "albedo", "fuzz", "ir", "emit", "texture_type", "texture_scale", "color1", "color2",
+        "image_idx", "is_medium", "medium_density", "medium_albedo")]
+
+
+class PtHostScene(C.Structure):
+    _fields_ = (
+        [(n, C.c_int32) for n in ("num_spheres", "num_quads", "num_triangles", "num_nodes", "num_images")]
+        + [(n, C.c_void_p) for n in ("sphere_data", "quad_Q", "quad_u", "quad_v", "quad_normal", "quad_D", "quad_w",
+                                     "tri_v0", "tri_edge1", "tri_edge2", "tri_normal")]
+        + [("mat", PtHostMaterials * 3)]
+        + [(n, C.c_void_p) for n in ("bvh_bbox_min", "bvh_bbox_max", "bvh_left", "bvh_right", "bvh_prim_type",
+                                     "bvh_prim_idx", "perlin_randvec", "perm_x", "perm_y", "perm_z")]
+        + [("images", C.c_void_p * PT_MAX_IMAGES), ("image_w", C.c_int32 * PT_MAX_IMAGES),
+           ("image_h", C.c_int32 * PT_MAX_IMAGES)]
+    )
+
+
+class PtPackedInfo(C.Structure):
+    _fields_ = (
+        [(n, C.c_uint64) for n in ("total_bytes", "off_nodes", "off_spheres", "off_quads", "off_tris", "off_prim_mat",
+                                   "off_materials", "off_perlin", "off_images")]
+        + [("image_off", C.c_uint64 * PT_MAX_IMAGES), ("image_w", C.c_int32 * PT_MAX_IMAGES),
+           ("image_h", C.c_int32 * PT_MAX_IMAGES)]
+        + [(n, C.c_int32) for n in ("num_inner", "num_spheres", "num_quads", "num_triangles", "num_materials",
+                                    "num_images", "max_depth_tree", "has_media")]
+    )
+
+
+class PtCamera(C.Structure):
+    _fields_ = [("center", C.c_float * 3), ("pixel00", C.c_float * 3), ("delta_u", C.c_float * 3),
+                ("delta_v", C.c_float * 3), ("defocus_disk_u", C.c_float * 3), ("defocus_disk_v", C.c_float * 3),
+                ("defocus_angle", C.c_float), ("background", C.c_float * 3), ("max_depth", C.c_int32)]
+
+
+class PtCounters(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("rays", "box_tests", "sphere_tests", "triangle_tests", "quad_tests",
+                                          "paths", "bounces")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+# every symbol include/b200pt.h declares (tests/test_abi.py checks the library exports them all)
+EXPORTS = [
+    "pt_last_error", "pt_version", "pt_pack_scene_info", "pt_pack_scene", "pt_bvh_build_sah", "pt_create",
+    "pt_destroy", "pt_set_option", "pt_set_scene", "pt_set_camera", "pt_render_megakernel",
+    "pt_wavefront_workspace_bytes", "pt_render_wavefront", "pt_generate_camera_rays", "pt_first_hit",
+    "pt_math_eval", "pt_tonemap", "pt_enable_counters", "pt_get_counters",
+]
+
+_lib = None
+
+
+class B200PTError(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    """Load libb200pt.so.  Raises if it has not been built (python -m path_tracer_python_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise B200PTError(
+            f"{LIB_PATH} not found: the CUDA extension is not built. Run `python -m path_tracer_python_b200.build` "
+            "(there is no CPU fallback).")
+    L = C.CDLL(LIB_PATH)
+    L.pt_last_error.restype = C.c_char_p
+    L.pt_version.restype = C.c_char_p
+    L.pt_wavefront_workspace_bytes.restype = C.c_size_t
+    L.pt_wavefront_workspace_bytes.argtypes = [C.c_int, C.c_int]
+    L.pt_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    L.pt_destroy.argtypes = [C.c_void_p]
+    L.pt_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
+    L.pt_set_scene.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(PtPackedInfo)]
+    L.pt_set_camera.argtypes = [C.c_void_p, C.POINTER(PtCamera)]
+    L.pt_pack_scene_info.argtypes = [C.POINTER(PtHostScene), C.POINTER(PtPackedInfo)]
+    L.pt_pack_scene.argtypes = [C.POINTER(PtHostScene), C.POINTER(PtPackedInfo), C.c_void_p]
+    L.pt_render_megakernel.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.c_uint32, C.c_void_p]
+    L.pt_render_wavefront.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.pt_generate_camera_rays.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p,
+                                          C.c_void_p]
+    L.pt_first_hit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p,
+                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pt_math_eval.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pt_tonemap.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.pt_enable_counters.argtypes = [C.c_void_p, C.c_int]
+    L.pt_get_counters.argtypes = [C.c_void_p, C.POINTER(PtCounters), C.c_int]
+    L.pt_bvh_build_sah.argtypes = [C.c_int32] + [C.c_void_p] * 12
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = lib().pt_last_error()
+        raise B200PTError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
+
+
+class HostScene:
+    """Contiguous typed copies of a CompiledScene dict + the PtHostScene view over them."""
+
+    def __init__(self, cs: dict):
+        self._keep = []
+        s = PtHostScene()
+
+        def f32(key, tail=()):
+            a = np.ascontiguousarray(cs.get(key, np.zeros((0,) + tail)), dtype=np.float32)
+            self._keep.append(a)
+            return a
+
+        def i32(key):
+            a = np.ascontiguousarray(cs.get(key, np.zeros((0,))), dtype=np.int32)
+            self._keep.append(a)
+            return a
+
+        sd = f32("sphere_data", (4,))
+        s.num_spheres, s.sphere_data = sd.shape[0], _ptr(sd)
+        for k in ("quad_Q", "quad_u", "quad_v", "quad_normal", "quad_D", "quad_w"):
+            a = f32(k, () if k == "quad_D" else (3,))
+            setattr(s, k, _ptr(a))
+            if k == "quad_Q":
+                s.num_quads = a.shape[0]
+        for k, dst in (("triangle_v0", "tri_v0"), ("triangle_edge1", "tri_edge1"), ("triangle_edge2", "tri_edge2"),
+                       ("triangle_normal", "tri_normal")):
+            a = f32(k, (3,))
+            setattr(s, dst, _ptr(a))
+            if dst == "tri_v0":
+                s.num_triangles = a.shape[0]
+        for pt, prefix in PRIM_PREFIX.items():
+            m = s.mat[pt]
+            m.material_type = _ptr(i32(f"{prefix}_material_type"))
+            m.albedo = _ptr(f32(f"{prefix}_material_albedo", (3,)))
+            m.fuzz = _ptr(f32(f"{prefix}_material_fuzz"))
+            m.ir = _ptr(f32(f"{prefix}_material_ir"))
+            m.emit = _ptr(f32(f"{prefix}_material_emit_color", (3,)))
+            m.texture_type = _ptr(i32(f"{prefix}_texture_type"))
+            m.texture_scale = _ptr(f32(f"{prefix}_texture_scale"))
+            m.color1 = _ptr(f32(f"{prefix}_texture_color1", (3,)))
+            m.color2 = _ptr(f32(f"{prefix}_texture_color2", (3,)))
+            m.image_idx = _ptr(i32(f"{prefix}_texture_image_idx"))
+            m.is_medium = _ptr(i32(f"{prefix}_is_constant_medium"))
+            m.medium_density = _ptr(f32(f"{prefix}_medium_density"))
+            m.medium_albedo = _ptr(f32(f"{prefix}_medium_albedo", (3,)))
+        bmin = f32("bvh_bbox_min", (3,))
+        s.num_nodes, s.bvh_bbox_min = bmin.shape[0], _ptr(bmin)
+        s.bvh_bbox_max = _ptr(f32("bvh_bbox_max", (3,)))
+        s.bvh_left = _ptr(i32("bvh_left_child"))
+        s.bvh_right = _ptr(i32("bvh_right_child"))
+        s.bvh_prim_type = _ptr(i32("bvh_prim_type"))
+        s.bvh_prim_idx = _ptr(i32("bvh_prim_idx"))
+        rv = np.ascontiguousarray(cs["perlin_randvec"] if "perlin_randvec" in cs else np.zeros((256, 3)), np.float32)
+        self._keep.append(rv)
+        s.perlin_randvec = _ptr(rv)
+        for k, dst in (("perlin_perm_x", "perm_x"), ("perlin_perm_y", "perm_y"), ("perlin_perm_z", "perm_z")):
+            a = np.ascontiguousarray(cs[k] if k in cs else np.arange(256), np.int32)
+            self._keep.append(a)
+            setattr(s, dst, _ptr(a))
+        n_img = int(cs.get("num_images", 0))
+        if n_img > PT_MAX_IMAGES:
+            raise B200PTError(f"{n_img} image textures > {PT_MAX_IMAGES}")
+        s.num_images = n_img
+        for i in range(n_img):
+            img = np.ascontiguousarray(cs[f"image_{i}"], dtype=np.uint8)
+            self._keep.append(img)
+            s.images[i] = img.ctypes.data
+            s.image_h[i], s.image_w[i] = img.shape[0], img.shape[1]
+        self.c = s
+        self.input_bytes = int(sum(a.nbytes for a in self._keep))
+
+
+def make_camera(cam: dict, background=(0.7, 0.8, 1.0), max_depth=50) -> PtCamera:
+    """The float64 -> float32 narrowing of _upload_camera (reference renderer.py:230-247)."""
+    c = PtCamera()
+    for src, dst in (("cam_center", "center"), ("cam_pixel00", "pixel00"), ("cam_delta_u", "delta_u"),
+                     ("cam_delta_v", "delta_v"), ("cam_defocus_disk_u", "defocus_disk_u"),
+                     ("cam_defocus_disk_v", "defocus_disk_v")):
+        v = np.asarray(cam[src], dtype=np.float64).astype(np.float32)
+        getattr(c, dst)[:] = [float(x) for x in v]
+    c.defocus_angle = float(np.float32(cam["cam_defocus_angle"]))
+    c.background[:] = [float(np.float32(x)) for x in background]
+    c.max_depth = int(max_depth)
+    return c

@@ -1,0 +1,60 @@
+"""Builds libb200pt.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+    python -m path_tracer_python_b200.build [--force] [--verbose]
+
+Flags that matter: ``--fmad=false`` (PT-F32 contract: no FFMA contraction), ``-lineinfo`` (ncu source
+page), ``-gencode arch=compute_100a,code=sm_100a`` (B200 only; no other architectures, no PTX JIT).
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_PATH = os.path.join(HERE, "libb200pt.so")
+SOURCES = ["b200pt.cu", "pt_host.cpp"]
+HEADERS = ["pt_device.cuh", "pt_math.cuh", os.path.join("..", "..", "include", "b200pt.h")]
+
+NVCC_FLAGS = [
+    "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+    "--fmad=false", "-ftz=false", "-prec-div=true", "-prec-sqrt=true",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-fast-math", "-Xcompiler", "-ffp-contract=off",
+    "-shared", "-cudart", "shared",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    return "nvcc"
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_native(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB_PATH
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else [])
+    if os.path.exists("/usr/bin/g++"):
+        cmd += ["-ccbin", "/usr/bin/g++"]
+    cmd += ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stdout + r.stderr)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    path = build_native(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    print(path)

@@ -1,0 +1,843 @@
+// libb200pt: CUDA kernels (sm_100a) and the C ABI declared in include/b200pt.h.
+//
+// Megakernel  : one persistent lane per pixel runs ALL samples of the launch as a state machine
+//               (generate -> traverse -> shade / medium-exit search -> regenerate), accumulating in
+//               registers in sample order; replaces kernels.py:1177-1187 + trace_ray :1024-1170.
+// Wavefront   : generate / extend / shade over SoA float4 ray queues in HBM, compaction and
+//               material binning with warp-aggregated atomics, no host read-back inside a sample;
+//               replaces kernels.py:1219-1418 + the host loop renderer.py:305-334.
+// Compile with: nvcc -gencode arch=compute_100a,code=sm_100a --fmad=false (PT-F32 contract).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include "pt_device.cuh"
+
+using namespace pt;
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+extern "C" std::string* pt_error_slot(void);   // pt_host.cpp: one thread-local slot for the whole library
+static int set_error(int code, const std::string& msg) {
+    *pt_error_slot() = msg;
+    return code;
+}
+#define PT_CUDA(call)                                                                         \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            return set_error(PT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+struct PtContext {
+    int device = 0;
+    bool has_scene = false;
+    bool has_camera = false;
+    DScene scene{};
+    PtPackedInfo info{};
+    PtCamera cam{};
+    int block_threads = 256;
+    int smem_nodes = -1;      // -1: auto
+    int wavefront_sort = 1;
+    int num_sms = 148;
+    int max_smem_optin = 0;
+    bool count = false;
+    DCounters* d_counters = nullptr;
+};
+
+// ------------------------------------------------------------------------------------------------
+// shared helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void stage_nodes(float4* s_nodes, const DScene& S, int n_snodes) {
+    const int n4 = n_snodes * 4;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) s_nodes[i] = __ldg(S.nodes + i);
+    __syncthreads();
+}
+
+__device__ __forceinline__ void flush_counters(DCounters* dc, const LocalCounters& lc) {
+    // one atomic per warp per counter (warp-aggregated)
+    unsigned v[7] = {lc.rays, lc.box_tests, lc.sphere_tests, lc.triangle_tests, lc.quad_tests, lc.paths, lc.bounces};
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(dc);
+#pragma unroll
+    for (int k = 0; k < 7; k++) {
+        unsigned long long s = v[k];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if ((threadIdx.x & 31) == 0 && s) atomicAdd(dst + k, s);
+    }
+}
+
+// The constant-medium decision once the exit search is done (kernels.py:421-448). Returns true if
+// the ray scatters inside the medium (t_scatter valid).
+__device__ __forceinline__ bool medium_sample(bool hit_exit, float t_exit_hit, float t_entry, f3 d, float density,
+                                              uint32_t& rng, float& t_exit, float& t_scatter) {
+    t_exit = 0.0f;
+    t_scatter = 0.0f;
+    if (!hit_exit) return false;
+    t_exit = t_exit_hit;
+    float t1 = max2(t_entry, 0.001f);
+    float t2 = min2(t_exit, 1e10f);
+    if (t1 < t2) {
+        if (t1 < 0.0f) t1 = 0.0f;
+        float ray_length = ptm::fsqrt(dot(d, d));
+        float distance_inside = (t2 - t1) * ray_length;
+        float hit_distance = ptm::fdiv(-ptm::log_c(max2(ptm::rng_next(rng), 1e-10f)), density);
+        if (hit_distance < distance_inside) {
+            t_scatter = t1 + ptm::fdiv(hit_distance, ray_length);
+            return true;
+        }
+    }
+    return false;
+}
+
+// ------------------------------------------------------------------------------------------------
+// megakernel
+// ------------------------------------------------------------------------------------------------
+struct MegaParams {
+    DScene S;
+    PtCamera cam;
+    float* accum;
+    int W, H, y0, y1;
+    int sample_begin, sample_count;
+    uint32_t seed;
+    int n_snodes;
+    int tiles_x;
+    DCounters* counters;
+};
+
+template <bool COUNT>
+__global__ void __launch_bounds__(256) k_megakernel(const __grid_constant__ MegaParams P) {
+    extern __shared__ float4 s_nodes[];
+    const DScene& S = P.S;
+    stage_nodes(s_nodes, S, P.n_snodes);
+
+    // one warp = one 8x4 pixel tile (coherent primary rays)
+    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int tx = gwarp % P.tiles_x, ty = gwarp / P.tiles_x;
+    const int px = tx * 8 + (lane & 7);
+    const int py = P.y0 + ty * 4 + (lane >> 3);
+    const bool valid = (px < P.W) && (py < P.y1);
+    LocalCounters lc;
+    if (valid) {
+        const int pixel = py * P.W + px;
+        float* ap = P.accum + 3 * (size_t)pixel;
+        f3 acc = mk3(ap[0], ap[1], ap[2]);
+        const int max_depth = P.cam.max_depth;
+        const f3 bg = mk3(P.cam.background[0], P.cam.background[1], P.cam.background[2]);
+        int s = P.sample_begin;
+        const int s_end = P.sample_begin + P.sample_count;
+
+        // per-path state
+        f3 o, d, thr, col;
+        uint32_t rng;
+        int depth;
+        int mode;            // 0: closest-hit search, 1: medium-exit search (kernels.py:417)
+        float t_entry = 0.0f;
+        int ref_entry = kRefNone;
+        bool done = (s >= s_end) || max_depth <= 0;
+
+        auto start_path = [&]() {
+            rng = ptm::rng_seed(P.seed, (uint32_t)pixel, (uint32_t)s);
+            get_ray(P.cam, px, py, rng, o, d);
+            d = normalized(d);                              // kernels.py:1042
+            thr = mk3(1.0f, 1.0f, 1.0f);
+            col = mk3(0.0f, 0.0f, 0.0f);
+            depth = 0;
+            mode = 0;
+            if (COUNT) lc.paths++;
+        };
+        if (!done) start_path();
+
+        while (!done) {
+            float t;
+            int ref;
+            const float t_min = mode == 0 ? 0.001f : t_entry + 0.0001f;
+            if (COUNT && mode == 0) lc.bounces++;
+            traverse<COUNT>(S, s_nodes, P.n_snodes, o, d, t_min, 1e10f, t, ref, lc);
+
+            bool end_path = false;
+            bool do_shade = false;       // surface shading of (sref, st)
+            bool scattered = false;
+            bool passthrough = false;
+            int sref = ref;
+            float st = t;
+            f3 hp, sdir, atten;
+            Mat m;
+            if (mode == 0) {
+                if (ref == kRefNone) {
+                    col = col + thr * bg;                   // kernels.py:1166
+                    end_path = true;
+                } else {
+                    m = load_mat(S, mat_id_of(S, ref));
+                    if (mat_is_medium(m.header)) {
+                        mode = 1;                           // run the exit search as the next traversal
+                        t_entry = t;
+                        ref_entry = ref;
+                        continue;
+                    }
+                    do_shade = true;
+                }
+            } else {
+                mode = 0;
+                const int mid = mat_id_of(S, ref_entry);
+                const float4 m2 = __ldg(S.materials + 3 * mid + 2);   // (density, medium albedo)
+                float t_exit, t_scatter;
+                if (medium_sample(ref != kRefNone, t, t_entry, d, m2.x, rng, t_exit, t_scatter)) {
+                    hp = o + t_scatter * d;                 // kernels.py:446
+                    sdir = random_unit_vector(rng);         // kernels.py:1088
+                    atten = mk3(m2.y, m2.z, m2.w);
+                    scattered = true;
+                } else if (t_exit > 0.0f) {
+                    passthrough = true;                     // kernels.py:1100-1110
+                    float eps_t = ptm::fdiv(0.001f, ptm::fsqrt(dot(d, d)));
+                    o = o + d * (t_exit + eps_t);
+                } else {
+                    m = load_mat(S, mid);                   // fallback: shade the boundary, :1111-1119
+                    sref = ref_entry;
+                    st = t_entry;
+                    do_shade = true;
+                }
+            }
+            if (do_shade) {
+                f3 n, emit;
+                finalize_hit(S, sref, o, d, st, hp, n);
+                scattered = shade_surface(S, m, sref, d, hp, n, rng, emit, sdir, atten);
+                col = col + thr * emit;                     // kernels.py:1116/1124
+            }
+            if (!end_path) {
+                if (scattered) {
+                    o = hp;
+                    d = sdir;
+                    thr = thr * atten;
+                    if (depth + 1 >= max_depth) {
+                        end_path = true;
+                    } else if (depth + 1 >= 5) {            // Russian roulette, kernels.py:1145-1157
+                        float survival = min2(max2(max2(thr.x, thr.y), thr.z), 0.95f);
+                        if (ptm::rng_next(rng) > survival) end_path = true;
+                        else thr = vdiv(thr, survival);
+                    }
+                    depth++;
+                } else if (passthrough) {
+                    depth++;                                // the for-loop index still advances
+                    if (depth >= max_depth) end_path = true;
+                } else {
+                    end_path = true;                        // absorbed
+                }
+            }
+            if (end_path) {
+                acc = acc + col;                            // kernels.py:1187
+                s++;
+                if (s < s_end) start_path();
+                else done = true;
+            }
+        }
+        ap[0] = acc.x; ap[1] = acc.y; ap[2] = acc.z;
+    }
+    if (COUNT) flush_counters(P.counters, lc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// wavefront
+// ------------------------------------------------------------------------------------------------
+// Ray record (48 B, three float4 planes): (o.xyz d.x) (d.yz thr.xy) (thr.z pixel rng depth)
+// Hit record (16 B): (t, ref, t_exit, exit_hit)
+struct WfQueues {
+    float4 *r0[2], *r1[2], *r2[2];
+    float4* hit;
+    uint32_t* bins;          // kNumBins regions of `capacity` ray indices
+    int* qcount;             // [2] ray counts of the two queues
+    int* bin_count;          // [2][kNumBins]
+    int capacity;
+};
+constexpr int kNumBins = 8;  // 0 miss, 1 medium boundary, 2.. = 2 + material type (0..4)
+
+struct WfParams {
+    DScene S;
+    PtCamera cam;
+    WfQueues Q;
+    float* accum;
+    int W, H, y0, y1;
+    int sample;
+    uint32_t seed;
+    int n_snodes;
+    int bounce;              // parity selects queue
+    int sort;
+    DCounters* counters;
+};
+
+__global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ WfParams P) {
+    const int n = P.W * (P.y1 - P.y0);
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int pixel = P.y0 * P.W + i;
+        const int py = pixel / P.W, px = pixel - py * P.W;
+        uint32_t rng = ptm::rng_seed(P.seed, (uint32_t)pixel, (uint32_t)P.sample);
+        f3 o, d;
+        get_ray(P.cam, px, py, rng, o, d);                  // NOT normalised, kernels.py:1229-1233
+        P.Q.r0[0][i] = make_float4(o.x, o.y, o.z, d.x);
+        P.Q.r1[0][i] = make_float4(d.y, d.z, 1.0f, 1.0f);
+        P.Q.r2[0][i] = make_float4(1.0f, __int_as_float(pixel), __uint_as_float(rng), __int_as_float(0));
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 2 * kNumBins) P.Q.bin_count[threadIdx.x] = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        P.Q.qcount[0] = n;
+        P.Q.qcount[1] = 0;
+    }
+}
+
+// warp-aggregated append: lanes with the same key share one atomicAdd
+__device__ __forceinline__ int warp_agg_append(int* counter_base, int key, bool active) {
+    const unsigned lane = threadIdx.x & 31;
+    unsigned amask = __ballot_sync(0xffffffffu, active);
+    int pos = 0;
+    if (active) {
+        unsigned peers = __match_any_sync(amask, key);
+        int leader = __ffs(peers) - 1;
+        int rank = __popc(peers & ((1u << lane) - 1));
+        int base = 0;
+        if ((int)lane == leader) base = atomicAdd(counter_base + key, __popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        pos = base + rank;
+    }
+    return pos;
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(256) k_wf_extend(const __grid_constant__ WfParams P) {
+    extern __shared__ float4 s_nodes[];
+    const DScene& S = P.S;
+    const int cur = P.bounce & 1;
+    const int count = P.Q.qcount[cur];
+    // reset_next_ray_count (:1283) -- also when this wave is empty, otherwise the stale count of
+    // the wave before last would be picked up again two launches later
+    if (blockIdx.x == 0 && threadIdx.x == 0) P.Q.qcount[cur ^ 1] = 0;
+    if (count == 0) return;
+    stage_nodes(s_nodes, S, P.n_snodes);
+    LocalCounters lc;
+    int* bin_count = P.Q.bin_count + cur * kNumBins;
+    const int stride = gridDim.x * blockDim.x;
+    const int rounds = (count + stride - 1) / stride;
+    for (int r = 0; r < rounds; r++) {
+        const int i = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        const bool active = i < count;
+        int bin = 0;
+        if (active) {
+            float4 a = P.Q.r0[cur][i], b = P.Q.r1[cur][i];
+            f3 o = mk3(a.x, a.y, a.z), d = mk3(a.w, b.x, b.y);
+            float t, t_exit = 0.0f;
+            int ref, exit_hit = 0;
+            if (COUNT) lc.bounces++;
+            traverse<COUNT>(S, s_nodes, P.n_snodes, o, d, 0.001f, 1e10f, t, ref, lc);   // intersect_rays, :1242
+            if (ref != kRefNone) {
+                int header = __float_as_int(__ldg(S.materials + 3 * mat_id_of(S, ref)).x);
+                if (mat_is_medium(header)) {
+                    // exit search of apply_constant_medium (kernels.py:417-419), done here so the
+                    // shade stage is traversal-free
+                    int eref;
+                    traverse<COUNT>(S, s_nodes, P.n_snodes, o, d, t + 0.0001f, 1e10f, t_exit, eref, lc);
+                    exit_hit = eref != kRefNone;
+                    bin = 1;
+                } else {
+                    bin = 2 + mat_type(header);
+                }
+            }
+            P.Q.hit[i] = make_float4(t, __int_as_float(ref), t_exit, __int_as_float(exit_hit));
+        }
+        if (P.sort) {
+            int pos = warp_agg_append(bin_count, bin, active);
+            if (active) P.Q.bins[(size_t)bin * P.Q.capacity + pos] = (uint32_t)i;
+        }
+    }
+    if (COUNT) flush_counters(P.counters, lc);
+}
+
+__global__ void __launch_bounds__(256) k_wf_shade(const __grid_constant__ WfParams P) {
+    const DScene& S = P.S;
+    const int cur = P.bounce & 1, nxt = cur ^ 1;
+    const int count = P.Q.qcount[cur];
+    if (count == 0) return;
+    const int* bin_count = P.Q.bin_count + cur * kNumBins;
+    int prefix[kNumBins + 1];
+    if (P.sort) {
+        prefix[0] = 0;
+#pragma unroll
+        for (int b = 0; b < kNumBins; b++) prefix[b + 1] = prefix[b] + bin_count[b];
+    }
+    if (blockIdx.x == 0 && threadIdx.x < kNumBins) P.Q.bin_count[nxt * kNumBins + threadIdx.x] = 0;
+    const int max_depth = P.cam.max_depth;
+    const f3 bg = mk3(P.cam.background[0], P.cam.background[1], P.cam.background[2]);
+    const int stride = gridDim.x * blockDim.x;
+    const int rounds = (count + stride - 1) / stride;
+    for (int r = 0; r < rounds; r++) {
+        const int j = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        const bool active = j < count;
+        bool emit_next = false;
+        f3 no, nd, nthr;
+        int pixel = 0, ndepth = 0;
+        uint32_t rng = 0;
+        if (active) {
+            int i = j;
+            if (P.sort) {
+                int b = 0;
+#pragma unroll
+                for (int k = 1; k < kNumBins; k++) b += (j >= prefix[k]) ? 1 : 0;
+                i = (int)P.Q.bins[(size_t)b * P.Q.capacity + (j - prefix[b])];
+            }
+            float4 a = P.Q.r0[cur][i], bq = P.Q.r1[cur][i], c = P.Q.r2[cur][i], h = P.Q.hit[i];
+            f3 o = mk3(a.x, a.y, a.z), d = mk3(a.w, bq.x, bq.y), thr = mk3(bq.z, bq.w, c.x);
+            pixel = __float_as_int(c.y);
+            rng = __float_as_uint(c.z);
+            int depth = __float_as_int(c.w);
+            float t = h.x;
+            int ref = __float_as_int(h.y);
+            float* ap = P.accum + 3 * (size_t)pixel;
+            if (ref == kRefNone) {                           // shade_miss_rays, kernels.py:1266-1280
+                f3 add = thr * bg;
+                ap[0] = ap[0] + add.x; ap[1] = ap[1] + add.y; ap[2] = ap[2] + add.z;
+            } else {                                         // shade_and_scatter, kernels.py:1289-1399
+                const int mid = mat_id_of(S, ref);
+                Mat m = load_mat(S, mid);
+                bool scattered = false, do_shade = true;
+                f3 hp, sdir, atten, emit = mk3(0.0f, 0.0f, 0.0f);
+                if (mat_is_medium(m.header)) {
+                    const float4 m2 = __ldg(S.materials + 3 * mid + 2);
+                    float t_exit, t_scatter;
+                    if (medium_sample(__float_as_int(h.w) != 0, h.z, t, d, m2.x, rng, t_exit, t_scatter)) {
+                        hp = o + t_scatter * d;
+                        sdir = random_unit_vector(rng);
+                        atten = mk3(m2.y, m2.z, m2.w);
+                        scattered = true;
+                        do_shade = false;
+                    } else if (t_exit > 0.0f) {              // passthrough: re-enqueue, same depth (:1342-1350)
+                        float eps_t = ptm::fdiv(0.001f, ptm::fsqrt(dot(d, d)));
+                        no = o + d * (t_exit + eps_t);
+                        nd = d;
+                        nthr = thr;
+                        ndepth = depth;
+                        emit_next = true;
+                        do_shade = false;
+                    }
+                }
+                if (do_shade) {
+                    f3 n;
+                    finalize_hit(S, ref, o, d, t, hp, n);
+                    scattered = shade_surface(S, m, ref, d, hp, n, rng, emit, sdir, atten);
+                }
+                if (emit.x > 0.0f || emit.y > 0.0f || emit.z > 0.0f) {      // kernels.py:1368-1375
+                    f3 add = thr * emit;
+                    ap[0] = ap[0] + add.x; ap[1] = ap[1] + add.y; ap[2] = ap[2] + add.z;
+                }
+                if (scattered) {
+                    f3 new_thr = thr * atten;
+                    int new_depth = depth + 1;
+                    if (new_depth < max_depth) {
+                        bool cont = true;
+                        if (new_depth >= 5) {
+                            float survival = min2(max2(max2(new_thr.x, new_thr.y), new_thr.z), 0.95f);
+                            if (ptm::rng_next(rng) > survival) cont = false;
+                            else new_thr = vdiv(new_thr, survival);
+                        }
+                        if (cont) {
+                            no = hp; nd = sdir; nthr = new_thr; ndepth = new_depth;
+                            emit_next = true;
+                        }
+                    }
+                }
+            }
+        }
+        // compaction: one atomic per warp (kernels.py:1345/:1394 use one per ray)
+        int pos = warp_agg_append(P.Q.qcount + nxt, 0, emit_next);
+        if (emit_next) {
+            P.Q.r0[nxt][pos] = make_float4(no.x, no.y, no.z, nd.x);
+            P.Q.r1[nxt][pos] = make_float4(nd.y, nd.z, nthr.x, nthr.y);
+            P.Q.r2[nxt][pos] = make_float4(nthr.z, __int_as_float(pixel), __uint_as_float(rng), __int_as_float(ndepth));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// probes, tonemap
+// ------------------------------------------------------------------------------------------------
+__global__ void k_generate_rays(PtCamera cam, int W, int H, uint32_t seed, int sample, float* o_out, float* d_out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= W * H) return;
+    int py = i / W, px = i - py * W;
+    uint32_t rng = ptm::rng_seed(seed, (uint32_t)i, (uint32_t)sample);
+    f3 o, d;
+    get_ray(cam, px, py, rng, o, d);
+    o_out[3 * i] = o.x; o_out[3 * i + 1] = o.y; o_out[3 * i + 2] = o.z;
+    d_out[3 * i] = d.x; d_out[3 * i + 1] = d.y; d_out[3 * i + 2] = d.z;
+}
+
+struct FirstHitParams {
+    DScene S;
+    const float* o;
+    const float* d;
+    int n;
+    float t_min, t_max;
+    float* out_t;
+    int32_t* out_prim;
+    float* out_p;
+    float* out_n;
+    int n_snodes;
+    DCounters* counters;
+};
+
+template <bool COUNT>
+__global__ void __launch_bounds__(256) k_first_hit(const __grid_constant__ FirstHitParams P) {
+    extern __shared__ float4 s_nodes[];
+    stage_nodes(s_nodes, P.S, P.n_snodes);
+    LocalCounters lc;
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += stride) {
+        f3 o = mk3(P.o[3 * i], P.o[3 * i + 1], P.o[3 * i + 2]);
+        f3 d = mk3(P.d[3 * i], P.d[3 * i + 1], P.d[3 * i + 2]);
+        float t;
+        int ref;
+        traverse<COUNT>(P.S, s_nodes, P.n_snodes, o, d, P.t_min, P.t_max, t, ref, lc);
+        P.out_t[i] = t;
+        P.out_prim[i] = ref == kRefNone ? -1 : ((ref_type(ref) << 28) | ref_index(ref));
+        if (P.out_p || P.out_n) {
+            f3 p = mk3(0.0f, 0.0f, 0.0f), n = mk3(0.0f, 0.0f, 0.0f);
+            if (ref != kRefNone) finalize_hit(P.S, ref, o, d, t, p, n);
+            if (P.out_p) { P.out_p[3 * i] = p.x; P.out_p[3 * i + 1] = p.y; P.out_p[3 * i + 2] = p.z; }
+            if (P.out_n) { P.out_n[3 * i] = n.x; P.out_n[3 * i + 1] = n.y; P.out_n[3 * i + 2] = n.z; }
+        }
+    }
+    if (COUNT) {
+        // lanes leave the loop at different times; re-converge before the shuffles
+        __syncwarp();
+        flush_counters(P.counters, lc);
+    }
+}
+
+__global__ void k_math_eval(int fn, int n, const float* a, const float* b, float* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (fn == 6) {
+        if (i == 0) {
+            uint32_t s = __float_as_uint(a[0]);
+            for (int k = 0; k < n; k++) out[k] = ptm::rng_next(s);
+        }
+        return;
+    }
+    if (i >= n) return;
+    float x = a[i], r = 0.0f;
+    switch (fn) {
+        case 0: r = ptm::sin_c(x); break;
+        case 1: r = ptm::cos_c(x); break;
+        case 2: r = ptm::log_c(x); break;
+        case 3: r = ptm::acos_c(x); break;
+        case 4: r = ptm::atan2_c(x, b[i]); break;
+        case 5: r = ptm::pow5_c(x); break;
+    }
+    out[i] = r;
+}
+
+// preview.py:117-132: u8 = clip(sqrt(max(0, accum * (1/spp))) * 255.999, 0, 255)
+__global__ void k_tonemap(const float* accum, int n, float scale, uint8_t* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v = accum[i] * scale;
+    v = v > 0.0f ? v : 0.0f;
+    float g = ptm::fsqrt(v) * 255.999f;
+    g = g < 0.0f ? 0.0f : (g > 255.0f ? 255.0f : g);
+    out[i] = (uint8_t)g;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+static int pick_snodes(const PtContext* ctx, int blocks_per_sm_hint) {
+    int n = ctx->smem_nodes;
+    const int cap_bytes = ctx->max_smem_optin / (blocks_per_sm_hint > 0 ? blocks_per_sm_hint : 1) - 1024;
+    int cap = cap_bytes > 0 ? cap_bytes / 64 : 0;
+    if (n < 0) n = 1024;                       // auto: 64 KB of the top of the tree
+    if (n > cap) n = cap;
+    if (n > ctx->scene.num_inner) n = ctx->scene.num_inner;
+    return n < 0 ? 0 : n;
+}
+
+template <typename K>
+static int set_smem(K kernel, size_t bytes) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return set_error(PT_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+    return PT_OK;
+}
+
+extern "C" {
+
+const char* pt_last_error(void) { return pt_error_slot()->c_str(); }
+const char* pt_version(void) { return "b200pt 0.1 (sm_100a, PT-F32 strict)"; }
+
+int pt_create(int device_ordinal, PtContext** out_ctx) {
+    if (!out_ctx) return set_error(PT_ERR_INVALID_ARG, "pt_create: out_ctx is NULL");
+    int n = 0;
+    PT_CUDA(cudaGetDeviceCount(&n));
+    if (device_ordinal < 0 || device_ordinal >= n) return set_error(PT_ERR_INVALID_ARG, "pt_create: bad device ordinal");
+    PT_CUDA(cudaSetDevice(device_ordinal));
+    PtContext* c = new PtContext();
+    c->device = device_ordinal;
+    cudaDeviceProp prop;
+    PT_CUDA(cudaGetDeviceProperties(&prop, device_ordinal));
+    c->num_sms = prop.multiProcessorCount;
+    c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    PT_CUDA(cudaMalloc(&c->d_counters, sizeof(DCounters)));
+    PT_CUDA(cudaMemset(c->d_counters, 0, sizeof(DCounters)));
+    *out_ctx = c;
+    return PT_OK;
+}
+
+int pt_destroy(PtContext* ctx) {
+    if (!ctx) return PT_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->d_counters) cudaFree(ctx->d_counters);
+    delete ctx;
+    return PT_OK;
+}
+
+int pt_set_option(PtContext* ctx, const char* name, int64_t value) {
+    if (!ctx || !name) return set_error(PT_ERR_INVALID_ARG, "pt_set_option: NULL argument");
+    std::string k(name);
+    if (k == "block_threads") {
+        if (value != 64 && value != 128 && value != 256) return set_error(PT_ERR_INVALID_ARG, "block_threads must be 64, 128 or 256");
+        ctx->block_threads = (int)value;
+    } else if (k == "smem_nodes") {
+        ctx->smem_nodes = (int)value;
+    } else if (k == "wavefront_sort") {
+        ctx->wavefront_sort = value ? 1 : 0;
+    } else {
+        return set_error(PT_ERR_INVALID_ARG, "pt_set_option: unknown option " + k);
+    }
+    return PT_OK;
+}
+
+int pt_set_scene(PtContext* ctx, const void* device_blob, const PtPackedInfo* info) {
+    if (!ctx || !info) return set_error(PT_ERR_INVALID_ARG, "pt_set_scene: NULL argument");
+    if (!device_blob && info->total_bytes) return set_error(PT_ERR_INVALID_ARG, "pt_set_scene: NULL blob");
+    const char* base = static_cast<const char*>(device_blob);
+    DScene& S = ctx->scene;
+    memset(&S, 0, sizeof S);
+    S.nodes = reinterpret_cast<const float4*>(base + info->off_nodes);
+    S.spheres = reinterpret_cast<const float4*>(base + info->off_spheres);
+    S.quads = reinterpret_cast<const float4*>(base + info->off_quads);
+    S.tris = reinterpret_cast<const float4*>(base + info->off_tris);
+    S.prim_mat = reinterpret_cast<const uint32_t*>(base + info->off_prim_mat);
+    S.materials = reinterpret_cast<const float4*>(base + info->off_materials);
+    S.perlin_vec = reinterpret_cast<const float4*>(base + info->off_perlin);
+    S.perlin_perm = reinterpret_cast<const uint8_t*>(base + info->off_perlin + 256 * 16);
+    for (int i = 0; i < PT_MAX_IMAGES; i++) {
+        if (i < info->num_images) {
+            S.image[i] = reinterpret_cast<const uchar4*>(base + info->off_images + info->image_off[i]);
+            S.image_w[i] = info->image_w[i];
+            S.image_h[i] = info->image_h[i];
+        }
+    }
+    S.num_inner = info->num_inner;
+    S.mat_base[PT_PRIM_SPHERE] = 0;
+    S.mat_base[PT_PRIM_TRIANGLE] = info->num_spheres;
+    S.mat_base[PT_PRIM_QUAD] = info->num_spheres + info->num_triangles;
+    S.has_media = info->has_media;
+    if (info->max_depth_tree > kStackSize)
+        return set_error(PT_ERR_CAPACITY, "pt_set_scene: BVH deeper than the 64-entry traversal stack (kernels.py:649)");
+    ctx->info = *info;
+    ctx->has_scene = true;
+    return PT_OK;
+}
+
+int pt_set_camera(PtContext* ctx, const PtCamera* cam) {
+    if (!ctx || !cam) return set_error(PT_ERR_INVALID_ARG, "pt_set_camera: NULL argument");
+    ctx->cam = *cam;
+    ctx->has_camera = true;
+    return PT_OK;
+}
+
+static int check_render_args(PtContext* ctx, const float* accum, int W, int H, int y0, int y1, int sample_count) {
+    if (!ctx || !accum) return set_error(PT_ERR_INVALID_ARG, "render: NULL argument");
+    if (!ctx->has_scene || !ctx->has_camera) return set_error(PT_ERR_NO_SCENE, "render: scene or camera not set");
+    if (W <= 0 || H <= 0 || y0 < 0 || y1 > H || y0 > y1 || sample_count < 0)
+        return set_error(PT_ERR_INVALID_ARG, "render: bad image window / sample range");
+    return PT_OK;
+}
+
+int pt_render_megakernel(PtContext* ctx, float* accum, int W, int H, int y0, int y1, int sample_begin, int sample_count,
+                         uint32_t seed, void* stream) {
+    int rc = check_render_args(ctx, accum, W, H, y0, y1, sample_count);
+    if (rc) return rc;
+    if (y0 == y1 || sample_count == 0) return PT_OK;
+    PT_CUDA(cudaSetDevice(ctx->device));
+    MegaParams P;
+    P.S = ctx->scene;
+    P.cam = ctx->cam;
+    P.accum = accum;
+    P.W = W; P.H = H; P.y0 = y0; P.y1 = y1;
+    P.sample_begin = sample_begin; P.sample_count = sample_count;
+    P.seed = seed;
+    P.tiles_x = (W + 7) / 8;
+    P.counters = ctx->d_counters;
+    const int tiles_y = (y1 - y0 + 3) / 4;
+    const long long warps = (long long)P.tiles_x * tiles_y;
+    const int bt = ctx->block_threads;
+    const int wpb = bt / 32;
+    const int blocks = (int)((warps + wpb - 1) / wpb);
+    P.n_snodes = pick_snodes(ctx, 2);
+    const size_t smem = (size_t)P.n_snodes * 64;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (ctx->count) {
+        if ((rc = set_smem(k_megakernel<true>, smem))) return rc;
+        k_megakernel<true><<<blocks, bt, smem, st>>>(P);
+    } else {
+        if ((rc = set_smem(k_megakernel<false>, smem))) return rc;
+        k_megakernel<false><<<blocks, bt, smem, st>>>(P);
+    }
+    PT_CUDA(cudaGetLastError());
+    return PT_OK;
+}
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+size_t pt_wavefront_workspace_bytes(int W, int rows) {
+    if (W <= 0 || rows <= 0) return 0;
+    const size_t n = (size_t)W * rows;
+    size_t b = 0;
+    b += 6 * align_up(n * 16, 256);          // two queues x three float4 planes
+    b += align_up(n * 16, 256);              // hit records
+    b += align_up((size_t)kNumBins * n * 4, 256);   // material bins
+    b += 256;                                // counters
+    return b;
+}
+
+int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int y1, int sample_begin, int sample_count,
+                        uint32_t seed, void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_render_args(ctx, accum, W, H, y0, y1, sample_count);
+    if (rc) return rc;
+    if (y0 == y1 || sample_count == 0) return PT_OK;
+    const int rows = y1 - y0;
+    if (!workspace || workspace_bytes < pt_wavefront_workspace_bytes(W, rows))
+        return set_error(PT_ERR_WORKSPACE, "pt_render_wavefront: workspace too small");
+    PT_CUDA(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)W * rows;
+    char* p = static_cast<char*>(workspace);
+    WfParams P;
+    P.S = ctx->scene;
+    P.cam = ctx->cam;
+    for (int q = 0; q < 2; q++) {
+        P.Q.r0[q] = reinterpret_cast<float4*>(p); p += align_up(n * 16, 256);
+        P.Q.r1[q] = reinterpret_cast<float4*>(p); p += align_up(n * 16, 256);
+        P.Q.r2[q] = reinterpret_cast<float4*>(p); p += align_up(n * 16, 256);
+    }
+    P.Q.hit = reinterpret_cast<float4*>(p); p += align_up(n * 16, 256);
+    P.Q.bins = reinterpret_cast<uint32_t*>(p); p += align_up((size_t)kNumBins * n * 4, 256);
+    P.Q.qcount = reinterpret_cast<int*>(p);
+    P.Q.bin_count = reinterpret_cast<int*>(p) + 8;
+    P.Q.capacity = (int)n;
+    P.accum = accum;
+    P.W = W; P.H = H; P.y0 = y0; P.y1 = y1;
+    P.seed = seed;
+    P.sort = ctx->wavefront_sort;
+    P.counters = ctx->d_counters;
+    P.n_snodes = pick_snodes(ctx, 4);
+    const size_t smem = (size_t)P.n_snodes * 64;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int bt = 256;
+    int per_sm = 4;
+    const int grid_full = (int)((n + bt - 1) / bt);
+    int grid = ctx->num_sms * per_sm;
+    if (grid > grid_full) grid = grid_full;
+    if (ctx->count) { if ((rc = set_smem(k_wf_extend<true>, smem))) return rc; }
+    else { if ((rc = set_smem(k_wf_extend<false>, smem))) return rc; }
+    const int max_depth = ctx->cam.max_depth;
+    for (int s = sample_begin; s < sample_begin + sample_count; s++) {
+        P.sample = s;
+        P.bounce = 0;
+        k_wf_generate<<<grid, bt, 0, st>>>(P);
+        for (int b = 0; b < max_depth; b++) {             // renderer.py:313; kernels exit at once when the queue is empty
+            P.bounce = b;
+            if (ctx->count) k_wf_extend<true><<<grid, bt, smem, st>>>(P);
+            else k_wf_extend<false><<<grid, bt, smem, st>>>(P);
+            k_wf_shade<<<grid, bt, 0, st>>>(P);
+        }
+    }
+    PT_CUDA(cudaGetLastError());
+    return PT_OK;
+}
+
+int pt_generate_camera_rays(PtContext* ctx, int W, int H, uint32_t seed, int sample, float* o, float* d, void* stream) {
+    if (!ctx || !o || !d) return set_error(PT_ERR_INVALID_ARG, "pt_generate_camera_rays: NULL argument");
+    if (!ctx->has_camera) return set_error(PT_ERR_NO_SCENE, "pt_generate_camera_rays: camera not set");
+    PT_CUDA(cudaSetDevice(ctx->device));
+    const int n = W * H;
+    k_generate_rays<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(ctx->cam, W, H, seed, sample, o, d);
+    PT_CUDA(cudaGetLastError());
+    return PT_OK;
+}
+
+int pt_first_hit(PtContext* ctx, const float* o, const float* d, int n, float t_min, float t_max, float* out_t,
+                 int32_t* out_prim, float* out_p, float* out_n, void* stream) {
+    if (!ctx || !o || !d || !out_t || !out_prim) return set_error(PT_ERR_INVALID_ARG, "pt_first_hit: NULL argument");
+    if (!ctx->has_scene) return set_error(PT_ERR_NO_SCENE, "pt_first_hit: scene not set");
+    if (n <= 0) return PT_OK;
+    PT_CUDA(cudaSetDevice(ctx->device));
+    FirstHitParams P;
+    P.S = ctx->scene;
+    P.o = o; P.d = d; P.n = n; P.t_min = t_min; P.t_max = t_max;
+    P.out_t = out_t; P.out_prim = out_prim; P.out_p = out_p; P.out_n = out_n;
+    P.n_snodes = pick_snodes(ctx, 4);
+    P.counters = ctx->d_counters;
+    const size_t smem = (size_t)P.n_snodes * 64;
+    int grid = (n + 255) / 256;
+    const int cap = ctx->num_sms * 8;
+    if (grid > cap) grid = cap;
+    int rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (ctx->count) {
+        if ((rc = set_smem(k_first_hit<true>, smem))) return rc;
+        k_first_hit<true><<<grid, 256, smem, st>>>(P);
+    } else {
+        if ((rc = set_smem(k_first_hit<false>, smem))) return rc;
+        k_first_hit<false><<<grid, 256, smem, st>>>(P);
+    }
+    PT_CUDA(cudaGetLastError());
+    return PT_OK;
+}
+
+int pt_math_eval(PtContext* ctx, int fn, int n, const float* a, const float* b, float* out, void* stream) {
+    if (!ctx || !a || !out) return set_error(PT_ERR_INVALID_ARG, "pt_math_eval: NULL argument");
+    if (n <= 0) return PT_OK;
+    PT_CUDA(cudaSetDevice(ctx->device));
+    k_math_eval<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(fn, n, a, b ? b : a, out);
+    PT_CUDA(cudaGetLastError());
+    return PT_OK;
+}
+
+int pt_tonemap(PtContext* ctx, const float* accum, int n_floats, int sample_count, uint8_t* out_rgb, void* stream) {
+    if (!ctx || !accum || !out_rgb) return set_error(PT_ERR_INVALID_ARG, "pt_tonemap: NULL argument");
+    if (n_floats <= 0) return PT_OK;
+    PT_CUDA(cudaSetDevice(ctx->device));
+    const float scale = 1.0f / (float)(sample_count > 1 ? sample_count : 1);
+    k_tonemap<<<(n_floats + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(accum, n_floats, scale, out_rgb);
+    PT_CUDA(cudaGetLastError());
+    return PT_OK;
+}
+
+int pt_enable_counters(PtContext* ctx, int enable) {
+    if (!ctx) return set_error(PT_ERR_INVALID_ARG, "pt_enable_counters: NULL context");
+    ctx->count = enable != 0;
+    return PT_OK;
+}
+
+int pt_get_counters(PtContext* ctx, PtCounters* out, int reset) {
+    if (!ctx || !out) return set_error(PT_ERR_INVALID_ARG, "pt_get_counters: NULL argument");
+    PT_CUDA(cudaSetDevice(ctx->device));
+    PT_CUDA(cudaDeviceSynchronize());
+    DCounters h;
+    PT_CUDA(cudaMemcpy(&h, ctx->d_counters, sizeof h, cudaMemcpyDeviceToHost));
+    out->rays = h.rays; out->box_tests = h.box_tests; out->sphere_tests = h.sphere_tests;
+    out->triangle_tests = h.triangle_tests; out->quad_tests = h.quad_tests; out->paths = h.paths; out->bounces = h.bounces;
+    if (reset) PT_CUDA(cudaMemset(ctx->d_counters, 0, sizeof(DCounters)));
+    return PT_OK;
+}
+
+}  // extern "C"

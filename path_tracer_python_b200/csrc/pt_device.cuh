@@ -1,0 +1,440 @@
+// Device-side building blocks of the B200 path tracer: vector type, packed-scene view, two-child
+// BVH traversal, primitive tests, material evaluation.  Semantics follow the reference's Taichi
+// functions (src/render_server/taichi_renderer/kernels.py, cited per function); the structure does
+// not: nodes hold both children's boxes (one 64-byte fetch per visit instead of three 44-byte
+// fetches, kernels.py:664,707-708), leaves are folded into child references, the top of the tree
+// is served from shared memory, hit point / normal are reconstructed after the loop instead of
+// being carried through it, and materials are de-duplicated records behind a per-primitive id.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "pt_math.cuh"
+#include "../../include/b200pt.h"
+
+namespace pt {
+
+struct f3 {
+    float x, y, z;
+};
+__device__ __forceinline__ f3 mk3(float x, float y, float z) { return f3{x, y, z}; }
+__device__ __forceinline__ f3 operator+(f3 a, f3 b) { return f3{a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ f3 operator-(f3 a, f3 b) { return f3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ f3 operator-(f3 a) { return f3{-a.x, -a.y, -a.z}; }
+__device__ __forceinline__ f3 operator*(f3 a, f3 b) { return f3{a.x * b.x, a.y * b.y, a.z * b.z}; }
+__device__ __forceinline__ f3 operator*(float s, f3 a) { return f3{s * a.x, s * a.y, s * a.z}; }
+__device__ __forceinline__ f3 operator*(f3 a, float s) { return f3{a.x * s, a.y * s, a.z * s}; }
+__device__ __forceinline__ f3 vdiv(f3 a, float s) { return f3{ptm::fdiv(a.x, s), ptm::fdiv(a.y, s), ptm::fdiv(a.z, s)}; }
+// Taichi Vector.dot: products summed left to right
+__device__ __forceinline__ float dot(f3 a, f3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+__device__ __forceinline__ f3 cross(f3 a, f3 b) {
+    return f3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+// Taichi Vector.normalized(): (1 / norm) * v
+__device__ __forceinline__ f3 normalized(f3 a) {
+    float inv = ptm::fdiv(1.0f, ptm::fsqrt(dot(a, a)));
+    return inv * a;
+}
+__device__ __forceinline__ float min2(float a, float b) { return a < b ? a : b; }
+__device__ __forceinline__ float max2(float a, float b) { return a > b ? a : b; }
+
+// ---- packed scene as the kernels see it (pointers into the caller's device blob)
+constexpr int kRefNone = (int)0x80000000;   // "no child" / "no hit"
+constexpr int kStackSize = 64;              // kernels.py:649
+
+struct DScene {
+    const float4* nodes;      // 4 x float4 per inner node: (lmin.x lmax.x rmin.x rmax.x) (..y) (..z) (left,right,-,-)
+    const float4* spheres;    // (cx cy cz r)
+    const float4* quads;      // (n.xyz D) (Q.xyz w.x) (u.xyz w.y) (v.xyz w.z)
+    const float4* tris;       // (v0.xyz n.x) (e1.xyz n.y) (e2.xyz n.z)
+    const uint32_t* prim_mat; // material id per primitive: [spheres | triangles | quads]
+    const float4* materials;  // 3 x float4 per unique material
+    const float4* perlin_vec; // 256 gradient vectors
+    const uint8_t* perlin_perm; // perm_x | perm_y | perm_z (256 each)
+    const uchar4* image[PT_MAX_IMAGES];
+    int image_w[PT_MAX_IMAGES], image_h[PT_MAX_IMAGES];
+    int num_inner;
+    int mat_base[3];          // offset of each prim type inside prim_mat
+    int has_media;
+};
+
+struct DCounters {
+    unsigned long long rays, box_tests, sphere_tests, triangle_tests, quad_tests, paths, bounces;
+};
+
+struct LocalCounters {
+    unsigned int rays = 0, box_tests = 0, sphere_tests = 0, triangle_tests = 0, quad_tests = 0, paths = 0, bounces = 0;
+};
+
+__device__ __forceinline__ int ref_type(int ref) { return (~ref) & 3; }
+__device__ __forceinline__ int ref_index(int ref) { return (~ref) >> 2; }
+
+// ---- primitive tests: arithmetic identical to hit_sphere / hit_triangle / hit_quad; they return
+//      only t (the caller keeps t and the primitive reference).
+// kernels.py:208-248
+__device__ __forceinline__ bool hit_sphere_t(const DScene& S, int idx, f3 o, f3 d, float t_min, float t_max, float& t) {
+    float4 s = __ldg(S.spheres + idx);
+    f3 oc = mk3(s.x, s.y, s.z) - o;
+    float a = dot(d, d);
+    float h = dot(d, oc);
+    float c = dot(oc, oc) - s.w * s.w;
+    float disc = h * h - a * c;
+    if (disc >= 0.0f) {
+        float sq = ptm::fsqrt(disc);
+        float root = ptm::fdiv(h - sq, a);
+        if (root < t_min || root > t_max) root = ptm::fdiv(h + sq, a);
+        if (root >= t_min && root <= t_max) { t = root; return true; }
+    }
+    return false;
+}
+// kernels.py:251-307
+__device__ __forceinline__ bool hit_triangle_t(const DScene& S, int idx, f3 o, f3 d, float t_min, float t_max, float& t) {
+    const float4* p = S.tris + 3 * idx;
+    float4 a0 = __ldg(p), a1 = __ldg(p + 1), a2 = __ldg(p + 2);
+    f3 v0 = mk3(a0.x, a0.y, a0.z), e1 = mk3(a1.x, a1.y, a1.z), e2 = mk3(a2.x, a2.y, a2.z);
+    f3 h = cross(d, e2);
+    float det = dot(e1, h);
+    if (fabsf(det) >= 1e-8f) {
+        float inv_det = ptm::fdiv(1.0f, det);
+        f3 s = o - v0;
+        float u = inv_det * dot(s, h);
+        if (u >= 0.0f && u <= 1.0f) {
+            f3 q = cross(s, e1);
+            float v = inv_det * dot(d, q);
+            if (v >= 0.0f && u + v <= 1.0f) {
+                float tt = inv_det * dot(e2, q);
+                if (tt >= t_min && tt <= t_max) { t = tt; return true; }
+            }
+        }
+    }
+    return false;
+}
+// kernels.py:310-362
+__device__ __forceinline__ bool hit_quad_t(const DScene& S, int idx, f3 o, f3 d, float t_min, float t_max, float& t) {
+    const float4* p = S.quads + 4 * idx;
+    float4 q0 = __ldg(p);
+    f3 n = mk3(q0.x, q0.y, q0.z);
+    float denom = dot(n, d);
+    if (fabsf(denom) >= 1e-8f) {
+        float tt = ptm::fdiv(q0.w - dot(n, o), denom);
+        if (tt >= t_min && tt <= t_max) {
+            float4 q1 = __ldg(p + 1), q2 = __ldg(p + 2), q3 = __ldg(p + 3);
+            f3 isect = o + tt * d;
+            f3 ph = isect - mk3(q1.x, q1.y, q1.z);
+            f3 u = mk3(q2.x, q2.y, q2.z), v = mk3(q3.x, q3.y, q3.z), w = mk3(q1.w, q2.w, q3.w);
+            float alpha = dot(w, cross(ph, v));
+            float beta = dot(w, cross(u, ph));
+            if (alpha >= 0.0f && alpha <= 1.0f && beta >= 0.0f && beta <= 1.0f) { t = tt; return true; }
+        }
+    }
+    return false;
+}
+
+// hit point and shading normal of the closest hit, exactly as hit_* would have returned them
+__device__ __forceinline__ void finalize_hit(const DScene& S, int ref, f3 o, f3 d, float t, f3& p, f3& n) {
+    int type = ref_type(ref), idx = ref_index(ref);
+    p = o + t * d;
+    if (type == PT_PRIM_SPHERE) {
+        float4 s = __ldg(S.spheres + idx);
+        n = vdiv(p - mk3(s.x, s.y, s.z), s.w);                 // kernels.py:246 (never flipped)
+    } else if (type == PT_PRIM_QUAD) {
+        float4 q0 = __ldg(S.quads + 4 * idx);
+        f3 nn = mk3(q0.x, q0.y, q0.z);
+        n = dot(nn, d) < 0.0f ? nn : -nn;                      // kernels.py:355-360
+    } else {
+        const float4* tp = S.tris + 3 * idx;
+        f3 nn = mk3(__ldg(tp).w, __ldg(tp + 1).w, __ldg(tp + 2).w);
+        n = dot(d, nn) > 0.0f ? -nn : nn;                      // kernels.py:300-305
+    }
+}
+
+// ---- BVH traversal: closest hit over the same primitive set the reference's traverse_bvh_legacy
+//      (kernels.py:624-742) reaches; the slab test is hit_aabb_optimized (kernels.py:600-621) with
+//      the reference's clamped reciprocal direction (kernels.py:642-646).  Children are visited
+//      nearest-entry first; a deferred child is skipped at pop time when its entry distance exceeds
+//      the current closest hit -- the same predicate the reference re-evaluates on pop (:667).
+template <bool COUNT>
+__device__ __forceinline__ void traverse(const DScene& S, const float4* __restrict__ snodes, int n_snodes, f3 o, f3 d,
+                                         float t_min, float t_max, float& best_t, int& best_ref, LocalCounters& lc) {
+    best_t = t_max;
+    best_ref = kRefNone;
+    if (COUNT) lc.rays++;
+    if (S.num_inner == 0) return;
+    f3 inv = mk3(fabsf(d.x) > 1e-8f ? ptm::fdiv(1.0f, d.x) : 1e8f, fabsf(d.y) > 1e-8f ? ptm::fdiv(1.0f, d.y) : 1e8f,
+                 fabsf(d.z) > 1e-8f ? ptm::fdiv(1.0f, d.z) : 1e8f);
+    int stack_ref[kStackSize];
+    float stack_t[kStackSize];
+    int sp = 0;
+    int cur = 0;
+    for (;;) {
+        while (cur >= 0) {
+            float4 nx, ny, nz, nc;
+            if (cur < n_snodes) {
+                const float4* p = snodes + 4 * cur;
+                nx = p[0]; ny = p[1]; nz = p[2]; nc = p[3];
+            } else {
+                const float4* p = S.nodes + 4 * cur;
+                nx = __ldg(p); ny = __ldg(p + 1); nz = __ldg(p + 2); nc = __ldg(p + 3);
+            }
+            if (COUNT) lc.box_tests += 2;
+            // left child box
+            float l0x = (nx.x - o.x) * inv.x, l1x = (nx.y - o.x) * inv.x;
+            float l0y = (ny.x - o.y) * inv.y, l1y = (ny.y - o.y) * inv.y;
+            float l0z = (nz.x - o.z) * inv.z, l1z = (nz.y - o.z) * inv.z;
+            float ltmin = max2(max2(min2(l0x, l1x), min2(l0y, l1y)), max2(min2(l0z, l1z), t_min));
+            float ltmax = min2(min2(max2(l0x, l1x), max2(l0y, l1y)), min2(max2(l0z, l1z), best_t));
+            // right child box
+            float r0x = (nx.z - o.x) * inv.x, r1x = (nx.w - o.x) * inv.x;
+            float r0y = (ny.z - o.y) * inv.y, r1y = (ny.w - o.y) * inv.y;
+            float r0z = (nz.z - o.z) * inv.z, r1z = (nz.w - o.z) * inv.z;
+            float rtmin = max2(max2(min2(r0x, r1x), min2(r0y, r1y)), max2(min2(r0z, r1z), t_min));
+            float rtmax = min2(min2(max2(r0x, r1x), max2(r0y, r1y)), min2(max2(r0z, r1z), best_t));
+            int lref = __float_as_int(nc.x), rref = __float_as_int(nc.y);
+            bool hl = (ltmax >= ltmin) && (lref != kRefNone);
+            bool hr = (rtmax >= rtmin) && (rref != kRefNone);
+            if (hl && hr) {
+                bool left_first = ltmin <= rtmin;
+                int far_ref = left_first ? rref : lref;
+                float far_t = left_first ? rtmin : ltmin;
+                cur = left_first ? lref : rref;
+                if (sp < kStackSize) { stack_ref[sp] = far_ref; stack_t[sp] = far_t; sp++; }
+            } else if (hl) {
+                cur = lref;
+            } else if (hr) {
+                cur = rref;
+            } else {
+                cur = kRefNone;
+                while (sp > 0) {
+                    --sp;
+                    if (stack_t[sp] <= best_t) { cur = stack_ref[sp]; break; }
+                }
+                if (cur == kRefNone) return;
+            }
+        }
+        // cur is a leaf reference
+        {
+            int type = ref_type(cur), idx = ref_index(cur);
+            float t;
+            bool hit;
+            if (type == PT_PRIM_SPHERE) { if (COUNT) lc.sphere_tests++; hit = hit_sphere_t(S, idx, o, d, t_min, best_t, t); }
+            else if (type == PT_PRIM_QUAD) { if (COUNT) lc.quad_tests++; hit = hit_quad_t(S, idx, o, d, t_min, best_t, t); }
+            else { if (COUNT) lc.triangle_tests++; hit = hit_triangle_t(S, idx, o, d, t_min, best_t, t); }
+            if (hit && t < best_t) { best_t = t; best_ref = cur; }   // kernels.py:691 (strict)
+        }
+        cur = kRefNone;
+        while (sp > 0) {
+            --sp;
+            if (stack_t[sp] <= best_t) { cur = stack_ref[sp]; break; }
+        }
+        if (cur == kRefNone) return;
+    }
+}
+
+// ---- samplers (kernels.py:16-71)
+__device__ __forceinline__ f3 random_in_unit_disk(uint32_t& rng) {
+    for (;;) {
+        float px = ptm::rng_next(rng) * 2.0f - 1.0f;
+        float py = ptm::rng_next(rng) * 2.0f - 1.0f;
+        f3 p = mk3(px, py, 0.0f);
+        if (dot(p, p) < 1.0f) return p;
+    }
+}
+__device__ __forceinline__ f3 random_unit_vector(uint32_t& rng) {
+    for (;;) {
+        float px = ptm::rng_next(rng) * 2.0f - 1.0f;
+        float py = ptm::rng_next(rng) * 2.0f - 1.0f;
+        float pz = ptm::rng_next(rng) * 2.0f - 1.0f;
+        f3 p = mk3(px, py, pz);
+        float l = dot(p, p);
+        if (l < 1.0f && l > 1e-20f) return normalized(p);
+    }
+}
+__device__ __forceinline__ f3 random_cosine_direction(f3 normal, uint32_t& rng) {
+    float r1 = ptm::rng_next(rng);
+    float r2 = ptm::rng_next(rng);
+    float z = ptm::fsqrt(1.0f - r2);
+    float phi = 6.283185307179586f * r1;
+    float st = ptm::fsqrt(r2);
+    float sn, cs;
+    ptm::sincos_c(phi, &sn, &cs);
+    float x = cs * st, y = sn * st;
+    f3 w = normalized(normal);
+    f3 a;
+    if (fabsf(w.x) < 0.9f) a = mk3(1.0f, 0.0f, 0.0f);
+    else if (fabsf(w.y) < 0.9f) a = mk3(0.0f, 1.0f, 0.0f);
+    else a = mk3(0.0f, 0.0f, 1.0f);
+    f3 v = normalized(cross(a, w));
+    f3 u = cross(v, w);
+    return normalized((x * u + y * v) + z * w);
+}
+
+// ---- camera (kernels.py:176-201)
+__device__ __forceinline__ void get_ray(const PtCamera& cam, int px, int py, uint32_t& rng, f3& o, f3& d) {
+    float ox = ptm::rng_next(rng) - 0.5f;
+    float oy = ptm::rng_next(rng) - 0.5f;
+    f3 p00 = mk3(cam.pixel00[0], cam.pixel00[1], cam.pixel00[2]);
+    f3 du = mk3(cam.delta_u[0], cam.delta_u[1], cam.delta_u[2]);
+    f3 dv = mk3(cam.delta_v[0], cam.delta_v[1], cam.delta_v[2]);
+    f3 c = mk3(cam.center[0], cam.center[1], cam.center[2]);
+    f3 ps = (p00 + ((float)px + ox) * du) + ((float)py + oy) * dv;
+    o = c;
+    if (cam.defocus_angle > 0.0f) {
+        f3 p = random_in_unit_disk(rng);
+        f3 ddu = mk3(cam.defocus_disk_u[0], cam.defocus_disk_u[1], cam.defocus_disk_u[2]);
+        f3 ddv = mk3(cam.defocus_disk_v[0], cam.defocus_disk_v[1], cam.defocus_disk_v[2]);
+        o = (c + p.x * ddu) + p.y * ddv;
+    }
+    d = ps - o;
+}
+
+// ---- textures (kernels.py:78-169, :924-1017)
+__device__ __forceinline__ float perlin_noise(const DScene& S, f3 p) {
+    float fx = floorf(p.x), fy = floorf(p.y), fz = floorf(p.z);
+    float u = p.x - fx, v = p.y - fy, w = p.z - fz;
+    int i = (int)fx, j = (int)fy, k = (int)fz;
+    float uu = u * u * (3.0f - 2.0f * u);
+    float vv = v * v * (3.0f - 2.0f * v);
+    float ww = w * w * (3.0f - 2.0f * w);
+    float accum = 0.0f;
+#pragma unroll
+    for (int di = 0; di < 2; di++)
+#pragma unroll
+        for (int dj = 0; dj < 2; dj++)
+#pragma unroll
+            for (int dk = 0; dk < 2; dk++) {
+                int idx = S.perlin_perm[(i + di) & 255] ^ S.perlin_perm[256 + ((j + dj) & 255)] ^
+                          S.perlin_perm[512 + ((k + dk) & 255)];
+                float4 g = __ldg(S.perlin_vec + idx);
+                float fi = (float)di, fj = (float)dj, fk = (float)dk;
+                f3 wt = mk3(u - fi, v - fj, w - fk);
+                accum = accum + (fi * uu + (1.0f - fi) * (1.0f - uu)) * (fj * vv + (1.0f - fj) * (1.0f - vv)) *
+                                    (fk * ww + (1.0f - fk) * (1.0f - ww)) * dot(mk3(g.x, g.y, g.z), wt);
+            }
+    return accum;
+}
+__device__ __forceinline__ float perlin_turb3(const DScene& S, f3 p) {
+    float accum = 0.0f, weight = 1.0f;
+    f3 tp = p;
+    for (int i = 0; i < 3; i++) {            // depth = 3, kernels.py:1013
+        accum = accum + weight * perlin_noise(S, tp);
+        weight = weight * 0.5f;
+        tp = tp * 2.0f;
+    }
+    return fabsf(accum);
+}
+
+// material record accessors
+struct Mat {
+    int header;     // mat_type | tex_type<<4 | is_medium<<8 | (image_idx+1)<<16
+    float scalar;   // Lambert/isotropic: texture scale; metal: fuzz; dielectric: ir
+    f3 c1, c2;      // Lambert: texture colours; metal: albedo; emissive: emit colour
+};
+__device__ __forceinline__ int mat_id_of(const DScene& S, int ref) {
+    return (int)__ldg(S.prim_mat + S.mat_base[ref_type(ref)] + ref_index(ref));
+}
+__device__ __forceinline__ Mat load_mat(const DScene& S, int mid) {
+    float4 m0 = __ldg(S.materials + 3 * mid), m1 = __ldg(S.materials + 3 * mid + 1);
+    Mat m;
+    m.header = __float_as_int(m0.x);
+    m.scalar = m0.y;
+    m.c1 = mk3(m0.z, m0.w, m1.x);
+    m.c2 = mk3(m1.y, m1.z, m1.w);
+    return m;
+}
+__device__ __forceinline__ int mat_type(int header) { return header & 15; }
+__device__ __forceinline__ int tex_type(int header) { return (header >> 4) & 15; }
+__device__ __forceinline__ bool mat_is_medium(int header) { return (header >> 8) & 1; }
+__device__ __forceinline__ int mat_image(int header) { return (header >> 16) - 1; }
+
+// kernels.py:924-1017
+__device__ __forceinline__ f3 eval_texture(const DScene& S, const Mat& m, int ref, f3 hp) {
+    int tt = tex_type(m.header);
+    f3 result = mk3(1.0f, 1.0f, 1.0f);
+    if (tt == 0) {
+        result = m.c1;
+    } else if (tt == 1) {
+        float inv_scale = ptm::fdiv(1.0f, m.scalar);
+        int s = (int)floorf(inv_scale * hp.x) + (int)floorf(inv_scale * hp.y) + (int)floorf(inv_scale * hp.z);
+        result = (s & 1) == 0 ? m.c1 : m.c2;     // Python-style (s % 2 == 0) for negative s too
+    } else if (tt == 2) {
+        if (ref_type(ref) == PT_PRIM_SPHERE) {
+            float4 sp = __ldg(S.spheres + ref_index(ref));
+            f3 on = normalized(hp - mk3(sp.x, sp.y, sp.z));                 // get_sphere_uv, :78-102
+            float phi = ptm::acos_c(-on.y);
+            float theta = ptm::atan2_c(-on.z, on.x) + 3.141592653589793f;
+            float u = ptm::fdiv(theta, 6.283185307179586f);
+            float v = ptm::fdiv(phi, 3.141592653589793f);
+            int img = mat_image(m.header);
+            if (img >= 0) {
+                int iw = S.image_w[img], ih = S.image_h[img];
+                u = max2(0.0f, min2(1.0f, u));
+                v = 1.0f - max2(0.0f, min2(1.0f, v));
+                int i = (int)(u * (float)iw), j = (int)(v * (float)ih);
+                i = max(0, min(iw - 1, i));
+                j = max(0, min(ih - 1, j));
+                uchar4 t = __ldg(S.image[img] + (size_t)j * iw + i);
+                result = mk3(ptm::fdiv((float)t.x, 255.0f), ptm::fdiv((float)t.y, 255.0f), ptm::fdiv((float)t.z, 255.0f));
+            }
+        } else {
+            result = mk3(1.0f, 0.0f, 1.0f);
+        }
+    } else if (tt == 3) {
+        float nv = ptm::sin_c(m.scalar * hp.z + 10.0f * perlin_turb3(S, hp));
+        result = (m.c1 * 0.5f) * (1.0f + nv);
+    }
+    return result;
+}
+
+__device__ __forceinline__ f3 reflect(f3 v, f3 n) { return v - (2.0f * dot(v, n)) * n; }
+__device__ __forceinline__ f3 refract(f3 uv, f3 n, float eta) {
+    float ct = min2(-dot(uv, n), 1.0f);
+    f3 perp = eta * (uv + ct * n);
+    f3 par = (-ptm::fsqrt(fabsf(1.0f - dot(perp, perp)))) * n;
+    return perp + par;
+}
+__device__ __forceinline__ float reflectance(float cosine, float ref_idx) {
+    float r0 = ptm::fdiv(1.0f - ref_idx, 1.0f + ref_idx);
+    r0 = r0 * r0;
+    return r0 + (1.0f - r0) * ptm::pow5_c(1.0f - cosine);
+}
+
+// emitted + scatter for a surface hit (kernels.py:789-917). Returns scattered.
+__device__ __forceinline__ bool shade_surface(const DScene& S, const Mat& m, int ref, f3 ray_dir, f3 hp, f3 normal,
+                                              uint32_t& rng, f3& emit, f3& scatter_dir, f3& attenuation) {
+    int mt = mat_type(m.header);
+    emit = mk3(0.0f, 0.0f, 0.0f);
+    scatter_dir = mk3(0.0f, 0.0f, 0.0f);
+    attenuation = mk3(1.0f, 1.0f, 1.0f);
+    if (mt == 0) {
+        attenuation = eval_texture(S, m, ref, hp);
+        scatter_dir = random_cosine_direction(normal, rng);
+        return true;
+    } else if (mt == 1) {
+        f3 reflected = reflect(normalized(ray_dir), normal);
+        scatter_dir = reflected + m.scalar * random_unit_vector(rng);
+        if (dot(scatter_dir, normal) > 0.0f) { attenuation = m.c1; return true; }
+        return false;
+    } else if (mt == 2) {
+        float ir = m.scalar;
+        bool front = dot(ray_dir, normal) < 0.0f;
+        f3 nf = front ? normal : -normal;
+        float ratio = front ? ptm::fdiv(1.0f, ir) : ir;
+        f3 ud = normalized(ray_dir);
+        float ct = min2(-dot(ud, nf), 1.0f);
+        float st = ptm::fsqrt(1.0f - ct * ct);
+        bool cannot = ratio * st > 1.0f;
+        bool refl = cannot;
+        if (!refl) refl = reflectance(ct, ratio) > ptm::rng_next(rng);   // `or` short-circuits, :894
+        scatter_dir = refl ? reflect(ud, nf) : refract(ud, nf, ratio);
+        return true;
+    } else if (mt == 3) {
+        emit = m.c1;
+        return false;
+    } else if (mt == 4) {
+        scatter_dir = random_unit_vector(rng);
+        attenuation = eval_texture(S, m, ref, hp);
+        return true;
+    }
+    return false;
+}
+
+}  // namespace pt

@@ -1,0 +1,161 @@
+"""Engine: the thin layer between the reference-shaped renderer class and the C ABI.
+
+PyTorch is used only for memory (pinned host blobs, device buffers, streams); every kernel is
+libb200pt's.  One Engine = one PtContext = one GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import HostScene, PtCamera, PtCounters, PtPackedInfo, check, make_camera
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise _lib.B200PTError("no CUDA device: path_tracer_python_b200 has no CPU path (by design)")
+
+
+class Engine:
+    def __init__(self, device: int | None = None):
+        _require_cuda()
+        self.L = _lib.lib()
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device("cuda", self.device_index)
+        ctx = C.c_void_p()
+        check(self.L.pt_create(self.device_index, C.byref(ctx)), "pt_create")
+        self.ctx = ctx
+        self.info: PtPackedInfo | None = None
+        self.scene_blob = None          # device uint8 tensor (owned here, borrowed by the library)
+        self._pinned_blob = None
+        self._workspace = None
+        self.h2d_bytes = 0
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.L.pt_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ configuration
+    def set_option(self, name: str, value: int):
+        check(self.L.pt_set_option(self.ctx, name.encode(), int(value)), f"pt_set_option({name})")
+
+    def _stream_ptr(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------ scene / camera
+    def set_scene(self, cs: dict):
+        """cs: CompiledScene dict (reference layout).  Packs on the host (C++), one pinned->device copy."""
+        hs = HostScene(cs)
+        info = PtPackedInfo()
+        check(self.L.pt_pack_scene_info(C.byref(hs.c), C.byref(info)), "pt_pack_scene_info")
+        nbytes = int(info.total_bytes)
+        if self._pinned_blob is None or self._pinned_blob.numel() < nbytes:
+            self._pinned_blob = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        pinned = self._pinned_blob[:nbytes]
+        check(self.L.pt_pack_scene(C.byref(hs.c), C.byref(info), C.c_void_p(pinned.data_ptr())), "pt_pack_scene")
+        with torch.cuda.device(self.device):
+            blob = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            blob.copy_(pinned, non_blocking=True)
+        check(self.L.pt_set_scene(self.ctx, C.c_void_p(blob.data_ptr()), C.byref(info)), "pt_set_scene")
+        self.scene_blob, self.info = blob, info
+        self.h2d_bytes = nbytes
+        return info
+
+    def set_camera(self, cam: dict | PtCamera, background=(0.7, 0.8, 1.0), max_depth=50):
+        pc = cam if isinstance(cam, PtCamera) else make_camera(cam, background, max_depth)
+        check(self.L.pt_set_camera(self.ctx, C.byref(pc)), "pt_set_camera")
+        self.camera = pc
+
+    # ------------------------------------------------------------------ rendering
+    def new_accum(self, W: int, H: int) -> torch.Tensor:
+        return torch.zeros((H, W, 3), dtype=torch.float32, device=self.device)
+
+    def render_megakernel(self, accum: torch.Tensor, sample_begin: int, sample_count: int, seed: int = 0,
+                          y0: int = 0, y1: int | None = None):
+        H, W, _ = accum.shape
+        assert accum.is_cuda and accum.dtype == torch.float32 and accum.is_contiguous()
+        y1 = H if y1 is None else y1
+        with torch.cuda.device(self.device):
+            check(self.L.pt_render_megakernel(self.ctx, C.c_void_p(accum.data_ptr()), W, H, y0, y1, sample_begin,
+                                              sample_count, C.c_uint32(seed & 0xFFFFFFFF), self._stream_ptr()),
+                  "pt_render_megakernel")
+
+    def render_wavefront(self, accum: torch.Tensor, sample_begin: int, sample_count: int, seed: int = 0,
+                         y0: int = 0, y1: int | None = None):
+        H, W, _ = accum.shape
+        assert accum.is_cuda and accum.dtype == torch.float32 and accum.is_contiguous()
+        y1 = H if y1 is None else y1
+        need = int(self.L.pt_wavefront_workspace_bytes(W, y1 - y0))
+        if self._workspace is None or self._workspace.numel() < need:
+            self._workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.L.pt_render_wavefront(self.ctx, C.c_void_p(accum.data_ptr()), W, H, y0, y1, sample_begin,
+                                             sample_count, C.c_uint32(seed & 0xFFFFFFFF),
+                                             C.c_void_p(self._workspace.data_ptr()), C.c_size_t(self._workspace.numel()),
+                                             self._stream_ptr()), "pt_render_wavefront")
+
+    # ------------------------------------------------------------------ probes
+    def generate_camera_rays(self, W: int, H: int, seed: int = 0, sample: int = 0):
+        o = torch.empty((H * W, 3), dtype=torch.float32, device=self.device)
+        d = torch.empty_like(o)
+        with torch.cuda.device(self.device):
+            check(self.L.pt_generate_camera_rays(self.ctx, W, H, C.c_uint32(seed & 0xFFFFFFFF), sample,
+                                                 C.c_void_p(o.data_ptr()), C.c_void_p(d.data_ptr()), self._stream_ptr()),
+                  "pt_generate_camera_rays")
+        return o, d
+
+    def first_hit(self, o: torch.Tensor, d: torch.Tensor, t_min=0.001, t_max=1e10, want_pn=True):
+        o = o.to(self.device, torch.float32).contiguous().view(-1, 3)
+        d = d.to(self.device, torch.float32).contiguous().view(-1, 3)
+        n = o.shape[0]
+        t = torch.empty(n, dtype=torch.float32, device=self.device)
+        prim = torch.empty(n, dtype=torch.int32, device=self.device)
+        p = torch.empty((n, 3), dtype=torch.float32, device=self.device) if want_pn else None
+        nn = torch.empty((n, 3), dtype=torch.float32, device=self.device) if want_pn else None
+        with torch.cuda.device(self.device):
+            check(self.L.pt_first_hit(self.ctx, C.c_void_p(o.data_ptr()), C.c_void_p(d.data_ptr()), n, t_min, t_max,
+                                      C.c_void_p(t.data_ptr()), C.c_void_p(prim.data_ptr()),
+                                      C.c_void_p(p.data_ptr()) if want_pn else None,
+                                      C.c_void_p(nn.data_ptr()) if want_pn else None, self._stream_ptr()), "pt_first_hit")
+        return t, prim, p, nn
+
+    def math_eval(self, fn: int, a: torch.Tensor, b: torch.Tensor | None = None):
+        a = a.to(self.device, torch.float32).contiguous()
+        b = a if b is None else b.to(self.device, torch.float32).contiguous()
+        out = torch.empty_like(a)
+        with torch.cuda.device(self.device):
+            check(self.L.pt_math_eval(self.ctx, fn, a.numel(), C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()),
+                                      C.c_void_p(out.data_ptr()), self._stream_ptr()), "pt_math_eval")
+        return out
+
+    def tonemap(self, accum: torch.Tensor, sample_count: int) -> torch.Tensor:
+        out = torch.empty(accum.shape, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.L.pt_tonemap(self.ctx, C.c_void_p(accum.data_ptr()), accum.numel(), int(sample_count),
+                                    C.c_void_p(out.data_ptr()), self._stream_ptr()), "pt_tonemap")
+        return out
+
+    # ------------------------------------------------------------------ statistics
+    def enable_counters(self, on: bool = True):
+        check(self.L.pt_enable_counters(self.ctx, 1 if on else 0), "pt_enable_counters")
+
+    def counters(self, reset: bool = True) -> dict:
+        c = PtCounters()
+        check(self.L.pt_get_counters(self.ctx, C.byref(c), 1 if reset else 0), "pt_get_counters")
+        return c.as_dict()
+
+
+def algorithmic_bytes(counters: dict) -> int:
+    """32 B per child-box test + primitive record bytes per leaf test."""
+    return (32 * counters["box_tests"] + 16 * counters["sphere_tests"] + 48 * counters["triangle_tests"]
+            + 64 * counters["quad_tests"])
