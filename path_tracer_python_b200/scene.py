@@ -1,0 +1,254 @@
+"""Light-weight scene description classes with the reference's names and attributes
+(src/core/{sphere,quad,triangle,hittable_list,constant_medium,material,texture,camera}.py), for
+building scenes where the reference's `src/core` package is not importable (the GPU boxes, the
+benchmarks, the tests).  They carry data only -- no CPU ``hit()`` / ``scatter()``: tracing happens
+on the GPU.  ``scene_compiler.compile_scene`` accepts these and the reference's own objects alike.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+
+class vec3:
+    __slots__ = ("x", "y", "z")
+
+    def __init__(self, x=0.0, y=0.0, z=0.0):
+        self.x, self.y, self.z = float(x), float(y), float(z)
+
+    def __add__(self, o):
+        return vec3(self.x + o.x, self.y + o.y, self.z + o.z)
+
+    def __sub__(self, o):
+        return vec3(self.x - o.x, self.y - o.y, self.z - o.z)
+
+    def __neg__(self):
+        return vec3(-self.x, -self.y, -self.z)
+
+    def __mul__(self, s):
+        if isinstance(s, vec3):
+            return vec3(self.x * s.x, self.y * s.y, self.z * s.z)
+        return vec3(self.x * s, self.y * s, self.z * s)
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, s):
+        return vec3(self.x / s, self.y / s, self.z / s)
+
+    def dot(self, o):
+        return self.x * o.x + self.y * o.y + self.z * o.z
+
+    def cross(self, o):
+        return vec3(self.y * o.z - self.z * o.y, self.z * o.x - self.x * o.z, self.x * o.y - self.y * o.x)
+
+    def length(self):
+        return math.sqrt(self.x ** 2 + self.y ** 2 + self.z ** 2)
+
+    def unit_vector(self):
+        return self / self.length()
+
+    def __repr__(self):
+        return f"vec3({self.x}, {self.y}, {self.z})"
+
+
+point3 = vec3
+color = vec3
+
+
+class _Path:
+    """center(time) = origin + time * direction, like the reference's Ray-valued Sphere.center."""
+
+    def __init__(self, origin, direction):
+        self.origin, self.direction = origin, direction
+
+    def at(self, t):
+        return self.origin + self.direction * t
+
+
+# ---- textures
+class solid_color:
+    def __init__(self, albedo):
+        self.albedo = albedo
+
+    @classmethod
+    def from_color(cls, albedo):
+        return cls(albedo)
+
+    def value(self, u, v, p):
+        return self.albedo
+
+
+class checker_texture:
+    def __init__(self, scale, even, odd):
+        self.inv_scale = 1.0 / scale
+        self.even, self.odd = even, odd
+
+    @classmethod
+    def from_colors(cls, scale, c1, c2):
+        return cls(scale, solid_color(c1), solid_color(c2))
+
+
+class noise_texture:
+    def __init__(self, scale=1.0):
+        self.scale = scale
+
+
+class _Image:
+    def __init__(self, u8):
+        self.bdata8 = np.ascontiguousarray(u8, np.uint8)
+        self.fdata = self.bdata8.astype(np.float32) / np.float32(255.0)
+
+
+class image_texture:
+    """8-bit RGB image; `source` is a file name (PIL) or an (H, W, 3) uint8 array."""
+
+    def __init__(self, source):
+        if isinstance(source, np.ndarray):
+            self.image = _Image(source)
+        else:
+            from PIL import Image
+            self.image = _Image(np.array(Image.open(source).convert("RGB"), dtype=np.uint8))
+
+
+# ---- materials
+class lambertian:
+    def __init__(self, tex):
+        self.tex = tex
+
+    @classmethod
+    def from_color(cls, albedo):
+        return cls(solid_color(albedo))
+
+    @classmethod
+    def from_texture(cls, tex):
+        return cls(tex)
+
+
+class metal:
+    def __init__(self, albedo, fuzz):
+        self.albedo = albedo
+        self.fuzz = fuzz if fuzz < 1.0 else 1.0
+
+
+class dielectric:
+    def __init__(self, index_of_refraction):
+        self.ir = index_of_refraction
+
+
+class diffuse_light:
+    def __init__(self, tex):
+        self.tex = tex
+
+    @classmethod
+    def from_color(cls, emit_color):
+        return cls(solid_color(emit_color))
+
+
+class isotropic:
+    def __init__(self, tex):
+        self.tex = tex
+
+    @classmethod
+    def from_color(cls, albedo):
+        return cls(solid_color(albedo))
+
+
+class subsurface_volumetric:
+    """Kept for API parity; the Taichi path (and therefore this renderer in its reference-compatible
+    mode) renders it as 0.8-grey Lambertian (reference scene_compiler.py:406-417)."""
+
+    def __init__(self, albedo, scattering_coeff=0.08, absorption_coeff=0.8, g=0.7):
+        self.albedo, self.scattering_coeff, self.absorption_coeff, self.g = albedo, scattering_coeff, absorption_coeff, g
+
+
+# ---- geometry
+class Sphere:
+    def __init__(self, center_path, radius, mat):
+        self.center = center_path
+        self.radius = max(0.0, radius)
+        self.material = mat
+
+    @classmethod
+    def stationary(cls, static_center, radius, mat):
+        return cls(_Path(static_center, vec3(0, 0, 0)), radius, mat)
+
+    @classmethod
+    def moving(cls, center1, center2, radius, mat):
+        return cls(_Path(center1, center2 - center1), radius, mat)
+
+
+class quad:
+    def __init__(self, Q, u, v, mat):
+        self.Q, self.u, self.v, self.mat = Q, u, v, mat
+        n = u.cross(v)
+        self.normal = n.unit_vector()
+        self.D = self.normal.dot(Q)
+        self.w = n / n.dot(n)
+
+
+class triangle:
+    def __init__(self, v0, v1, v2, mat):
+        self.v0, self.v1, self.v2, self.mat = v0, v1, v2, mat
+        self.edge1 = v1 - v0
+        self.edge2 = v2 - v0
+        self.normal = self.edge1.cross(self.edge2).unit_vector()
+
+
+class hittable_list:
+    def __init__(self, objects=None):
+        self.objects = list(objects) if objects else []
+
+    def add(self, obj):
+        self.objects.append(obj)
+
+
+class constant_medium:
+    def __init__(self, boundary, phase_function, density):
+        self.boundary = boundary
+        self.phase_function = phase_function
+        self.neg_inv_density = -1 / density
+
+    @classmethod
+    def from_color(cls, boundary, albedo, density):
+        return cls(boundary, isotropic.from_color(albedo), density)
+
+
+def box(a, b, mat, angle: float = 0.0) -> hittable_list:
+    """Six quads of an axis-aligned box, optionally rotated about Y through its centre by `angle`
+    degrees (same faces, order and winding as the reference's scenes.box, src/scenes.py:961-1024)."""
+    lo = vec3(min(a.x, b.x), min(a.y, b.y), min(a.z, b.z))
+    hi = vec3(max(a.x, b.x), max(a.y, b.y), max(a.z, b.z))
+    dx, dy, dz = vec3(hi.x - lo.x, 0, 0), vec3(0, hi.y - lo.y, 0), vec3(0, 0, hi.z - lo.z)
+    corners = [(vec3(lo.x, lo.y, hi.z), dx, dy), (vec3(hi.x, lo.y, hi.z), -dz, dy), (vec3(hi.x, lo.y, lo.z), -dx, dy),
+               (vec3(lo.x, lo.y, lo.z), dz, dy), (vec3(lo.x, hi.y, hi.z), dx, -dz), (vec3(lo.x, lo.y, lo.z), dx, dz)]
+    if angle != 0.0:
+        th = math.radians(angle)
+        c, s = math.cos(th), math.sin(th)
+        rot = lambda p: vec3(c * p.x + s * p.z, p.y, -s * p.x + c * p.z)
+        ctr = (lo + hi) * 0.5
+        corners = [(rot(q - ctr) + ctr, rot(u), rot(v)) for q, u, v in corners]
+    return hittable_list([quad(q, u, v, mat) for q, u, v in corners])
+
+
+class camera:
+    aspect_ratio = 1.0
+    img_width = 100
+    samples_per_pixel = 10
+    vfov = 90
+    lookfrom = point3(0, 0, 0)
+    lookat = point3(0, 0, -1)
+    vup = vec3(0, 1, 0)
+    defocus_angle = 0.0
+    focus_distance = 10.0
+
+    def initialize(self):
+        from .scenes import camera_vectors
+        cam, h = camera_vectors([self.lookfrom.x, self.lookfrom.y, self.lookfrom.z],
+                                [self.lookat.x, self.lookat.y, self.lookat.z], [self.vup.x, self.vup.y, self.vup.z],
+                                self.vfov, self.img_width, self.aspect_ratio, self.defocus_angle, self.focus_distance)
+        self.img_height = h
+        self.center = vec3(*cam["cam_center"])
+        self.pixel00_loc = vec3(*cam["cam_pixel00"])
+        self.delta_u, self.delta_v = vec3(*cam["cam_delta_u"]), vec3(*cam["cam_delta_v"])
+        self.defocus_disk_u, self.defocus_disk_v = vec3(*cam["cam_defocus_disk_u"]), vec3(*cam["cam_defocus_disk_v"])

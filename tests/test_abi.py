@@ -1,0 +1,63 @@
+"""The C-ABI library loads on a machine without a GPU and exports every symbol the header declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from path_tracer_python_b200 import _lib, build
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def L():
+    build.build_native()
+    return _lib.lib()
+
+
+def _declared():
+    text = open(os.path.join(REPO, "include", "b200pt.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pt_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported(L):
+    names = _declared()
+    assert len(names) >= 19
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/b200pt.h but not exported"
+    assert sorted(_lib.EXPORTS) == names
+
+
+def test_struct_sizes_match_header(L):
+    # PtCamera: 6*3 floats + angle + 3 bg + max_depth; PtCounters: 7 u64
+    assert ctypes.sizeof(_lib.PtCamera) == 4 * (18 + 1 + 3 + 1)
+    assert ctypes.sizeof(_lib.PtCounters) == 56
+    assert ctypes.sizeof(_lib.PtHostMaterials) == 13 * 8
+
+
+def test_errors_are_reported_without_a_gpu(L):
+    info = _lib.PtPackedInfo()
+    rc = L.pt_pack_scene_info(None, ctypes.byref(info))
+    assert rc == -1 and b"NULL" in L.pt_last_error()
+    assert L.pt_wavefront_workspace_bytes(0, 10) == 0
+    assert L.pt_wavefront_workspace_bytes(1920, 1080) > 1920 * 1080 * (6 * 16 + 16)
+    assert b"sm_100a" in L.pt_version()
+
+
+def test_no_cpu_fallback_when_library_missing(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.B200PTError):
+        _lib.lib()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(REPO, "path_tracer_python_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(root, f)).read()
+                assert "import oracle" not in src and "liboracle" not in src and "oracle/" not in src.replace(
+                    "oracle/oracle_math.h", "").replace("oracle/gen_golden.py", ""), f

@@ -1,0 +1,105 @@
+"""Host compile: my scene classes + compiler against hand-computed values, and (when the reference is
+mounted) array-for-array against the reference's own compile_scene / compile_bvh / perlin()."""
+import os
+import random
+import sys
+
+import numpy as np
+import pytest
+
+from path_tracer_python_b200 import bvh, scene as sc, scene_compiler as SC
+
+REF = os.path.isdir("/root/reference/src/render_server/taichi_renderer")
+
+
+def _mini_world():
+    w = sc.hittable_list()
+    w.add(sc.Sphere.stationary(sc.point3(0, -100, 0), 100, sc.lambertian.from_texture(
+        sc.checker_texture.from_colors(0.5, sc.color(0.1, 0.2, 0.3), sc.color(0.9, 0.8, 0.7)))))
+    w.add(sc.Sphere.moving(sc.point3(1, 1, 1), sc.point3(2, 1, 1), 0.5, sc.metal(sc.color(0.8, 0.6, 0.2), 1.7)))
+    glass = sc.Sphere.stationary(sc.point3(0, 1, 0), 1.0, sc.dielectric(1.5))
+    w.add(glass)
+    w.add(sc.constant_medium.from_color(glass, sc.color(0.2, 0.4, 0.9), 0.25))
+    w.add(sc.quad(sc.point3(-1, 3, -1), sc.vec3(2, 0, 0), sc.vec3(0, 0, 2), sc.diffuse_light.from_color(sc.color(4, 5, 6))))
+    w.add(sc.triangle(sc.point3(0, 0, 2), sc.point3(1, 0, 2), sc.point3(0, 1, 2), sc.lambertian.from_texture(sc.noise_texture(3.0))))
+    w.add(sc.constant_medium.from_color(sc.box(sc.point3(3, 0, 0), sc.point3(4, 1, 1), sc.lambertian.from_color(sc.color(1, 1, 1))),
+                                        sc.color(1, 1, 1), 0.01))
+    w.add(sc.Sphere.stationary(sc.point3(5, 5, 5), 1.0, sc.subsurface_volumetric(sc.color(0.2, 0.5, 0.2))))
+    return w
+
+
+def test_compile_own_classes():
+    cs = SC.compile_scene(_mini_world())
+    assert cs["sphere_data"].shape == (4, 4) and cs["quad_Q"].shape == (7, 3) and cs["triangle_v0"].shape == (1, 3)
+    assert cs["sphere_data"].dtype == np.float32
+    assert cs["sphere_material_type"].tolist() == [0, 1, 2, 0]           # subsurface -> grey Lambert
+    assert np.allclose(cs["sphere_material_albedo"][3], 0.8) and np.allclose(cs["sphere_texture_color1"][3], 0.8)
+    assert cs["sphere_data"][1].tolist() == [1.0, 1.0, 1.0, 0.5]         # centre baked at time 0
+    assert cs["sphere_material_fuzz"][1] == 1.0                          # fuzz clamped to 1
+    assert cs["sphere_texture_type"][0] == 1 and cs["sphere_texture_scale"][0] == np.float32(0.5)
+    assert cs["sphere_is_constant_medium"].tolist() == [0, 0, 1, 0]
+    assert cs["sphere_medium_density"][2] == np.float32(0.25)
+    assert np.allclose(cs["sphere_medium_albedo"][2], [0.2, 0.4, 0.9])
+    assert cs["quad_material_type"][0] == 3 and cs["quad_material_emit_color"][0].tolist() == [4.0, 5.0, 6.0]
+    assert cs["quad_is_constant_medium"].tolist() == [0, 1, 1, 1, 1, 1, 1]
+    assert np.allclose(cs["quad_medium_density"][1:], 0.01)
+    assert cs["triangle_texture_type"][0] == 3 and cs["triangle_texture_scale"][0] == 3.0
+    assert np.allclose(cs["quad_normal"][0], [0, -1, 0]) and np.isclose(cs["quad_D"][0], -3.0)
+    tree = bvh.compile_bvh(cs)
+    assert len(tree["bvh_prim_idx"]) == 2 * 12 - 1
+
+
+def test_empty_world():
+    cs = SC.compile_scene(sc.hittable_list())
+    assert cs["sphere_data"].shape == (0, 4) and cs["quad_D"].shape == (0,) and cs["num_images"] == 0
+    assert len(bvh.compile_bvh(cs)["bvh_prim_idx"]) == 0
+
+
+def test_image_texture_roundtrip():
+    img = (np.arange(4 * 6 * 3) % 256).astype(np.uint8).reshape(4, 6, 3)
+    w = sc.hittable_list([sc.Sphere.stationary(sc.point3(0, 0, 0), 1, sc.lambertian.from_texture(sc.image_texture(img)))])
+    cs = SC.compile_scene(w)
+    assert cs["num_images"] == 1 and np.array_equal(cs["image_0"], img)
+    assert cs["sphere_texture_type"][0] == 2 and cs["sphere_texture_image_idx"][0] == 0
+
+
+def test_perlin_tables_follow_the_random_stream():
+    random.seed(42)
+    a = SC.perlin_tables()
+    random.seed(42)
+    b = SC.perlin_tables()
+    assert all(np.array_equal(a[k], b[k]) for k in a)
+    assert sorted(a["perlin_perm_x"].tolist()) == list(range(256)) and a["perlin_randvec"].shape == (256, 3)
+    assert np.abs(a["perlin_randvec"]).max() <= 1.0
+
+
+@pytest.mark.skipif(not REF, reason="reference not mounted")
+@pytest.mark.parametrize("name", ["wavefront_comparison", "cornell_smoke", "cornell_box", "simple_light", "vol2_final_scene"])
+def test_against_reference_compiler(name):
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import refimport as R
+    world, cam = R.capture_scene(name)
+    state = random.getstate()
+    ref = R.reference_compile(world)
+    mine = SC.compile_scene(world)
+    mine.update(bvh.compile_bvh(mine))
+    for k, v in ref.items():
+        assert np.array_equal(np.asarray(v), np.asarray(mine[k])), k
+        assert np.asarray(v).dtype == np.asarray(mine[k]).dtype or k == "num_images", k
+    random.setstate(state)
+    rp = R.reference_perlin_tables()
+    random.setstate(state)
+    mp = SC.perlin_tables()
+    assert all(np.array_equal(rp[k], mp[k]) for k in rp)
+    # camera vectors: my stand-in camera class against the reference's camera.initialize()
+    rc = R.camera_arrays(cam)
+    c2 = sc.camera()
+    for a in ("aspect_ratio", "img_width", "samples_per_pixel", "vfov", "defocus_angle", "focus_distance"):
+        setattr(c2, a, getattr(cam, a))
+    c2.lookfrom, c2.lookat, c2.vup = cam.lookfrom, cam.lookat, cam.vup
+    c2.initialize()
+    assert c2.img_height == int(rc["img_height"])
+    for k, attr in (("cam_center", "center"), ("cam_pixel00", "pixel00_loc"), ("cam_delta_u", "delta_u"),
+                    ("cam_delta_v", "delta_v"), ("cam_defocus_disk_u", "defocus_disk_u")):
+        v = getattr(c2, attr)
+        assert np.array_equal(rc[k], np.array([v.x, v.y, v.z])), k
