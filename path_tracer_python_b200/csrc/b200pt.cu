@@ -41,6 +41,7 @@ struct PtContext {
     int block_threads = 256;
     int smem_nodes = -1;      // -1: auto
     int wavefront_sort = 1;
+    int burst_num = 20;
     int num_sms = 148;
     int max_smem_optin = 0;
     bool count = false;
@@ -104,8 +105,12 @@ struct MegaParams {
     uint32_t seed;
     int n_snodes;
     int tiles_x;
+    int burst_num;       // leave a traversal burst when < burst_num/32 of the live lanes still traverse
     DCounters* counters;
 };
+
+// Lane states of the persistent megakernel
+enum : int { LANE_NEED_PATH = 0, LANE_HAVE_RESULT = 1, LANE_TRAVERSING = 2, LANE_DONE = 3 };
 
 template <bool COUNT>
 __global__ void __launch_bounds__(256) k_megakernel(const __grid_constant__ MegaParams P) {
@@ -120,51 +125,40 @@ __global__ void __launch_bounds__(256) k_megakernel(const __grid_constant__ Mega
     const int px = tx * 8 + (lane & 7);
     const int py = P.y0 + ty * 4 + (lane >> 3);
     const bool valid = (px < P.W) && (py < P.y1);
+    const int pixel = py * P.W + px;
+    float* ap = P.accum + 3 * (size_t)(valid ? pixel : 0);
     LocalCounters lc;
-    if (valid) {
-        const int pixel = py * P.W + px;
-        float* ap = P.accum + 3 * (size_t)pixel;
-        f3 acc = mk3(ap[0], ap[1], ap[2]);
-        const int max_depth = P.cam.max_depth;
-        const f3 bg = mk3(P.cam.background[0], P.cam.background[1], P.cam.background[2]);
-        int s = P.sample_begin;
-        const int s_end = P.sample_begin + P.sample_count;
+    f3 acc = mk3(0.0f, 0.0f, 0.0f);
+    if (valid) acc = mk3(ap[0], ap[1], ap[2]);
+    const int max_depth = P.cam.max_depth;
+    const f3 bg = mk3(P.cam.background[0], P.cam.background[1], P.cam.background[2]);
+    int s = P.sample_begin;
+    const int s_end = P.sample_begin + P.sample_count;
 
-        // per-path state
-        f3 o, d, thr, col;
-        uint32_t rng;
-        int depth;
-        int mode;            // 0: closest-hit search, 1: medium-exit search (kernels.py:417)
-        float t_entry = 0.0f;
-        int ref_entry = kRefNone;
-        bool done = (s >= s_end) || max_depth <= 0;
+    // per-path state
+    f3 thr = mk3(1.0f, 1.0f, 1.0f), col = mk3(0.0f, 0.0f, 0.0f);
+    uint32_t rng = 0;
+    int depth = 0;
+    int mode = 0;            // 0: closest-hit search, 1: medium-exit search (kernels.py:417)
+    float t_entry = 0.0f;
+    int ref_entry = kRefNone;
+    // traversal state (persists across bursts)
+    TravState T;
+    T.cur = kRefNone;
+    int stack_ref[kStackSize];
+    float stack_t[kStackSize];
+    int st = (valid && s < s_end && max_depth > 0) ? LANE_NEED_PATH : LANE_DONE;
 
-        auto start_path = [&]() {
-            rng = ptm::rng_seed(P.seed, (uint32_t)pixel, (uint32_t)s);
-            get_ray(P.cam, px, py, rng, o, d);
-            d = normalized(d);                              // kernels.py:1042
-            thr = mk3(1.0f, 1.0f, 1.0f);
-            col = mk3(0.0f, 0.0f, 0.0f);
-            depth = 0;
-            mode = 0;
-            if (COUNT) lc.paths++;
-        };
-        if (!done) start_path();
-
-        while (!done) {
-            float t;
-            int ref;
-            const float t_min = mode == 0 ? 0.001f : t_entry + 0.0001f;
-            if (COUNT && mode == 0) lc.bounces++;
-            traverse<COUNT>(S, s_nodes, P.n_snodes, o, d, t_min, 1e10f, t, ref, lc);
-
-            bool end_path = false;
-            bool do_shade = false;       // surface shading of (sref, st)
-            bool scattered = false;
-            bool passthrough = false;
+    for (;;) {
+        // ---- (a) lanes whose traversal finished: medium logic / shading / Russian roulette
+        if (st == LANE_HAVE_RESULT) {
+            const f3 o = T.o, d = T.d;
+            const float t = T.best_t;
+            const int ref = T.best_ref;
+            bool end_path = false, do_shade = false, scattered = false, passthrough = false, restart = false;
             int sref = ref;
-            float st = t;
-            f3 hp, sdir, atten;
+            float stt = t;
+            f3 hp = o, sdir = d, atten = mk3(1.0f, 1.0f, 1.0f);
             Mat m;
             if (mode == 0) {
                 if (ref == kRefNone) {
@@ -173,12 +167,14 @@ __global__ void __launch_bounds__(256) k_megakernel(const __grid_constant__ Mega
                 } else {
                     m = load_mat(S, mat_id_of(S, ref));
                     if (mat_is_medium(m.header)) {
-                        mode = 1;                           // run the exit search as the next traversal
+                        mode = 1;                           // the exit search is simply the next traversal
                         t_entry = t;
                         ref_entry = ref;
-                        continue;
+                        trav_begin<COUNT>(T, S, o, d, t + 0.0001f, 1e10f, lc);
+                        restart = true;
+                    } else {
+                        do_shade = true;
                     }
-                    do_shade = true;
                 }
             } else {
                 mode = 0;
@@ -193,49 +189,79 @@ __global__ void __launch_bounds__(256) k_megakernel(const __grid_constant__ Mega
                 } else if (t_exit > 0.0f) {
                     passthrough = true;                     // kernels.py:1100-1110
                     float eps_t = ptm::fdiv(0.001f, ptm::fsqrt(dot(d, d)));
-                    o = o + d * (t_exit + eps_t);
+                    hp = o + d * (t_exit + eps_t);
                 } else {
                     m = load_mat(S, mid);                   // fallback: shade the boundary, :1111-1119
                     sref = ref_entry;
-                    st = t_entry;
+                    stt = t_entry;
                     do_shade = true;
                 }
             }
             if (do_shade) {
                 f3 n, emit;
-                finalize_hit(S, sref, o, d, st, hp, n);
+                finalize_hit(S, sref, o, d, stt, hp, n);
                 scattered = shade_surface(S, m, sref, d, hp, n, rng, emit, sdir, atten);
                 col = col + thr * emit;                     // kernels.py:1116/1124
             }
-            if (!end_path) {
-                if (scattered) {
-                    o = hp;
-                    d = sdir;
-                    thr = thr * atten;
-                    if (depth + 1 >= max_depth) {
-                        end_path = true;
-                    } else if (depth + 1 >= 5) {            // Russian roulette, kernels.py:1145-1157
-                        float survival = min2(max2(max2(thr.x, thr.y), thr.z), 0.95f);
-                        if (ptm::rng_next(rng) > survival) end_path = true;
-                        else thr = vdiv(thr, survival);
+            if (!restart) {
+                if (!end_path) {
+                    if (scattered) {
+                        thr = thr * atten;
+                        if (depth + 1 >= max_depth) {
+                            end_path = true;
+                        } else if (depth + 1 >= 5) {        // Russian roulette, kernels.py:1145-1157
+                            float survival = min2(max2(max2(thr.x, thr.y), thr.z), 0.95f);
+                            if (ptm::rng_next(rng) > survival) end_path = true;
+                            else thr = vdiv(thr, survival);
+                        }
+                        depth++;
+                    } else if (passthrough) {
+                        depth++;                            // the for-loop index still advances
+                        if (depth >= max_depth) end_path = true;
+                    } else {
+                        end_path = true;                    // absorbed
                     }
-                    depth++;
-                } else if (passthrough) {
-                    depth++;                                // the for-loop index still advances
-                    if (depth >= max_depth) end_path = true;
-                } else {
-                    end_path = true;                        // absorbed
                 }
-            }
-            if (end_path) {
-                acc = acc + col;                            // kernels.py:1187
-                s++;
-                if (s < s_end) start_path();
-                else done = true;
+                if (end_path) {
+                    acc = acc + col;                        // kernels.py:1187
+                    s++;
+                    st = LANE_NEED_PATH;
+                } else {
+                    if (COUNT) lc.bounces++;
+                    trav_begin<COUNT>(T, S, hp, sdir, 0.001f, 1e10f, lc);
+                    st = LANE_TRAVERSING;
+                }
+            } else {
+                st = LANE_TRAVERSING;
             }
         }
-        ap[0] = acc.x; ap[1] = acc.y; ap[2] = acc.z;
+        // ---- (b) path regeneration: the lane moves on to its next sample
+        if (st == LANE_NEED_PATH) {
+            if (s < s_end) {
+                rng = ptm::rng_seed(P.seed, (uint32_t)pixel, (uint32_t)s);
+                f3 o, d;
+                get_ray(P.cam, px, py, rng, o, d);
+                d = normalized(d);                          // kernels.py:1042
+                thr = mk3(1.0f, 1.0f, 1.0f);
+                col = mk3(0.0f, 0.0f, 0.0f);
+                depth = 0;
+                mode = 0;
+                if (COUNT) { lc.paths++; lc.bounces++; }
+                trav_begin<COUNT>(T, S, o, d, 0.001f, 1e10f, lc);
+                st = LANE_TRAVERSING;
+            } else {
+                st = LANE_DONE;
+            }
+        }
+        // ---- (c) traversal burst: leave when fewer than ~burst_frac of the live lanes still traverse
+        const unsigned live = __ballot_sync(0xffffffffu, st != LANE_DONE);
+        if (live == 0u) break;
+        const int min_active = (__popc(live) * P.burst_num + 31) >> 5;
+        if (st == LANE_TRAVERSING) {
+            if (trav_run<COUNT>(T, S, s_nodes, P.n_snodes, stack_ref, stack_t, min_active, lc)) st = LANE_HAVE_RESULT;
+        }
     }
+    if (valid) { ap[0] = acc.x; ap[1] = acc.y; ap[2] = acc.z; }
     if (COUNT) flush_counters(P.counters, lc);
 }
 
@@ -606,6 +632,9 @@ int pt_set_option(PtContext* ctx, const char* name, int64_t value) {
         ctx->block_threads = (int)value;
     } else if (k == "smem_nodes") {
         ctx->smem_nodes = (int)value;
+    } else if (k == "burst_num") {
+        if (value < 0 || value > 32) return set_error(PT_ERR_INVALID_ARG, "burst_num must be in [0, 32]");
+        ctx->burst_num = (int)value;
     } else if (k == "wavefront_sort") {
         ctx->wavefront_sort = value ? 1 : 0;
     } else {
@@ -676,6 +705,7 @@ int pt_render_megakernel(PtContext* ctx, float* accum, int W, int H, int y0, int
     P.sample_begin = sample_begin; P.sample_count = sample_count;
     P.seed = seed;
     P.tiles_x = (W + 7) / 8;
+    P.burst_num = ctx->burst_num;
     P.counters = ctx->d_counters;
     const int tiles_y = (y1 - y0 + 3) / 4;
     const long long warps = (long long)P.tiles_x * tiles_y;

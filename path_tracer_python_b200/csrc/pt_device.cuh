@@ -152,81 +152,133 @@ __device__ __forceinline__ void finalize_hit(const DScene& S, int ref, f3 o, f3 
 //      the reference's clamped reciprocal direction (kernels.py:642-646).  Children are visited
 //      nearest-entry first; a deferred child is skipped at pop time when its entry distance exceeds
 //      the current closest hit -- the same predicate the reference re-evaluates on pop (:667).
+//
+//      The traversal is *resumable*: all of its state lives in TravState (+ the per-lane stack), so a
+//      warp can leave the loop when too few of its lanes are still traversing, let the finished
+//      lanes shade / fetch new work, and come back (persistent-lane scheduling).
+
+// min/max of the slab test map to single FMNMX / FMNMX3 instructions (sm_100a).  Float min/max is
+// exact and order-independent for non-NaN inputs; the results only feed comparisons, so the sign of
+// a zero cannot matter either.
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+    float d;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+struct TravState {
+    f3 o, d, inv;
+    float t_min, best_t;
+    int best_ref;
+    int cur;     // >= 0 inner node, < 0 leaf reference, kRefNone = traversal finished
+    int sp;
+};
+
 template <bool COUNT>
-__device__ __forceinline__ void traverse(const DScene& S, const float4* __restrict__ snodes, int n_snodes, f3 o, f3 d,
-                                         float t_min, float t_max, float& best_t, int& best_ref, LocalCounters& lc) {
-    best_t = t_max;
-    best_ref = kRefNone;
+__device__ __forceinline__ void trav_begin(TravState& T, const DScene& S, f3 o, f3 d, float t_min, float t_max,
+                                           LocalCounters& lc) {
+    T.o = o;
+    T.d = d;
+    T.inv = mk3(fabsf(d.x) > 1e-8f ? ptm::fdiv(1.0f, d.x) : 1e8f, fabsf(d.y) > 1e-8f ? ptm::fdiv(1.0f, d.y) : 1e8f,
+                fabsf(d.z) > 1e-8f ? ptm::fdiv(1.0f, d.z) : 1e8f);
+    T.t_min = t_min;
+    T.best_t = t_max;
+    T.best_ref = kRefNone;
+    T.cur = S.num_inner > 0 ? 0 : kRefNone;
+    T.sp = 0;
     if (COUNT) lc.rays++;
-    if (S.num_inner == 0) return;
-    f3 inv = mk3(fabsf(d.x) > 1e-8f ? ptm::fdiv(1.0f, d.x) : 1e8f, fabsf(d.y) > 1e-8f ? ptm::fdiv(1.0f, d.y) : 1e8f,
-                 fabsf(d.z) > 1e-8f ? ptm::fdiv(1.0f, d.z) : 1e8f);
-    int stack_ref[kStackSize];
-    float stack_t[kStackSize];
-    int sp = 0;
-    int cur = 0;
-    for (;;) {
-        while (cur >= 0) {
+}
+
+__device__ __forceinline__ int trav_pop(TravState& T, const int* stack_ref, const float* stack_t) {
+    int next = kRefNone;
+    while (T.sp > 0) {
+        --T.sp;
+        if (stack_t[T.sp] <= T.best_t) { next = stack_ref[T.sp]; break; }
+    }
+    return next;
+}
+
+// Runs the traversal until it finishes (returns true) or, when min_active > 0, until fewer than
+// min_active lanes of the warp are still inside the loop (returns false; call again to resume).
+template <bool COUNT>
+__device__ __forceinline__ bool trav_run(TravState& T, const DScene& S, const float4* __restrict__ s_nodes, int n_snodes,
+                                         int* stack_ref, float* stack_t, int min_active, LocalCounters& lc) {
+    const f3 o = T.o, inv = T.inv;
+    const float t_min = T.t_min;
+    while (T.cur != kRefNone) {
+        while (T.cur >= 0) {
             float4 nx, ny, nz, nc;
-            if (cur < n_snodes) {
-                const float4* p = snodes + 4 * cur;
+            if (T.cur < n_snodes) {
+                const float4* p = s_nodes + 4 * T.cur;
                 nx = p[0]; ny = p[1]; nz = p[2]; nc = p[3];
             } else {
-                const float4* p = S.nodes + 4 * cur;
+                const float4* p = S.nodes + 4 * T.cur;
                 nx = __ldg(p); ny = __ldg(p + 1); nz = __ldg(p + 2); nc = __ldg(p + 3);
             }
             if (COUNT) lc.box_tests += 2;
+            const float best_t = T.best_t;
             // left child box
             float l0x = (nx.x - o.x) * inv.x, l1x = (nx.y - o.x) * inv.x;
             float l0y = (ny.x - o.y) * inv.y, l1y = (ny.y - o.y) * inv.y;
             float l0z = (nz.x - o.z) * inv.z, l1z = (nz.y - o.z) * inv.z;
-            float ltmin = max2(max2(min2(l0x, l1x), min2(l0y, l1y)), max2(min2(l0z, l1z), t_min));
-            float ltmax = min2(min2(max2(l0x, l1x), max2(l0y, l1y)), min2(max2(l0z, l1z), best_t));
+            float ltmin = fmax3(fminf(l0x, l1x), fminf(l0y, l1y), fmaxf(fminf(l0z, l1z), t_min));
+            float ltmax = fmin3(fmaxf(l0x, l1x), fmaxf(l0y, l1y), fminf(fmaxf(l0z, l1z), best_t));
             // right child box
             float r0x = (nx.z - o.x) * inv.x, r1x = (nx.w - o.x) * inv.x;
             float r0y = (ny.z - o.y) * inv.y, r1y = (ny.w - o.y) * inv.y;
             float r0z = (nz.z - o.z) * inv.z, r1z = (nz.w - o.z) * inv.z;
-            float rtmin = max2(max2(min2(r0x, r1x), min2(r0y, r1y)), max2(min2(r0z, r1z), t_min));
-            float rtmax = min2(min2(max2(r0x, r1x), max2(r0y, r1y)), min2(max2(r0z, r1z), best_t));
-            int lref = __float_as_int(nc.x), rref = __float_as_int(nc.y);
-            bool hl = (ltmax >= ltmin) && (lref != kRefNone);
-            bool hr = (rtmax >= rtmin) && (rref != kRefNone);
+            float rtmin = fmax3(fminf(r0x, r1x), fminf(r0y, r1y), fmaxf(fminf(r0z, r1z), t_min));
+            float rtmax = fmin3(fmaxf(r0x, r1x), fmaxf(r0y, r1y), fminf(fmaxf(r0z, r1z), best_t));
+            const int lref = __float_as_int(nc.x), rref = __float_as_int(nc.y);
+            const bool hl = (ltmax >= ltmin) && (lref != kRefNone);
+            const bool hr = (rtmax >= rtmin) && (rref != kRefNone);
             if (hl && hr) {
-                bool left_first = ltmin <= rtmin;
-                int far_ref = left_first ? rref : lref;
-                float far_t = left_first ? rtmin : ltmin;
-                cur = left_first ? lref : rref;
-                if (sp < kStackSize) { stack_ref[sp] = far_ref; stack_t[sp] = far_t; sp++; }
-            } else if (hl) {
-                cur = lref;
-            } else if (hr) {
-                cur = rref;
-            } else {
-                cur = kRefNone;
-                while (sp > 0) {
-                    --sp;
-                    if (stack_t[sp] <= best_t) { cur = stack_ref[sp]; break; }
+                const bool left_first = ltmin <= rtmin;
+                if (T.sp < kStackSize) {
+                    stack_ref[T.sp] = left_first ? rref : lref;
+                    stack_t[T.sp] = left_first ? rtmin : ltmin;
+                    T.sp++;
                 }
-                if (cur == kRefNone) return;
+                T.cur = left_first ? lref : rref;
+            } else if (hl) {
+                T.cur = lref;
+            } else if (hr) {
+                T.cur = rref;
+            } else {
+                T.cur = trav_pop(T, stack_ref, stack_t);
             }
         }
-        // cur is a leaf reference
-        {
-            int type = ref_type(cur), idx = ref_index(cur);
+        if (T.cur != kRefNone) {   // a leaf reference
+            const int type = ref_type(T.cur), idx = ref_index(T.cur);
             float t;
             bool hit;
-            if (type == PT_PRIM_SPHERE) { if (COUNT) lc.sphere_tests++; hit = hit_sphere_t(S, idx, o, d, t_min, best_t, t); }
-            else if (type == PT_PRIM_QUAD) { if (COUNT) lc.quad_tests++; hit = hit_quad_t(S, idx, o, d, t_min, best_t, t); }
-            else { if (COUNT) lc.triangle_tests++; hit = hit_triangle_t(S, idx, o, d, t_min, best_t, t); }
-            if (hit && t < best_t) { best_t = t; best_ref = cur; }   // kernels.py:691 (strict)
+            if (type == PT_PRIM_SPHERE) { if (COUNT) lc.sphere_tests++; hit = hit_sphere_t(S, idx, T.o, T.d, t_min, T.best_t, t); }
+            else if (type == PT_PRIM_QUAD) { if (COUNT) lc.quad_tests++; hit = hit_quad_t(S, idx, T.o, T.d, t_min, T.best_t, t); }
+            else { if (COUNT) lc.triangle_tests++; hit = hit_triangle_t(S, idx, T.o, T.d, t_min, T.best_t, t); }
+            if (hit && t < T.best_t) { T.best_t = t; T.best_ref = T.cur; }   // kernels.py:691 (strict)
+            T.cur = trav_pop(T, stack_ref, stack_t);
         }
-        cur = kRefNone;
-        while (sp > 0) {
-            --sp;
-            if (stack_t[sp] <= best_t) { cur = stack_ref[sp]; break; }
-        }
-        if (cur == kRefNone) return;
+        if (min_active > 0 && __popc(__activemask()) < min_active) break;
     }
+    return T.cur == kRefNone;
+}
+
+// One-shot traversal (probe / wavefront kernels).
+template <bool COUNT>
+__device__ __forceinline__ void traverse(const DScene& S, const float4* __restrict__ s_nodes, int n_snodes, f3 o, f3 d,
+                                         float t_min, float t_max, float& best_t, int& best_ref, LocalCounters& lc) {
+    int stack_ref[kStackSize];
+    float stack_t[kStackSize];
+    TravState T;
+    trav_begin<COUNT>(T, S, o, d, t_min, t_max, lc);
+    trav_run<COUNT>(T, S, s_nodes, n_snodes, stack_ref, stack_t, 0, lc);
+    best_t = T.best_t;
+    best_ref = T.best_ref;
 }
 
 // ---- samplers (kernels.py:16-71)
