@@ -41,7 +41,8 @@ struct PtContext {
     int block_threads = 256;
     int smem_nodes = -1;      // -1: auto
     int wavefront_sort = 1;
-    int burst_num = 20;
+    int burst_num = 16;
+    int sync_samples = 0;
     int num_sms = 148;
     int max_smem_optin = 0;
     bool count = false;
@@ -106,11 +107,12 @@ struct MegaParams {
     int n_snodes;
     int tiles_x;
     int burst_num;       // leave a traversal burst when < burst_num/32 of the live lanes still traverse
+    int sync_samples;    // > 0: lanes of a warp re-synchronise every sync_samples samples
     DCounters* counters;
 };
 
 // Lane states of the persistent megakernel
-enum : int { LANE_NEED_PATH = 0, LANE_HAVE_RESULT = 1, LANE_TRAVERSING = 2, LANE_DONE = 3 };
+enum : int { LANE_NEED_PATH = 0, LANE_HAVE_RESULT = 1, LANE_TRAVERSING = 2, LANE_DONE = 3, LANE_WAIT = 4 };
 
 template <bool COUNT>
 __global__ void __launch_bounds__(256) k_megakernel(const __grid_constant__ MegaParams P) {
@@ -225,7 +227,10 @@ __global__ void __launch_bounds__(256) k_megakernel(const __grid_constant__ Mega
                 if (end_path) {
                     acc = acc + col;                        // kernels.py:1187
                     s++;
-                    st = LANE_NEED_PATH;
+                    // optional warp re-synchronisation every sync_samples samples: the lanes of a
+                    // tile start their next primary rays together (coherent again)
+                    st = (P.sync_samples > 0 && s < s_end && ((s - P.sample_begin) % P.sync_samples) == 0) ? LANE_WAIT
+                                                                                                           : LANE_NEED_PATH;
                 } else {
                     if (COUNT) lc.bounces++;
                     trav_begin<COUNT>(T, S, hp, sdir, 0.001f, 1e10f, lc);
@@ -256,6 +261,10 @@ __global__ void __launch_bounds__(256) k_megakernel(const __grid_constant__ Mega
         // ---- (c) traversal burst: leave when fewer than ~burst_frac of the live lanes still traverse
         const unsigned live = __ballot_sync(0xffffffffu, st != LANE_DONE);
         if (live == 0u) break;
+        if (P.sync_samples > 0) {
+            const unsigned busy = __ballot_sync(0xffffffffu, st == LANE_TRAVERSING || st == LANE_HAVE_RESULT || st == LANE_NEED_PATH);
+            if (busy == 0u && st == LANE_WAIT) st = LANE_NEED_PATH;
+        }
         const int min_active = (__popc(live) * P.burst_num + 31) >> 5;
         if (st == LANE_TRAVERSING) {
             if (trav_run<COUNT>(T, S, s_nodes, P.n_snodes, stack_ref, stack_t, min_active, lc)) st = LANE_HAVE_RESULT;
@@ -580,7 +589,7 @@ static int pick_snodes(const PtContext* ctx, int blocks_per_sm_hint) {
     int n = ctx->smem_nodes;
     const int cap_bytes = ctx->max_smem_optin / (blocks_per_sm_hint > 0 ? blocks_per_sm_hint : 1) - 1024;
     int cap = cap_bytes > 0 ? cap_bytes / 64 : 0;
-    if (n < 0) n = 1024;                       // auto: 64 KB of the top of the tree
+    if (n < 0) n = 256;                        // auto: the top 16 KB of the tree (more would eat L1)
     if (n > cap) n = cap;
     if (n > ctx->scene.num_inner) n = ctx->scene.num_inner;
     return n < 0 ? 0 : n;
@@ -635,6 +644,8 @@ int pt_set_option(PtContext* ctx, const char* name, int64_t value) {
     } else if (k == "burst_num") {
         if (value < 0 || value > 32) return set_error(PT_ERR_INVALID_ARG, "burst_num must be in [0, 32]");
         ctx->burst_num = (int)value;
+    } else if (k == "sync_samples") {
+        ctx->sync_samples = value < 0 ? 0 : (int)value;
     } else if (k == "wavefront_sort") {
         ctx->wavefront_sort = value ? 1 : 0;
     } else {
@@ -706,6 +717,7 @@ int pt_render_megakernel(PtContext* ctx, float* accum, int W, int H, int y0, int
     P.seed = seed;
     P.tiles_x = (W + 7) / 8;
     P.burst_num = ctx->burst_num;
+    P.sync_samples = ctx->sync_samples;
     P.counters = ctx->d_counters;
     const int tiles_y = (y1 - y0 + 3) / 4;
     const long long warps = (long long)P.tiles_x * tiles_y;

@@ -11,6 +11,7 @@ e.set_scene(cs); e.set_camera(meta["camera"], (0, 0, 0), 50)
 H = meta["height"]
 acc = e.new_accum(W, H)
 def run(mode="megakernel"):
+    global SPP
     fn = e.render_megakernel if mode == "megakernel" else e.render_wavefront
     acc.zero_(); fn(acc, 0, 2, 7); torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -19,8 +20,11 @@ def run(mode="megakernel"):
 bursts = [int(x) for x in os.environ.get("BURSTS", "0,8,12,16,20,24,28").split(",")]
 snodes = [int(x) for x in os.environ.get("SNODES", "1024").split(",")]
 blocks = [int(x) for x in os.environ.get("BLOCKS", "256").split(",")]
-for bt, sn, bn in itertools.product(blocks, snodes, bursts):
-    e.set_option("block_threads", bt); e.set_option("smem_nodes", sn); e.set_option("burst_num", bn)
-    print(f"block={bt} smem_nodes={sn} burst={bn}: {run():.1f} Mpaths/s", flush=True)
+syncs = [int(x) for x in os.environ.get("SYNCS", "0").split(",")]
+spps = [int(x) for x in os.environ.get("SPPS", str(SPP)).split(",")]
+for bt, sn, bn, sy, sp in itertools.product(blocks, snodes, bursts, syncs, spps):
+    e.set_option("block_threads", bt); e.set_option("smem_nodes", sn); e.set_option("burst_num", bn); e.set_option("sync_samples", sy)
+    SPP = sp
+    print(f"block={bt} smem_nodes={sn} burst={bn} sync={sy} spp={sp}: {run():.1f} Mpaths/s", flush=True)
 if os.environ.get("WAVE"):
     print(f"wavefront: {run('wavefront'):.1f} Mpaths/s")
