@@ -136,7 +136,8 @@ int pt_bvh_build_sah(int32_t n_prims, const float* prim_bbox_min, const float* p
 int pt_create(int device_ordinal, PtContext** out_ctx);   /* replaces ti.init (renderer.py:16) */
 int pt_destroy(PtContext* ctx);
 /* tuning knobs: "block_threads", "smem_nodes" (inner nodes staged in shared memory; -1 = auto),
- * "wavefront_sort" (0/1) */
+ * "burst_num" / "wf_burst_num" (a warp leaves the traversal loop when fewer than n/32 of its live
+ * lanes still traverse), "sync_samples", "wf_blocks_per_sm", "wavefront_sort" (0/1) */
 int pt_set_option(PtContext* ctx, const char* name, int64_t value);
 
 /* `device_blob` (device, info->total_bytes) stays owned by the caller and must outlive its use. */
@@ -152,7 +153,10 @@ int pt_render_megakernel(PtContext* ctx, float* accum, int W, int H, int y0, int
 /* ---- wavefront: replaces generate_camera_rays / intersect_rays / shade_miss_rays /
  *      reset_next_ray_count / shade_and_scatter / swap_ray_buffers (kernels.py:1219-1418) and
  *      their host loop (renderer.py:305-334).  workspace: device, >= pt_wavefront_workspace_bytes. */
-size_t pt_wavefront_workspace_bytes(int W, int rows);
+size_t pt_wavefront_workspace_bytes(int W, int rows);   /* minimum: one sample of the window in flight */
+/* workspace for `samples_in_flight` samples of every pixel in flight at once (bigger waves: fewer,
+ * fuller launches).  pt_render_wavefront uses as many as the workspace it is given can hold. */
+size_t pt_wavefront_workspace_bytes_for(int W, int rows, int samples_in_flight);
 int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int y1, int sample_begin,
                         int sample_count, uint32_t seed, void* workspace, size_t workspace_bytes, void* stream);
 

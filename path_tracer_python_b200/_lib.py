@@ -63,7 +63,7 @@ class PtCounters(C.Structure):
 EXPORTS = [
     "pt_last_error", "pt_version", "pt_pack_scene_info", "pt_pack_scene", "pt_bvh_build_sah", "pt_create",
     "pt_destroy", "pt_set_option", "pt_set_scene", "pt_set_camera", "pt_render_megakernel",
-    "pt_wavefront_workspace_bytes", "pt_render_wavefront", "pt_generate_camera_rays", "pt_first_hit",
+    "pt_wavefront_workspace_bytes", "pt_wavefront_workspace_bytes_for", "pt_render_wavefront", "pt_generate_camera_rays", "pt_first_hit",
     "pt_math_eval", "pt_tonemap", "pt_enable_counters", "pt_get_counters",
 ]
 
@@ -88,6 +88,8 @@ def lib() -> C.CDLL:
     L.pt_version.restype = C.c_char_p
     L.pt_wavefront_workspace_bytes.restype = C.c_size_t
     L.pt_wavefront_workspace_bytes.argtypes = [C.c_int, C.c_int]
+    L.pt_wavefront_workspace_bytes_for.restype = C.c_size_t
+    L.pt_wavefront_workspace_bytes_for.argtypes = [C.c_int, C.c_int, C.c_int]
     L.pt_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
     L.pt_destroy.argtypes = [C.c_void_p]
     L.pt_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]

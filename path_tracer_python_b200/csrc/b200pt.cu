@@ -43,6 +43,8 @@ struct PtContext {
     int wavefront_sort = 1;
     int burst_num = 16;
     int sync_samples = 0;
+    int wf_burst_num = 24;
+    int wf_blocks_per_sm = 3;
     int num_sms = 148;
     int max_smem_optin = 0;
     bool count = false;
@@ -277,15 +279,23 @@ __global__ void __launch_bounds__(256) k_megakernel(const __grid_constant__ Mega
 // ------------------------------------------------------------------------------------------------
 // wavefront
 // ------------------------------------------------------------------------------------------------
-// Ray record (48 B, three float4 planes): (o.xyz d.x) (d.yz thr.xy) (thr.z pixel rng depth)
-// Hit record (16 B): (t, ref, t_exit, exit_hit)
+// A *batch* of B samples of every pixel of the window is in flight at once (B*N paths, N = W*rows;
+// B is whatever fits the caller's workspace).  Per wave: k_wf_extend (closest hit, dynamic ray
+// fetch) then k_wf_shade (material-binned, compaction).  A path's radiance contribution is written
+// to slab[slot][pixel] and k_wf_resolve adds the slabs to the accumulation buffer in sample order,
+// so the sums are the ones the reference's one-sample-at-a-time loop produces.
+//
+// Ray record (48 B, three float4 planes): (o.xyz d.x) (d.yz thr.xy) (thr.z path_id rng depth)
+//   path_id = slot * N + local pixel.        Hit record (16 B): (t, ref, t_exit, exit_hit)
 struct WfQueues {
     float4 *r0[2], *r1[2], *r2[2];
     float4* hit;
     uint32_t* bins;          // kNumBins regions of `capacity` ray indices
+    float* slab;             // [B][N][3] radiance contribution of each path of the batch
     int* qcount;             // [2] ray counts of the two queues
     int* bin_count;          // [2][kNumBins]
-    int capacity;
+    int* cursor;             // dynamic-fetch cursor of k_wf_extend
+    int capacity;            // B * N
 };
 constexpr int kNumBins = 8;  // 0 miss, 1 medium boundary, 2.. = 2 + material type (0..4)
 
@@ -295,31 +305,39 @@ struct WfParams {
     WfQueues Q;
     float* accum;
     int W, H, y0, y1;
-    int sample;
+    int N;                   // W * (y1 - y0)
+    int sample_base;         // first sample index of this batch
+    int batch;               // samples in this batch (<= B)
     uint32_t seed;
     int n_snodes;
     int bounce;              // parity selects queue
     int sort;
+    int burst_num;
     DCounters* counters;
 };
 
 __global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ WfParams P) {
-    const int n = P.W * (P.y1 - P.y0);
+    const int total = P.N * P.batch;
     const int stride = gridDim.x * blockDim.x;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const int pixel = P.y0 * P.W + i;
+    for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < total; id += stride) {
+        const int slot = id / P.N;
+        const int pixel = P.y0 * P.W + (id - slot * P.N);
         const int py = pixel / P.W, px = pixel - py * P.W;
-        uint32_t rng = ptm::rng_seed(P.seed, (uint32_t)pixel, (uint32_t)P.sample);
+        uint32_t rng = ptm::rng_seed(P.seed, (uint32_t)pixel, (uint32_t)(P.sample_base + slot));
         f3 o, d;
         get_ray(P.cam, px, py, rng, o, d);                  // NOT normalised, kernels.py:1229-1233
-        P.Q.r0[0][i] = make_float4(o.x, o.y, o.z, d.x);
-        P.Q.r1[0][i] = make_float4(d.y, d.z, 1.0f, 1.0f);
-        P.Q.r2[0][i] = make_float4(1.0f, __int_as_float(pixel), __uint_as_float(rng), __int_as_float(0));
+        P.Q.r0[0][id] = make_float4(o.x, o.y, o.z, d.x);
+        P.Q.r1[0][id] = make_float4(d.y, d.z, 1.0f, 1.0f);
+        P.Q.r2[0][id] = make_float4(1.0f, __int_as_float(id), __uint_as_float(rng), __int_as_float(0));
+        P.Q.slab[3 * (size_t)id] = 0.0f;
+        P.Q.slab[3 * (size_t)id + 1] = 0.0f;
+        P.Q.slab[3 * (size_t)id + 2] = 0.0f;
     }
     if (blockIdx.x == 0 && threadIdx.x < 2 * kNumBins) P.Q.bin_count[threadIdx.x] = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        P.Q.qcount[0] = n;
+        P.Q.qcount[0] = total;
         P.Q.qcount[1] = 0;
+        P.Q.cursor[0] = 0;
     }
 }
 
@@ -340,6 +358,10 @@ __device__ __forceinline__ int warp_agg_append(int* counter_base, int key, bool 
     return pos;
 }
 
+// intersect_rays (kernels.py:1242-1263) + the exit search of apply_constant_medium (:417-419).
+// Persistent warps: a lane that finishes its ray writes the hit record, bins the ray and fetches
+// the next ray index from a global cursor, while the other lanes of the warp keep traversing
+// (resumable traversal, same scheme as the megakernel).
 template <bool COUNT>
 __global__ void __launch_bounds__(256) k_wf_extend(const __grid_constant__ WfParams P) {
     extern __shared__ float4 s_nodes[];
@@ -353,37 +375,80 @@ __global__ void __launch_bounds__(256) k_wf_extend(const __grid_constant__ WfPar
     stage_nodes(s_nodes, S, P.n_snodes);
     LocalCounters lc;
     int* bin_count = P.Q.bin_count + cur * kNumBins;
-    const int stride = gridDim.x * blockDim.x;
-    const int rounds = (count + stride - 1) / stride;
-    for (int r = 0; r < rounds; r++) {
-        const int i = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
-        const bool active = i < count;
+    const unsigned lane = threadIdx.x & 31;
+
+    TravState T;
+    T.cur = kRefNone;
+    int stack_ref[kStackSize];
+    float stack_t[kStackSize];
+    int st = LANE_NEED_PATH;     // NEED_PATH: wants a ray; TRAVERSING; HAVE_RESULT; DONE: queue exhausted
+    int ray = 0, mode = 0, ref_entry = kRefNone;
+    float t_entry = 0.0f;
+
+    for (;;) {
+        // ---- finished lanes: second traversal for medium boundaries, else emit the hit record
+        bool emit = false;
         int bin = 0;
-        if (active) {
-            float4 a = P.Q.r0[cur][i], b = P.Q.r1[cur][i];
-            f3 o = mk3(a.x, a.y, a.z), d = mk3(a.w, b.x, b.y);
-            float t, t_exit = 0.0f;
-            int ref, exit_hit = 0;
-            if (COUNT) lc.bounces++;
-            traverse<COUNT>(S, s_nodes, P.n_snodes, o, d, 0.001f, 1e10f, t, ref, lc);   // intersect_rays, :1242
-            if (ref != kRefNone) {
-                int header = __float_as_int(__ldg(S.materials + 3 * mat_id_of(S, ref)).x);
-                if (mat_is_medium(header)) {
-                    // exit search of apply_constant_medium (kernels.py:417-419), done here so the
-                    // shade stage is traversal-free
-                    int eref;
-                    traverse<COUNT>(S, s_nodes, P.n_snodes, o, d, t + 0.0001f, 1e10f, t_exit, eref, lc);
-                    exit_hit = eref != kRefNone;
-                    bin = 1;
-                } else {
-                    bin = 2 + mat_type(header);
+        if (st == LANE_HAVE_RESULT) {
+            if (mode == 0) {
+                const int ref = T.best_ref;
+                bin = 0;
+                if (ref != kRefNone) {
+                    const int header = __float_as_int(__ldg(S.materials + 3 * mat_id_of(S, ref)).x);
+                    if (mat_is_medium(header)) {
+                        mode = 1;
+                        t_entry = T.best_t;
+                        ref_entry = ref;
+                        trav_begin<COUNT>(T, S, T.o, T.d, t_entry + 0.0001f, 1e10f, lc);
+                        st = LANE_TRAVERSING;
+                    } else {
+                        bin = 2 + mat_type(header);
+                    }
                 }
+                if (st == LANE_HAVE_RESULT) {
+                    P.Q.hit[ray] = make_float4(T.best_t, __int_as_float(ref), 0.0f, __int_as_float(0));
+                    emit = true;
+                }
+            } else {
+                mode = 0;
+                P.Q.hit[ray] = make_float4(t_entry, __int_as_float(ref_entry), T.best_t,
+                                           __int_as_float(T.best_ref != kRefNone ? 1 : 0));
+                bin = 1;
+                emit = true;
             }
-            P.Q.hit[i] = make_float4(t, __int_as_float(ref), t_exit, __int_as_float(exit_hit));
         }
         if (P.sort) {
-            int pos = warp_agg_append(bin_count, bin, active);
-            if (active) P.Q.bins[(size_t)bin * P.Q.capacity + pos] = (uint32_t)i;
+            const int pos = warp_agg_append(bin_count, bin, emit);
+            if (emit) P.Q.bins[(size_t)bin * P.Q.capacity + pos] = (uint32_t)ray;
+        }
+        if (emit) st = LANE_NEED_PATH;
+        // ---- dynamic fetch: one atomic per warp hands consecutive ray indices to the idle lanes
+        {
+            const unsigned want = __ballot_sync(0xffffffffu, st == LANE_NEED_PATH);
+            if (want) {
+                int base = 0;
+                const int leader = __ffs(want) - 1;
+                if ((int)lane == leader) base = atomicAdd(P.Q.cursor, __popc(want));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (st == LANE_NEED_PATH) {
+                    ray = base + __popc(want & ((1u << lane) - 1));
+                    if (ray < count) {
+                        const float4 a = P.Q.r0[cur][ray], b = P.Q.r1[cur][ray];
+                        if (COUNT) lc.bounces++;
+                        trav_begin<COUNT>(T, S, mk3(a.x, a.y, a.z), mk3(a.w, b.x, b.y), 0.001f, 1e10f, lc);
+                        mode = 0;
+                        st = LANE_TRAVERSING;
+                    } else {
+                        st = LANE_DONE;
+                    }
+                }
+            }
+        }
+        const unsigned live = __ballot_sync(0xffffffffu, st != LANE_DONE);
+        if (live == 0u) break;
+        const int min_active = (__popc(live) * P.burst_num + 31) >> 5;
+        if (st == LANE_TRAVERSING) {
+            if (trav_run<COUNT>(T, S, s_nodes, P.n_snodes, stack_ref, stack_t, min_active, lc)) st = LANE_HAVE_RESULT;
         }
     }
     if (COUNT) flush_counters(P.counters, lc);
@@ -393,6 +458,7 @@ __global__ void __launch_bounds__(256) k_wf_shade(const __grid_constant__ WfPara
     const DScene& S = P.S;
     const int cur = P.bounce & 1, nxt = cur ^ 1;
     const int count = P.Q.qcount[cur];
+    if (blockIdx.x == 0 && threadIdx.x == 0) P.Q.cursor[0] = 0;       // for the next k_wf_extend
     if (count == 0) return;
     const int* bin_count = P.Q.bin_count + cur * kNumBins;
     int prefix[kNumBins + 1];
@@ -411,7 +477,7 @@ __global__ void __launch_bounds__(256) k_wf_shade(const __grid_constant__ WfPara
         const bool active = j < count;
         bool emit_next = false;
         f3 no, nd, nthr;
-        int pixel = 0, ndepth = 0;
+        int path_id = 0, ndepth = 0;
         uint32_t rng = 0;
         if (active) {
             int i = j;
@@ -423,15 +489,15 @@ __global__ void __launch_bounds__(256) k_wf_shade(const __grid_constant__ WfPara
             }
             float4 a = P.Q.r0[cur][i], bq = P.Q.r1[cur][i], c = P.Q.r2[cur][i], h = P.Q.hit[i];
             f3 o = mk3(a.x, a.y, a.z), d = mk3(a.w, bq.x, bq.y), thr = mk3(bq.z, bq.w, c.x);
-            pixel = __float_as_int(c.y);
+            path_id = __float_as_int(c.y);
             rng = __float_as_uint(c.z);
             int depth = __float_as_int(c.w);
             float t = h.x;
             int ref = __float_as_int(h.y);
-            float* ap = P.accum + 3 * (size_t)pixel;
+            float* sp = P.Q.slab + 3 * (size_t)path_id;       // this path's (single) radiance contribution
             if (ref == kRefNone) {                           // shade_miss_rays, kernels.py:1266-1280
                 f3 add = thr * bg;
-                ap[0] = ap[0] + add.x; ap[1] = ap[1] + add.y; ap[2] = ap[2] + add.z;
+                sp[0] = sp[0] + add.x; sp[1] = sp[1] + add.y; sp[2] = sp[2] + add.z;
             } else {                                         // shade_and_scatter, kernels.py:1289-1399
                 const int mid = mat_id_of(S, ref);
                 Mat m = load_mat(S, mid);
@@ -463,7 +529,7 @@ __global__ void __launch_bounds__(256) k_wf_shade(const __grid_constant__ WfPara
                 }
                 if (emit.x > 0.0f || emit.y > 0.0f || emit.z > 0.0f) {      // kernels.py:1368-1375
                     f3 add = thr * emit;
-                    ap[0] = ap[0] + add.x; ap[1] = ap[1] + add.y; ap[2] = ap[2] + add.z;
+                    sp[0] = sp[0] + add.x; sp[1] = sp[1] + add.y; sp[2] = sp[2] + add.z;
                 }
                 if (scattered) {
                     f3 new_thr = thr * atten;
@@ -488,8 +554,22 @@ __global__ void __launch_bounds__(256) k_wf_shade(const __grid_constant__ WfPara
         if (emit_next) {
             P.Q.r0[nxt][pos] = make_float4(no.x, no.y, no.z, nd.x);
             P.Q.r1[nxt][pos] = make_float4(nd.y, nd.z, nthr.x, nthr.y);
-            P.Q.r2[nxt][pos] = make_float4(nthr.z, __int_as_float(pixel), __uint_as_float(rng), __int_as_float(ndepth));
+            P.Q.r2[nxt][pos] = make_float4(nthr.z, __int_as_float(path_id), __uint_as_float(rng), __int_as_float(ndepth));
         }
+    }
+}
+
+// accum[pixel] += slab[0][pixel]; += slab[1][pixel]; ... in sample order (kernels.py:1280/:1373)
+__global__ void __launch_bounds__(256) k_wf_resolve(const __grid_constant__ WfParams P) {
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.N; i += stride) {
+        float* ap = P.accum + 3 * ((size_t)P.y0 * P.W + i);
+        f3 acc = mk3(ap[0], ap[1], ap[2]);
+        for (int s = 0; s < P.batch; s++) {
+            const float* sp = P.Q.slab + 3 * ((size_t)s * P.N + i);
+            acc = acc + mk3(sp[0], sp[1], sp[2]);
+        }
+        ap[0] = acc.x; ap[1] = acc.y; ap[2] = acc.z;
     }
 }
 
@@ -644,6 +724,12 @@ int pt_set_option(PtContext* ctx, const char* name, int64_t value) {
     } else if (k == "burst_num") {
         if (value < 0 || value > 32) return set_error(PT_ERR_INVALID_ARG, "burst_num must be in [0, 32]");
         ctx->burst_num = (int)value;
+    } else if (k == "wf_burst_num") {
+        if (value < 0 || value > 32) return set_error(PT_ERR_INVALID_ARG, "wf_burst_num must be in [0, 32]");
+        ctx->wf_burst_num = (int)value;
+    } else if (k == "wf_blocks_per_sm") {
+        if (value < 1 || value > 8) return set_error(PT_ERR_INVALID_ARG, "wf_blocks_per_sm must be in [1, 8]");
+        ctx->wf_blocks_per_sm = (int)value;
     } else if (k == "sync_samples") {
         ctx->sync_samples = value < 0 ? 0 : (int)value;
     } else if (k == "wavefront_sort") {
@@ -740,15 +826,20 @@ int pt_render_megakernel(PtContext* ctx, float* accum, int W, int H, int y0, int
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-size_t pt_wavefront_workspace_bytes(int W, int rows) {
-    if (W <= 0 || rows <= 0) return 0;
-    const size_t n = (size_t)W * rows;
-    size_t b = 0;
-    b += 6 * align_up(n * 16, 256);          // two queues x three float4 planes
-    b += align_up(n * 16, 256);              // hit records
-    b += align_up((size_t)kNumBins * n * 4, 256);   // material bins
-    b += 256;                                // counters
-    return b;
+// bytes of workspace one in-flight sample of an N-pixel window needs
+static size_t wf_bytes_per_sample(size_t n) {
+    return 6 * n * 16      // two queues x three float4 planes
+           + n * 16        // hit records
+           + (size_t)kNumBins * n * 4   // material bins
+           + n * 12;       // radiance slab
+}
+static const size_t kWfFixedBytes = 4096 + 16 * 256;   // counters + per-section alignment slack
+
+size_t pt_wavefront_workspace_bytes(int W, int rows) { return pt_wavefront_workspace_bytes_for(W, rows, 1); }
+
+size_t pt_wavefront_workspace_bytes_for(int W, int rows, int samples_in_flight) {
+    if (W <= 0 || rows <= 0 || samples_in_flight <= 0) return 0;
+    return wf_bytes_per_sample((size_t)W * rows) * (size_t)samples_in_flight + kWfFixedBytes;
 }
 
 int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int y1, int sample_begin, int sample_count,
@@ -757,50 +848,68 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
     if (rc) return rc;
     if (y0 == y1 || sample_count == 0) return PT_OK;
     const int rows = y1 - y0;
+    const size_t n = (size_t)W * rows;
     if (!workspace || workspace_bytes < pt_wavefront_workspace_bytes(W, rows))
         return set_error(PT_ERR_WORKSPACE, "pt_render_wavefront: workspace too small");
+    // samples in flight: as many as the workspace holds (and the 31-bit path id allows)
+    size_t B = (workspace_bytes - kWfFixedBytes) / wf_bytes_per_sample(n);
+    if (B > (size_t)sample_count) B = (size_t)sample_count;
+    if (B > 64) B = 64;
+    while (B > 1 && B * n > (size_t)0x7fffffff) B--;
+    if (B * n > (size_t)0x7fffffff) return set_error(PT_ERR_CAPACITY, "pt_render_wavefront: window too large");
     PT_CUDA(cudaSetDevice(ctx->device));
-    const size_t n = (size_t)W * rows;
+    const size_t cap = B * n;
     char* p = static_cast<char*>(workspace);
     WfParams P;
     P.S = ctx->scene;
     P.cam = ctx->cam;
+    auto take = [&](size_t bytes) { char* q = p; p += align_up(bytes, 256); return q; };
     for (int q = 0; q < 2; q++) {
-        P.Q.r0[q] = reinterpret_cast<float4*>(p); p += align_up(n * 16, 256);
-        P.Q.r1[q] = reinterpret_cast<float4*>(p); p += align_up(n * 16, 256);
-        P.Q.r2[q] = reinterpret_cast<float4*>(p); p += align_up(n * 16, 256);
+        P.Q.r0[q] = reinterpret_cast<float4*>(take(cap * 16));
+        P.Q.r1[q] = reinterpret_cast<float4*>(take(cap * 16));
+        P.Q.r2[q] = reinterpret_cast<float4*>(take(cap * 16));
     }
-    P.Q.hit = reinterpret_cast<float4*>(p); p += align_up(n * 16, 256);
-    P.Q.bins = reinterpret_cast<uint32_t*>(p); p += align_up((size_t)kNumBins * n * 4, 256);
-    P.Q.qcount = reinterpret_cast<int*>(p);
-    P.Q.bin_count = reinterpret_cast<int*>(p) + 8;
-    P.Q.capacity = (int)n;
+    P.Q.hit = reinterpret_cast<float4*>(take(cap * 16));
+    P.Q.bins = reinterpret_cast<uint32_t*>(take((size_t)kNumBins * cap * 4));
+    P.Q.slab = reinterpret_cast<float*>(take(cap * 12));
+    int* counters = reinterpret_cast<int*>(take(256));
+    P.Q.qcount = counters;
+    P.Q.bin_count = counters + 8;
+    P.Q.cursor = counters + 32;
+    P.Q.capacity = (int)cap;
     P.accum = accum;
     P.W = W; P.H = H; P.y0 = y0; P.y1 = y1;
+    P.N = (int)n;
     P.seed = seed;
     P.sort = ctx->wavefront_sort;
+    P.burst_num = ctx->wf_burst_num;
     P.counters = ctx->d_counters;
     P.n_snodes = pick_snodes(ctx, 4);
     const size_t smem = (size_t)P.n_snodes * 64;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int bt = 256;
-    int per_sm = 4;
-    const int grid_full = (int)((n + bt - 1) / bt);
-    int grid = ctx->num_sms * per_sm;
-    if (grid > grid_full) grid = grid_full;
+    const int grid_persist = ctx->num_sms * ctx->wf_blocks_per_sm;
     if (ctx->count) { if ((rc = set_smem(k_wf_extend<true>, smem))) return rc; }
     else { if ((rc = set_smem(k_wf_extend<false>, smem))) return rc; }
     const int max_depth = ctx->cam.max_depth;
-    for (int s = sample_begin; s < sample_begin + sample_count; s++) {
-        P.sample = s;
+    for (int s = sample_begin; s < sample_begin + sample_count; s += (int)B) {
+        P.sample_base = s;
+        P.batch = (int)B < sample_begin + sample_count - s ? (int)B : sample_begin + sample_count - s;
+        const size_t total = n * (size_t)P.batch;
+        int grid_full = (int)((total + bt - 1) / bt);
+        int grid = grid_persist < grid_full ? grid_persist : grid_full;
+        int grid_wide = ctx->num_sms * 8 < grid_full ? ctx->num_sms * 8 : grid_full;
         P.bounce = 0;
-        k_wf_generate<<<grid, bt, 0, st>>>(P);
+        k_wf_generate<<<grid_wide, bt, 0, st>>>(P);
         for (int b = 0; b < max_depth; b++) {             // renderer.py:313; kernels exit at once when the queue is empty
             P.bounce = b;
             if (ctx->count) k_wf_extend<true><<<grid, bt, smem, st>>>(P);
             else k_wf_extend<false><<<grid, bt, smem, st>>>(P);
-            k_wf_shade<<<grid, bt, 0, st>>>(P);
+            k_wf_shade<<<grid_wide, bt, 0, st>>>(P);
         }
+        int grid_res = (int)((n + bt - 1) / bt);
+        if (grid_res > ctx->num_sms * 8) grid_res = ctx->num_sms * 8;
+        k_wf_resolve<<<grid_res, bt, 0, st>>>(P);
     }
     PT_CUDA(cudaGetLastError());
     return PT_OK;

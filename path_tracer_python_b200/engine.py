@@ -33,6 +33,8 @@ class Engine:
         self._pinned_blob = None
         self._workspace = None
         self.h2d_bytes = 0
+        self.wavefront_samples_in_flight = 16   # bigger waves = fewer, fuller launches; bounded by max_workspace_bytes
+        self.max_workspace_bytes = 12 << 30
 
     def close(self):
         if getattr(self, "ctx", None):
@@ -95,7 +97,11 @@ class Engine:
         H, W, _ = accum.shape
         assert accum.is_cuda and accum.dtype == torch.float32 and accum.is_contiguous()
         y1 = H if y1 is None else y1
-        need = int(self.L.pt_wavefront_workspace_bytes(W, y1 - y0))
+        b = max(1, min(self.wavefront_samples_in_flight, sample_count))
+        need = int(self.L.pt_wavefront_workspace_bytes_for(W, y1 - y0, b))
+        while b > 1 and need > self.max_workspace_bytes:
+            b -= 1
+            need = int(self.L.pt_wavefront_workspace_bytes_for(W, y1 - y0, b))
         if self._workspace is None or self._workspace.numel() < need:
             self._workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
         with torch.cuda.device(self.device):

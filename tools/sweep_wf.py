@@ -1,0 +1,22 @@
+"""Tuning sweep for the wavefront pipeline on config 2 (development aid)."""
+import os, sys, itertools
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from path_tracer_python_b200.engine import Engine
+from path_tracer_python_b200 import scenes
+W = int(os.environ.get("W", 1920)); SPP = int(os.environ.get("SPP", 32))
+e = Engine(0)
+cs, meta = scenes.load_config("vol2_final_scene", W, 16 / 9)
+e.set_scene(cs); e.set_camera(meta["camera"], (0, 0, 0), 50)
+H = meta["height"]
+acc = e.new_accum(W, H)
+def run():
+    acc.zero_(); e.render_wavefront(acc, 0, 2, 7); torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    acc.zero_(); a.record(); e.render_wavefront(acc, 0, SPP, 7); b.record(); torch.cuda.synchronize()
+    return W * H * SPP / a.elapsed_time(b) / 1e3
+L = lambda k, d: [int(x) for x in os.environ.get(k, d).split(",")]
+for fl, bn, bps, sn, so in itertools.product(L("FLIGHT", "1,4,16"), L("BURSTS", "24"), L("BPS", "3"), L("SNODES", "256"), L("SORT", "1")):
+    e.wavefront_samples_in_flight = fl
+    e.set_option("wf_burst_num", bn); e.set_option("wf_blocks_per_sm", bps); e.set_option("smem_nodes", sn); e.set_option("wavefront_sort", so)
+    print(f"in_flight={fl} wf_burst={bn} blocks/sm={bps} smem_nodes={sn} sort={so}: {run():.1f} Mpaths/s", flush=True)
