@@ -159,7 +159,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default="megakernel", choices=["megakernel", "wavefront"])
+    ap.add_argument("--mode", default="wavefront", choices=["megakernel", "wavefront"])
     ap.add_argument("--width", type=int, default=WIDTH)
     ap.add_argument("--spp", type=int, default=SPP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -271,6 +271,24 @@ def main():
     e2e_value = paths_per_step / e2e_s / 1e6
     mean_radiance = float(host_accum.mean() / cam.samples_per_pixel)
 
+    # ---- the other architecture, for the record (BASELINE config 2 is "megakernel vs wavefront")
+    other_mode = "megakernel" if args.mode == "wavefront" else "wavefront"
+    other_render = eng.render_megakernel if other_mode == "megakernel" else eng.render_wavefront
+    barrier()
+    r._accum.zero_()
+    other_render(r._accum, s_begin, n_samples, SEED)
+    barrier()
+    oa, ob = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r._accum.zero_()
+    oa.record()
+    other_render(r._accum, s_begin, n_samples, SEED)
+    ob.record()
+    barrier()
+    t = torch.tensor([oa.elapsed_time(ob)], dtype=torch.float64, device=dev)
+    if group is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    other_value = paths_per_step / (float(t.item()) * 1e-3) / 1e6
+
     # ---- roofline of the dominant kernel: algorithmic bytes from the counting instantiation on the
     #      identical (seed, samples) launch, divided by the live CUDA-event duration above
     roof = cpu = None
@@ -287,7 +305,7 @@ def main():
         achieved = alg / (k_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": which,
-                "kernel": "k_megakernel" if args.mode == "megakernel" else "k_wf_extend",
+                "kernel": "k_megakernel" if args.mode == "megakernel" else "k_wf_extend (+k_wf_shade/generate/resolve: whole pipeline timed)",
                 "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg,
                 "note": "node/primitive fetches are served by shared memory + L1/L2 (scene = 2.5 MB); "
                         "HBM traffic is compulsory only, see profiles/",
@@ -298,7 +316,8 @@ def main():
             cpu = {"value": v, "unit": "Mpaths/s", "cores": cores, "kind": "port", "sample": sample}
 
     if rank == 0:
-        launches_per_step = 1 if args.mode == "megakernel" else n_samples * (1 + 2 * MAX_DEPTH)
+        flight = max(1, min(eng.wavefront_samples_in_flight, n_samples))
+        launches_per_step = 1 if args.mode == "megakernel" else -(-n_samples // flight) * (2 + 2 * MAX_DEPTH)
         line = {
             "metric": METRIC, "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -312,6 +331,7 @@ def main():
                     "d2h_bytes_per_step": r.frame_d2h_bytes, "ms_per_step": e2e_s * 1e3},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": roof, "cpu_baseline": cpu, "mean_radiance": mean_radiance,
+            "modes": {args.mode: value, other_mode: other_value},
         }
         print(json.dumps(line))
     if group is not None:

@@ -43,8 +43,8 @@ struct PtContext {
     int wavefront_sort = 1;
     int burst_num = 16;
     int sync_samples = 0;
-    int wf_burst_num = 24;
-    int wf_blocks_per_sm = 3;
+    int wf_burst_num = 20;
+    int wf_blocks_per_sm = 6;
     int num_sms = 148;
     int max_smem_optin = 0;
     bool count = false;

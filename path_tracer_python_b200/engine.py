@@ -33,7 +33,7 @@ class Engine:
         self._pinned_blob = None
         self._workspace = None
         self.h2d_bytes = 0
-        self.wavefront_samples_in_flight = 16   # bigger waves = fewer, fuller launches; bounded by max_workspace_bytes
+        self.wavefront_samples_in_flight = 32   # bigger waves = fewer, fuller launches; bounded by max_workspace_bytes
         self.max_workspace_bytes = 12 << 30
 
     def close(self):
