@@ -88,3 +88,89 @@ def load_config(name: str, img_width: int, aspect_ratio: float):
     cam, h = camera_vectors(img_width=img_width, aspect_ratio=aspect_ratio, **_CAMERAS[name])
     meta = dict(meta, width=img_width, height=h, camera=cam)
     return cs, meta
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json configs 3 and 4: built here (the reference ships no OBJ asset and caps triangles
+# at 4096), with the reference's own float64 -> float32 conventions.
+# ---------------------------------------------------------------------------------------------
+def _material_block(prefix, n, mat_type=0, color=(0.8, 0.8, 0.8), emit=(0, 0, 0), fuzz=0.0, ir=1.0):
+    c = np.tile(np.asarray(color, np.float32), (n, 1))
+    return {
+        f"{prefix}_material_type": np.full(n, mat_type, np.int32), f"{prefix}_material_albedo": c.copy(),
+        f"{prefix}_material_fuzz": np.full(n, fuzz, np.float32), f"{prefix}_material_ir": np.full(n, ir, np.float32),
+        f"{prefix}_material_emit_color": np.tile(np.asarray(emit, np.float32), (n, 1)),
+        f"{prefix}_texture_type": np.zeros(n, np.int32), f"{prefix}_texture_scale": np.ones(n, np.float32),
+        f"{prefix}_texture_color1": c.copy(), f"{prefix}_texture_color2": c.copy(),
+        f"{prefix}_texture_image_idx": np.full(n, -1, np.int32), f"{prefix}_is_constant_medium": np.zeros(n, np.int32),
+        f"{prefix}_medium_density": np.zeros(n, np.float32), f"{prefix}_medium_albedo": np.zeros((n, 3), np.float32),
+    }
+
+
+def heightfield_scene(nx: int = 1000, ny: int = 500, seed: int = 7, img_width: int = 1920, aspect_ratio: float = 16 / 9):
+    """Config 3 stand-in: a seeded height field of nx*ny cells = 2*nx*ny triangles (1 M by default),
+    Lambert (0.6, 0.4, 0.2), over a ground sphere, lit by one emissive quad; max_depth 8.
+    Triangle records follow core/triangle.py:14-33 (edges and unit normal in float64, then narrowed
+    to float32 like compile_triangle_geometry, scene_compiler.py:214-251)."""
+    from . import bvh as _bvh
+
+    rng = np.random.default_rng(seed)
+    xs = np.linspace(-10.0, 10.0, nx + 1)
+    ys = np.linspace(-5.0, 5.0, ny + 1)
+    X, Y = np.meshgrid(xs, ys, indexing="xy")
+    Z = np.zeros_like(X)
+    for k in range(1, 5):
+        Z += (0.15 / k) * np.sin(0.7 * k * X + 0.3 * k) * np.sin(0.9 * k * Y + 1.1 * k)
+    Z += rng.uniform(-0.01, 0.01, Z.shape)
+    P = np.stack([X, Z, Y], axis=-1)                      # y is up
+    p00, p10, p01, p11 = P[:-1, :-1], P[:-1, 1:], P[1:, :-1], P[1:, 1:]
+    v0 = np.concatenate([p00.reshape(-1, 3), p11.reshape(-1, 3)])
+    v1 = np.concatenate([p01.reshape(-1, 3), p10.reshape(-1, 3)])
+    v2 = np.concatenate([p10.reshape(-1, 3), p01.reshape(-1, 3)])
+    e1, e2 = v1 - v0, v2 - v0
+    nrm = np.cross(e1, e2)
+    nrm /= np.sqrt((nrm ** 2).sum(axis=1, keepdims=True))
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    cs = {"triangle_v0": f32(v0), "triangle_v1": f32(v1), "triangle_v2": f32(v2), "triangle_edge1": f32(e1),
+          "triangle_edge2": f32(e2), "triangle_normal": f32(nrm)}
+    cs.update(_material_block("triangle", len(v0), 0, (0.6, 0.4, 0.2)))
+    cs["sphere_data"] = np.array([[0.0, -1000.6, 0.0, 1000.0]], np.float32)
+    cs.update(_material_block("sphere", 1, 0, (0.5, 0.5, 0.5)))
+    Q, u, v = np.array([-4.0, 6.0, -3.0]), np.array([8.0, 0.0, 0.0]), np.array([0.0, 0.0, 6.0])
+    n = np.cross(u, v)
+    unit = n / np.sqrt(n @ n)
+    cs.update({"quad_Q": f32([Q]), "quad_u": f32([u]), "quad_v": f32([v]), "quad_normal": f32([unit]),
+               "quad_D": f32([unit @ Q]), "quad_w": f32([n / (n @ n)])})
+    cs.update(_material_block("quad", 1, 3, (0, 0, 0), emit=(6, 6, 6)))
+    cs["num_images"] = 0
+    cs.update(_bvh.compile_bvh(cs))
+    cam, h = camera_vectors((0.0, 7.0, 13.0), (0.0, 0.0, 0.0), (0, 1, 0), 40, img_width, aspect_ratio)
+    meta = {"width": img_width, "height": h, "camera": cam, "background": (0.6, 0.7, 0.9), "max_depth": 8}
+    return cs, meta
+
+
+def cornell_config4(img_width: int = 1024, spp: int = 4096):
+    """Config 4: Cornell box (src/scenes.py:1031-1041, light 15) + the tall box as a constant medium
+    (density 0.01, white; :1114-1124) + a glass sphere r=90 at (190,90,190) + a subsurface sphere
+    r=80 at (400,80,150) -- which the Taichi path renders as 0.8-grey Lambert
+    (scene_compiler.py:406-417).  Returns (world, camera) built from path_tracer_python_b200.scene."""
+    from . import scene as sc
+
+    w = sc.hittable_list()
+    red, white, green = (sc.lambertian.from_color(sc.color(*c)) for c in ((.65, .05, .05), (.73, .73, .73), (.12, .45, .15)))
+    light = sc.diffuse_light.from_color(sc.color(15, 15, 15))
+    P, V = sc.point3, sc.vec3
+    w.add(sc.quad(P(555, 0, 0), V(0, 0, 555), V(0, 555, 0), green))
+    w.add(sc.quad(P(0, 0, 0), V(0, 555, 0), V(0, 0, 555), red))
+    w.add(sc.quad(P(343, 554, 332), V(-130, 0, 0), V(0, 0, -105), light))
+    w.add(sc.quad(P(0, 0, 0), V(0, 0, 555), V(555, 0, 0), white))
+    w.add(sc.quad(P(555, 555, 555), V(-555, 0, 0), V(0, 0, -555), white))
+    w.add(sc.quad(P(0, 0, 555), V(0, 555, 0), V(555, 0, 0), white))
+    w.add(sc.constant_medium.from_color(sc.box(P(265, 0, 295), P(430, 330, 460), white, 15), sc.color(1, 1, 1), 0.01))
+    w.add(sc.Sphere.stationary(P(190, 90, 190), 90, sc.dielectric(1.5)))
+    w.add(sc.Sphere.stationary(P(400, 80, 150), 80, sc.subsurface_volumetric(sc.color(.2, .5, .2), 0.08, 0.8, 0.7)))
+    cam = sc.camera()
+    cam.aspect_ratio, cam.img_width, cam.samples_per_pixel = 1.0, img_width, spp
+    cam.vfov, cam.lookfrom, cam.lookat, cam.vup = 40, P(278, 278, -800), P(278, 278, 0), V(0, 1, 0)
+    cam.defocus_angle = 0
+    return w, cam
