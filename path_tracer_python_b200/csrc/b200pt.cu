@@ -43,6 +43,7 @@ struct PtContext {
     int wavefront_sort = 1;
     int burst_num = 16;
     int sync_samples = 0;
+    int vote_num = 16;
     int wf_burst_num = 20;
     int wf_blocks_per_sm = 6;
     int num_sms = 148;
@@ -110,6 +111,7 @@ struct MegaParams {
     int tiles_x;
     int burst_num;       // leave a traversal burst when < burst_num/32 of the live lanes still traverse
     int sync_samples;    // > 0: lanes of a warp re-synchronise every sync_samples samples
+    int vote_num;        // > 0: warp-voting traversal; descend when >= vote_num/32 of the traversing lanes want to
     DCounters* counters;
 };
 
@@ -268,7 +270,12 @@ __global__ void __launch_bounds__(256) k_megakernel(const __grid_constant__ Mega
             if (busy == 0u && st == LANE_WAIT) st = LANE_NEED_PATH;
         }
         const int min_active = (__popc(live) * P.burst_num + 31) >> 5;
-        if (st == LANE_TRAVERSING) {
+        if (P.vote_num > 0) {
+            bool fin;
+            trav_run_vote<COUNT>(T, st == LANE_TRAVERSING, fin, S, s_nodes, P.n_snodes, stack_ref, stack_t,
+                                 min_active > 0 ? min_active : 1, P.vote_num, lc);
+            if (fin) st = LANE_HAVE_RESULT;
+        } else if (st == LANE_TRAVERSING) {
             if (trav_run<COUNT>(T, S, s_nodes, P.n_snodes, stack_ref, stack_t, min_active, lc)) st = LANE_HAVE_RESULT;
         }
     }
@@ -313,6 +320,7 @@ struct WfParams {
     int bounce;              // parity selects queue
     int sort;
     int burst_num;
+    int vote_num;
     DCounters* counters;
 };
 
@@ -447,7 +455,12 @@ __global__ void __launch_bounds__(256) k_wf_extend(const __grid_constant__ WfPar
         const unsigned live = __ballot_sync(0xffffffffu, st != LANE_DONE);
         if (live == 0u) break;
         const int min_active = (__popc(live) * P.burst_num + 31) >> 5;
-        if (st == LANE_TRAVERSING) {
+        if (P.vote_num > 0) {
+            bool fin;
+            trav_run_vote<COUNT>(T, st == LANE_TRAVERSING, fin, S, s_nodes, P.n_snodes, stack_ref, stack_t,
+                                 min_active > 0 ? min_active : 1, P.vote_num, lc);
+            if (fin) st = LANE_HAVE_RESULT;
+        } else if (st == LANE_TRAVERSING) {
             if (trav_run<COUNT>(T, S, s_nodes, P.n_snodes, stack_ref, stack_t, min_active, lc)) st = LANE_HAVE_RESULT;
         }
     }
@@ -724,6 +737,9 @@ int pt_set_option(PtContext* ctx, const char* name, int64_t value) {
     } else if (k == "burst_num") {
         if (value < 0 || value > 32) return set_error(PT_ERR_INVALID_ARG, "burst_num must be in [0, 32]");
         ctx->burst_num = (int)value;
+    } else if (k == "vote_num") {
+        if (value < 0 || value > 32) return set_error(PT_ERR_INVALID_ARG, "vote_num must be in [0, 32]");
+        ctx->vote_num = (int)value;
     } else if (k == "wf_burst_num") {
         if (value < 0 || value > 32) return set_error(PT_ERR_INVALID_ARG, "wf_burst_num must be in [0, 32]");
         ctx->wf_burst_num = (int)value;
@@ -804,6 +820,7 @@ int pt_render_megakernel(PtContext* ctx, float* accum, int W, int H, int y0, int
     P.tiles_x = (W + 7) / 8;
     P.burst_num = ctx->burst_num;
     P.sync_samples = ctx->sync_samples;
+    P.vote_num = ctx->vote_num;
     P.counters = ctx->d_counters;
     const int tiles_y = (y1 - y0 + 3) / 4;
     const long long warps = (long long)P.tiles_x * tiles_y;
@@ -883,6 +900,7 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
     P.seed = seed;
     P.sort = ctx->wavefront_sort;
     P.burst_num = ctx->wf_burst_num;
+    P.vote_num = ctx->vote_num;
     P.counters = ctx->d_counters;
     P.n_snodes = pick_snodes(ctx, 4);
     const size_t smem = (size_t)P.n_snodes * 64;

@@ -22,9 +22,10 @@ snodes = [int(x) for x in os.environ.get("SNODES", "1024").split(",")]
 blocks = [int(x) for x in os.environ.get("BLOCKS", "256").split(",")]
 syncs = [int(x) for x in os.environ.get("SYNCS", "0").split(",")]
 spps = [int(x) for x in os.environ.get("SPPS", str(SPP)).split(",")]
-for bt, sn, bn, sy, sp in itertools.product(blocks, snodes, bursts, syncs, spps):
-    e.set_option("block_threads", bt); e.set_option("smem_nodes", sn); e.set_option("burst_num", bn); e.set_option("sync_samples", sy)
+votes = [int(x) for x in os.environ.get("VOTES", "16").split(",")]
+for bt, sn, bn, sy, sp, vn in itertools.product(blocks, snodes, bursts, syncs, spps, votes):
+    e.set_option("block_threads", bt); e.set_option("smem_nodes", sn); e.set_option("burst_num", bn); e.set_option("sync_samples", sy); e.set_option("vote_num", vn)
     SPP = sp
-    print(f"block={bt} smem_nodes={sn} burst={bn} sync={sy} spp={sp}: {run():.1f} Mpaths/s", flush=True)
+    print(f"block={bt} smem_nodes={sn} burst={bn} sync={sy} spp={sp} vote={vn}: {run():.1f} Mpaths/s", flush=True)
 if os.environ.get("WAVE"):
     print(f"wavefront: {run('wavefront'):.1f} Mpaths/s")
