@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200pt.so")
+LIB_PATH = os.environ.get("PT_LIB_PATH") or os.path.join(_HERE, "libb200pt.so")   # PT_LIB_PATH: A/B builds
 
 PT_MAX_IMAGES = 16
 PRIM_SPHERE, PRIM_TRIANGLE, PRIM_QUAD = 0, 1, 2

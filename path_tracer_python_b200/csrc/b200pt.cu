@@ -44,6 +44,7 @@ struct PtContext {
     int burst_num = 16;
     int sync_samples = 0;
     int vote_num = 16;
+    int wf_waves = 8;        // full waves per batch before the tail kernel takes over
     int wf_burst_num = 20;
     int wf_blocks_per_sm = 6;
     int num_sms = 148;
@@ -297,10 +298,10 @@ __global__ void __launch_bounds__(256) k_megakernel(const __grid_constant__ Mega
 struct WfQueues {
     float4 *r0[2], *r1[2], *r2[2];
     float4* hit;
-    uint32_t* bins;          // kNumBins regions of `capacity` ray indices
+    uint32_t* bins;          // kNumBins regions of `capacity` ray indices (material binning)
+    int* bin_count;          // [kNumBins]
     float* slab;             // [B][N][3] radiance contribution of each path of the batch
     int* qcount;             // [2] ray counts of the two queues
-    int* bin_count;          // [2][kNumBins]
     int* cursor;             // dynamic-fetch cursor of k_wf_extend
     int capacity;            // B * N
 };
@@ -341,7 +342,6 @@ __global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ WfP
         P.Q.slab[3 * (size_t)id + 1] = 0.0f;
         P.Q.slab[3 * (size_t)id + 2] = 0.0f;
     }
-    if (blockIdx.x == 0 && threadIdx.x < 2 * kNumBins) P.Q.bin_count[threadIdx.x] = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         P.Q.qcount[0] = total;
         P.Q.qcount[1] = 0;
@@ -366,24 +366,76 @@ __device__ __forceinline__ int warp_agg_append(int* counter_base, int key, bool 
     return pos;
 }
 
+// ---- cp.async helpers (LDGSTS: global -> shared without passing through registers)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+constexpr int kWfReserve = 128;   // ray indices a warp reserves per atomic on the global cursor
+constexpr int kWfWarps = 8;       // warps per CTA of the wavefront kernels (256 threads)
+
 // intersect_rays (kernels.py:1242-1263) + the exit search of apply_constant_medium (:417-419).
-// Persistent warps: a lane that finishes its ray writes the hit record, bins the ray and fetches
-// the next ray index from a global cursor, while the other lanes of the warp keep traversing
-// (resumable traversal, same scheme as the megakernel).
+// Persistent warps with dynamic ray fetch.  Each warp reserves kWfReserve consecutive ray indices
+// with one atomic, stages them 32 at a time into shared memory with cp.async (double-buffered, so
+// the HBM latency of the queue read overlaps traversal), and hands staged rays to lanes as they
+// finish; the other lanes keep traversing (resumable warp-voting traversal).  Results go to the
+// hit-record array in ray order: no atomics, no binning here.
 template <bool COUNT>
 __global__ void __launch_bounds__(256) k_wf_extend(const __grid_constant__ WfParams P) {
-    extern __shared__ float4 s_nodes[];
+    extern __shared__ float4 s_dyn[];
+    __shared__ float4 s_ray[kWfWarps][2][32][2];      // (o.xyz d.x)(d.yz ..) of staged rays, 16 KB
+    float4* s_nodes = s_dyn;
     const DScene& S = P.S;
     const int cur = P.bounce & 1;
     const int count = P.Q.qcount[cur];
     // reset_next_ray_count (:1283) -- also when this wave is empty, otherwise the stale count of
     // the wave before last would be picked up again two launches later
     if (blockIdx.x == 0 && threadIdx.x == 0) P.Q.qcount[cur ^ 1] = 0;
-    if (count == 0) return;
+    if (blockIdx.x == 0 && threadIdx.x < kNumBins) P.Q.bin_count[threadIdx.x] = 0;   // for this wave's k_wf_bin
+    // small waves: only as many CTAs as there are 256-ray slices take part (the rest would just
+    // hammer the cursor with atomics and stage nodes for nothing)
+    if ((long long)blockIdx.x * 256 >= count) return;
     stage_nodes(s_nodes, S, P.n_snodes);
     LocalCounters lc;
-    int* bin_count = P.Q.bin_count + cur * kNumBins;
     const unsigned lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const float4* __restrict__ q0 = P.Q.r0[cur];
+    const float4* __restrict__ q1 = P.Q.r1[cur];
+
+    // warp-uniform staging state
+    int res_next = 0, res_end = 0;      // reserved, not yet staged ray indices
+    bool exhausted = false;             // the global cursor is past the end of the queue
+    int stg_base[2] = {0, 0}, stg_n[2] = {0, 0};
+    int buf = 0, stg_pos = 0;
+    // small waves reserve 32 rays at a time so that the work spreads over all warps
+    const int reserve = (long long)count >= (long long)gridDim.x * kWfWarps * 2 * kWfReserve ? kWfReserve : 32;
+    auto stage = [&](int b) {           // start the async copy of up to 32 more rays into buffer b
+        if (res_next >= res_end && !exhausted) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(P.Q.cursor, reserve);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            res_next = base;
+            res_end = base + reserve < count ? base + reserve : count;
+            if (base >= count) { exhausted = true; res_next = res_end = 0; }
+        }
+        int n = res_end - res_next;
+        n = n > 32 ? 32 : (n < 0 ? 0 : n);
+        if ((int)lane < n) {
+            cp_async16(&s_ray[warp][b][lane][0], q0 + res_next + lane);
+            cp_async16(&s_ray[warp][b][lane][1], q1 + res_next + lane);
+        }
+        cp_async_commit();
+        stg_base[b] = res_next;
+        stg_n[b] = n;
+        res_next += n;
+    };
+    stage(0);
+    cp_async_wait_all();
+    __syncwarp();
+    stage(1);
 
     TravState T;
     T.cur = kRefNone;
@@ -394,63 +446,62 @@ __global__ void __launch_bounds__(256) k_wf_extend(const __grid_constant__ WfPar
     float t_entry = 0.0f;
 
     for (;;) {
-        // ---- finished lanes: second traversal for medium boundaries, else emit the hit record
-        bool emit = false;
-        int bin = 0;
+        // ---- finished lanes: second traversal for medium boundaries, else write the hit record
         if (st == LANE_HAVE_RESULT) {
             if (mode == 0) {
                 const int ref = T.best_ref;
-                bin = 0;
-                if (ref != kRefNone) {
+                bool is_med = false;
+                if (ref != kRefNone && S.has_media) {
                     const int header = __float_as_int(__ldg(S.materials + 3 * mat_id_of(S, ref)).x);
-                    if (mat_is_medium(header)) {
-                        mode = 1;
-                        t_entry = T.best_t;
-                        ref_entry = ref;
-                        trav_begin<COUNT>(T, S, T.o, T.d, t_entry + 0.0001f, 1e10f, lc);
-                        st = LANE_TRAVERSING;
-                    } else {
-                        bin = 2 + mat_type(header);
-                    }
+                    is_med = mat_is_medium(header);
                 }
-                if (st == LANE_HAVE_RESULT) {
+                if (is_med) {
+                    mode = 1;
+                    t_entry = T.best_t;
+                    ref_entry = ref;
+                    trav_begin<COUNT>(T, S, T.o, T.d, t_entry + 0.0001f, 1e10f, lc);
+                    st = LANE_TRAVERSING;
+                } else {
                     P.Q.hit[ray] = make_float4(T.best_t, __int_as_float(ref), 0.0f, __int_as_float(0));
-                    emit = true;
+                    st = LANE_NEED_PATH;
                 }
             } else {
                 mode = 0;
                 P.Q.hit[ray] = make_float4(t_entry, __int_as_float(ref_entry), T.best_t,
                                            __int_as_float(T.best_ref != kRefNone ? 1 : 0));
-                bin = 1;
-                emit = true;
+                st = LANE_NEED_PATH;
             }
         }
-        if (P.sort) {
-            const int pos = warp_agg_append(bin_count, bin, emit);
-            if (emit) P.Q.bins[(size_t)bin * P.Q.capacity + pos] = (uint32_t)ray;
-        }
-        if (emit) st = LANE_NEED_PATH;
-        // ---- dynamic fetch: one atomic per warp hands consecutive ray indices to the idle lanes
-        {
-            const unsigned want = __ballot_sync(0xffffffffu, st == LANE_NEED_PATH);
-            if (want) {
-                int base = 0;
-                const int leader = __ffs(want) - 1;
-                if ((int)lane == leader) base = atomicAdd(P.Q.cursor, __popc(want));
-                base = __shfl_sync(0xffffffffu, base, leader);
-                if (st == LANE_NEED_PATH) {
-                    ray = base + __popc(want & ((1u << lane) - 1));
-                    if (ray < count) {
-                        const float4 a = P.Q.r0[cur][ray], b = P.Q.r1[cur][ray];
-                        if (COUNT) lc.bounces++;
-                        trav_begin<COUNT>(T, S, mk3(a.x, a.y, a.z), mk3(a.w, b.x, b.y), 0.001f, 1e10f, lc);
-                        mode = 0;
-                        st = LANE_TRAVERSING;
-                    } else {
-                        st = LANE_DONE;
-                    }
+        // ---- hand staged rays to idle lanes
+        unsigned want = __ballot_sync(0xffffffffu, st == LANE_NEED_PATH);
+        while (want) {
+            const int avail = stg_n[buf] - stg_pos;
+            if (avail == 0) {
+                if (stg_n[buf ^ 1] == 0) {               // nothing staged, nothing left to stage
+                    if (st == LANE_NEED_PATH) st = LANE_DONE;
+                    break;
                 }
+                cp_async_wait_all();
+                __syncwarp();
+                buf ^= 1;
+                stg_pos = 0;
+                stage(buf ^ 1);
+                continue;
             }
+            const int n_want = __popc(want);
+            const int take = avail < n_want ? avail : n_want;
+            const int rank = __popc(want & ((1u << lane) - 1));
+            if (st == LANE_NEED_PATH && rank < take) {
+                const int slot = stg_pos + rank;
+                const float4 a = s_ray[warp][buf][slot][0], b = s_ray[warp][buf][slot][1];
+                ray = stg_base[buf] + slot;
+                if (COUNT) lc.bounces++;
+                trav_begin<COUNT>(T, S, mk3(a.x, a.y, a.z), mk3(a.w, b.x, b.y), 0.001f, 1e10f, lc);
+                mode = 0;
+                st = LANE_TRAVERSING;
+            }
+            stg_pos += take;
+            want = __ballot_sync(0xffffffffu, st == LANE_NEED_PATH);
         }
         const unsigned live = __ballot_sync(0xffffffffu, st != LANE_DONE);
         if (live == 0u) break;
@@ -464,23 +515,113 @@ __global__ void __launch_bounds__(256) k_wf_extend(const __grid_constant__ WfPar
             if (trav_run<COUNT>(T, S, s_nodes, P.n_snodes, stack_ref, stack_t, min_active, lc)) st = LANE_HAVE_RESULT;
         }
     }
+    cp_async_wait_all();
     if (COUNT) flush_counters(P.counters, lc);
 }
 
+// One ray of shade_miss_rays + shade_and_scatter (kernels.py:1266-1399): adds the ray's radiance
+// contribution (miss -> background, hit -> emission) to `sp` and returns true with the next ray
+// (origin, direction, throughput, depth) if the path goes on.
+__device__ __forceinline__ bool wf_shade_one(const DScene& S, f3 bg, int max_depth, float* sp, f3 o, f3 d, f3 thr,
+                                             int depth, uint32_t& rng, float t, int ref, float t_exit_hit, bool exit_hit,
+                                             f3& no, f3& nd, f3& nthr, int& ndepth) {
+    if (ref == kRefNone) {                           // shade_miss_rays, kernels.py:1266-1280
+        f3 add = thr * bg;
+        sp[0] = sp[0] + add.x; sp[1] = sp[1] + add.y; sp[2] = sp[2] + add.z;
+        return false;
+    }
+    const int mid = mat_id_of(S, ref);               // shade_and_scatter, kernels.py:1289-1399
+    Mat m = load_mat(S, mid);
+    bool scattered = false, do_shade = true, emit_next = false;
+    f3 hp, sdir, atten, emit = mk3(0.0f, 0.0f, 0.0f);
+    if (mat_is_medium(m.header)) {
+        const float4 m2 = __ldg(S.materials + 3 * mid + 2);
+        float t_exit, t_scatter;
+        if (medium_sample(exit_hit, t_exit_hit, t, d, m2.x, rng, t_exit, t_scatter)) {
+            hp = o + t_scatter * d;
+            sdir = random_unit_vector(rng);
+            atten = mk3(m2.y, m2.z, m2.w);
+            scattered = true;
+            do_shade = false;
+        } else if (t_exit > 0.0f) {                  // passthrough: re-enqueue, same depth (:1342-1350)
+            float eps_t = ptm::fdiv(0.001f, ptm::fsqrt(dot(d, d)));
+            no = o + d * (t_exit + eps_t);
+            nd = d;
+            nthr = thr;
+            ndepth = depth;
+            emit_next = true;
+            do_shade = false;
+        }
+    }
+    if (do_shade) {
+        f3 n;
+        finalize_hit(S, ref, o, d, t, hp, n);
+        scattered = shade_surface(S, m, ref, d, hp, n, rng, emit, sdir, atten);
+    }
+    if (emit.x > 0.0f || emit.y > 0.0f || emit.z > 0.0f) {      // kernels.py:1368-1375
+        f3 add = thr * emit;
+        sp[0] = sp[0] + add.x; sp[1] = sp[1] + add.y; sp[2] = sp[2] + add.z;
+    }
+    if (scattered) {
+        f3 new_thr = thr * atten;
+        int new_depth = depth + 1;
+        if (new_depth < max_depth) {
+            bool cont = true;
+            if (new_depth >= 5) {
+                float survival = min2(max2(max2(new_thr.x, new_thr.y), new_thr.z), 0.95f);
+                if (ptm::rng_next(rng) > survival) cont = false;
+                else new_thr = vdiv(new_thr, survival);
+            }
+            if (cont) {
+                no = hp; nd = sdir; nthr = new_thr; ndepth = new_depth;
+                emit_next = true;
+            }
+        }
+    }
+    return emit_next;
+}
+
+// Material binning: a streaming pass over the hit records (16 B each, coalesced) that appends every
+// ray index to the bin of its class -- 0 miss, 1 medium boundary, 2 + material type -- with one
+// atomic per (warp, class) (__match_any_sync).  k_wf_shade then walks the bins in class order, so
+// its warps shade one material at a time.
+__global__ void __launch_bounds__(256) k_wf_bin(const __grid_constant__ WfParams P) {
+    const DScene& S = P.S;
+    const int cur = P.bounce & 1;
+    const int count = P.Q.qcount[cur];
+    if ((long long)blockIdx.x * 256 >= count) return;
+    const int stride = gridDim.x * blockDim.x;
+    const int rounds = (count + stride - 1) / stride;
+    for (int r = 0; r < rounds; r++) {
+        const int i = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        const bool active = i < count;
+        int cls = 0;
+        if (active) {
+            const int ref = __float_as_int(P.Q.hit[i].y);
+            if (ref != kRefNone) {
+                const int header = __float_as_int(__ldg(S.materials + 3 * mat_id_of(S, ref)).x);
+                cls = mat_is_medium(header) ? 1 : 2 + mat_type(header);
+            }
+        }
+        const int pos = warp_agg_append(P.Q.bin_count, cls, active);
+        if (active) P.Q.bins[(size_t)cls * P.Q.capacity + pos] = (uint32_t)i;
+    }
+}
+
+// shade_miss_rays + shade_and_scatter (kernels.py:1266-1399) over the material bins; survivors are
+// appended to the other queue with one atomic per warp.
 __global__ void __launch_bounds__(256) k_wf_shade(const __grid_constant__ WfParams P) {
     const DScene& S = P.S;
     const int cur = P.bounce & 1, nxt = cur ^ 1;
     const int count = P.Q.qcount[cur];
     if (blockIdx.x == 0 && threadIdx.x == 0) P.Q.cursor[0] = 0;       // for the next k_wf_extend
-    if (count == 0) return;
-    const int* bin_count = P.Q.bin_count + cur * kNumBins;
+    if ((long long)blockIdx.x * 256 >= count) return;
     int prefix[kNumBins + 1];
     if (P.sort) {
         prefix[0] = 0;
 #pragma unroll
-        for (int b = 0; b < kNumBins; b++) prefix[b + 1] = prefix[b] + bin_count[b];
+        for (int b = 0; b < kNumBins; b++) prefix[b + 1] = prefix[b] + P.Q.bin_count[b];
     }
-    if (blockIdx.x == 0 && threadIdx.x < kNumBins) P.Q.bin_count[nxt * kNumBins + threadIdx.x] = 0;
     const int max_depth = P.cam.max_depth;
     const f3 bg = mk3(P.cam.background[0], P.cam.background[1], P.cam.background[2]);
     const int stride = gridDim.x * blockDim.x;
@@ -488,10 +629,7 @@ __global__ void __launch_bounds__(256) k_wf_shade(const __grid_constant__ WfPara
     for (int r = 0; r < rounds; r++) {
         const int j = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
         const bool active = j < count;
-        bool emit_next = false;
-        f3 no, nd, nthr;
-        int path_id = 0, ndepth = 0;
-        uint32_t rng = 0;
+        float4 a, bq, c, h;
         if (active) {
             int i = j;
             if (P.sort) {
@@ -500,67 +638,18 @@ __global__ void __launch_bounds__(256) k_wf_shade(const __grid_constant__ WfPara
                 for (int k = 1; k < kNumBins; k++) b += (j >= prefix[k]) ? 1 : 0;
                 i = (int)P.Q.bins[(size_t)b * P.Q.capacity + (j - prefix[b])];
             }
-            float4 a = P.Q.r0[cur][i], bq = P.Q.r1[cur][i], c = P.Q.r2[cur][i], h = P.Q.hit[i];
-            f3 o = mk3(a.x, a.y, a.z), d = mk3(a.w, bq.x, bq.y), thr = mk3(bq.z, bq.w, c.x);
+            a = P.Q.r0[cur][i]; bq = P.Q.r1[cur][i]; c = P.Q.r2[cur][i]; h = P.Q.hit[i];
+        }
+        bool emit_next = false;
+        f3 no, nd, nthr;
+        int path_id = 0, ndepth = 0;
+        uint32_t rng = 0;
+        if (active) {
             path_id = __float_as_int(c.y);
             rng = __float_as_uint(c.z);
-            int depth = __float_as_int(c.w);
-            float t = h.x;
-            int ref = __float_as_int(h.y);
-            float* sp = P.Q.slab + 3 * (size_t)path_id;       // this path's (single) radiance contribution
-            if (ref == kRefNone) {                           // shade_miss_rays, kernels.py:1266-1280
-                f3 add = thr * bg;
-                sp[0] = sp[0] + add.x; sp[1] = sp[1] + add.y; sp[2] = sp[2] + add.z;
-            } else {                                         // shade_and_scatter, kernels.py:1289-1399
-                const int mid = mat_id_of(S, ref);
-                Mat m = load_mat(S, mid);
-                bool scattered = false, do_shade = true;
-                f3 hp, sdir, atten, emit = mk3(0.0f, 0.0f, 0.0f);
-                if (mat_is_medium(m.header)) {
-                    const float4 m2 = __ldg(S.materials + 3 * mid + 2);
-                    float t_exit, t_scatter;
-                    if (medium_sample(__float_as_int(h.w) != 0, h.z, t, d, m2.x, rng, t_exit, t_scatter)) {
-                        hp = o + t_scatter * d;
-                        sdir = random_unit_vector(rng);
-                        atten = mk3(m2.y, m2.z, m2.w);
-                        scattered = true;
-                        do_shade = false;
-                    } else if (t_exit > 0.0f) {              // passthrough: re-enqueue, same depth (:1342-1350)
-                        float eps_t = ptm::fdiv(0.001f, ptm::fsqrt(dot(d, d)));
-                        no = o + d * (t_exit + eps_t);
-                        nd = d;
-                        nthr = thr;
-                        ndepth = depth;
-                        emit_next = true;
-                        do_shade = false;
-                    }
-                }
-                if (do_shade) {
-                    f3 n;
-                    finalize_hit(S, ref, o, d, t, hp, n);
-                    scattered = shade_surface(S, m, ref, d, hp, n, rng, emit, sdir, atten);
-                }
-                if (emit.x > 0.0f || emit.y > 0.0f || emit.z > 0.0f) {      // kernels.py:1368-1375
-                    f3 add = thr * emit;
-                    sp[0] = sp[0] + add.x; sp[1] = sp[1] + add.y; sp[2] = sp[2] + add.z;
-                }
-                if (scattered) {
-                    f3 new_thr = thr * atten;
-                    int new_depth = depth + 1;
-                    if (new_depth < max_depth) {
-                        bool cont = true;
-                        if (new_depth >= 5) {
-                            float survival = min2(max2(max2(new_thr.x, new_thr.y), new_thr.z), 0.95f);
-                            if (ptm::rng_next(rng) > survival) cont = false;
-                            else new_thr = vdiv(new_thr, survival);
-                        }
-                        if (cont) {
-                            no = hp; nd = sdir; nthr = new_thr; ndepth = new_depth;
-                            emit_next = true;
-                        }
-                    }
-                }
-            }
+            emit_next = wf_shade_one(S, bg, max_depth, P.Q.slab + 3 * (size_t)path_id, mk3(a.x, a.y, a.z),
+                                     mk3(a.w, bq.x, bq.y), mk3(bq.z, bq.w, c.x), __float_as_int(c.w), rng, h.x,
+                                     __float_as_int(h.y), h.z, __float_as_int(h.w) != 0, no, nd, nthr, ndepth);
         }
         // compaction: one atomic per warp (kernels.py:1345/:1394 use one per ray)
         int pos = warp_agg_append(P.Q.qcount + nxt, 0, emit_next);
@@ -570,6 +659,50 @@ __global__ void __launch_bounds__(256) k_wf_shade(const __grid_constant__ WfPara
             P.Q.r2[nxt][pos] = make_float4(nthr.z, __int_as_float(path_id), __uint_as_float(rng), __int_as_float(ndepth));
         }
     }
+}
+
+// The tail of a batch: after `P.bounce` full waves only a small fraction of the paths is still
+// alive, and running them as ever smaller waves (three launches each, latency-bound) costs more
+// than the work itself.  This kernel finishes them megakernel-style: one lane per remaining ray,
+// looping wave by wave (traverse, exit search for medium boundaries, wf_shade_one) until the path
+// ends or the wave budget max_depth (renderer.py:313) is used up -- the same per-ray operations in
+// the same order as the wave kernels, so results are identical.
+template <bool COUNT>
+__global__ void __launch_bounds__(256) k_wf_tail(const __grid_constant__ WfParams P) {
+    extern __shared__ float4 s_nodes[];
+    const DScene& S = P.S;
+    const int cur = P.bounce & 1;
+    const int count = P.Q.qcount[cur];
+    if ((long long)blockIdx.x * 256 >= count) return;
+    stage_nodes(s_nodes, S, P.n_snodes);
+    LocalCounters lc;
+    const int max_depth = P.cam.max_depth;
+    const f3 bg = mk3(P.cam.background[0], P.cam.background[1], P.cam.background[2]);
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        const float4 a = P.Q.r0[cur][i], bq = P.Q.r1[cur][i], c = P.Q.r2[cur][i];
+        f3 o = mk3(a.x, a.y, a.z), d = mk3(a.w, bq.x, bq.y), thr = mk3(bq.z, bq.w, c.x);
+        const int path_id = __float_as_int(c.y);
+        uint32_t rng = __float_as_uint(c.z);
+        int depth = __float_as_int(c.w);
+        float* sp = P.Q.slab + 3 * (size_t)path_id;
+        for (int wave = P.bounce; wave < max_depth; wave++) {
+            float t, t_exit = 0.0f;
+            int ref, eref = kRefNone;
+            if (COUNT) lc.bounces++;
+            traverse<COUNT>(S, s_nodes, P.n_snodes, o, d, 0.001f, 1e10f, t, ref, lc);
+            if (ref != kRefNone && S.has_media) {
+                const int header = __float_as_int(__ldg(S.materials + 3 * mat_id_of(S, ref)).x);
+                if (mat_is_medium(header)) traverse<COUNT>(S, s_nodes, P.n_snodes, o, d, t + 0.0001f, 1e10f, t_exit, eref, lc);
+            }
+            f3 no, nd, nthr;
+            int ndepth;
+            if (!wf_shade_one(S, bg, max_depth, sp, o, d, thr, depth, rng, t, ref, t_exit, eref != kRefNone, no, nd, nthr, ndepth))
+                break;
+            o = no; d = nd; thr = nthr; depth = ndepth;
+        }
+    }
+    if (COUNT) { __syncwarp(); flush_counters(P.counters, lc); }
 }
 
 // accum[pixel] += slab[0][pixel]; += slab[1][pixel]; ... in sample order (kernels.py:1280/:1373)
@@ -740,6 +873,9 @@ int pt_set_option(PtContext* ctx, const char* name, int64_t value) {
     } else if (k == "vote_num") {
         if (value < 0 || value > 32) return set_error(PT_ERR_INVALID_ARG, "vote_num must be in [0, 32]");
         ctx->vote_num = (int)value;
+    } else if (k == "wf_waves") {
+        if (value < 1) return set_error(PT_ERR_INVALID_ARG, "wf_waves must be >= 1");
+        ctx->wf_waves = (int)value;
     } else if (k == "wf_burst_num") {
         if (value < 0 || value > 32) return set_error(PT_ERR_INVALID_ARG, "wf_burst_num must be in [0, 32]");
         ctx->wf_burst_num = (int)value;
@@ -907,8 +1043,8 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int bt = 256;
     const int grid_persist = ctx->num_sms * ctx->wf_blocks_per_sm;
-    if (ctx->count) { if ((rc = set_smem(k_wf_extend<true>, smem))) return rc; }
-    else { if ((rc = set_smem(k_wf_extend<false>, smem))) return rc; }
+    if (ctx->count) { if ((rc = set_smem(k_wf_extend<true>, smem))) return rc; if ((rc = set_smem(k_wf_tail<true>, smem))) return rc; }
+    else { if ((rc = set_smem(k_wf_extend<false>, smem))) return rc; if ((rc = set_smem(k_wf_tail<false>, smem))) return rc; }
     const int max_depth = ctx->cam.max_depth;
     for (int s = sample_begin; s < sample_begin + sample_count; s += (int)B) {
         P.sample_base = s;
@@ -919,11 +1055,18 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
         int grid_wide = ctx->num_sms * 8 < grid_full ? ctx->num_sms * 8 : grid_full;
         P.bounce = 0;
         k_wf_generate<<<grid_wide, bt, 0, st>>>(P);
-        for (int b = 0; b < max_depth; b++) {             // renderer.py:313; kernels exit at once when the queue is empty
+        const int waves = max_depth < ctx->wf_waves ? max_depth : ctx->wf_waves;
+        for (int b = 0; b < waves; b++) {                 // renderer.py:313; no host read-back of the ray count
             P.bounce = b;
             if (ctx->count) k_wf_extend<true><<<grid, bt, smem, st>>>(P);
             else k_wf_extend<false><<<grid, bt, smem, st>>>(P);
+            if (P.sort) k_wf_bin<<<grid_wide, bt, 0, st>>>(P);
             k_wf_shade<<<grid_wide, bt, 0, st>>>(P);
+        }
+        if (waves < max_depth) {                          // whatever is still alive: finish in one launch
+            P.bounce = waves;
+            if (ctx->count) k_wf_tail<true><<<grid_wide, bt, smem, st>>>(P);
+            else k_wf_tail<false><<<grid_wide, bt, smem, st>>>(P);
         }
         int grid_res = (int)((n + bt - 1) / bt);
         if (grid_res > ctx->num_sms * 8) grid_res = ctx->num_sms * 8;
