@@ -44,7 +44,8 @@ struct PtContext {
     int burst_num = 16;
     int sync_samples = 0;
     int vote_num = 16;
-    int wf_waves = 8;        // full waves per batch before the tail kernel takes over
+    int wf_waves = 12;       // full waves per batch before the tail kernel takes over
+    int wf_fuse_primary = 1; // wave 0 (camera rays) as one fused kernel
     int wf_burst_num = 20;
     int wf_blocks_per_sm = 6;
     int num_sms = 148;
@@ -661,6 +662,66 @@ __global__ void __launch_bounds__(256) k_wf_shade(const __grid_constant__ WfPara
     }
 }
 
+// Wave 0 fused: generate_camera_rays + intersect_rays + shade_miss_rays + shade_and_scatter for the
+// primary rays (kernels.py:1219-1399) in one kernel.  Camera rays are coherent, so nothing is gained
+// by sending them through the queues: the ray is generated in registers, traced, shaded, and only
+// the surviving bounce ray is appended (one atomic per warp) to queue 1, where wave 1 picks it up.
+template <bool COUNT>
+__global__ void __launch_bounds__(256) k_wf_primary(const __grid_constant__ WfParams P) {
+    extern __shared__ float4 s_nodes[];
+    const DScene& S = P.S;
+    stage_nodes(s_nodes, S, P.n_snodes);
+    LocalCounters lc;
+    const int max_depth = P.cam.max_depth;
+    const f3 bg = mk3(P.cam.background[0], P.cam.background[1], P.cam.background[2]);
+    const int total = P.N * P.batch;
+    const int stride = gridDim.x * blockDim.x;
+    const int rounds = (total + stride - 1) / stride;
+    for (int r = 0; r < rounds; r++) {
+        const int id = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        bool emit_next = false;
+        f3 no, nd, nthr;
+        int ndepth = 0;
+        uint32_t rng = 0;
+        if (id < total) {
+            const int slot = id / P.N;
+            const int pixel = P.y0 * P.W + (id - slot * P.N);
+            const int py = pixel / P.W, px = pixel - py * P.W;
+            rng = ptm::rng_seed(P.seed, (uint32_t)pixel, (uint32_t)(P.sample_base + slot));
+            f3 o, d;
+            get_ray(P.cam, px, py, rng, o, d);                  // NOT normalised, kernels.py:1229-1233
+            float* sp = P.Q.slab + 3 * (size_t)id;
+            sp[0] = 0.0f; sp[1] = 0.0f; sp[2] = 0.0f;
+            if (max_depth > 0) {
+                float t, t_exit = 0.0f;
+                int ref, eref = kRefNone;
+                if (COUNT) lc.bounces++;
+                traverse<COUNT>(S, s_nodes, P.n_snodes, o, d, 0.001f, 1e10f, t, ref, lc);
+                if (ref != kRefNone && S.has_media) {
+                    const int header = __float_as_int(__ldg(S.materials + 3 * mat_id_of(S, ref)).x);
+                    if (mat_is_medium(header)) traverse<COUNT>(S, s_nodes, P.n_snodes, o, d, t + 0.0001f, 1e10f, t_exit, eref, lc);
+                }
+                emit_next = wf_shade_one(S, bg, max_depth, sp, o, d, mk3(1.0f, 1.0f, 1.0f), 0, rng, t, ref, t_exit,
+                                         eref != kRefNone, no, nd, nthr, ndepth);
+            }
+        }
+        int pos = warp_agg_append(P.Q.qcount + 1, 0, emit_next);
+        if (emit_next) {
+            const int id2 = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
+            P.Q.r0[1][pos] = make_float4(no.x, no.y, no.z, nd.x);
+            P.Q.r1[1][pos] = make_float4(nd.y, nd.z, nthr.x, nthr.y);
+            P.Q.r2[1][pos] = make_float4(nthr.z, __int_as_float(id2), __uint_as_float(rng), __int_as_float(ndepth));
+        }
+    }
+    if (COUNT) flush_counters(P.counters, lc);
+}
+
+// zeroes the per-batch counters before k_wf_primary
+__global__ void k_wf_reset(const __grid_constant__ WfParams P) {
+    if (threadIdx.x < kNumBins) P.Q.bin_count[threadIdx.x] = 0;
+    if (threadIdx.x == 0) { P.Q.qcount[0] = 0; P.Q.qcount[1] = 0; P.Q.cursor[0] = 0; }
+}
+
 // The tail of a batch: after `P.bounce` full waves only a small fraction of the paths is still
 // alive, and running them as ever smaller waves (three launches each, latency-bound) costs more
 // than the work itself.  This kernel finishes them megakernel-style: one lane per remaining ray,
@@ -873,6 +934,8 @@ int pt_set_option(PtContext* ctx, const char* name, int64_t value) {
     } else if (k == "vote_num") {
         if (value < 0 || value > 32) return set_error(PT_ERR_INVALID_ARG, "vote_num must be in [0, 32]");
         ctx->vote_num = (int)value;
+    } else if (k == "wf_fuse_primary") {
+        ctx->wf_fuse_primary = value ? 1 : 0;
     } else if (k == "wf_waves") {
         if (value < 1) return set_error(PT_ERR_INVALID_ARG, "wf_waves must be >= 1");
         ctx->wf_waves = (int)value;
@@ -1043,8 +1106,11 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int bt = 256;
     const int grid_persist = ctx->num_sms * ctx->wf_blocks_per_sm;
-    if (ctx->count) { if ((rc = set_smem(k_wf_extend<true>, smem))) return rc; if ((rc = set_smem(k_wf_tail<true>, smem))) return rc; }
-    else { if ((rc = set_smem(k_wf_extend<false>, smem))) return rc; if ((rc = set_smem(k_wf_tail<false>, smem))) return rc; }
+    if (ctx->count) {
+        if ((rc = set_smem(k_wf_extend<true>, smem)) || (rc = set_smem(k_wf_tail<true>, smem)) || (rc = set_smem(k_wf_primary<true>, smem))) return rc;
+    } else {
+        if ((rc = set_smem(k_wf_extend<false>, smem)) || (rc = set_smem(k_wf_tail<false>, smem)) || (rc = set_smem(k_wf_primary<false>, smem))) return rc;
+    }
     const int max_depth = ctx->cam.max_depth;
     for (int s = sample_begin; s < sample_begin + sample_count; s += (int)B) {
         P.sample_base = s;
@@ -1053,10 +1119,19 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
         int grid_full = (int)((total + bt - 1) / bt);
         int grid = grid_persist < grid_full ? grid_persist : grid_full;
         int grid_wide = ctx->num_sms * 8 < grid_full ? ctx->num_sms * 8 : grid_full;
-        P.bounce = 0;
-        k_wf_generate<<<grid_wide, bt, 0, st>>>(P);
         const int waves = max_depth < ctx->wf_waves ? max_depth : ctx->wf_waves;
-        for (int b = 0; b < waves; b++) {                 // renderer.py:313; no host read-back of the ray count
+        int first_wave = 0;
+        P.bounce = 0;
+        if (ctx->wf_fuse_primary && max_depth > 0) {
+            // wave 0 in one kernel; survivors land in queue 1
+            k_wf_reset<<<1, 32, 0, st>>>(P);
+            if (ctx->count) k_wf_primary<true><<<grid_wide, bt, smem, st>>>(P);
+            else k_wf_primary<false><<<grid_wide, bt, smem, st>>>(P);
+            first_wave = 1;
+        } else {
+            k_wf_generate<<<grid_wide, bt, 0, st>>>(P);
+        }
+        for (int b = first_wave; b < waves; b++) {        // renderer.py:313; no host read-back of the ray count
             P.bounce = b;
             if (ctx->count) k_wf_extend<true><<<grid, bt, smem, st>>>(P);
             else k_wf_extend<false><<<grid, bt, smem, st>>>(P);
@@ -1064,7 +1139,7 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
             k_wf_shade<<<grid_wide, bt, 0, st>>>(P);
         }
         if (waves < max_depth) {                          // whatever is still alive: finish in one launch
-            P.bounce = waves;
+            P.bounce = waves > first_wave ? waves : first_wave;
             if (ctx->count) k_wf_tail<true><<<grid_wide, bt, smem, st>>>(P);
             else k_wf_tail<false><<<grid_wide, bt, smem, st>>>(P);
         }

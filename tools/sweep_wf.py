@@ -16,7 +16,7 @@ def run():
     acc.zero_(); a.record(); e.render_wavefront(acc, 0, SPP, 7); b.record(); torch.cuda.synchronize()
     return W * H * SPP / a.elapsed_time(b) / 1e3
 L = lambda k, d: [int(x) for x in os.environ.get(k, d).split(",")]
-for fl, bn, bps, sn, so, vn, wv in itertools.product(L("FLIGHT", "32"), L("BURSTS", "20"), L("BPS", "6"), L("SNODES", "256"), L("SORT", "1"), L("VOTES", "12"), L("WAVES", "8")):
+for fl, bn, bps, sn, so, vn, wv, fu in itertools.product(L("FLIGHT", "32"), L("BURSTS", "20"), L("BPS", "6"), L("SNODES", "256"), L("SORT", "1"), L("VOTES", "12"), L("WAVES", "12"), L("FUSE", "1")):
     e.wavefront_samples_in_flight = fl
-    e.set_option("wf_burst_num", bn); e.set_option("wf_blocks_per_sm", bps); e.set_option("smem_nodes", sn); e.set_option("wavefront_sort", so); e.set_option("vote_num", vn); e.set_option("wf_waves", wv)
-    print(f"in_flight={fl} wf_burst={bn} blocks/sm={bps} smem_nodes={sn} sort={so} vote={vn} waves={wv}: {run():.1f} Mpaths/s", flush=True)
+    e.set_option("wf_burst_num", bn); e.set_option("wf_blocks_per_sm", bps); e.set_option("smem_nodes", sn); e.set_option("wavefront_sort", so); e.set_option("vote_num", vn); e.set_option("wf_waves", wv); e.set_option("wf_fuse_primary", fu)
+    print(f"in_flight={fl} wf_burst={bn} blocks/sm={bps} smem_nodes={sn} sort={so} vote={vn} waves={wv} fuse={fu}: {run():.1f} Mpaths/s", flush=True)
