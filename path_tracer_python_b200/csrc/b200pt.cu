@@ -323,6 +323,7 @@ struct WfParams {
     int sort;
     int burst_num;
     int vote_num;
+    int fused_waves;         // waves k_wf_primary runs in registers before handing paths to the queues
     DCounters* counters;
 };
 
@@ -692,7 +693,10 @@ __global__ void __launch_bounds__(256) k_wf_primary(const __grid_constant__ WfPa
             get_ray(P.cam, px, py, rng, o, d);                  // NOT normalised, kernels.py:1229-1233
             float* sp = P.Q.slab + 3 * (size_t)id;
             sp[0] = 0.0f; sp[1] = 0.0f; sp[2] = 0.0f;
-            if (max_depth > 0) {
+            f3 thr = mk3(1.0f, 1.0f, 1.0f);
+            int depth = 0;
+            emit_next = max_depth > 0;
+            for (int w = 0; w < P.fused_waves && emit_next; w++) {
                 float t, t_exit = 0.0f;
                 int ref, eref = kRefNone;
                 if (COUNT) lc.bounces++;
@@ -701,16 +705,18 @@ __global__ void __launch_bounds__(256) k_wf_primary(const __grid_constant__ WfPa
                     const int header = __float_as_int(__ldg(S.materials + 3 * mat_id_of(S, ref)).x);
                     if (mat_is_medium(header)) traverse<COUNT>(S, s_nodes, P.n_snodes, o, d, t + 0.0001f, 1e10f, t_exit, eref, lc);
                 }
-                emit_next = wf_shade_one(S, bg, max_depth, sp, o, d, mk3(1.0f, 1.0f, 1.0f), 0, rng, t, ref, t_exit,
-                                         eref != kRefNone, no, nd, nthr, ndepth);
+                emit_next = wf_shade_one(S, bg, max_depth, sp, o, d, thr, depth, rng, t, ref, t_exit, eref != kRefNone,
+                                         no, nd, nthr, ndepth);
+                o = no; d = nd; thr = nthr; depth = ndepth;
             }
         }
-        int pos = warp_agg_append(P.Q.qcount + 1, 0, emit_next);
+        const int qd = P.fused_waves & 1;               // the queue wave `fused_waves` reads from
+        int pos = warp_agg_append(P.Q.qcount + qd, 0, emit_next);
         if (emit_next) {
             const int id2 = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
-            P.Q.r0[1][pos] = make_float4(no.x, no.y, no.z, nd.x);
-            P.Q.r1[1][pos] = make_float4(nd.y, nd.z, nthr.x, nthr.y);
-            P.Q.r2[1][pos] = make_float4(nthr.z, __int_as_float(id2), __uint_as_float(rng), __int_as_float(ndepth));
+            P.Q.r0[qd][pos] = make_float4(no.x, no.y, no.z, nd.x);
+            P.Q.r1[qd][pos] = make_float4(nd.y, nd.z, nthr.x, nthr.y);
+            P.Q.r2[qd][pos] = make_float4(nthr.z, __int_as_float(id2), __uint_as_float(rng), __int_as_float(ndepth));
         }
     }
     if (COUNT) flush_counters(P.counters, lc);
@@ -935,7 +941,7 @@ int pt_set_option(PtContext* ctx, const char* name, int64_t value) {
         if (value < 0 || value > 32) return set_error(PT_ERR_INVALID_ARG, "vote_num must be in [0, 32]");
         ctx->vote_num = (int)value;
     } else if (k == "wf_fuse_primary") {
-        ctx->wf_fuse_primary = value ? 1 : 0;
+        ctx->wf_fuse_primary = value < 0 ? 0 : (int)value;   // number of leading waves run fused (0 = off)
     } else if (k == "wf_waves") {
         if (value < 1) return set_error(PT_ERR_INVALID_ARG, "wf_waves must be >= 1");
         ctx->wf_waves = (int)value;
@@ -1123,11 +1129,12 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
         int first_wave = 0;
         P.bounce = 0;
         if (ctx->wf_fuse_primary && max_depth > 0) {
-            // wave 0 in one kernel; survivors land in queue 1
+            // the first wave(s) in one kernel; survivors land in the queue the next wave reads
+            P.fused_waves = ctx->wf_fuse_primary < waves ? ctx->wf_fuse_primary : waves;
             k_wf_reset<<<1, 32, 0, st>>>(P);
             if (ctx->count) k_wf_primary<true><<<grid_wide, bt, smem, st>>>(P);
             else k_wf_primary<false><<<grid_wide, bt, smem, st>>>(P);
-            first_wave = 1;
+            first_wave = P.fused_waves;
         } else {
             k_wf_generate<<<grid_wide, bt, 0, st>>>(P);
         }
