@@ -453,9 +453,11 @@ __global__ void __launch_bounds__(256) k_wf_extend(const __grid_constant__ WfPar
             if (mode == 0) {
                 const int ref = T.best_ref;
                 bool is_med = false;
-                if (ref != kRefNone && S.has_media) {
+                int cls = 0;                                   // 0 miss, 1 medium boundary, 2 + material type
+                if (ref != kRefNone) {
                     const int header = __float_as_int(__ldg(S.materials + 3 * mat_id_of(S, ref)).x);
                     is_med = mat_is_medium(header);
+                    cls = is_med ? 1 : 2 + mat_type(header);
                 }
                 if (is_med) {
                     mode = 1;
@@ -464,13 +466,13 @@ __global__ void __launch_bounds__(256) k_wf_extend(const __grid_constant__ WfPar
                     trav_begin<COUNT>(T, S, T.o, T.d, t_entry + 0.0001f, 1e10f, lc);
                     st = LANE_TRAVERSING;
                 } else {
-                    P.Q.hit[ray] = make_float4(T.best_t, __int_as_float(ref), 0.0f, __int_as_float(0));
+                    P.Q.hit[ray] = make_float4(T.best_t, __int_as_float(ref), 0.0f, __int_as_float(cls << 8));
                     st = LANE_NEED_PATH;
                 }
             } else {
                 mode = 0;
                 P.Q.hit[ray] = make_float4(t_entry, __int_as_float(ref_entry), T.best_t,
-                                           __int_as_float(T.best_ref != kRefNone ? 1 : 0));
+                                           __int_as_float((T.best_ref != kRefNone ? 1 : 0) | (1 << 8)));
                 st = LANE_NEED_PATH;
             }
         }
@@ -583,30 +585,58 @@ __device__ __forceinline__ bool wf_shade_one(const DScene& S, f3 bg, int max_dep
     return emit_next;
 }
 
-// Material binning: a streaming pass over the hit records (16 B each, coalesced) that appends every
-// ray index to the bin of its class -- 0 miss, 1 medium boundary, 2 + material type -- with one
-// atomic per (warp, class) (__match_any_sync).  k_wf_shade then walks the bins in class order, so
-// its warps shade one material at a time.
+// Material binning: a streaming pass over the hit records that appends every ray index to the bin of
+// its class (written by k_wf_extend into the record's flag word).  Each CTA handles a contiguous
+// slice of 2048 rays: classes are counted per warp with ballots, reduced in shared memory, and the
+// CTA reserves its space in every bin with ONE atomic per class.  k_wf_shade then walks the bins in
+// class order, so its warps shade one material at a time.
+constexpr int kBinRounds = 8;
 __global__ void __launch_bounds__(256) k_wf_bin(const __grid_constant__ WfParams P) {
-    const DScene& S = P.S;
+    __shared__ int s_cnt[kNumBins][kWfWarps];
+    __shared__ int s_base[kNumBins];
     const int cur = P.bounce & 1;
     const int count = P.Q.qcount[cur];
-    if ((long long)blockIdx.x * 256 >= count) return;
-    const int stride = gridDim.x * blockDim.x;
-    const int rounds = (count + stride - 1) / stride;
-    for (int r = 0; r < rounds; r++) {
-        const int i = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
-        const bool active = i < count;
-        int cls = 0;
-        if (active) {
-            const int ref = __float_as_int(P.Q.hit[i].y);
-            if (ref != kRefNone) {
-                const int header = __float_as_int(__ldg(S.materials + 3 * mat_id_of(S, ref)).x);
-                cls = mat_is_medium(header) ? 1 : 2 + mat_type(header);
+    const unsigned lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int slice = 256 * kBinRounds;
+    for (long long base = (long long)blockIdx.x * slice; base < count; base += (long long)gridDim.x * slice) {
+        int cls[kBinRounds], rank[kBinRounds];
+        int mine[kNumBins];
+#pragma unroll
+        for (int k = 0; k < kNumBins; k++) mine[k] = 0;
+#pragma unroll
+        for (int r = 0; r < kBinRounds; r++) {
+            const long long i = base + r * 256 + threadIdx.x;
+            cls[r] = i < count ? ((__float_as_int(P.Q.hit[i].w) >> 8) & (kNumBins - 1)) : -1;
+            rank[r] = 0;
+#pragma unroll
+            for (int k = 0; k < kNumBins; k++) {
+                const unsigned m = __ballot_sync(0xffffffffu, cls[r] == k);
+                if (cls[r] == k) rank[r] = mine[k] + __popc(m & ((1u << lane) - 1));
+                mine[k] += __popc(m);                  // warp-uniform running count of class k
             }
         }
-        const int pos = warp_agg_append(P.Q.bin_count, cls, active);
-        if (active) P.Q.bins[(size_t)cls * P.Q.capacity + pos] = (uint32_t)i;
+        if (lane < kNumBins) {
+            int v = 0;
+#pragma unroll
+            for (int k = 0; k < kNumBins; k++) v = lane == k ? mine[k] : v;
+            s_cnt[lane][warp] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x < kNumBins) {
+            int tot = 0;
+            for (int w = 0; w < kWfWarps; w++) { int v = s_cnt[threadIdx.x][w]; s_cnt[threadIdx.x][w] = tot; tot += v; }
+            s_base[threadIdx.x] = tot ? atomicAdd(P.Q.bin_count + threadIdx.x, tot) : 0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < kBinRounds; r++) {
+            if (cls[r] >= 0) {
+                const int pos = s_base[cls[r]] + s_cnt[cls[r]][warp] + rank[r];
+                P.Q.bins[(size_t)cls[r] * P.Q.capacity + pos] = (uint32_t)(base + r * 256 + threadIdx.x);
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -651,7 +681,7 @@ __global__ void __launch_bounds__(256) k_wf_shade(const __grid_constant__ WfPara
             rng = __float_as_uint(c.z);
             emit_next = wf_shade_one(S, bg, max_depth, P.Q.slab + 3 * (size_t)path_id, mk3(a.x, a.y, a.z),
                                      mk3(a.w, bq.x, bq.y), mk3(bq.z, bq.w, c.x), __float_as_int(c.w), rng, h.x,
-                                     __float_as_int(h.y), h.z, __float_as_int(h.w) != 0, no, nd, nthr, ndepth);
+                                     __float_as_int(h.y), h.z, (__float_as_int(h.w) & 1) != 0, no, nd, nthr, ndepth);
         }
         // compaction: one atomic per warp (kernels.py:1345/:1394 use one per ray)
         int pos = warp_agg_append(P.Q.qcount + nxt, 0, emit_next);
