@@ -153,8 +153,7 @@ __global__ void __launch_bounds__(256) k_megakernel(const __grid_constant__ Mega
     // traversal state (persists across bursts)
     TravState T;
     T.cur = kRefNone;
-    int stack_ref[kStackSize];
-    float stack_t[kStackSize];
+    StackEntry stack[kStackSize];
     int st = (valid && s < s_end && max_depth > 0) ? LANE_NEED_PATH : LANE_DONE;
 
     for (;;) {
@@ -274,11 +273,11 @@ __global__ void __launch_bounds__(256) k_megakernel(const __grid_constant__ Mega
         const int min_active = (__popc(live) * P.burst_num + 31) >> 5;
         if (P.vote_num > 0) {
             bool fin;
-            trav_run_vote<COUNT>(T, st == LANE_TRAVERSING, fin, S, s_nodes, P.n_snodes, stack_ref, stack_t,
+            trav_run_vote<COUNT>(T, st == LANE_TRAVERSING, fin, S, s_nodes, P.n_snodes, stack,
                                  min_active > 0 ? min_active : 1, P.vote_num, lc);
             if (fin) st = LANE_HAVE_RESULT;
         } else if (st == LANE_TRAVERSING) {
-            if (trav_run<COUNT>(T, S, s_nodes, P.n_snodes, stack_ref, stack_t, min_active, lc)) st = LANE_HAVE_RESULT;
+            if (trav_run<COUNT>(T, S, s_nodes, P.n_snodes, stack, min_active, lc)) st = LANE_HAVE_RESULT;
         }
     }
     if (valid) { ap[0] = acc.x; ap[1] = acc.y; ap[2] = acc.z; }
@@ -441,8 +440,7 @@ __global__ void __launch_bounds__(256) k_wf_extend(const __grid_constant__ WfPar
 
     TravState T;
     T.cur = kRefNone;
-    int stack_ref[kStackSize];
-    float stack_t[kStackSize];
+    StackEntry stack[kStackSize];
     int st = LANE_NEED_PATH;     // NEED_PATH: wants a ray; TRAVERSING; HAVE_RESULT; DONE: queue exhausted
     int ray = 0, mode = 0, ref_entry = kRefNone;
     float t_entry = 0.0f;
@@ -512,11 +510,11 @@ __global__ void __launch_bounds__(256) k_wf_extend(const __grid_constant__ WfPar
         const int min_active = (__popc(live) * P.burst_num + 31) >> 5;
         if (P.vote_num > 0) {
             bool fin;
-            trav_run_vote<COUNT>(T, st == LANE_TRAVERSING, fin, S, s_nodes, P.n_snodes, stack_ref, stack_t,
+            trav_run_vote<COUNT>(T, st == LANE_TRAVERSING, fin, S, s_nodes, P.n_snodes, stack,
                                  min_active > 0 ? min_active : 1, P.vote_num, lc);
             if (fin) st = LANE_HAVE_RESULT;
         } else if (st == LANE_TRAVERSING) {
-            if (trav_run<COUNT>(T, S, s_nodes, P.n_snodes, stack_ref, stack_t, min_active, lc)) st = LANE_HAVE_RESULT;
+            if (trav_run<COUNT>(T, S, s_nodes, P.n_snodes, stack, min_active, lc)) st = LANE_HAVE_RESULT;
         }
     }
     cp_async_wait_all();

@@ -194,11 +194,18 @@ __device__ __forceinline__ void trav_begin(TravState& T, const DScene& S, f3 o, 
     if (COUNT) lc.rays++;
 }
 
-__device__ __forceinline__ int trav_pop(TravState& T, const int* stack_ref, const float* stack_t) {
+// A stack entry packs the deferred child's reference and its slab entry distance into one 8-byte
+// word, so that a push / pop is a single local-memory instruction (STL.64 / LDL.64).
+typedef unsigned long long StackEntry;
+__device__ __forceinline__ StackEntry stack_pack(int ref, float t) {
+    return ((StackEntry)__float_as_uint(t) << 32) | (StackEntry)(unsigned)ref;
+}
+__device__ __forceinline__ int trav_pop(TravState& T, const StackEntry* stack) {
     int next = kRefNone;
     while (T.sp > 0) {
         --T.sp;
-        if (stack_t[T.sp] <= T.best_t) { next = stack_ref[T.sp]; break; }
+        const StackEntry e = stack[T.sp];
+        if (__uint_as_float((unsigned)(e >> 32)) <= T.best_t) { next = (int)(unsigned)e; break; }
     }
     return next;
 }
@@ -207,7 +214,7 @@ __device__ __forceinline__ int trav_pop(TravState& T, const int* stack_ref, cons
 // min_active lanes of the warp are still inside the loop (returns false; call again to resume).
 template <bool COUNT>
 __device__ __forceinline__ bool trav_run(TravState& T, const DScene& S, const float4* __restrict__ s_nodes, int n_snodes,
-                                         int* stack_ref, float* stack_t, int min_active, LocalCounters& lc) {
+                                         StackEntry* stack, int min_active, LocalCounters& lc) {
     const f3 o = T.o, inv = T.inv;
     const float t_min = T.t_min;
     while (T.cur != kRefNone) {
@@ -240,8 +247,7 @@ __device__ __forceinline__ bool trav_run(TravState& T, const DScene& S, const fl
             if (hl && hr) {
                 const bool left_first = ltmin <= rtmin;
                 if (T.sp < kStackSize) {
-                    stack_ref[T.sp] = left_first ? rref : lref;
-                    stack_t[T.sp] = left_first ? rtmin : ltmin;
+                    stack[T.sp] = stack_pack(left_first ? rref : lref, left_first ? rtmin : ltmin);
                     T.sp++;
                 }
                 T.cur = left_first ? lref : rref;
@@ -250,7 +256,7 @@ __device__ __forceinline__ bool trav_run(TravState& T, const DScene& S, const fl
             } else if (hr) {
                 T.cur = rref;
             } else {
-                T.cur = trav_pop(T, stack_ref, stack_t);
+                T.cur = trav_pop(T, stack);
             }
         }
         if (T.cur != kRefNone) {   // a leaf reference
@@ -261,7 +267,7 @@ __device__ __forceinline__ bool trav_run(TravState& T, const DScene& S, const fl
             else if (type == PT_PRIM_QUAD) { if (COUNT) lc.quad_tests++; hit = hit_quad_t(S, idx, T.o, T.d, t_min, T.best_t, t); }
             else { if (COUNT) lc.triangle_tests++; hit = hit_triangle_t(S, idx, T.o, T.d, t_min, T.best_t, t); }
             if (hit && t < T.best_t) { T.best_t = t; T.best_ref = T.cur; }   // kernels.py:691 (strict)
-            T.cur = trav_pop(T, stack_ref, stack_t);
+            T.cur = trav_pop(T, stack);
         }
         if (min_active > 0 && __popc(__activemask()) < min_active) break;
     }
@@ -278,8 +284,8 @@ __device__ __forceinline__ bool trav_run(TravState& T, const DScene& S, const fl
 // so results are bit-identical to trav_run.
 template <bool COUNT>
 __device__ __forceinline__ void trav_run_vote(TravState& T, bool active, bool& done, const DScene& S,
-                                              const float4* __restrict__ s_nodes, int n_snodes, int* stack_ref,
-                                              float* stack_t, int min_active, int vote_num, LocalCounters& lc) {
+                                              const float4* __restrict__ s_nodes, int n_snodes, StackEntry* stack,
+                                              int min_active, int vote_num, LocalCounters& lc) {
     const f3 o = T.o, inv = T.inv;
     const float t_min = T.t_min;
     for (;;) {
@@ -322,8 +328,7 @@ __device__ __forceinline__ void trav_run_vote(TravState& T, bool active, bool& d
                 if (hl && hr) {
                     const bool left_first = ltmin <= rtmin;
                     if (T.sp < kStackSize) {
-                        stack_ref[T.sp] = left_first ? rref : lref;
-                        stack_t[T.sp] = left_first ? rtmin : ltmin;
+                        stack[T.sp] = stack_pack(left_first ? rref : lref, left_first ? rtmin : ltmin);
                         T.sp++;
                     }
                     T.cur = left_first ? lref : rref;
@@ -332,7 +337,7 @@ __device__ __forceinline__ void trav_run_vote(TravState& T, bool active, bool& d
                 } else if (hr) {
                     T.cur = rref;
                 } else {
-                    T.cur = trav_pop(T, stack_ref, stack_t);
+                    T.cur = trav_pop(T, stack);
                 }
             }
         } else {
@@ -344,7 +349,7 @@ __device__ __forceinline__ void trav_run_vote(TravState& T, bool active, bool& d
                 else if (type == PT_PRIM_QUAD) { if (COUNT) lc.quad_tests++; hit = hit_quad_t(S, idx, T.o, T.d, t_min, T.best_t, t); }
                 else { if (COUNT) lc.triangle_tests++; hit = hit_triangle_t(S, idx, T.o, T.d, t_min, T.best_t, t); }
                 if (hit && t < T.best_t) { T.best_t = t; T.best_ref = T.cur; }   // kernels.py:691 (strict)
-                T.cur = trav_pop(T, stack_ref, stack_t);
+                T.cur = trav_pop(T, stack);
             }
         }
     }
@@ -355,11 +360,10 @@ __device__ __forceinline__ void trav_run_vote(TravState& T, bool active, bool& d
 template <bool COUNT>
 __device__ __forceinline__ void traverse(const DScene& S, const float4* __restrict__ s_nodes, int n_snodes, f3 o, f3 d,
                                          float t_min, float t_max, float& best_t, int& best_ref, LocalCounters& lc) {
-    int stack_ref[kStackSize];
-    float stack_t[kStackSize];
+    StackEntry stack[kStackSize];
     TravState T;
     trav_begin<COUNT>(T, S, o, d, t_min, t_max, lc);
-    trav_run<COUNT>(T, S, s_nodes, n_snodes, stack_ref, stack_t, 0, lc);
+    trav_run<COUNT>(T, S, s_nodes, n_snodes, stack, 0, lc);
     best_t = T.best_t;
     best_ref = T.best_ref;
 }
