@@ -310,7 +310,7 @@ def main():
                 "note": "node/primitive fetches are served by shared memory + L1/L2 (scene = 2.5 MB); "
                         "HBM traffic is compulsory only, see profiles/",
                 "counters": cnt, "mrays_per_s": cnt["rays"] / (k_ms * 1e-3) / 1e6,
-                "bytes_per_path": alg / max(1, cnt["paths"])}
+                "bytes_per_path": alg / max(1, W * H * n_samples)}
         if not args.no_cpu_baseline and world == 1:
             v, cores, sample = cpu_oracle_rate(cs)
             cpu = {"value": v, "unit": "Mpaths/s", "cores": cores, "kind": "port", "sample": sample}

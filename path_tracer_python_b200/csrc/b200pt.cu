@@ -721,6 +721,7 @@ __global__ void __launch_bounds__(256) k_wf_primary(const __grid_constant__ WfPa
             get_ray(P.cam, px, py, rng, o, d);                  // NOT normalised, kernels.py:1229-1233
             float* sp = P.Q.slab + 3 * (size_t)id;
             sp[0] = 0.0f; sp[1] = 0.0f; sp[2] = 0.0f;
+            if (COUNT) lc.paths++;
             f3 thr = mk3(1.0f, 1.0f, 1.0f);
             int depth = 0;
             emit_next = max_depth > 0;

@@ -11,7 +11,7 @@ e.set_scene(cs); e.set_camera(meta["camera"], (0, 0, 0), 50)
 H = meta["height"]
 acc = e.new_accum(W, H)
 def run():
-    acc.zero_(); e.render_wavefront(acc, 0, 2, 7); torch.cuda.synchronize()
+    acc.zero_(); e.render_wavefront(acc, 0, SPP, 7); torch.cuda.synchronize()   # same size as the timed call (workspace allocation)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     acc.zero_(); a.record(); e.render_wavefront(acc, 0, SPP, 7); b.record(); torch.cuda.synchronize()
     return W * H * SPP / a.elapsed_time(b) / 1e3
