@@ -78,6 +78,10 @@ typedef struct PtHostScene {
     const int32_t *perm_x, *perm_y, *perm_z;                    /* [256] */
     const uint8_t* images[PT_MAX_IMAGES];                       /* [h][w][3] */
     int32_t image_w[PT_MAX_IMAGES], image_h[PT_MAX_IMAGES];
+    /* "full" feature mode -- what the Taichi path dropped but src/core renders: */
+    const float* sphere_motion;                                 /* [n][3] centre(1)-centre(0) (core/sphere.py:22-36) or NULL */
+    int32_t full_features;                                      /* 0 = taichi_compat; 1 = moving spheres + material types 5/6
+                                                                 * (subsurface_simple / _volumetric, core/material.py:144-276) */
 } PtHostScene;
 
 /* Layout of the packed device blob.  Offsets are bytes from blob start,
@@ -97,6 +101,9 @@ typedef struct PtPackedInfo {
     int32_t num_inner, num_spheres, num_quads, num_triangles, num_materials, num_images;
     int32_t max_depth_tree;  /* depth of the tree (stack bound check) */
     int32_t has_media;       /* any is_medium flag set */
+    uint64_t off_sphere_motion; /* num_spheres * 16 B, present iff full_features */
+    int32_t full_features;
+    int32_t reserved_;
 } PtPackedInfo;
 
 /* Camera + render settings: what _upload_camera writes (renderer.py:230-247; fields.py:159-172) */

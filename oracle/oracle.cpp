@@ -11,6 +11,11 @@
  * PT-F32 contract (oracle_math.h): strict IEEE binary32, no contraction (build with
  * -ffp-contract=off), contract-defined elementary functions and random stream.
  *
+ * Full-feature mode (OScene.full_features): moving spheres (core/sphere.py:22-36) and the two
+ * subsurface materials (core/material.py:144-276), which exist only in the reference's pure-Python
+ * tracer; semantics restated here in the same f32 contract and pinned *statistically* against that
+ * tracer (tests/test_full_features.py) -- the Taichi path has nothing to compare bits with.
+ *
  * Pinning: tests/test_oracle_golden.py checks this file bit-for-bit against fixtures produced by
  * executing the reference's unmodified renderer.py/kernels.py/fields.py under oracle/taichi_shim
  * (a pure-Python stand-in for the absent `taichi` module); see oracle/gen_golden.py.
@@ -55,6 +60,10 @@ typedef struct {
     const int32_t *perm_x, *perm_y, *perm_z;
     const uint8_t* images[16];      /* [h][w][3] u8; texel value = u8 / 255.0f (rtw_image.py:66) */
     int32_t image_w[16], image_h[16];
+    /* ---- full-feature mode (features the Taichi path dropped but the reference's pure-Python
+     * tracer has; SURVEY.md "three facts" #2): moving spheres and subsurface materials */
+    const float* sphere_motion;     /* [n][3] centre(1) - centre(0), or NULL (core/sphere.py:22-35) */
+    int32_t full_features;
 } OScene;
 
 typedef struct {
@@ -117,7 +126,17 @@ struct Ctx {
     const OScene* sc;
     const OCamera* cam;
     OCounters cnt;
+    float time = 0.0f;   /* shutter time of the path being traced (full-feature mode) */
 };
+
+/* centre of sphere idx at the current path's time: Ray.at(time) = origin + time * direction
+ * (core/sphere.py:36, util/ray.py:38) */
+inline V3 sphere_center(const Ctx& c, int idx) {
+    const float* s = c.sc->sphere_data + 4 * idx;
+    V3 center = v3(s[0], s[1], s[2]);
+    if (c.sc->full_features && c.sc->sphere_motion) center = center + c.time * ld3(c.sc->sphere_motion + 3 * idx);
+    return center;
+}
 
 /* kernels.py:16-25 */
 V3 random_in_unit_disk(Rng& rng) {
@@ -224,7 +243,7 @@ void get_ray(const OCamera* cam, int px, int py, Rng& rng, V3* o, V3* d) {
 bool hit_sphere(Ctx& c, int idx, V3 o, V3 d, float t_min, float t_max, float* t, V3* p, V3* n) {
     c.cnt.sphere_tests++;
     const float* s = c.sc->sphere_data + 4 * idx;
-    V3 center = v3(s[0], s[1], s[2]);
+    V3 center = sphere_center(c, idx);
     float radius = s[3];
     V3 oc = center - o;
     float a = dot(d, d);
@@ -437,13 +456,76 @@ V3 eval_texture(const OScene* sc, int prim_type, int prim_idx, V3 hp) {
 }
 
 /* kernels.py:817-917 */
+/* core/material.py:258-276 _sample_henyey_greenstein */
+V3 sample_henyey_greenstein(V3 incident, float g, Rng& rng) {
+    if (fabsf(g) < 1e-3f) return random_unit_vector(rng);
+    float sqr_term = (1.0f - g * g) / (1.0f - g + 2.0f * g * rng.next());
+    float cos_theta = (1.0f + g * g - sqr_term * sqr_term) / (2.0f * g);
+    float sin_theta = sqrtf(fmax2(0.0f, 1.0f - cos_theta * cos_theta));
+    float phi = 6.2831853f * rng.next();                       /* 2 * 3.14159265 */
+    V3 w = normalized(incident);
+    V3 a = fabsf(w.x) > 0.9f ? v3(1, 0, 0) : v3(0, 1, 0);
+    V3 v = normalized(cross(w, a));
+    V3 u = cross(w, v);
+    return normalized(((u * o_cosf(phi)) * sin_theta + (v * o_sinf(phi)) * sin_theta) + w * cos_theta);
+}
+
+bool near_zero(V3 v) { return fabsf(v.x) < 1e-8f && fabsf(v.y) < 1e-8f && fabsf(v.z) < 1e-8f; }
+
 bool scatter(const OScene* sc, V3 ray_dir, V3 hp, V3 normal, int prim_type, int prim_idx, Rng& rng,
-             V3* scatter_dir, V3* attenuation) {
+             V3* scatter_dir, V3* attenuation, V3* scatter_origin) {
     const OMaterials& m = sc->mat[prim_type];
     int mat_type = m.material_type[prim_idx];
     *scatter_dir = v3(0, 0, 0);
     *attenuation = v3(1, 1, 1);
+    *scatter_origin = hp;
     bool scattered = false;
+    if (sc->full_features && (mat_type == 5 || mat_type == 6)) {
+        /* the pure-Python tracer's materials see the face-forwarded normal (core/hittable.py:17-22) */
+        V3 nf = dot(ray_dir, normal) < 0.0f ? normal : -normal;
+        V3 albedo = ld3(m.albedo + 3 * prim_idx);
+        if (mat_type == 5) {                                   /* subsurface_simple, core/material.py:144-173 */
+            float scatter_distance = m.fuzz[prim_idx];
+            V3 dir;
+            if (rng.next() < 0.5f) {
+                dir = nf + random_unit_vector(rng);
+            } else {
+                V3 ruv = random_unit_vector(rng);
+                V3 displacement = (ruv * scatter_distance) * rng.next();
+                *scatter_origin = hp + displacement;
+                dir = nf + random_unit_vector(rng);
+            }
+            if (near_zero(dir)) dir = nf;
+            *scatter_dir = dir;
+            *attenuation = albedo;
+            return true;
+        }
+        /* subsurface_volumetric, core/material.py:175-256 */
+        float sigma_s = m.fuzz[prim_idx], sigma_a = m.ir[prim_idx], g = m.texture_scale[prim_idx];
+        float sigma_t = sigma_s + sigma_a;
+        V3 pos = hp - nf * 0.001f;
+        V3 dirn = normalized(ray_dir);
+        V3 thr = v3(1, 1, 1);
+        for (int it = 0; it < 64; it++) {
+            float t = -o_logf(fmax2(rng.next(), 1e-10f)) / sigma_t;
+            pos = pos + dirn * t;
+            V3 dv = pos - hp;
+            float dist = sqrtf(dot(dv, dv));
+            float exit_probability = 1.0f - o_expf(-dist * 0.5f);
+            if (rng.next() < exit_probability) {
+                V3 dir = nf + random_unit_vector(rng);
+                if (near_zero(dir)) dir = nf;
+                *scatter_origin = pos;
+                *scatter_dir = dir;
+                *attenuation = thr * albedo;
+                return true;
+            }
+            if (rng.next() < sigma_a / sigma_t) { *attenuation = v3(0, 0, 0); return false; }
+            dirn = sample_henyey_greenstein(dirn, g, rng);
+            thr = thr * albedo;
+        }
+        return false;
+    }
     if (mat_type == 0) {
         V3 albedo = eval_texture(sc, prim_type, prim_idx, hp);
         *scatter_dir = random_cosine_direction(normal, rng);
@@ -555,15 +637,15 @@ V3 trace_ray(Ctx& c, V3 ray_origin, V3 ray_dir, Rng& rng) {
                 } else {
                     V3 emit = emitted(sc, h.prim_type, h.prim_idx);
                     color = color + throughput * emit;
-                    scattered = scatter(sc, cur_d, hit_point, normal, h.prim_type, h.prim_idx, rng, &scatter_dir, &attenuation);
+                    scattered = scatter(sc, cur_d, hit_point, normal, h.prim_type, h.prim_idx, rng, &scatter_dir, &attenuation, &hit_point);
                 }
             } else {
                 V3 emit = emitted(sc, h.prim_type, h.prim_idx);
                 color = color + throughput * emit;
-                scattered = scatter(sc, cur_d, hit_point, normal, h.prim_type, h.prim_idx, rng, &scatter_dir, &attenuation);
+                scattered = scatter(sc, cur_d, hit_point, normal, h.prim_type, h.prim_idx, rng, &scatter_dir, &attenuation, &hit_point);
             }
             if (scattered) {
-                cur_o = hit_point;
+                cur_o = hit_point;     /* = the hit point, or the displaced exit point of a subsurface material */
                 cur_d = scatter_dir;
                 throughput = throughput * attenuation;
                 if (depth + 1 >= max_depth) break;
@@ -603,6 +685,7 @@ void o_math_eval(int fn, int n, const float* a, const float* b, float* out) {
             case 3: out[i] = o_acosf(a[i]); break;
             case 4: out[i] = o_atan2f(a[i], b[i]); break;
             case 5: out[i] = o_pow5f(a[i]); break;
+            case 7: out[i] = o_expf(a[i]); break;
             default: out[i] = 0.0f;
         }
     }
@@ -682,6 +765,7 @@ void o_render_megakernel(const OScene* sc, const OCamera* cam, int W, int H, int
                 V3 acc = ld3(accum + 3 * (size_t)idx);
                 for (int s = sample_begin; s < sample_begin + sample_count; s++) {
                     Rng rng{o_rng_seed(seed, (uint32_t)idx, (uint32_t)s)};
+                    c.time = sc->full_features ? o_path_time(rng.s) : 0.0f;
                     V3 o, d;
                     get_ray(cam, px, py, rng, &o, &d);
                     V3 col = trace_ray(c, o, d, rng);
@@ -725,6 +809,7 @@ void o_render_wavefront(const OScene* sc, const OCamera* cam, int W, int H, int 
                 for (int s = sample_begin; s < sample_begin + sample_count; s++) {
                     c.cnt.paths++;
                     Rng rng{o_rng_seed(seed, (uint32_t)idx, (uint32_t)s)};
+                    c.time = sc->full_features ? o_path_time(rng.s) : 0.0f;
                     /* generate_camera_rays: direction NOT normalised (kernels.py:1229-1233) */
                     V3 ro, rd;
                     get_ray(cam, px, py, rng, &ro, &rd);
@@ -760,11 +845,11 @@ void o_render_wavefront(const OScene* sc, const OCamera* cam, int W, int H, int 
                                 passthrough = true; /* re-enqueued with unchanged depth/throughput */
                             } else {
                                 emit = emitted(sc, h.prim_type, h.prim_idx);
-                                scattered = scatter(sc, rd, hit_point, normal, h.prim_type, h.prim_idx, rng, &scatter_dir, &attenuation);
+                                scattered = scatter(sc, rd, hit_point, normal, h.prim_type, h.prim_idx, rng, &scatter_dir, &attenuation, &hit_point);
                             }
                         } else {
                             emit = emitted(sc, h.prim_type, h.prim_idx);
-                            scattered = scatter(sc, rd, hit_point, normal, h.prim_type, h.prim_idx, rng, &scatter_dir, &attenuation);
+                            scattered = scatter(sc, rd, hit_point, normal, h.prim_type, h.prim_idx, rng, &scatter_dir, &attenuation, &hit_point);
                         }
                         if (emit.x > 0.0f || emit.y > 0.0f || emit.z > 0.0f) {
                             V3 add = thr * emit;

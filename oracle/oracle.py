@@ -32,6 +32,7 @@ class OScene(C.Structure):
         + [(n, C.c_void_p) for n in ("bvh_bbox_min", "bvh_bbox_max", "bvh_left", "bvh_right", "bvh_prim_type",
                                      "bvh_prim_idx", "perlin_randvec", "perm_x", "perm_y", "perm_z")]
         + [("images", C.c_void_p * 16), ("image_w", C.c_int32 * 16), ("image_h", C.c_int32 * 16)]
+        + [("sphere_motion", C.c_void_p), ("full_features", C.c_int32)]
     )
 
 
@@ -160,6 +161,9 @@ class OracleScene:
             self._keep.append(img)
             s.images[i] = img.ctypes.data
             s.image_h[i], s.image_w[i] = img.shape[0], img.shape[1]
+        s.full_features = int(cs.get("full_features", 0))
+        if s.full_features and "sphere_motion" in cs:
+            s.sphere_motion = _ptr(f32("sphere_motion", (3,)))
         self.c = s
 
 
@@ -216,7 +220,7 @@ def first_hit(scene: OracleScene, o, d, t_min=0.001, t_max=1e10, nthreads=0):
     return out
 
 
-_FN = {"sin": 0, "cos": 1, "log": 2, "acos": 3, "atan2": 4, "pow5": 5}
+_FN = {"sin": 0, "cos": 1, "log": 2, "acos": 3, "atan2": 4, "pow5": 5, "exp": 7}
 
 
 def math_eval(fn: str, a, b=None):

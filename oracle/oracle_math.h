@@ -158,6 +158,27 @@ static inline float o_atan2f(float y, float x) {
     return w + o_atanf(y / x);
 }
 
+/* exp (full-feature mode only: subsurface_volumetric's exit probability, core/material.py:213).
+ * Cephes expf: range reduction by ln2 split in two constants, degree-5 polynomial, ldexp. */
+static inline float o_ldexpf(float z, int n) {
+    if (n < -126) { z = z * o_u2f(0x00800000u); n += 126; if (n < -126) n = -126; }   /* 2^-126 first */
+    if (n > 127) { z = z * o_u2f(0x7f000000u); n -= 127; if (n > 127) n = 127; }
+    return z * o_u2f((uint32_t)(n + 127) << 23);
+}
+static inline float o_expf(float xx) {
+    float x = xx;
+    if (x > 88.72283905206835f) return INFINITY;
+    if (x < -103.278929903431851103f) return 0.0f;
+    float z = floorf(1.44269504088896341f * x + 0.5f);
+    x = x - z * 0.693359375f;
+    x = x - z * -2.12194440e-4f;
+    int n = (int)z;
+    z = x * x;
+    z = (((((1.9875691500e-4f * x + 1.3981999507e-3f) * x + 8.3334519073e-3f) * x + 4.1665795894e-2f) * x
+          + 1.6666665459e-1f) * x + 5.0000001201e-1f) * z + x + 1.0f;
+    return o_ldexpf(z, n);
+}
+
 /* ti.pow(x, 5.0) (kernels.py:786): the only call site has the literal exponent 5 */
 static inline float o_pow5f(float x) {
     float x2 = x * x;
@@ -179,6 +200,11 @@ static inline uint32_t o_rng_seed(uint32_t seed, uint32_t pixel_index, uint32_t 
     h = o_mix32(h + pixel_index);
     h = o_mix32(h + sample_index);
     return h;
+}
+/* full-feature mode: a path's shutter time (camera.py:136 `ray_time = random()`) is a pure function
+ * of the path key, so that both kernel architectures can recompute it without carrying it */
+static inline float o_path_time(uint32_t key) {
+    return (float)(o_mix32(key ^ 0x7157a3d1u) >> 8) * 5.9604644775390625e-8f;
 }
 static inline float o_rng_next(uint32_t* state) {
     *state += 0x9e3779b9u;

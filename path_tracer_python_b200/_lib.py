@@ -31,6 +31,7 @@ class PtHostScene(C.Structure):
                                      "bvh_prim_idx", "perlin_randvec", "perm_x", "perm_y", "perm_z")]
         + [("images", C.c_void_p * PT_MAX_IMAGES), ("image_w", C.c_int32 * PT_MAX_IMAGES),
            ("image_h", C.c_int32 * PT_MAX_IMAGES)]
+        + [("sphere_motion", C.c_void_p), ("full_features", C.c_int32)]
     )
 
 
@@ -42,6 +43,7 @@ class PtPackedInfo(C.Structure):
            ("image_h", C.c_int32 * PT_MAX_IMAGES)]
         + [(n, C.c_int32) for n in ("num_inner", "num_spheres", "num_quads", "num_triangles", "num_materials",
                                     "num_images", "max_depth_tree", "has_media")]
+        + [("off_sphere_motion", C.c_uint64), ("full_features", C.c_int32), ("reserved_", C.c_int32)]
     )
 
 
@@ -192,6 +194,11 @@ class HostScene:
             self._keep.append(img)
             s.images[i] = img.ctypes.data
             s.image_h[i], s.image_w[i] = img.shape[0], img.shape[1]
+        s.full_features = int(cs.get("full_features", 0))
+        if s.full_features:
+            mo = np.ascontiguousarray(cs["sphere_motion"] if "sphere_motion" in cs else np.zeros((sd.shape[0], 3)), np.float32)
+            self._keep.append(mo)
+            s.sphere_motion = _ptr(mo)
         self.c = s
         self.input_bytes = int(sum(a.nbytes for a in self._keep))
 

@@ -35,7 +35,12 @@ def primitive_bounds(cs: dict):
     sd = np.asarray(cs.get("sphere_data", np.zeros((0, 4))), np.float32)
     if len(sd):
         c, r = sd[:, :3], sd[:, 3:4]
-        parts.append((c - r, c + r, c.copy(), PRIM_SPHERE, len(sd)))
+        lo, hi = c - r, c + r
+        if int(cs.get("full_features", 0)) and "sphere_motion" in cs:
+            # full feature mode: box = union of the boxes at both ends of the motion (core/sphere.py:27-32)
+            c1 = c + np.asarray(cs["sphere_motion"], np.float32)
+            lo, hi = np.minimum(lo, c1 - r), np.maximum(hi, c1 + r)
+        parts.append((lo, hi, c.copy(), PRIM_SPHERE, len(sd)))
     Q = np.asarray(cs.get("quad_Q", np.zeros((0, 3))), np.float32)
     if len(Q):
         u, v = np.asarray(cs["quad_u"], np.float32), np.asarray(cs["quad_v"], np.float32)

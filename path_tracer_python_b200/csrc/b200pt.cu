@@ -120,7 +120,7 @@ struct MegaParams {
 // Lane states of the persistent megakernel
 enum : int { LANE_NEED_PATH = 0, LANE_HAVE_RESULT = 1, LANE_TRAVERSING = 2, LANE_DONE = 3, LANE_WAIT = 4 };
 
-template <bool COUNT>
+template <bool COUNT, bool FULL>
 __global__ void __launch_bounds__(256) k_megakernel(const __grid_constant__ MegaParams P) {
     extern __shared__ float4 s_nodes[];
     const DScene& S = P.S;
@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(256) k_megakernel(const __grid_constant__ Mega
     // per-path state
     f3 thr = mk3(1.0f, 1.0f, 1.0f), col = mk3(0.0f, 0.0f, 0.0f);
     uint32_t rng = 0;
+    float time = 0.0f;       // shutter time of the current path (full feature mode)
     int depth = 0;
     int mode = 0;            // 0: closest-hit search, 1: medium-exit search (kernels.py:417)
     float t_entry = 0.0f;
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(256) k_megakernel(const __grid_constant__ Mega
                         mode = 1;                           // the exit search is simply the next traversal
                         t_entry = t;
                         ref_entry = ref;
-                        trav_begin<COUNT>(T, S, o, d, t + 0.0001f, 1e10f, lc);
+                        trav_begin<COUNT>(T, S, o, d, t + 0.0001f, 1e10f, lc, time);
                         restart = true;
                     } else {
                         do_shade = true;
@@ -206,8 +207,8 @@ __global__ void __launch_bounds__(256) k_megakernel(const __grid_constant__ Mega
             }
             if (do_shade) {
                 f3 n, emit;
-                finalize_hit(S, sref, o, d, stt, hp, n);
-                scattered = shade_surface(S, m, sref, d, hp, n, rng, emit, sdir, atten);
+                finalize_hit<FULL>(S, sref, o, d, stt, hp, n, time);
+                scattered = shade_surface<FULL>(S, m, sref, d, hp, n, rng, emit, sdir, atten);
                 col = col + thr * emit;                     // kernels.py:1116/1124
             }
             if (!restart) {
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(256) k_megakernel(const __grid_constant__ Mega
                                                                                                            : LANE_NEED_PATH;
                 } else {
                     if (COUNT) lc.bounces++;
-                    trav_begin<COUNT>(T, S, hp, sdir, 0.001f, 1e10f, lc);
+                    trav_begin<COUNT>(T, S, hp, sdir, 0.001f, 1e10f, lc, time);
                     st = LANE_TRAVERSING;
                 }
             } else {
@@ -249,6 +250,7 @@ __global__ void __launch_bounds__(256) k_megakernel(const __grid_constant__ Mega
         if (st == LANE_NEED_PATH) {
             if (s < s_end) {
                 rng = ptm::rng_seed(P.seed, (uint32_t)pixel, (uint32_t)s);
+                time = FULL ? ptm::path_time(rng) : 0.0f;
                 f3 o, d;
                 get_ray(P.cam, px, py, rng, o, d);
                 d = normalized(d);                          // kernels.py:1042
@@ -257,7 +259,7 @@ __global__ void __launch_bounds__(256) k_megakernel(const __grid_constant__ Mega
                 depth = 0;
                 mode = 0;
                 if (COUNT) { lc.paths++; lc.bounces++; }
-                trav_begin<COUNT>(T, S, o, d, 0.001f, 1e10f, lc);
+                trav_begin<COUNT>(T, S, o, d, 0.001f, 1e10f, lc, time);
                 st = LANE_TRAVERSING;
             } else {
                 st = LANE_DONE;
@@ -273,11 +275,11 @@ __global__ void __launch_bounds__(256) k_megakernel(const __grid_constant__ Mega
         const int min_active = (__popc(live) * P.burst_num + 31) >> 5;
         if (P.vote_num > 0) {
             bool fin;
-            trav_run_vote<COUNT>(T, st == LANE_TRAVERSING, fin, S, s_nodes, P.n_snodes, stack,
+            trav_run_vote<COUNT, FULL>(T, st == LANE_TRAVERSING, fin, S, s_nodes, P.n_snodes, stack,
                                  min_active > 0 ? min_active : 1, P.vote_num, lc);
             if (fin) st = LANE_HAVE_RESULT;
         } else if (st == LANE_TRAVERSING) {
-            if (trav_run<COUNT>(T, S, s_nodes, P.n_snodes, stack, min_active, lc)) st = LANE_HAVE_RESULT;
+            if (trav_run<COUNT, FULL>(T, S, s_nodes, P.n_snodes, stack, min_active, lc)) st = LANE_HAVE_RESULT;
         }
     }
     if (valid) { ap[0] = acc.x; ap[1] = acc.y; ap[2] = acc.z; }
@@ -325,6 +327,15 @@ struct WfParams {
     int fused_waves;         // waves k_wf_primary runs in registers before handing paths to the queues
     DCounters* counters;
 };
+
+// full feature mode: the shutter time of the path that owns a queue entry, recomputed from its id
+template <bool FULL>
+__device__ __forceinline__ float wf_path_time(const WfParams& P, int path_id) {
+    if (!FULL) return 0.0f;
+    const int slot = path_id / P.N;
+    const int pixel = P.y0 * P.W + (path_id - slot * P.N);
+    return ptm::path_time(ptm::rng_seed(P.seed, (uint32_t)pixel, (uint32_t)(P.sample_base + slot)));
+}
 
 __global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ WfParams P) {
     const int total = P.N * P.batch;
@@ -384,7 +395,7 @@ constexpr int kWfWarps = 8;       // warps per CTA of the wavefront kernels (256
 // the HBM latency of the queue read overlaps traversal), and hands staged rays to lanes as they
 // finish; the other lanes keep traversing (resumable warp-voting traversal).  Results go to the
 // hit-record array in ray order: no atomics, no binning here.
-template <bool COUNT>
+template <bool COUNT, bool FULL>
 __global__ void __launch_bounds__(256) k_wf_extend(const __grid_constant__ WfParams P) {
     extern __shared__ float4 s_dyn[];
     __shared__ float4 s_ray[kWfWarps][2][32][2];      // (o.xyz d.x)(d.yz ..) of staged rays, 16 KB
@@ -456,12 +467,13 @@ __global__ void __launch_bounds__(256) k_wf_extend(const __grid_constant__ WfPar
                     const int header = __float_as_int(__ldg(S.materials + 3 * mat_id_of(S, ref)).x);
                     is_med = mat_is_medium(header);
                     cls = is_med ? 1 : 2 + mat_type(header);
+                    cls = cls > kNumBins - 1 ? kNumBins - 1 : cls;     // subsurface materials share the last bin
                 }
                 if (is_med) {
                     mode = 1;
                     t_entry = T.best_t;
                     ref_entry = ref;
-                    trav_begin<COUNT>(T, S, T.o, T.d, t_entry + 0.0001f, 1e10f, lc);
+                    trav_begin<COUNT>(T, S, T.o, T.d, t_entry + 0.0001f, 1e10f, lc, T.time);
                     st = LANE_TRAVERSING;
                 } else {
                     P.Q.hit[ray] = make_float4(T.best_t, __int_as_float(ref), 0.0f, __int_as_float(cls << 8));
@@ -498,7 +510,8 @@ __global__ void __launch_bounds__(256) k_wf_extend(const __grid_constant__ WfPar
                 const float4 a = s_ray[warp][buf][slot][0], b = s_ray[warp][buf][slot][1];
                 ray = stg_base[buf] + slot;
                 if (COUNT) lc.bounces++;
-                trav_begin<COUNT>(T, S, mk3(a.x, a.y, a.z), mk3(a.w, b.x, b.y), 0.001f, 1e10f, lc);
+                const float time = FULL ? wf_path_time<FULL>(P, __float_as_int(P.Q.r2[cur][ray].y)) : 0.0f;
+                trav_begin<COUNT>(T, S, mk3(a.x, a.y, a.z), mk3(a.w, b.x, b.y), 0.001f, 1e10f, lc, time);
                 mode = 0;
                 st = LANE_TRAVERSING;
             }
@@ -510,11 +523,11 @@ __global__ void __launch_bounds__(256) k_wf_extend(const __grid_constant__ WfPar
         const int min_active = (__popc(live) * P.burst_num + 31) >> 5;
         if (P.vote_num > 0) {
             bool fin;
-            trav_run_vote<COUNT>(T, st == LANE_TRAVERSING, fin, S, s_nodes, P.n_snodes, stack,
+            trav_run_vote<COUNT, FULL>(T, st == LANE_TRAVERSING, fin, S, s_nodes, P.n_snodes, stack,
                                  min_active > 0 ? min_active : 1, P.vote_num, lc);
             if (fin) st = LANE_HAVE_RESULT;
         } else if (st == LANE_TRAVERSING) {
-            if (trav_run<COUNT>(T, S, s_nodes, P.n_snodes, stack, min_active, lc)) st = LANE_HAVE_RESULT;
+            if (trav_run<COUNT, FULL>(T, S, s_nodes, P.n_snodes, stack, min_active, lc)) st = LANE_HAVE_RESULT;
         }
     }
     cp_async_wait_all();
@@ -524,9 +537,10 @@ __global__ void __launch_bounds__(256) k_wf_extend(const __grid_constant__ WfPar
 // One ray of shade_miss_rays + shade_and_scatter (kernels.py:1266-1399): adds the ray's radiance
 // contribution (miss -> background, hit -> emission) to `sp` and returns true with the next ray
 // (origin, direction, throughput, depth) if the path goes on.
+template <bool FULL>
 __device__ __forceinline__ bool wf_shade_one(const DScene& S, f3 bg, int max_depth, float* sp, f3 o, f3 d, f3 thr,
                                              int depth, uint32_t& rng, float t, int ref, float t_exit_hit, bool exit_hit,
-                                             f3& no, f3& nd, f3& nthr, int& ndepth) {
+                                             f3& no, f3& nd, f3& nthr, int& ndepth, float time = 0.0f) {
     if (ref == kRefNone) {                           // shade_miss_rays, kernels.py:1266-1280
         f3 add = thr * bg;
         sp[0] = sp[0] + add.x; sp[1] = sp[1] + add.y; sp[2] = sp[2] + add.z;
@@ -557,8 +571,8 @@ __device__ __forceinline__ bool wf_shade_one(const DScene& S, f3 bg, int max_dep
     }
     if (do_shade) {
         f3 n;
-        finalize_hit(S, ref, o, d, t, hp, n);
-        scattered = shade_surface(S, m, ref, d, hp, n, rng, emit, sdir, atten);
+        finalize_hit<FULL>(S, ref, o, d, t, hp, n, time);
+        scattered = shade_surface<FULL>(S, m, ref, d, hp, n, rng, emit, sdir, atten);
     }
     if (emit.x > 0.0f || emit.y > 0.0f || emit.z > 0.0f) {      // kernels.py:1368-1375
         f3 add = thr * emit;
@@ -640,6 +654,7 @@ __global__ void __launch_bounds__(256) k_wf_bin(const __grid_constant__ WfParams
 
 // shade_miss_rays + shade_and_scatter (kernels.py:1266-1399) over the material bins; survivors are
 // appended to the other queue with one atomic per warp.
+template <bool FULL>
 __global__ void __launch_bounds__(256) k_wf_shade(const __grid_constant__ WfParams P) {
     const DScene& S = P.S;
     const int cur = P.bounce & 1, nxt = cur ^ 1;
@@ -677,9 +692,10 @@ __global__ void __launch_bounds__(256) k_wf_shade(const __grid_constant__ WfPara
         if (active) {
             path_id = __float_as_int(c.y);
             rng = __float_as_uint(c.z);
-            emit_next = wf_shade_one(S, bg, max_depth, P.Q.slab + 3 * (size_t)path_id, mk3(a.x, a.y, a.z),
+            emit_next = wf_shade_one<FULL>(S, bg, max_depth, P.Q.slab + 3 * (size_t)path_id, mk3(a.x, a.y, a.z),
                                      mk3(a.w, bq.x, bq.y), mk3(bq.z, bq.w, c.x), __float_as_int(c.w), rng, h.x,
-                                     __float_as_int(h.y), h.z, (__float_as_int(h.w) & 1) != 0, no, nd, nthr, ndepth);
+                                     __float_as_int(h.y), h.z, (__float_as_int(h.w) & 1) != 0, no, nd, nthr, ndepth,
+                                     wf_path_time<FULL>(P, path_id));
         }
         // compaction: one atomic per warp (kernels.py:1345/:1394 use one per ray)
         int pos = warp_agg_append(P.Q.qcount + nxt, 0, emit_next);
@@ -695,7 +711,7 @@ __global__ void __launch_bounds__(256) k_wf_shade(const __grid_constant__ WfPara
 // primary rays (kernels.py:1219-1399) in one kernel.  Camera rays are coherent, so nothing is gained
 // by sending them through the queues: the ray is generated in registers, traced, shaded, and only
 // the surviving bounce ray is appended (one atomic per warp) to queue 1, where wave 1 picks it up.
-template <bool COUNT>
+template <bool COUNT, bool FULL>
 __global__ void __launch_bounds__(256) k_wf_primary(const __grid_constant__ WfParams P) {
     extern __shared__ float4 s_nodes[];
     const DScene& S = P.S;
@@ -717,6 +733,7 @@ __global__ void __launch_bounds__(256) k_wf_primary(const __grid_constant__ WfPa
             const int pixel = P.y0 * P.W + (id - slot * P.N);
             const int py = pixel / P.W, px = pixel - py * P.W;
             rng = ptm::rng_seed(P.seed, (uint32_t)pixel, (uint32_t)(P.sample_base + slot));
+            const float time = FULL ? ptm::path_time(rng) : 0.0f;
             f3 o, d;
             get_ray(P.cam, px, py, rng, o, d);                  // NOT normalised, kernels.py:1229-1233
             float* sp = P.Q.slab + 3 * (size_t)id;
@@ -729,13 +746,13 @@ __global__ void __launch_bounds__(256) k_wf_primary(const __grid_constant__ WfPa
                 float t, t_exit = 0.0f;
                 int ref, eref = kRefNone;
                 if (COUNT) lc.bounces++;
-                traverse<COUNT>(S, s_nodes, P.n_snodes, o, d, 0.001f, 1e10f, t, ref, lc);
+                traverse<COUNT, FULL>(S, s_nodes, P.n_snodes, o, d, 0.001f, 1e10f, t, ref, lc, time);
                 if (ref != kRefNone && S.has_media) {
                     const int header = __float_as_int(__ldg(S.materials + 3 * mat_id_of(S, ref)).x);
-                    if (mat_is_medium(header)) traverse<COUNT>(S, s_nodes, P.n_snodes, o, d, t + 0.0001f, 1e10f, t_exit, eref, lc);
+                    if (mat_is_medium(header)) traverse<COUNT, FULL>(S, s_nodes, P.n_snodes, o, d, t + 0.0001f, 1e10f, t_exit, eref, lc, time);
                 }
-                emit_next = wf_shade_one(S, bg, max_depth, sp, o, d, thr, depth, rng, t, ref, t_exit, eref != kRefNone,
-                                         no, nd, nthr, ndepth);
+                emit_next = wf_shade_one<FULL>(S, bg, max_depth, sp, o, d, thr, depth, rng, t, ref, t_exit, eref != kRefNone,
+                                         no, nd, nthr, ndepth, time);
                 o = no; d = nd; thr = nthr; depth = ndepth;
             }
         }
@@ -763,7 +780,7 @@ __global__ void k_wf_reset(const __grid_constant__ WfParams P) {
 // looping wave by wave (traverse, exit search for medium boundaries, wf_shade_one) until the path
 // ends or the wave budget max_depth (renderer.py:313) is used up -- the same per-ray operations in
 // the same order as the wave kernels, so results are identical.
-template <bool COUNT>
+template <bool COUNT, bool FULL>
 __global__ void __launch_bounds__(256) k_wf_tail(const __grid_constant__ WfParams P) {
     extern __shared__ float4 s_nodes[];
     const DScene& S = P.S;
@@ -782,18 +799,19 @@ __global__ void __launch_bounds__(256) k_wf_tail(const __grid_constant__ WfParam
         uint32_t rng = __float_as_uint(c.z);
         int depth = __float_as_int(c.w);
         float* sp = P.Q.slab + 3 * (size_t)path_id;
+        const float time = wf_path_time<FULL>(P, path_id);
         for (int wave = P.bounce; wave < max_depth; wave++) {
             float t, t_exit = 0.0f;
             int ref, eref = kRefNone;
             if (COUNT) lc.bounces++;
-            traverse<COUNT>(S, s_nodes, P.n_snodes, o, d, 0.001f, 1e10f, t, ref, lc);
+            traverse<COUNT, FULL>(S, s_nodes, P.n_snodes, o, d, 0.001f, 1e10f, t, ref, lc, time);
             if (ref != kRefNone && S.has_media) {
                 const int header = __float_as_int(__ldg(S.materials + 3 * mat_id_of(S, ref)).x);
-                if (mat_is_medium(header)) traverse<COUNT>(S, s_nodes, P.n_snodes, o, d, t + 0.0001f, 1e10f, t_exit, eref, lc);
+                if (mat_is_medium(header)) traverse<COUNT, FULL>(S, s_nodes, P.n_snodes, o, d, t + 0.0001f, 1e10f, t_exit, eref, lc, time);
             }
             f3 no, nd, nthr;
             int ndepth;
-            if (!wf_shade_one(S, bg, max_depth, sp, o, d, thr, depth, rng, t, ref, t_exit, eref != kRefNone, no, nd, nthr, ndepth))
+            if (!wf_shade_one<FULL>(S, bg, max_depth, sp, o, d, thr, depth, rng, t, ref, t_exit, eref != kRefNone, no, nd, nthr, ndepth, time))
                 break;
             o = no; d = nd; thr = nthr; depth = ndepth;
         }
@@ -889,6 +907,7 @@ __global__ void k_math_eval(int fn, int n, const float* a, const float* b, float
         case 3: r = ptm::acos_c(x); break;
         case 4: r = ptm::atan2_c(x, b[i]); break;
         case 5: r = ptm::pow5_c(x); break;
+        case 7: r = ptm::exp_c(x); break;
     }
     out[i] = r;
 }
@@ -1016,6 +1035,8 @@ int pt_set_scene(PtContext* ctx, const void* device_blob, const PtPackedInfo* in
     S.mat_base[PT_PRIM_TRIANGLE] = info->num_spheres;
     S.mat_base[PT_PRIM_QUAD] = info->num_spheres + info->num_triangles;
     S.has_media = info->has_media;
+    S.full_features = info->full_features;
+    S.sphere_motion = reinterpret_cast<const float4*>(base + info->off_sphere_motion);
     if (info->max_depth_tree > kStackSize)
         return set_error(PT_ERR_CAPACITY, "pt_set_scene: BVH deeper than the 64-entry traversal stack (kernels.py:649)");
     ctx->info = *info;
@@ -1064,13 +1085,16 @@ int pt_render_megakernel(PtContext* ctx, float* accum, int W, int H, int y0, int
     P.n_snodes = pick_snodes(ctx, 2);
     const size_t smem = (size_t)P.n_snodes * 64;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (ctx->count) {
-        if ((rc = set_smem(k_megakernel<true>, smem))) return rc;
-        k_megakernel<true><<<blocks, bt, smem, st>>>(P);
-    } else {
-        if ((rc = set_smem(k_megakernel<false>, smem))) return rc;
-        k_megakernel<false><<<blocks, bt, smem, st>>>(P);
-    }
+    const bool full = ctx->scene.full_features != 0;
+    auto go = [&](auto kernel) -> int {
+        int r = set_smem(kernel, smem);
+        if (r) return r;
+        kernel<<<blocks, bt, smem, st>>>(P);
+        return PT_OK;
+    };
+    if (ctx->count) rc = full ? go(k_megakernel<true, true>) : go(k_megakernel<true, false>);
+    else rc = full ? go(k_megakernel<false, true>) : go(k_megakernel<false, false>);
+    if (rc) return rc;
     PT_CUDA(cudaGetLastError());
     return PT_OK;
 }
@@ -1141,11 +1165,22 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int bt = 256;
     const int grid_persist = ctx->num_sms * ctx->wf_blocks_per_sm;
+    const bool full = ctx->scene.full_features != 0;
+    // kernel instantiations for this context: counting on/off x feature mode
+    void (*k_primary)(const WfParams) = nullptr;
+    void (*k_extend)(const WfParams) = nullptr;
+    void (*k_tail)(const WfParams) = nullptr;
+    void (*k_shade)(const WfParams) = full ? k_wf_shade<true> : k_wf_shade<false>;
     if (ctx->count) {
-        if ((rc = set_smem(k_wf_extend<true>, smem)) || (rc = set_smem(k_wf_tail<true>, smem)) || (rc = set_smem(k_wf_primary<true>, smem))) return rc;
+        k_primary = full ? k_wf_primary<true, true> : k_wf_primary<true, false>;
+        k_extend = full ? k_wf_extend<true, true> : k_wf_extend<true, false>;
+        k_tail = full ? k_wf_tail<true, true> : k_wf_tail<true, false>;
     } else {
-        if ((rc = set_smem(k_wf_extend<false>, smem)) || (rc = set_smem(k_wf_tail<false>, smem)) || (rc = set_smem(k_wf_primary<false>, smem))) return rc;
+        k_primary = full ? k_wf_primary<false, true> : k_wf_primary<false, false>;
+        k_extend = full ? k_wf_extend<false, true> : k_wf_extend<false, false>;
+        k_tail = full ? k_wf_tail<false, true> : k_wf_tail<false, false>;
     }
+    if ((rc = set_smem(k_primary, smem)) || (rc = set_smem(k_extend, smem)) || (rc = set_smem(k_tail, smem))) return rc;
     const int max_depth = ctx->cam.max_depth;
     for (int s = sample_begin; s < sample_begin + sample_count; s += (int)B) {
         P.sample_base = s;
@@ -1161,23 +1196,20 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
             // the first wave(s) in one kernel; survivors land in the queue the next wave reads
             P.fused_waves = ctx->wf_fuse_primary < waves ? ctx->wf_fuse_primary : waves;
             k_wf_reset<<<1, 32, 0, st>>>(P);
-            if (ctx->count) k_wf_primary<true><<<grid_wide, bt, smem, st>>>(P);
-            else k_wf_primary<false><<<grid_wide, bt, smem, st>>>(P);
+            k_primary<<<grid_wide, bt, smem, st>>>(P);
             first_wave = P.fused_waves;
         } else {
             k_wf_generate<<<grid_wide, bt, 0, st>>>(P);
         }
         for (int b = first_wave; b < waves; b++) {        // renderer.py:313; no host read-back of the ray count
             P.bounce = b;
-            if (ctx->count) k_wf_extend<true><<<grid, bt, smem, st>>>(P);
-            else k_wf_extend<false><<<grid, bt, smem, st>>>(P);
+            k_extend<<<grid, bt, smem, st>>>(P);
             if (P.sort) k_wf_bin<<<grid_wide, bt, 0, st>>>(P);
-            k_wf_shade<<<grid_wide, bt, 0, st>>>(P);
+            k_shade<<<grid_wide, bt, 0, st>>>(P);
         }
         if (waves < max_depth) {                          // whatever is still alive: finish in one launch
             P.bounce = waves > first_wave ? waves : first_wave;
-            if (ctx->count) k_wf_tail<true><<<grid_wide, bt, smem, st>>>(P);
-            else k_wf_tail<false><<<grid_wide, bt, smem, st>>>(P);
+            k_tail<<<grid_wide, bt, smem, st>>>(P);
         }
         int grid_res = (int)((n + bt - 1) / bt);
         if (grid_res > ctx->num_sms * 8) grid_res = ctx->num_sms * 8;

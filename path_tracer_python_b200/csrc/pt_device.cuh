@@ -55,6 +55,9 @@ struct DScene {
     int num_inner;
     int mat_base[3];          // offset of each prim type inside prim_mat
     int has_media;
+    // "full" feature mode (moving spheres, subsurface materials); 0 = the reference's Taichi path
+    const float4* sphere_motion;   // centre(1) - centre(0) per sphere
+    int full_features;
 };
 
 struct DCounters {
@@ -71,9 +74,21 @@ __device__ __forceinline__ int ref_index(int ref) { return (~ref) >> 2; }
 // ---- primitive tests: arithmetic identical to hit_sphere / hit_triangle / hit_quad; they return
 //      only t (the caller keeps t and the primitive reference).
 // kernels.py:208-248
-__device__ __forceinline__ bool hit_sphere_t(const DScene& S, int idx, f3 o, f3 d, float t_min, float t_max, float& t) {
+// centre(time) = centre(0) + time * motion (core/sphere.py:36); time is only used in full mode
+template <bool FULL>
+__device__ __forceinline__ f3 sphere_center(const DScene& S, int idx, float4 s, float time) {
+    f3 c = mk3(s.x, s.y, s.z);
+    if (FULL) {
+        float4 m = __ldg(S.sphere_motion + idx);
+        c = c + time * mk3(m.x, m.y, m.z);
+    }
+    return c;
+}
+template <bool FULL>
+__device__ __forceinline__ bool hit_sphere_t(const DScene& S, int idx, f3 o, f3 d, float t_min, float t_max, float& t,
+                                             float time) {
     float4 s = __ldg(S.spheres + idx);
-    f3 oc = mk3(s.x, s.y, s.z) - o;
+    f3 oc = sphere_center<FULL>(S, idx, s, time) - o;
     float a = dot(d, d);
     float h = dot(d, oc);
     float c = dot(oc, oc) - s.w * s.w;
@@ -130,12 +145,14 @@ __device__ __forceinline__ bool hit_quad_t(const DScene& S, int idx, f3 o, f3 d,
 }
 
 // hit point and shading normal of the closest hit, exactly as hit_* would have returned them
-__device__ __forceinline__ void finalize_hit(const DScene& S, int ref, f3 o, f3 d, float t, f3& p, f3& n) {
+template <bool FULL = false>
+__device__ __forceinline__ void finalize_hit(const DScene& S, int ref, f3 o, f3 d, float t, f3& p, f3& n,
+                                             float time = 0.0f) {
     int type = ref_type(ref), idx = ref_index(ref);
     p = o + t * d;
     if (type == PT_PRIM_SPHERE) {
         float4 s = __ldg(S.spheres + idx);
-        n = vdiv(p - mk3(s.x, s.y, s.z), s.w);                 // kernels.py:246 (never flipped)
+        n = vdiv(p - sphere_center<FULL>(S, idx, s, time), s.w);     // kernels.py:246 (never flipped)
     } else if (type == PT_PRIM_QUAD) {
         float4 q0 = __ldg(S.quads + 4 * idx);
         f3 nn = mk3(q0.x, q0.y, q0.z);
@@ -173,6 +190,7 @@ __device__ __forceinline__ float fmin3(float a, float b, float c) {
 
 struct TravState {
     f3 o, d, inv;
+    float time;          // shutter time of the path (full feature mode; 0 otherwise)
     float t_min, best_t;
     int best_ref;
     int cur;     // >= 0 inner node, < 0 leaf reference, kRefNone = traversal finished
@@ -181,9 +199,10 @@ struct TravState {
 
 template <bool COUNT>
 __device__ __forceinline__ void trav_begin(TravState& T, const DScene& S, f3 o, f3 d, float t_min, float t_max,
-                                           LocalCounters& lc) {
+                                           LocalCounters& lc, float time = 0.0f) {
     T.o = o;
     T.d = d;
+    T.time = time;
     T.inv = mk3(fabsf(d.x) > 1e-8f ? ptm::fdiv(1.0f, d.x) : 1e8f, fabsf(d.y) > 1e-8f ? ptm::fdiv(1.0f, d.y) : 1e8f,
                 fabsf(d.z) > 1e-8f ? ptm::fdiv(1.0f, d.z) : 1e8f);
     T.t_min = t_min;
@@ -212,7 +231,7 @@ __device__ __forceinline__ int trav_pop(TravState& T, const StackEntry* stack) {
 
 // Runs the traversal until it finishes (returns true) or, when min_active > 0, until fewer than
 // min_active lanes of the warp are still inside the loop (returns false; call again to resume).
-template <bool COUNT>
+template <bool COUNT, bool FULL = false>
 __device__ __forceinline__ bool trav_run(TravState& T, const DScene& S, const float4* __restrict__ s_nodes, int n_snodes,
                                          StackEntry* stack, int min_active, LocalCounters& lc) {
     const f3 o = T.o, inv = T.inv;
@@ -263,7 +282,7 @@ __device__ __forceinline__ bool trav_run(TravState& T, const DScene& S, const fl
             const int type = ref_type(T.cur), idx = ref_index(T.cur);
             float t;
             bool hit;
-            if (type == PT_PRIM_SPHERE) { if (COUNT) lc.sphere_tests++; hit = hit_sphere_t(S, idx, T.o, T.d, t_min, T.best_t, t); }
+            if (type == PT_PRIM_SPHERE) { if (COUNT) lc.sphere_tests++; hit = hit_sphere_t<FULL>(S, idx, T.o, T.d, t_min, T.best_t, t, T.time); }
             else if (type == PT_PRIM_QUAD) { if (COUNT) lc.quad_tests++; hit = hit_quad_t(S, idx, T.o, T.d, t_min, T.best_t, t); }
             else { if (COUNT) lc.triangle_tests++; hit = hit_triangle_t(S, idx, T.o, T.d, t_min, T.best_t, t); }
             if (hit && t < T.best_t) { T.best_t = t; T.best_ref = T.cur; }   // kernels.py:691 (strict)
@@ -282,7 +301,7 @@ __device__ __forceinline__ bool trav_run(TravState& T, const DScene& S, const fl
 // model of this policy predicts ~25).  Returns when fewer than min_active lanes still traverse.
 // `done` is set for a lane when its traversal has finished.  Visiting order per lane is unchanged,
 // so results are bit-identical to trav_run.
-template <bool COUNT>
+template <bool COUNT, bool FULL = false>
 __device__ __forceinline__ void trav_run_vote(TravState& T, bool active, bool& done, const DScene& S,
                                               const float4* __restrict__ s_nodes, int n_snodes, StackEntry* stack,
                                               int min_active, int vote_num, LocalCounters& lc) {
@@ -345,7 +364,7 @@ __device__ __forceinline__ void trav_run_vote(TravState& T, bool active, bool& d
                 const int type = ref_type(T.cur), idx = ref_index(T.cur);
                 float t;
                 bool hit;
-                if (type == PT_PRIM_SPHERE) { if (COUNT) lc.sphere_tests++; hit = hit_sphere_t(S, idx, T.o, T.d, t_min, T.best_t, t); }
+                if (type == PT_PRIM_SPHERE) { if (COUNT) lc.sphere_tests++; hit = hit_sphere_t<FULL>(S, idx, T.o, T.d, t_min, T.best_t, t, T.time); }
                 else if (type == PT_PRIM_QUAD) { if (COUNT) lc.quad_tests++; hit = hit_quad_t(S, idx, T.o, T.d, t_min, T.best_t, t); }
                 else { if (COUNT) lc.triangle_tests++; hit = hit_triangle_t(S, idx, T.o, T.d, t_min, T.best_t, t); }
                 if (hit && t < T.best_t) { T.best_t = t; T.best_ref = T.cur; }   // kernels.py:691 (strict)
@@ -357,13 +376,14 @@ __device__ __forceinline__ void trav_run_vote(TravState& T, bool active, bool& d
 }
 
 // One-shot traversal (probe / wavefront kernels).
-template <bool COUNT>
+template <bool COUNT, bool FULL = false>
 __device__ __forceinline__ void traverse(const DScene& S, const float4* __restrict__ s_nodes, int n_snodes, f3 o, f3 d,
-                                         float t_min, float t_max, float& best_t, int& best_ref, LocalCounters& lc) {
+                                         float t_min, float t_max, float& best_t, int& best_ref, LocalCounters& lc,
+                                         float time = 0.0f) {
     StackEntry stack[kStackSize];
     TravState T;
-    trav_begin<COUNT>(T, S, o, d, t_min, t_max, lc);
-    trav_run<COUNT>(T, S, s_nodes, n_snodes, stack, 0, lc);
+    trav_begin<COUNT>(T, S, o, d, t_min, t_max, lc, time);
+    trav_run<COUNT, FULL>(T, S, s_nodes, n_snodes, stack, 0, lc);
     best_t = T.best_t;
     best_ref = T.best_ref;
 }
@@ -536,13 +556,81 @@ __device__ __forceinline__ float reflectance(float cosine, float ref_idx) {
     return r0 + (1.0f - r0) * ptm::pow5_c(1.0f - cosine);
 }
 
-// emitted + scatter for a surface hit (kernels.py:789-917). Returns scattered.
-__device__ __forceinline__ bool shade_surface(const DScene& S, const Mat& m, int ref, f3 ray_dir, f3 hp, f3 normal,
+// core/material.py:258-276 _sample_henyey_greenstein (full feature mode)
+__device__ __noinline__ f3 sample_henyey_greenstein(f3 incident, float g, uint32_t& rng) {
+    if (fabsf(g) < 1e-3f) return random_unit_vector(rng);
+    float sqr_term = ptm::fdiv(1.0f - g * g, 1.0f - g + 2.0f * g * ptm::rng_next(rng));
+    float cos_theta = ptm::fdiv(1.0f + g * g - sqr_term * sqr_term, 2.0f * g);
+    float sin_theta = ptm::fsqrt(max2(0.0f, 1.0f - cos_theta * cos_theta));
+    float phi = 6.2831853f * ptm::rng_next(rng);
+    f3 w = normalized(incident);
+    f3 a = fabsf(w.x) > 0.9f ? mk3(1.0f, 0.0f, 0.0f) : mk3(0.0f, 1.0f, 0.0f);
+    f3 v = normalized(cross(w, a));
+    f3 u = cross(w, v);
+    float sn, cs;
+    ptm::sincos_c(phi, &sn, &cs);
+    return normalized(((u * cs) * sin_theta + (v * sn) * sin_theta) + w * cos_theta);
+}
+
+// subsurface_simple / subsurface_volumetric (core/material.py:144-256), full feature mode only.
+// `hp` is replaced by the (possibly displaced) origin of the scattered ray.
+__device__ __noinline__ bool shade_subsurface(const Mat& m, f3 ray_dir, f3& hp, f3 normal, uint32_t& rng,
+                                              f3& scatter_dir, f3& attenuation) {
+    const f3 nf = dot(ray_dir, normal) < 0.0f ? normal : -normal;     // face-forwarded, core/hittable.py:17-22
+    const f3 albedo = m.c1;
+    if (mat_type(m.header) == 5) {
+        const float scatter_distance = m.scalar;
+        f3 dir;
+        if (ptm::rng_next(rng) < 0.5f) {
+            dir = nf + random_unit_vector(rng);
+        } else {
+            f3 ruv = random_unit_vector(rng);
+            f3 displacement = (ruv * scatter_distance) * ptm::rng_next(rng);
+            hp = hp + displacement;
+            dir = nf + random_unit_vector(rng);
+        }
+        if (fabsf(dir.x) < 1e-8f && fabsf(dir.y) < 1e-8f && fabsf(dir.z) < 1e-8f) dir = nf;
+        scatter_dir = dir;
+        attenuation = albedo;
+        return true;
+    }
+    const float sigma_s = m.scalar, sigma_a = m.c2.x, g = m.c2.y;
+    const float sigma_t = sigma_s + sigma_a;
+    const f3 entry = hp;
+    f3 pos = hp - nf * 0.001f;
+    f3 dirn = normalized(ray_dir);
+    f3 thr = mk3(1.0f, 1.0f, 1.0f);
+    for (int it = 0; it < 64; it++) {
+        float t = ptm::fdiv(-ptm::log_c(max2(ptm::rng_next(rng), 1e-10f)), sigma_t);
+        pos = pos + dirn * t;
+        f3 dv = pos - entry;
+        float dist = ptm::fsqrt(dot(dv, dv));
+        float exit_probability = 1.0f - ptm::exp_c(-dist * 0.5f);
+        if (ptm::rng_next(rng) < exit_probability) {
+            f3 dir = nf + random_unit_vector(rng);
+            if (fabsf(dir.x) < 1e-8f && fabsf(dir.y) < 1e-8f && fabsf(dir.z) < 1e-8f) dir = nf;
+            hp = pos;
+            scatter_dir = dir;
+            attenuation = thr * albedo;
+            return true;
+        }
+        if (ptm::rng_next(rng) < ptm::fdiv(sigma_a, sigma_t)) { attenuation = mk3(0.0f, 0.0f, 0.0f); return false; }
+        dirn = sample_henyey_greenstein(dirn, g, rng);
+        thr = thr * albedo;
+    }
+    return false;
+}
+
+// emitted + scatter for a surface hit (kernels.py:789-917). Returns scattered.  `hp` is in/out: the
+// scattered ray starts at the hit point, except for the full-mode subsurface materials.
+template <bool FULL = false>
+__device__ __forceinline__ bool shade_surface(const DScene& S, const Mat& m, int ref, f3 ray_dir, f3& hp, f3 normal,
                                               uint32_t& rng, f3& emit, f3& scatter_dir, f3& attenuation) {
     int mt = mat_type(m.header);
     emit = mk3(0.0f, 0.0f, 0.0f);
     scatter_dir = mk3(0.0f, 0.0f, 0.0f);
     attenuation = mk3(1.0f, 1.0f, 1.0f);
+    if (mt >= 5) return FULL ? shade_subsurface(m, ray_dir, hp, normal, rng, scatter_dir, attenuation) : false;
     if (mt == 0) {
         attenuation = eval_texture(S, m, ref, hp);
         scatter_dir = random_cosine_direction(normal, rng);

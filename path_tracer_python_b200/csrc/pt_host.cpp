@@ -60,12 +60,19 @@ MatRec make_mat(const PtHostMaterials& m, int i) {
         scalar = m.ir[i];
     } else if (mt == 3) {
         c1 = m.emit + 3 * i;
+    } else if (mt == 5) {                  // subsurface_simple (full feature mode): scalar = scatter distance
+        scalar = m.fuzz[i];
+        c1 = m.albedo + 3 * i;
+    } else if (mt == 6) {                  // subsurface_volumetric: scalar = sigma_s, c2 = (sigma_a, g, 0)
+        scalar = m.fuzz[i];
+        c1 = m.albedo + 3 * i;
     }
     const int is_med = m.is_medium[i] > 0 ? 1 : 0;
     r.w[0] = (uint32_t)(mt & 15) | ((uint32_t)(tt & 15) << 4) | ((uint32_t)is_med << 8) | ((uint32_t)(img + 1) << 16);
     r.w[1] = fbits(scalar);
     if (c1) for (int k = 0; k < 3; k++) r.w[2 + k] = fbits(c1[k]);
     if (c2) for (int k = 0; k < 3; k++) r.w[5 + k] = fbits(c2[k]);
+    if (mt == 6) { r.w[5] = fbits(m.ir[i]); r.w[6] = fbits(m.texture_scale[i]); }
     if (is_med) {
         r.w[8] = fbits(m.medium_density[i]);
         for (int k = 0; k < 3; k++) r.w[9 + k] = fbits(m.medium_albedo[3 * i + k]);
@@ -168,6 +175,8 @@ int pt_pack_scene_info(const PtHostScene* s, PtPackedInfo* info) {
     info->off_prim_mat = section((uint64_t)mt.ids.size() * 4);
     info->off_materials = section((uint64_t)mt.recs.size() * 48);
     info->off_perlin = section(256 * 16 + 768);
+    info->full_features = s->full_features ? 1 : 0;
+    info->off_sphere_motion = info->full_features ? section((uint64_t)s->num_spheres * 16) : 0;
     info->off_images = off;
     uint64_t ioff = 0;
     for (int i = 0; i < s->num_images; i++) {
@@ -229,6 +238,11 @@ int pt_pack_scene(const PtHostScene* s, const PtPackedInfo* info, void* host_blo
         t[0] = v0[0]; t[1] = v0[1]; t[2] = v0[2]; t[3] = n[0];
         t[4] = e1[0]; t[5] = e1[1]; t[6] = e1[2]; t[7] = n[1];
         t[8] = e2[0]; t[9] = e2[1]; t[10] = e2[2]; t[11] = n[2];
+    }
+
+    if (info->full_features && s->sphere_motion) {
+        float* mo = reinterpret_cast<float*>(base + info->off_sphere_motion);
+        for (int i = 0; i < s->num_spheres; i++) { mo[4 * i] = s->sphere_motion[3 * i]; mo[4 * i + 1] = s->sphere_motion[3 * i + 1]; mo[4 * i + 2] = s->sphere_motion[3 * i + 2]; }
     }
 
     // ---- materials

@@ -11,7 +11,9 @@ no per-sample host synchronisation, no CPU fallback.
 Extra (keyword-only) knobs: ``seed`` (device RNG key), ``device`` (GPU ordinal),
 ``spp_per_launch`` (samples folded into one megakernel launch; None = all), ``process_group``
 (torch.distributed group: samples are split across ranks and the accumulation buffer is summed
-with NCCL, see distributed.py).
+with NCCL, see distributed.py), ``features`` ("taichi_compat" = exactly what the reference's Taichi
+path renders; "full" = additionally motion blur and the subsurface materials, which only the
+reference's pure-Python tracer has).
 """
 from __future__ import annotations
 
@@ -35,7 +37,7 @@ def _color_tuple(c):
 class TaichiRenderer:
     def __init__(self, world, cam, img_path: str, *, seed: int = 0, device: int | None = None,
                  spp_per_launch: int | None = None, process_group=None, compiled_scene: dict | None = None,
-                 quiet: bool = False):
+                 quiet: bool = False, features: str = "taichi_compat"):
         self.timing = {k: 0.0 for k in ("taichi_init", "scene_compile", "bvh_compile", "bvh_flatten", "camera_upload",
                                         "gpu_upload", "kernel_warmup", "total_setup")}
         self.sample_times = []
@@ -62,7 +64,7 @@ class TaichiRenderer:
         perlin = _sc.perlin_tables()
 
         t0 = time.time()
-        cs = dict(compiled_scene) if compiled_scene is not None else _sc.compile_scene(world)
+        cs = dict(compiled_scene) if compiled_scene is not None else _sc.compile_scene(world, features)
         self.timing["scene_compile"] = time.time() - t0
 
         t0 = time.time()

@@ -154,12 +154,21 @@ class isotropic:
         return cls(solid_color(albedo))
 
 
-class subsurface_volumetric:
-    """Kept for API parity; the Taichi path (and therefore this renderer in its reference-compatible
-    mode) renders it as 0.8-grey Lambertian (reference scene_compiler.py:406-417)."""
+class subsurface_simple:
+    """core/material.py:144-173.  Rendered by the `full` feature mode; the reference's Taichi path
+    (and this renderer's default `taichi_compat` mode) turns it into 0.8-grey Lambertian."""
 
-    def __init__(self, albedo, scattering_coeff=0.08, absorption_coeff=0.8, g=0.7):
-        self.albedo, self.scattering_coeff, self.absorption_coeff, self.g = albedo, scattering_coeff, absorption_coeff, g
+    def __init__(self, albedo, scatter_distance):
+        self.albedo, self.scatter_distance = albedo, scatter_distance
+
+
+class subsurface_volumetric:
+    """core/material.py:175-276 (random walk with Henyey-Greenstein phase function)."""
+
+    def __init__(self, albedo, scatter_coeff=0.08, absorb_coeff=0.8, g=0.0):
+        self.albedo = albedo
+        self.sigma_s, self.sigma_a, self.g = scatter_coeff, absorb_coeff, g
+        self.sigma_t = scatter_coeff + absorb_coeff
 
 
 # ---- geometry

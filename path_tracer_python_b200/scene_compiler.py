@@ -18,6 +18,7 @@ import numpy as np
 
 PRIM_SPHERE, PRIM_TRIANGLE, PRIM_QUAD = 0, 1, 2
 MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC, MAT_EMISSIVE, MAT_ISOTROPIC = 0, 1, 2, 3, 4
+MAT_SSS_SIMPLE, MAT_SSS_VOLUMETRIC = 5, 6        # `full` feature mode only
 TEX_SOLID, TEX_CHECKER, TEX_IMAGE, TEX_NOISE = 0, 1, 2, 3
 
 _PREFIX = {PRIM_SPHERE: "sphere", PRIM_TRIANGLE: "triangle", PRIM_QUAD: "quad"}
@@ -120,7 +121,7 @@ def build_medium_registry(world):
     return reg
 
 
-def _material_arrays(prims, ref_point_of, image_registry, medium_registry):
+def _material_arrays(prims, ref_point_of, image_registry, medium_registry, full=False):
     n = len(prims)
     a = {
         "material_type": np.zeros(n, np.int32), "material_albedo": np.zeros((n, 3), np.float32),
@@ -170,7 +171,15 @@ def _material_arrays(prims, ref_point_of, image_registry, medium_registry):
             except Exception:
                 emit = (1.0, 1.0, 1.0)
             albedo = c1 = c2 = (0.0, 0.0, 0.0)
-        # anything else (isotropic, subsurface_*, ...) stays 0.8-grey Lambertian (:406-417)
+        elif full and mk == "subsurface_simple":
+            # full feature mode: parameters ride in the existing arrays (fuzz = scatter distance)
+            mtype, fuzz = MAT_SSS_SIMPLE, mat.scatter_distance
+            albedo = c1 = c2 = _xyz(mat.albedo)
+        elif full and mk == "subsurface_volumetric":
+            # fuzz = sigma_s, ir = sigma_a, texture_scale = g
+            mtype, fuzz, ir, scale = MAT_SSS_VOLUMETRIC, mat.sigma_s, mat.sigma_a, mat.g
+            albedo = c1 = c2 = _xyz(mat.albedo)
+        # anything else (isotropic, subsurface_* in compat mode, ...) stays 0.8-grey Lambertian (:406-417)
         a["material_type"][i] = mtype
         a["material_albedo"][i] = albedo
         a["material_fuzz"][i] = fuzz
@@ -189,8 +198,16 @@ def _material_arrays(prims, ref_point_of, image_registry, medium_registry):
     return a
 
 
-def compile_scene(world) -> dict:
-    """world -> CompiledScene dict (geometry, materials, image textures; no BVH, no Perlin)."""
+def compile_scene(world, features: str = "taichi_compat") -> dict:
+    """world -> CompiledScene dict (geometry, materials, image textures; no BVH, no Perlin).
+
+    features="taichi_compat" (default) reproduces the reference's Taichi path exactly: sphere
+    motion baked at time 0, subsurface materials -> grey Lambertian.  features="full" additionally
+    exports what only the reference's pure-Python tracer renders: `sphere_motion` (centre(1) -
+    centre(0), core/sphere.py:22-36) and the two subsurface materials (core/material.py:144-276)."""
+    if features not in ("taichi_compat", "full"):
+        raise ValueError("features must be 'taichi_compat' or 'full'")
+    full = features == "full"
     image_registry, image_list = build_image_registry(world)
     medium_registry = build_medium_registry(world)
     spheres, quads, triangles = extract_primitives(world)
@@ -215,8 +232,15 @@ def compile_scene(world) -> dict:
     per_type = ((PRIM_SPHERE, spheres, lambda s: s.center.at(0.0)), (PRIM_QUAD, quads, lambda q: q.Q),
                 (PRIM_TRIANGLE, triangles, lambda t: t.v0))
     for pt, prims, ref_of in per_type:
-        for k, v in _material_arrays(prims, ref_of, image_registry, medium_registry).items():
+        for k, v in _material_arrays(prims, ref_of, image_registry, medium_registry, full).items():
             cs[f"{_PREFIX[pt]}_{k}"] = v
+    if full:
+        mo = np.zeros((len(spheres), 3), np.float32)
+        for i, sp in enumerate(spheres):
+            c0, c1 = sp.center.at(0.0), sp.center.at(1.0)
+            mo[i] = (c1.x - c0.x, c1.y - c0.y, c1.z - c0.z)
+        cs["sphere_motion"] = mo
+        cs["full_features"] = 1
     cs["num_images"] = len(image_list)
     for i, tex in enumerate(image_list):
         cs[f"image_{i}"] = image_to_u8(tex)
