@@ -37,6 +37,14 @@ class LivePreview:
         self._photo = ImageTk.PhotoImage(img)
         self.label.config(image=self._photo)
 
+    def update_image(self, img_u8: np.ndarray):
+        """Show an already tonemapped 8-bit frame (the renderer tonemaps on the device)."""
+        if self.window is None:
+            return
+        from PIL import Image, ImageTk
+        self._photo = ImageTk.PhotoImage(Image.fromarray(img_u8, mode="RGB"))
+        self.label.config(image=self._photo)
+
     def process_events(self):
         if self.window is not None:
             try:

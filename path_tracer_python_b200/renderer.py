@@ -140,7 +140,12 @@ class TaichiRenderer:
             s += n
             self.current_sample = s - s_begin
             if preview:
-                preview.update(self._accum.cpu().numpy(), self.current_sample, s_end - s_begin)
+                # progressive display without stalling the render: tonemap on the device, copy the
+                # 8-bit frame (W*H*3 bytes instead of 12x that) to pinned memory on a side stream,
+                # show the frame whose copy finished last time round
+                frame = self._preview_frame_async()
+                if frame is not None:
+                    preview.update_image(frame)
                 preview.process_events()
         if self.process_group is not None:
             from .distributed import reduce_accum
@@ -184,6 +189,35 @@ class TaichiRenderer:
         self.frame_h2d_bytes = int(self.engine.h2d_bytes) if reupload_scene else 0
         self.frame_d2h_bytes = int(self._host_accum.numel() * 4)
         return self._host_accum.numpy()
+
+    def _preview_frame_async(self):
+        """Returns the most recent *completed* 8-bit frame (or None) and starts the next device
+        tonemap + device->pinned-host copy on a side stream (reference: a blocking
+        `accum_buffer.to_numpy()` of the float buffer every sample, renderer.py:420-423)."""
+        dev = self.engine.device
+        if not hasattr(self, "_pv_stream"):
+            self._pv_stream = torch.cuda.Stream(device=dev)
+            self._pv_host = [torch.empty(self._accum.shape, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+            self._pv_event = [None, None]
+            self._pv_idx = 0
+        done = None
+        prev = self._pv_idx ^ 1
+        if self._pv_event[prev] is not None and self._pv_event[prev].query():
+            done = self._pv_host[prev].numpy()
+        i = self._pv_idx
+        if self._pv_event[i] is None or self._pv_event[i].query():
+            u8 = self.engine.tonemap(self._accum, max(1, self.current_sample))     # on the render stream, in order
+            ready = torch.cuda.Event()
+            ready.record()
+            with torch.cuda.stream(self._pv_stream):
+                self._pv_stream.wait_event(ready)
+                self._pv_host[i].copy_(u8, non_blocking=True)
+                u8.record_stream(self._pv_stream)
+                ev = torch.cuda.Event()
+                ev.record()
+            self._pv_event[i] = ev
+            self._pv_idx ^= 1
+        return done
 
     # ------------------------------------------------------------------ output
     def accum_numpy(self) -> np.ndarray:

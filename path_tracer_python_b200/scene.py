@@ -204,6 +204,81 @@ class triangle:
         self.normal = self.edge1.cross(self.edge2).unit_vector()
 
 
+class mesh:
+    """Triangle mesh from a Wavefront OBJ file, with the reference's constructor
+    (core/mesh.py:25-62: model folder or file, material, scale, offset) but its own parser -- no
+    pywavefront -- and array storage: vertices are transformed as `v * scale + offset`
+    (core/mesh.py:207-222), polygons fan-triangulated (:134-139), zero-area triangles dropped
+    (:224-246).  A million-triangle mesh stays three numpy arrays; `triangles` materialises
+    `triangle` objects only if somebody asks for them."""
+
+    def __init__(self, model_path, mat, scale: float = 1.0, offset=None, obj_filename=None, use_bvh: bool = True):
+        import os
+        self.mat, self.scale, self.offset = mat, scale, offset if offset is not None else point3(0, 0, 0)
+        path = str(model_path)
+        if os.path.isdir(path):
+            found = None
+            for root, _, files in sorted(os.walk(path)):
+                for f in sorted(files):
+                    if f.lower().endswith(".obj") and (obj_filename is None or f == obj_filename):
+                        found = os.path.join(root, f)
+                        break
+                if found:
+                    break
+            if not found:
+                raise FileNotFoundError(f"No OBJ files found in {path}")
+            path = found
+        elif not os.path.exists(path):
+            raise FileNotFoundError(f"Model path does not exist: {path}")
+        self.obj_file = path
+        self._load(path)
+
+    @classmethod
+    def from_arrays(cls, v0, v1, v2, mat):
+        self = cls.__new__(cls)
+        self.mat, self.scale, self.offset, self.obj_file = mat, 1.0, point3(0, 0, 0), None
+        self._set(np.asarray(v0, np.float64), np.asarray(v1, np.float64), np.asarray(v2, np.float64))
+        return self
+
+    def _load(self, path):
+        verts, faces = [], []
+        with open(path) as f:
+            for line in f:
+                if line.startswith("v "):
+                    p = line.split()
+                    verts.append((float(p[1]), float(p[2]), float(p[3])))
+                elif line.startswith("f "):
+                    idx = [int(tok.split("/")[0]) for tok in line.split()[1:]]
+                    idx = [i - 1 if i > 0 else len(verts) + i for i in idx]
+                    for k in range(1, len(idx) - 1):
+                        faces.append((idx[0], idx[k], idx[k + 1]))
+        if not faces:
+            raise ValueError("No valid triangles created from OBJ file")
+        V = np.asarray(verts, np.float64) * self.scale + np.array([self.offset.x, self.offset.y, self.offset.z])
+        F = np.asarray(faces, np.int64)
+        self._set(V[F[:, 0]], V[F[:, 1]], V[F[:, 2]])
+
+    def _set(self, v0, v1, v2):
+        cr = np.cross(v1 - v0, v2 - v0)
+        keep = (cr ** 2).sum(axis=1) >= 1e-10
+        self.v0, self.v1, self.v2 = v0[keep], v1[keep], v2[keep]
+        self.num_degenerate = int((~keep).sum())
+        if not len(self.v0):
+            raise ValueError("No valid triangles created from OBJ file")
+        self._triangles = None
+
+    def tri_arrays(self):
+        """(v0, v1, v2) float64 arrays -- the scene compiler's fast path."""
+        return self.v0, self.v1, self.v2
+
+    @property
+    def triangles(self):
+        if self._triangles is None:
+            self._triangles = [triangle(point3(*a), point3(*b), point3(*c), self.mat)
+                               for a, b, c in zip(self.v0, self.v1, self.v2)]
+        return self._triangles
+
+
 class hittable_list:
     def __init__(self, objects=None):
         self.objects = list(objects) if objects else []

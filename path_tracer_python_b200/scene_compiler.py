@@ -44,8 +44,11 @@ def _walk(obj, visit, through_media: bool, through_mesh: bool):
             _walk(obj.boundary, visit, through_media, through_mesh)
     elif k == "mesh":
         if through_mesh:
-            for tri in obj.triangles:
-                visit(tri)
+            if hasattr(obj, "tri_arrays"):
+                visit(obj)                      # array-backed mesh: one chunk, no per-triangle objects
+            else:
+                for tri in obj.triangles:
+                    visit(tri)
     elif k in ("Sphere", "quad", "triangle"):
         visit(obj)
     elif k == "hittable_list":
@@ -66,7 +69,7 @@ def extract_primitives(world):
     def visit(p):
         if id(p) not in seen:
             seen.add(id(p))
-            out[_kind(p)].append(p)
+            out["triangle" if _kind(p) == "mesh" else _kind(p)].append(p)
 
     _walk(world, visit, through_media=True, through_mesh=True)
     return out["Sphere"], out["quad"], out["triangle"]
@@ -198,6 +201,15 @@ def _material_arrays(prims, ref_point_of, image_registry, medium_registry, full=
     return a
 
 
+class _MeshTri:
+    """Stand-in for "a triangle of this mesh" when evaluating the mesh's material once."""
+
+    def __init__(self, m):
+        self.mat = m.mat
+        a = m.tri_arrays()[0][0]
+        self.v0 = type("P", (), {"x": float(a[0]), "y": float(a[1]), "z": float(a[2])})()
+
+
 def compile_scene(world, features: str = "taichi_compat") -> dict:
     """world -> CompiledScene dict (geometry, materials, image textures; no BVH, no Perlin).
 
@@ -227,11 +239,49 @@ def compile_scene(world, features: str = "taichi_compat") -> dict:
     for attr in ("Q", "u", "v", "normal", "w"):
         cs[f"quad_{attr}"] = vec_array(quads, attr)
     cs["quad_D"] = np.array([q.D for q in quads], np.float32).reshape(len(quads))
-    for attr in ("v0", "v1", "v2", "edge1", "edge2", "normal"):
-        cs[f"triangle_{attr}"] = vec_array(triangles, attr)
+    # triangles: single objects and array-backed mesh chunks, in traversal order; edges and the unit
+    # normal are computed in float64 like core/triangle.py:23-30, then narrowed to float32
+    chunks, tri_ref, tri_mat = [], [], []
+    for t in triangles:
+        if _kind(t) == "mesh":
+            v0, v1, v2 = t.tri_arrays()
+            chunks.append((np.asarray(v0, np.float64), np.asarray(v1, np.float64), np.asarray(v2, np.float64)))
+            tri_mat.append((t.mat, len(v0)))
+        else:
+            chunks.append(tuple(np.array([_xyz(getattr(t, a))], np.float64) for a in ("v0", "v1", "v2")))
+            tri_mat.append((t, 1))
+    if chunks:
+        v0, v1, v2 = (np.concatenate([c[k] for c in chunks]) for k in range(3))
+    else:
+        v0 = v1 = v2 = np.zeros((0, 3), np.float64)
+    e1, e2 = v1 - v0, v2 - v0
+    nrm = np.cross(e1, e2)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        nrm = nrm / np.sqrt((nrm ** 2).sum(axis=1, keepdims=True))
+    # single triangle objects carry their own (identically computed) attributes: use them verbatim
+    row = 0
+    for (obj, n) in tri_mat:
+        if n == 1 and _kind(obj) == "triangle":
+            e1[row], e2[row], nrm[row] = _xyz(obj.edge1), _xyz(obj.edge2), _xyz(obj.normal)
+        row += n
+    for name, arr in (("v0", v0), ("v1", v1), ("v2", v2), ("edge1", e1), ("edge2", e2), ("normal", nrm)):
+        cs[f"triangle_{name}"] = np.ascontiguousarray(arr, np.float32)
     per_type = ((PRIM_SPHERE, spheres, lambda s: s.center.at(0.0)), (PRIM_QUAD, quads, lambda q: q.Q),
                 (PRIM_TRIANGLE, triangles, lambda t: t.v0))
     for pt, prims, ref_of in per_type:
+        if pt == PRIM_TRIANGLE and any(_kind(t) == "mesh" for t in prims):
+            # one material row per mesh, repeated for its triangles
+            parts = []
+            for t in prims:
+                if _kind(t) == "mesh":
+                    proxy = _MeshTri(t)
+                    rows = _material_arrays([proxy], lambda q: q.v0, image_registry, medium_registry, full)
+                    parts.append({k: np.repeat(v, len(t.tri_arrays()[0]), axis=0) for k, v in rows.items()})
+                else:
+                    parts.append(_material_arrays([t], ref_of, image_registry, medium_registry, full))
+            for k in parts[0]:
+                cs[f"triangle_{k}"] = np.concatenate([p[k] for p in parts])
+            continue
         for k, v in _material_arrays(prims, ref_of, image_registry, medium_registry, full).items():
             cs[f"{_PREFIX[pt]}_{k}"] = v
     if full:

@@ -63,6 +63,27 @@ def test_image_texture_roundtrip():
     assert cs["sphere_texture_type"][0] == 2 and cs["sphere_texture_image_idx"][0] == 0
 
 
+def test_obj_mesh_loader_and_array_fast_path(tmp_path):
+    """core/mesh.py semantics without pywavefront: scale then offset, fan triangulation, negative
+    and v/vt/vn indices, degenerate faces dropped; array-backed compile == per-object compile."""
+    (tmp_path / "m").mkdir()
+    (tmp_path / "m" / "cube.obj").write_text(
+        "v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nv 0 0 1\nv 1 0 1\nv 1 1 1\nv 0 1 1\n"
+        "f 1 2 3 4\nf 5/1/1 6/2/1 7/3/1 8/4/1\nf -8 -7 -3\nf 1 1 2\n")
+    m = sc.mesh(str(tmp_path / "m"), sc.lambertian.from_color(sc.color(.1, .2, .3)), scale=2.0, offset=sc.point3(1, 0, 0))
+    assert len(m.v0) == 5 and m.num_degenerate == 1
+    assert m.v0[0].tolist() == [1, 0, 0] and m.v1[0].tolist() == [3, 0, 0] and m.v2[0].tolist() == [3, 2, 0]
+    extra = sc.triangle(sc.point3(0, 0, 5), sc.point3(1, 0, 5), sc.point3(0, 1, 5), sc.metal(sc.color(.5, .5, .5), 0.1))
+    a = SC.compile_scene(sc.hittable_list([m, extra]))
+    b = SC.compile_scene(sc.hittable_list(list(m.triangles) + [extra]))
+    assert a["triangle_v0"].shape == (6, 3) and a["triangle_material_type"].tolist() == [0, 0, 0, 0, 0, 1]
+    for k in a:
+        if k.startswith("triangle_"):
+            assert np.array_equal(a[k], b[k]) and a[k].dtype == b[k].dtype, k
+    with pytest.raises(FileNotFoundError):
+        sc.mesh(str(tmp_path / "nope"), None)
+
+
 def test_perlin_tables_follow_the_random_stream():
     random.seed(42)
     a = SC.perlin_tables()
