@@ -272,7 +272,8 @@ __global__ void __launch_bounds__(256) k_megakernel(const __grid_constant__ Mega
             const unsigned busy = __ballot_sync(0xffffffffu, st == LANE_TRAVERSING || st == LANE_HAVE_RESULT || st == LANE_NEED_PATH);
             if (busy == 0u && st == LANE_WAIT) st = LANE_NEED_PATH;
         }
-        const int min_active = (__popc(live) * P.burst_num + 31) >> 5;
+        // leave the burst when fewer than burst_num/32 of the lanes that entered it still traverse
+        const int min_active = (__popc(__ballot_sync(0xffffffffu, st == LANE_TRAVERSING)) * P.burst_num + 31) >> 5;
         if (P.vote_num > 0) {
             bool fin;
             trav_run_vote<COUNT, FULL>(T, st == LANE_TRAVERSING, fin, S, s_nodes, P.n_snodes, stack,

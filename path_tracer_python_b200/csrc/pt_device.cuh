@@ -307,18 +307,20 @@ __device__ __forceinline__ void trav_run_vote(TravState& T, bool active, bool& d
                                               int min_active, int vote_num, LocalCounters& lc) {
     const f3 o = T.o, inv = T.inv;
     const float t_min = T.t_min;
+    bool progressed = false;     // at least one block is executed per call (no livelock whatever min_active is)
     for (;;) {
         // common case first: enough lanes want to descend -> one ballot, no further bookkeeping
         const bool want_node = active && T.cur >= 0;
         const unsigned m_node = __ballot_sync(0xffffffffu, want_node);
-        bool do_node = __popc(m_node) >= vote_num;
+        bool do_node = __popc(m_node) >= vote_num && m_node != 0u;
         if (!do_node) {
             const bool want_leaf = active && T.cur < 0 && T.cur != kRefNone;
             const unsigned m_leaf = __ballot_sync(0xffffffffu, want_leaf);
             const int n_all = __popc(m_node | m_leaf);
-            if (n_all < min_active || n_all == 0) break;
+            if (n_all == 0 || (progressed && n_all < min_active)) break;
             do_node = (m_leaf == 0u);
         }
+        progressed = true;
         if (do_node) {
             if (want_node) {
                 float4 nx, ny, nz, nc;

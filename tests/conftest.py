@@ -13,6 +13,13 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_collection_modifyitems(config, items):
+    # a kernel that never returns must fail the test, not hang the box (pytest-timeout)
+    for item in items:
+        if "gpu" in item.keywords and item.get_closest_marker("timeout") is None:
+            item.add_marker(pytest.mark.timeout(240))
+
+
 @pytest.fixture(scope="session")
 def oracle_mod():
     import oracle as O  # oracle/oracle.py (test infrastructure)

@@ -147,3 +147,37 @@ def test_counters_match_oracle_semantics(oracle_mod):
     _, c = O.render(S, cam, meta["width"], meta["height"], meta["spp"], seed=meta["rng_seed"])
     assert g["paths"] == c["paths"] and g["bounces"] == c["bounces"] and g["rays"] == c["rays"]
     assert 0.3 < g["box_tests"] / c["node_tests"] < 2.0
+
+
+@pytest.mark.parametrize("scene_name", ["feature_zoo", "vol2_final_scene"])
+def test_results_do_not_depend_on_tuning_options(scene_name):
+    """Scheduling knobs (burst / vote thresholds, shared-memory nodes, block size, wavefront batch
+    size, number of full waves, fused leading waves, material sort) change how the work is laid out
+    on the machine, never the result: every combination reproduces the reference bit for bit."""
+    from path_tracer_python_b200 import scenes
+    from path_tracer_python_b200.engine import Engine
+    cs, meta, out = scenes.load_fixture(scene_name)
+    e = Engine(0)
+    e.set_scene(cs)
+    e.set_camera(meta["camera"], meta["background"], meta["max_depth"])
+    W, H, spp, seed = meta["width"], meta["height"], meta["spp"], meta["rng_seed"]
+    mega_opts = [dict(burst_num=0, vote_num=0), dict(burst_num=32, vote_num=32), dict(burst_num=7, vote_num=3, smem_nodes=0),
+                 dict(block_threads=64, smem_nodes=9), dict(block_threads=128, sync_samples=1), dict(sync_samples=3, smem_nodes=100000)]
+    for o in mega_opts:
+        for k, v in dict(dict(burst_num=12, vote_num=10, smem_nodes=-1, block_threads=256, sync_samples=0), **o).items():
+            e.set_option(k, v)
+        acc = e.new_accum(W, H)
+        e.render_megakernel(acc, 0, spp, seed)
+        assert np.array_equal(acc.cpu().numpy(), out["accum_megakernel"]), o
+    wf_opts = [dict(wf_waves=1), dict(wf_waves=2, wf_fuse_primary=0), dict(wf_waves=50, wf_fuse_primary=0, wavefront_sort=0),
+               dict(wf_fuse_primary=3, wf_waves=4), dict(wf_fuse_primary=7, wf_waves=3), dict(wf_burst_num=0, vote_num=0, wf_blocks_per_sm=1),
+               dict(wf_burst_num=32, vote_num=32, wf_blocks_per_sm=8, smem_nodes=0)]
+    for o in wf_opts:
+        for k, v in dict(dict(wf_waves=12, wf_fuse_primary=1, wavefront_sort=1, wf_burst_num=20, vote_num=12, wf_blocks_per_sm=6,
+                              smem_nodes=-1), **o).items():
+            e.set_option(k, v)
+        for flight in (1, 3, 32):
+            e.wavefront_samples_in_flight = flight
+            acc = e.new_accum(W, H)
+            e.render_wavefront(acc, 0, spp, seed)
+            assert np.array_equal(acc.cpu().numpy(), out["accum_wavefront"]), (o, flight)
