@@ -48,6 +48,8 @@ struct PtContext {
     int wf_fuse_primary = 1; // wave 0 (camera rays) as one fused kernel
     int wf_burst_num = 20;
     int wf_blocks_per_sm = 6;
+    int wf_extend_minb = 4;
+    int wf_tile = 1;
     int num_sms = 148;
     int max_smem_optin = 0;
     bool count = false;
@@ -326,6 +328,7 @@ struct WfParams {
     int burst_num;
     int vote_num;
     int fused_waves;         // waves k_wf_primary runs in registers before handing paths to the queues
+    int tile;                // k_wf_primary walks the window in 8x4-pixel tiles (one warp = one tile)
     DCounters* counters;
 };
 
@@ -396,8 +399,8 @@ constexpr int kWfWarps = 8;       // warps per CTA of the wavefront kernels (256
 // the HBM latency of the queue read overlaps traversal), and hands staged rays to lanes as they
 // finish; the other lanes keep traversing (resumable warp-voting traversal).  Results go to the
 // hit-record array in ray order: no atomics, no binning here.
-template <bool COUNT, bool FULL>
-__global__ void __launch_bounds__(256) k_wf_extend(const __grid_constant__ WfParams P) {
+template <bool COUNT, bool FULL, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_wf_extend(const __grid_constant__ WfParams P) {
     extern __shared__ float4 s_dyn[];
     __shared__ float4 s_ray[kWfWarps][2][32][2];      // (o.xyz d.x)(d.yz ..) of staged rays, 16 KB
     float4* s_nodes = s_dyn;
@@ -462,15 +465,9 @@ __global__ void __launch_bounds__(256) k_wf_extend(const __grid_constant__ WfPar
         if (st == LANE_HAVE_RESULT) {
             if (mode == 0) {
                 const int ref = T.best_ref;
-                bool is_med = false;
-                int cls = 0;                                   // 0 miss, 1 medium boundary, 2 + material type
-                if (ref != kRefNone) {
-                    const int header = __float_as_int(__ldg(S.materials + 3 * mat_id_of(S, ref)).x);
-                    is_med = mat_is_medium(header);
-                    cls = is_med ? 1 : 2 + mat_type(header);
-                    cls = cls > kNumBins - 1 ? kNumBins - 1 : cls;     // subsurface materials share the last bin
-                }
-                if (is_med) {
+                // 0 miss, 1 medium boundary, 2 + material type (subsurface materials share the last bin)
+                const int cls = ref != kRefNone ? ref_class(ref) : 0;
+                if (cls == 1) {
                     mode = 1;
                     t_entry = T.best_t;
                     ref_entry = ref;
@@ -708,6 +705,34 @@ __global__ void __launch_bounds__(256) k_wf_shade(const __grid_constant__ WfPara
     }
 }
 
+// Lane -> pixel map of k_wf_primary: the window is walked in 8x4-pixel tiles so that the 32 primary
+// rays of a warp span a compact patch (and so do the bounce rays they append, which the next wave
+// fetches 32 at a time); columns / rows that do not fill a tile follow in scanline order.  Any
+// bijection is allowed here: a path is keyed by its (pixel, sample), never by the lane that runs it.
+__device__ __forceinline__ int tile_local_pixel(int local, int W, int rows) {
+    const int tw = W >> 3, th = rows >> 2;
+    const int tiled = tw * th * 32;
+    int px, py;
+    if (local < tiled) {
+        const int t = local >> 5, in = local & 31;
+        const int ty = t / tw, tx = t - ty * tw;
+        px = tx * 8 + (in & 7);
+        py = ty * 4 + (in >> 3);
+    } else {
+        int r = local - tiled;
+        const int rw = W - tw * 8, right = rw * th * 4;
+        if (r < right) {
+            py = r / rw;
+            px = tw * 8 + (r - py * rw);
+        } else {
+            r -= right;
+            py = th * 4 + r / W;
+            px = r - (r / W) * W;
+        }
+    }
+    return py * W + px;
+}
+
 // Wave 0 fused: generate_camera_rays + intersect_rays + shade_miss_rays + shade_and_scatter for the
 // primary rays (kernels.py:1219-1399) in one kernel.  Camera rays are coherent, so nothing is gained
 // by sending them through the queues: the ray is generated in registers, traced, shaded, and only
@@ -724,14 +749,17 @@ __global__ void __launch_bounds__(256) k_wf_primary(const __grid_constant__ WfPa
     const int stride = gridDim.x * blockDim.x;
     const int rounds = (total + stride - 1) / stride;
     for (int r = 0; r < rounds; r++) {
-        const int id = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        const int j = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        int id = j;
         bool emit_next = false;
         f3 no, nd, nthr;
         int ndepth = 0;
         uint32_t rng = 0;
-        if (id < total) {
-            const int slot = id / P.N;
-            const int pixel = P.y0 * P.W + (id - slot * P.N);
+        if (j < total) {
+            const int slot = j / P.N;
+            const int local = P.tile ? tile_local_pixel(j - slot * P.N, P.W, P.y1 - P.y0) : j - slot * P.N;
+            id = slot * P.N + local;
+            const int pixel = P.y0 * P.W + local;
             const int py = pixel / P.W, px = pixel - py * P.W;
             rng = ptm::rng_seed(P.seed, (uint32_t)pixel, (uint32_t)(P.sample_base + slot));
             const float time = FULL ? ptm::path_time(rng) : 0.0f;
@@ -748,10 +776,8 @@ __global__ void __launch_bounds__(256) k_wf_primary(const __grid_constant__ WfPa
                 int ref, eref = kRefNone;
                 if (COUNT) lc.bounces++;
                 traverse<COUNT, FULL>(S, s_nodes, P.n_snodes, o, d, 0.001f, 1e10f, t, ref, lc, time);
-                if (ref != kRefNone && S.has_media) {
-                    const int header = __float_as_int(__ldg(S.materials + 3 * mat_id_of(S, ref)).x);
-                    if (mat_is_medium(header)) traverse<COUNT, FULL>(S, s_nodes, P.n_snodes, o, d, t + 0.0001f, 1e10f, t_exit, eref, lc, time);
-                }
+                if (ref != kRefNone && ref_is_medium(ref))
+                    traverse<COUNT, FULL>(S, s_nodes, P.n_snodes, o, d, t + 0.0001f, 1e10f, t_exit, eref, lc, time);
                 emit_next = wf_shade_one<FULL>(S, bg, max_depth, sp, o, d, thr, depth, rng, t, ref, t_exit, eref != kRefNone,
                                          no, nd, nthr, ndepth, time);
                 o = no; d = nd; thr = nthr; depth = ndepth;
@@ -760,7 +786,7 @@ __global__ void __launch_bounds__(256) k_wf_primary(const __grid_constant__ WfPa
         const int qd = P.fused_waves & 1;               // the queue wave `fused_waves` reads from
         int pos = warp_agg_append(P.Q.qcount + qd, 0, emit_next);
         if (emit_next) {
-            const int id2 = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
+            const int id2 = id;
             P.Q.r0[qd][pos] = make_float4(no.x, no.y, no.z, nd.x);
             P.Q.r1[qd][pos] = make_float4(nd.y, nd.z, nthr.x, nthr.y);
             P.Q.r2[qd][pos] = make_float4(nthr.z, __int_as_float(id2), __uint_as_float(rng), __int_as_float(ndepth));
@@ -806,10 +832,8 @@ __global__ void __launch_bounds__(256) k_wf_tail(const __grid_constant__ WfParam
             int ref, eref = kRefNone;
             if (COUNT) lc.bounces++;
             traverse<COUNT, FULL>(S, s_nodes, P.n_snodes, o, d, 0.001f, 1e10f, t, ref, lc, time);
-            if (ref != kRefNone && S.has_media) {
-                const int header = __float_as_int(__ldg(S.materials + 3 * mat_id_of(S, ref)).x);
-                if (mat_is_medium(header)) traverse<COUNT, FULL>(S, s_nodes, P.n_snodes, o, d, t + 0.0001f, 1e10f, t_exit, eref, lc, time);
-            }
+            if (ref != kRefNone && ref_is_medium(ref))
+                traverse<COUNT, FULL>(S, s_nodes, P.n_snodes, o, d, t + 0.0001f, 1e10f, t_exit, eref, lc, time);
             f3 no, nd, nthr;
             int ndepth;
             if (!wf_shade_one<FULL>(S, bg, max_depth, sp, o, d, thr, depth, rng, t, ref, t_exit, eref != kRefNone, no, nd, nthr, ndepth, time))
@@ -997,6 +1021,11 @@ int pt_set_option(PtContext* ctx, const char* name, int64_t value) {
     } else if (k == "wf_burst_num") {
         if (value < 0 || value > 32) return set_error(PT_ERR_INVALID_ARG, "wf_burst_num must be in [0, 32]");
         ctx->wf_burst_num = (int)value;
+    } else if (k == "wf_tile") {
+        ctx->wf_tile = value ? 1 : 0;
+    } else if (k == "wf_extend_minb") {
+        if (value < 4 || value > 6) return set_error(PT_ERR_INVALID_ARG, "wf_extend_minb must be 4, 5 or 6");
+        ctx->wf_extend_minb = (int)value;
     } else if (k == "wf_blocks_per_sm") {
         if (value < 1 || value > 8) return set_error(PT_ERR_INVALID_ARG, "wf_blocks_per_sm must be in [1, 8]");
         ctx->wf_blocks_per_sm = (int)value;
@@ -1160,6 +1189,7 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
     P.sort = ctx->wavefront_sort;
     P.burst_num = ctx->wf_burst_num;
     P.vote_num = ctx->vote_num;
+    P.tile = ctx->wf_tile;
     P.counters = ctx->d_counters;
     P.n_snodes = pick_snodes(ctx, 4);
     const size_t smem = (size_t)P.n_snodes * 64;
@@ -1174,11 +1204,14 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
     void (*k_shade)(const WfParams) = full ? k_wf_shade<true> : k_wf_shade<false>;
     if (ctx->count) {
         k_primary = full ? k_wf_primary<true, true> : k_wf_primary<true, false>;
-        k_extend = full ? k_wf_extend<true, true> : k_wf_extend<true, false>;
+        k_extend = full ? k_wf_extend<true, true, 4> : k_wf_extend<true, false, 4>;
         k_tail = full ? k_wf_tail<true, true> : k_wf_tail<true, false>;
     } else {
         k_primary = full ? k_wf_primary<false, true> : k_wf_primary<false, false>;
-        k_extend = full ? k_wf_extend<false, true> : k_wf_extend<false, false>;
+        // MINB = resident CTAs per SM the register allocation is capped for (4: 64 regs, 5: 48, 6: 40)
+        if (ctx->wf_extend_minb >= 6) k_extend = full ? k_wf_extend<false, true, 6> : k_wf_extend<false, false, 6>;
+        else if (ctx->wf_extend_minb == 5) k_extend = full ? k_wf_extend<false, true, 5> : k_wf_extend<false, false, 5>;
+        else k_extend = full ? k_wf_extend<false, true, 4> : k_wf_extend<false, false, 4>;
         k_tail = full ? k_wf_tail<false, true> : k_wf_tail<false, false>;
     }
     if ((rc = set_smem(k_primary, smem)) || (rc = set_smem(k_extend, smem)) || (rc = set_smem(k_tail, smem))) return rc;

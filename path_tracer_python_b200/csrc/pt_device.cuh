@@ -31,7 +31,7 @@ __device__ __forceinline__ f3 cross(f3 a, f3 b) {
 }
 // Taichi Vector.normalized(): (1 / norm) * v
 __device__ __forceinline__ f3 normalized(f3 a) {
-    float inv = ptm::fdiv(1.0f, ptm::fsqrt(dot(a, a)));
+    float inv = ptm::frcp(ptm::fsqrt(dot(a, a)));
     return inv * a;
 }
 __device__ __forceinline__ float min2(float a, float b) { return a < b ? a : b; }
@@ -69,7 +69,11 @@ struct LocalCounters {
 };
 
 __device__ __forceinline__ int ref_type(int ref) { return (~ref) & 3; }
-__device__ __forceinline__ int ref_index(int ref) { return (~ref) >> 2; }
+__device__ __forceinline__ int ref_index(int ref) { return (~ref) >> 5; }
+// shading class packed into the reference by the host packer: 1 = constant-medium boundary,
+// 2 + material type otherwise (capped at 7)
+__device__ __forceinline__ int ref_class(int ref) { return ((~ref) >> 2) & 7; }
+__device__ __forceinline__ bool ref_is_medium(int ref) { return ref_class(ref) == 1; }
 
 // ---- primitive tests: arithmetic identical to hit_sphere / hit_triangle / hit_quad; they return
 //      only t (the caller keeps t and the primitive reference).
@@ -109,7 +113,7 @@ __device__ __forceinline__ bool hit_triangle_t(const DScene& S, int idx, f3 o, f
     f3 h = cross(d, e2);
     float det = dot(e1, h);
     if (fabsf(det) >= 1e-8f) {
-        float inv_det = ptm::fdiv(1.0f, det);
+        float inv_det = ptm::frcp(det);
         f3 s = o - v0;
         float u = inv_det * dot(s, h);
         if (u >= 0.0f && u <= 1.0f) {
@@ -203,8 +207,8 @@ __device__ __forceinline__ void trav_begin(TravState& T, const DScene& S, f3 o, 
     T.o = o;
     T.d = d;
     T.time = time;
-    T.inv = mk3(fabsf(d.x) > 1e-8f ? ptm::fdiv(1.0f, d.x) : 1e8f, fabsf(d.y) > 1e-8f ? ptm::fdiv(1.0f, d.y) : 1e8f,
-                fabsf(d.z) > 1e-8f ? ptm::fdiv(1.0f, d.z) : 1e8f);
+    T.inv = mk3(fabsf(d.x) > 1e-8f ? ptm::frcp(d.x) : 1e8f, fabsf(d.y) > 1e-8f ? ptm::frcp(d.y) : 1e8f,
+                fabsf(d.z) > 1e-8f ? ptm::frcp(d.z) : 1e8f);
     T.t_min = t_min;
     T.best_t = t_max;
     T.best_ref = kRefNone;
@@ -513,7 +517,7 @@ __device__ __forceinline__ f3 eval_texture(const DScene& S, const Mat& m, int re
     if (tt == 0) {
         result = m.c1;
     } else if (tt == 1) {
-        float inv_scale = ptm::fdiv(1.0f, m.scalar);
+        float inv_scale = ptm::frcp(m.scalar);
         int s = (int)floorf(inv_scale * hp.x) + (int)floorf(inv_scale * hp.y) + (int)floorf(inv_scale * hp.z);
         result = (s & 1) == 0 ? m.c1 : m.c2;     // Python-style (s % 2 == 0) for negative s too
     } else if (tt == 2) {
@@ -646,7 +650,7 @@ __device__ __forceinline__ bool shade_surface(const DScene& S, const Mat& m, int
         float ir = m.scalar;
         bool front = dot(ray_dir, normal) < 0.0f;
         f3 nf = front ? normal : -normal;
-        float ratio = front ? ptm::fdiv(1.0f, ir) : ir;
+        float ratio = front ? ptm::frcp(ir) : ir;
         f3 ud = normalized(ray_dir);
         float ct = min2(-dot(ud, nf), 1.0f);
         float st = ptm::fsqrt(1.0f - ct * ct);

@@ -16,7 +16,16 @@ thread_local std::string g_host_error_storage;
 #define g_host_error (g_host_error_storage)
 
 constexpr int kRefNone = (int)0x80000000;
-inline int leaf_ref(int prim_type, int prim_idx) { return ~((prim_idx << 2) | prim_type); }
+// Leaf reference: ~(prim_idx << 5 | shading_class << 2 | prim_type).  The shading class (1 = medium
+// boundary, 2 + material type otherwise, capped at 7) rides along so that the kernels can tell a
+// medium boundary and pick the material bin of a hit without touching the material tables.
+constexpr int kMaxPrimsPerType = 1 << 26;
+inline int leaf_ref(int prim_type, int prim_idx, int cls) { return ~((prim_idx << 5) | ((cls & 7) << 2) | prim_type); }
+inline int shading_class(const PtHostMaterials& m, int i) {
+    if (m.is_medium[i] > 0) return 1;
+    const int c = 2 + (m.material_type[i] & 15);
+    return c > 7 ? 7 : c;
+}
 inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 
 struct MatRec {
@@ -152,6 +161,10 @@ std::string* pt_error_slot(void) { return &g_host_error_storage; }
 int pt_pack_scene_info(const PtHostScene* s, PtPackedInfo* info) {
     if (!s || !info) { g_host_error = "pt_pack_scene_info: NULL argument"; return PT_ERR_INVALID_ARG; }
     if (s->num_images > PT_MAX_IMAGES) { g_host_error = "too many image textures"; return PT_ERR_CAPACITY; }
+    if (s->num_spheres >= kMaxPrimsPerType || s->num_quads >= kMaxPrimsPerType || s->num_triangles >= kMaxPrimsPerType) {
+        g_host_error = "more than 2^26 primitives of one type";
+        return PT_ERR_CAPACITY;
+    }
     memset(info, 0, sizeof *info);
     Collapsed c;
     int rc = collapse(s, c);
@@ -204,7 +217,10 @@ int pt_pack_scene(const PtHostScene* s, const PtPackedInfo* info, void* host_blo
     auto child = [&](int ref_node, float* bmin, float* bmax) -> int {
         if (ref_node < 0) { for (int k = 0; k < 3; k++) { bmin[k] = 0.0f; bmax[k] = 0.0f; } return kRefNone; }
         for (int k = 0; k < 3; k++) { bmin[k] = s->bvh_bbox_min[3 * ref_node + k]; bmax[k] = s->bvh_bbox_max[3 * ref_node + k]; }
-        if (s->bvh_prim_idx[ref_node] >= 0) return leaf_ref(s->bvh_prim_type[ref_node], s->bvh_prim_idx[ref_node]);
+        if (s->bvh_prim_idx[ref_node] >= 0) {
+            const int pt = s->bvh_prim_type[ref_node], pi = s->bvh_prim_idx[ref_node];
+            return leaf_ref(pt, pi, shading_class(s->mat[pt], pi));
+        }
         return c.new_index[ref_node];
     };
     auto write_node = [&](int k, int lnode, int rnode) {
