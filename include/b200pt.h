@@ -175,7 +175,9 @@ int pt_generate_camera_rays(PtContext* ctx, int W, int H, uint32_t seed, int sam
 int pt_first_hit(PtContext* ctx, const float* o, const float* d, int n, float t_min, float t_max, float* out_t,
                  int32_t* out_prim, float* out_p, float* out_n, void* stream);
 /* the contract's elementary functions: fn 0 sin 1 cos 2 log 3 acos 4 atan2(a,b) 5 pow(a,5);
- * fn 6: a/b unused, out[i] = i-th draw of the random stream with state seed (uint32 bits of a[0]) */
+ * fn 6: a/b unused, out[i] = i-th draw of the random stream with state seed (uint32 bits of a[0]);
+ * fn 7 exp; fn 8 the slab test's reciprocal direction (|x| > 1e-8 ? 1/x : 1e8) of a[i] (even i) or
+ * b[i] (odd i) */
 int pt_math_eval(PtContext* ctx, int fn, int n, const float* a, const float* b, float* out, void* stream);
 
 /* ---- output: replaces LivePreview.buffer_to_image (preview.py:117-132) on the device */

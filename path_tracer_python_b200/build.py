@@ -40,21 +40,27 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_native(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
-        return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else [])
+def build_native(force: bool = False, verbose: bool = False, defines=(), out: str | None = None) -> str:
+    """`defines` / `out` build an experimental variant next to the product library (A/B
+    measurements through the PT_LIB_PATH override of _lib.py); the default build takes neither."""
+    if out is None and not defines:
+        if not force and not needs_build():
+            return LIB_PATH
+    out = out or LIB_PATH
+    cmd = [_nvcc()] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else [])
     if os.path.exists("/usr/bin/g++"):
         cmd += ["-ccbin", "/usr/bin/g++"]
-    cmd += ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd += ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
     if verbose:
         print(r.stdout + r.stderr)
-    return LIB_PATH
+    return out
 
 
 if __name__ == "__main__":
-    path = build_native(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")]
+    path = build_native(force="--force" in sys.argv, verbose="--verbose" in sys.argv, defines=defs, out=outs[0] if outs else None)
     print(path)

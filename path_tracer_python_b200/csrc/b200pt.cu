@@ -59,9 +59,9 @@ struct PtContext {
 // ------------------------------------------------------------------------------------------------
 // shared helpers
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void stage_nodes(float4* s_nodes, const DScene& S, int n_snodes) {
+__device__ __forceinline__ void stage_nodes(float4* s_node_mem, const DScene& S, int n_snodes) {
     const int n4 = n_snodes * 4;
-    for (int i = threadIdx.x; i < n4; i += blockDim.x) s_nodes[i] = __ldg(S.nodes + i);
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) s_node_mem[i] = __ldg(S.nodes + i);
     __syncthreads();
 }
 
@@ -123,10 +123,11 @@ struct MegaParams {
 enum : int { LANE_NEED_PATH = 0, LANE_HAVE_RESULT = 1, LANE_TRAVERSING = 2, LANE_DONE = 3, LANE_WAIT = 4 };
 
 template <bool COUNT, bool FULL>
-__global__ void __launch_bounds__(256) k_megakernel(const __grid_constant__ MegaParams P) {
-    extern __shared__ float4 s_nodes[];
+__global__ void __launch_bounds__(256, 3) k_megakernel(const __grid_constant__ MegaParams P) {
+    extern __shared__ float4 s_node_mem[];
     const DScene& S = P.S;
-    stage_nodes(s_nodes, S, P.n_snodes);
+    stage_nodes(s_node_mem, S, P.n_snodes);
+    const SNodeBase s_nodes = snode_base(s_node_mem);
 
     // one warp = one 8x4 pixel tile (coherent primary rays)
     const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -403,7 +404,7 @@ template <bool COUNT, bool FULL, int MINB>
 __global__ void __launch_bounds__(256, MINB) k_wf_extend(const __grid_constant__ WfParams P) {
     extern __shared__ float4 s_dyn[];
     __shared__ float4 s_ray[kWfWarps][2][32][2];      // (o.xyz d.x)(d.yz ..) of staged rays, 16 KB
-    float4* s_nodes = s_dyn;
+    float4* s_node_mem = s_dyn;
     const DScene& S = P.S;
     const int cur = P.bounce & 1;
     const int count = P.Q.qcount[cur];
@@ -414,7 +415,8 @@ __global__ void __launch_bounds__(256, MINB) k_wf_extend(const __grid_constant__
     // small waves: only as many CTAs as there are 256-ray slices take part (the rest would just
     // hammer the cursor with atomics and stage nodes for nothing)
     if ((long long)blockIdx.x * 256 >= count) return;
-    stage_nodes(s_nodes, S, P.n_snodes);
+    stage_nodes(s_node_mem, S, P.n_snodes);
+    const SNodeBase s_nodes = snode_base(s_node_mem);
     LocalCounters lc;
     const unsigned lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -738,10 +740,11 @@ __device__ __forceinline__ int tile_local_pixel(int local, int W, int rows) {
 // by sending them through the queues: the ray is generated in registers, traced, shaded, and only
 // the surviving bounce ray is appended (one atomic per warp) to queue 1, where wave 1 picks it up.
 template <bool COUNT, bool FULL>
-__global__ void __launch_bounds__(256) k_wf_primary(const __grid_constant__ WfParams P) {
-    extern __shared__ float4 s_nodes[];
+__global__ void __launch_bounds__(256, 3) k_wf_primary(const __grid_constant__ WfParams P) {
+    extern __shared__ float4 s_node_mem[];
     const DScene& S = P.S;
-    stage_nodes(s_nodes, S, P.n_snodes);
+    stage_nodes(s_node_mem, S, P.n_snodes);
+    const SNodeBase s_nodes = snode_base(s_node_mem);
     LocalCounters lc;
     const int max_depth = P.cam.max_depth;
     const f3 bg = mk3(P.cam.background[0], P.cam.background[1], P.cam.background[2]);
@@ -808,13 +811,14 @@ __global__ void k_wf_reset(const __grid_constant__ WfParams P) {
 // ends or the wave budget max_depth (renderer.py:313) is used up -- the same per-ray operations in
 // the same order as the wave kernels, so results are identical.
 template <bool COUNT, bool FULL>
-__global__ void __launch_bounds__(256) k_wf_tail(const __grid_constant__ WfParams P) {
-    extern __shared__ float4 s_nodes[];
+__global__ void __launch_bounds__(256, 3) k_wf_tail(const __grid_constant__ WfParams P) {
+    extern __shared__ float4 s_node_mem[];
     const DScene& S = P.S;
     const int cur = P.bounce & 1;
     const int count = P.Q.qcount[cur];
     if ((long long)blockIdx.x * 256 >= count) return;
-    stage_nodes(s_nodes, S, P.n_snodes);
+    stage_nodes(s_node_mem, S, P.n_snodes);
+    const SNodeBase s_nodes = snode_base(s_node_mem);
     LocalCounters lc;
     const int max_depth = P.cam.max_depth;
     const f3 bg = mk3(P.cam.background[0], P.cam.background[1], P.cam.background[2]);
@@ -888,8 +892,9 @@ struct FirstHitParams {
 
 template <bool COUNT>
 __global__ void __launch_bounds__(256) k_first_hit(const __grid_constant__ FirstHitParams P) {
-    extern __shared__ float4 s_nodes[];
-    stage_nodes(s_nodes, P.S, P.n_snodes);
+    extern __shared__ float4 s_node_mem[];
+    stage_nodes(s_node_mem, P.S, P.n_snodes);
+    const SNodeBase s_nodes = snode_base(s_node_mem);
     LocalCounters lc;
     const int stride = gridDim.x * blockDim.x;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += stride) {
@@ -933,6 +938,7 @@ __global__ void k_math_eval(int fn, int n, const float* a, const float* b, float
         case 4: r = ptm::atan2_c(x, b[i]); break;
         case 5: r = ptm::pow5_c(x); break;
         case 7: r = ptm::exp_c(x); break;
+        case 8: { float iy, iz; ptm::inv_dir3(x, b[i], 1.0f, r, iy, iz); r = (i & 1) ? iy : r; break; }   // traversal reciprocal
     }
     out[i] = r;
 }

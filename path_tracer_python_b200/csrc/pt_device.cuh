@@ -192,13 +192,21 @@ __device__ __forceinline__ float fmin3(float a, float b, float c) {
     return d;
 }
 
+typedef unsigned long long StackEntry;
+#ifndef PT_STACK_TOP
+#define PT_STACK_TOP 0      // see trav_push / trav_pop
+#endif
+
 struct TravState {
     f3 o, d, inv;
     float time;          // shutter time of the path (full feature mode; 0 otherwise)
     float t_min, best_t;
     int best_ref;
     int cur;     // >= 0 inner node, < 0 leaf reference, kRefNone = traversal finished
-    int sp;
+    int sp;      // entries in the local-memory part of the stack
+#if PT_STACK_TOP
+    unsigned long long top;   // newest stack entry, held in registers (low word kRefNone = stack empty)
+#endif
 };
 
 template <bool COUNT>
@@ -207,49 +215,102 @@ __device__ __forceinline__ void trav_begin(TravState& T, const DScene& S, f3 o, 
     T.o = o;
     T.d = d;
     T.time = time;
-    T.inv = mk3(fabsf(d.x) > 1e-8f ? ptm::frcp(d.x) : 1e8f, fabsf(d.y) > 1e-8f ? ptm::frcp(d.y) : 1e8f,
-                fabsf(d.z) > 1e-8f ? ptm::frcp(d.z) : 1e8f);
+    ptm::inv_dir3(d.x, d.y, d.z, T.inv.x, T.inv.y, T.inv.z);
     T.t_min = t_min;
     T.best_t = t_max;
     T.best_ref = kRefNone;
     T.cur = S.num_inner > 0 ? 0 : kRefNone;
     T.sp = 0;
+#if PT_STACK_TOP
+    T.top = (unsigned long long)(unsigned)kRefNone;
+#endif
     if (COUNT) lc.rays++;
 }
 
 // A stack entry packs the deferred child's reference and its slab entry distance into one 8-byte
 // word, so that a push / pop is a single local-memory instruction (STL.64 / LDL.64).
-typedef unsigned long long StackEntry;
 __device__ __forceinline__ StackEntry stack_pack(int ref, float t) {
     return ((StackEntry)__float_as_uint(t) << 32) | (StackEntry)(unsigned)ref;
 }
+// PT_STACK_TOP=1 keeps the newest entry in registers (T.top) and local memory holds the rest, so
+// that a pop hands out T.top and only *starts* the load of its successor.  Measured on config 2
+// (tools/ab.py, same box): wavefront +-0.0 %, megakernel -1.4 % (two more live registers at the
+// 80-register cap) -- so the default is the plain local-memory stack; the variant stays buildable.
+// Either way, entries whose slab entry distance is already beyond the closest hit are skipped on
+// pop (the box test would reject them anyway).
+__device__ __forceinline__ void trav_push(TravState& T, StackEntry* stack, StackEntry e) {
+#if PT_STACK_TOP
+    if ((int)(unsigned)T.top != kRefNone && T.sp < kStackSize) {
+        stack[T.sp] = T.top;
+        T.sp++;
+    }
+    T.top = e;
+#else
+    if (T.sp < kStackSize) {
+        stack[T.sp] = e;
+        T.sp++;
+    }
+#endif
+}
 __device__ __forceinline__ int trav_pop(TravState& T, const StackEntry* stack) {
     int next = kRefNone;
+#if PT_STACK_TOP
+    while ((int)(unsigned)T.top != kRefNone) {
+        const StackEntry e = T.top;
+        if (T.sp > 0) {
+            --T.sp;
+            T.top = stack[T.sp];
+        } else {
+            T.top = (StackEntry)(unsigned)kRefNone;
+        }
+        if (__uint_as_float((unsigned)(e >> 32)) <= T.best_t) { next = (int)(unsigned)e; break; }
+    }
+#else
     while (T.sp > 0) {
         --T.sp;
         const StackEntry e = stack[T.sp];
         if (__uint_as_float((unsigned)(e >> 32)) <= T.best_t) { next = (int)(unsigned)e; break; }
     }
+#endif
     return next;
+}
+
+// Fetch of one 64-byte node: the top n_snodes nodes (breadth-first order) are staged in shared
+// memory, the rest comes through L1.  The shared copy is addressed by its 32-bit shared-space
+// address, formed ONCE per kernel (snode_base): left to the compiler, the generic-pointer form has
+// the shared window base rebuilt (S2R CgaCtaId, shifts, adds) on every node visit.
+typedef unsigned SNodeBase;
+__device__ __forceinline__ SNodeBase snode_base(const float4* s_node_mem) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(s_node_mem), r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(a));      // opaque: keeps the value in a register
+    return r;
+}
+__device__ __forceinline__ void load_node(const DScene& S, SNodeBase s_nodes, int n_snodes, int cur,
+                                          float4& nx, float4& ny, float4& nz, float4& nc) {
+    if (cur < n_snodes) {
+        const unsigned sa = s_nodes + (unsigned)cur * 64u;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(nx.x), "=f"(nx.y), "=f"(nx.z), "=f"(nx.w) : "r"(sa));
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+16];" : "=f"(ny.x), "=f"(ny.y), "=f"(ny.z), "=f"(ny.w) : "r"(sa));
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+32];" : "=f"(nz.x), "=f"(nz.y), "=f"(nz.z), "=f"(nz.w) : "r"(sa));
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+48];" : "=f"(nc.x), "=f"(nc.y) : "r"(sa));
+        nc.z = 0.0f; nc.w = 0.0f;
+    } else {
+        const float4* p = S.nodes + 4 * cur;
+        nx = __ldg(p); ny = __ldg(p + 1); nz = __ldg(p + 2); nc = __ldg(p + 3);
+    }
 }
 
 // Runs the traversal until it finishes (returns true) or, when min_active > 0, until fewer than
 // min_active lanes of the warp are still inside the loop (returns false; call again to resume).
 template <bool COUNT, bool FULL = false>
-__device__ __forceinline__ bool trav_run(TravState& T, const DScene& S, const float4* __restrict__ s_nodes, int n_snodes,
+__device__ __forceinline__ bool trav_run(TravState& T, const DScene& S, SNodeBase s_nodes, int n_snodes,
                                          StackEntry* stack, int min_active, LocalCounters& lc) {
     const f3 o = T.o, inv = T.inv;
     const float t_min = T.t_min;
     while (T.cur != kRefNone) {
         while (T.cur >= 0) {
             float4 nx, ny, nz, nc;
-            if (T.cur < n_snodes) {
-                const float4* p = s_nodes + 4 * T.cur;
-                nx = p[0]; ny = p[1]; nz = p[2]; nc = p[3];
-            } else {
-                const float4* p = S.nodes + 4 * T.cur;
-                nx = __ldg(p); ny = __ldg(p + 1); nz = __ldg(p + 2); nc = __ldg(p + 3);
-            }
+            load_node(S, s_nodes, n_snodes, T.cur, nx, ny, nz, nc);
             if (COUNT) lc.box_tests += 2;
             const float best_t = T.best_t;
             // left child box
@@ -269,10 +330,7 @@ __device__ __forceinline__ bool trav_run(TravState& T, const DScene& S, const fl
             const bool hr = (rtmax >= rtmin) && (rref != kRefNone);
             if (hl && hr) {
                 const bool left_first = ltmin <= rtmin;
-                if (T.sp < kStackSize) {
-                    stack[T.sp] = stack_pack(left_first ? rref : lref, left_first ? rtmin : ltmin);
-                    T.sp++;
-                }
+                trav_push(T, stack, stack_pack(left_first ? rref : lref, left_first ? rtmin : ltmin));
                 T.cur = left_first ? lref : rref;
             } else if (hl) {
                 T.cur = lref;
@@ -307,7 +365,7 @@ __device__ __forceinline__ bool trav_run(TravState& T, const DScene& S, const fl
 // so results are bit-identical to trav_run.
 template <bool COUNT, bool FULL = false>
 __device__ __forceinline__ void trav_run_vote(TravState& T, bool active, bool& done, const DScene& S,
-                                              const float4* __restrict__ s_nodes, int n_snodes, StackEntry* stack,
+                                              SNodeBase s_nodes, int n_snodes, StackEntry* stack,
                                               int min_active, int vote_num, LocalCounters& lc) {
     const f3 o = T.o, inv = T.inv;
     const float t_min = T.t_min;
@@ -328,13 +386,7 @@ __device__ __forceinline__ void trav_run_vote(TravState& T, bool active, bool& d
         if (do_node) {
             if (want_node) {
                 float4 nx, ny, nz, nc;
-                if (T.cur < n_snodes) {
-                    const float4* p = s_nodes + 4 * T.cur;
-                    nx = p[0]; ny = p[1]; nz = p[2]; nc = p[3];
-                } else {
-                    const float4* p = S.nodes + 4 * T.cur;
-                    nx = __ldg(p); ny = __ldg(p + 1); nz = __ldg(p + 2); nc = __ldg(p + 3);
-                }
+                load_node(S, s_nodes, n_snodes, T.cur, nx, ny, nz, nc);
                 if (COUNT) lc.box_tests += 2;
                 const float best_t = T.best_t;
                 float l0x = (nx.x - o.x) * inv.x, l1x = (nx.y - o.x) * inv.x;
@@ -352,10 +404,7 @@ __device__ __forceinline__ void trav_run_vote(TravState& T, bool active, bool& d
                 const bool hr = (rtmax >= rtmin) && (rref != kRefNone);
                 if (hl && hr) {
                     const bool left_first = ltmin <= rtmin;
-                    if (T.sp < kStackSize) {
-                        stack[T.sp] = stack_pack(left_first ? rref : lref, left_first ? rtmin : ltmin);
-                        T.sp++;
-                    }
+                    trav_push(T, stack, stack_pack(left_first ? rref : lref, left_first ? rtmin : ltmin));
                     T.cur = left_first ? lref : rref;
                 } else if (hl) {
                     T.cur = lref;
@@ -383,7 +432,7 @@ __device__ __forceinline__ void trav_run_vote(TravState& T, bool active, bool& d
 
 // One-shot traversal (probe / wavefront kernels).
 template <bool COUNT, bool FULL = false>
-__device__ __forceinline__ void traverse(const DScene& S, const float4* __restrict__ s_nodes, int n_snodes, f3 o, f3 d,
+__device__ __forceinline__ void traverse(const DScene& S, SNodeBase s_nodes, int n_snodes, f3 o, f3 d,
                                          float t_min, float t_max, float& best_t, int& best_ref, LocalCounters& lc,
                                          float time = 0.0f) {
     StackEntry stack[kStackSize];

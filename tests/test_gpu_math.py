@@ -39,6 +39,25 @@ def test_atan2_bit_exact(engine, oracle_mod):
     assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
 
 
+def test_traversal_reciprocal_bit_exact(engine):
+    """inv = |d| > 1e-8 ? 1/d : 1e8 (kernels.py:602-607) through the merged-guard fast path ==
+    IEEE division, over random bit patterns of every exponent (denormals, huge values, zeros, infs
+    included -- those take the library fallback)."""
+    rng = np.random.default_rng(11)
+    bits = rng.integers(0, 2 ** 32, size=8_000_000, dtype=np.uint64).astype(np.uint32)
+    edge = np.float32([0.0, -0.0, 1e-8, -1e-8, 1.0000001e-8, 1e-45, 1e-38, 1.1754944e-38, 8.5e37, 1.7e38, 3.4e38, np.inf, -np.inf,
+                       1.0, -1.0, 3.0, 2.0 ** -126, 2.0 ** 126, 2.0 ** 125, 1.9999999 * 2.0 ** 125])
+    a = np.concatenate([bits.view(np.float32), edge, np.linspace(-2, 2, 100001, dtype=np.float32)[:-1]])
+    a = a[~np.isnan(a)]
+    a = a[: len(a) // 2 * 2]
+    b = a[::-1].copy()
+    got = engine.math_eval(8, torch.from_numpy(a), torch.from_numpy(b)).cpu().numpy()
+    x = np.where(np.arange(len(a)) & 1, b, a).astype(np.float32)
+    with np.errstate(divide="ignore", over="ignore"):
+        ref = np.where(np.abs(x) > np.float32(1e-8), np.float32(1.0) / x, np.float32(1e8)).astype(np.float32)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+
+
 def test_random_stream_bit_exact(engine, oracle_mod):
     for key in [(1234, 0, 0), (1234, 2073599, 255), (0xFFFFFFFF, 17, 3)]:
         s0 = oracle_mod.rng_seed(*key)
