@@ -188,6 +188,26 @@ int pt_tonemap(PtContext* ctx, const float* accum, int n_floats, int sample_coun
 int pt_enable_counters(PtContext* ctx, int enable);
 int pt_get_counters(PtContext* ctx, PtCounters* out, int reset);
 
+/* ---- per-stage device times of the LAST pt_render_wavefront call (what renderer.py:305-334 prints
+ *      as its per-bounce timing): when enabled, every kernel launch of the call is bracketed by CUDA
+ *      events on the launching stream.  pt_get_stage_times synchronises the device, writes up to
+ *      max_entries records in launch order and returns the total number in *n_entries. */
+#define PT_STAGE_RESET 0
+#define PT_STAGE_GENERATE 1
+#define PT_STAGE_PRIMARY 2
+#define PT_STAGE_EXTEND 3
+#define PT_STAGE_BIN 4
+#define PT_STAGE_SHADE 5
+#define PT_STAGE_TAIL 6
+#define PT_STAGE_RESOLVE 7
+typedef struct PtStageTime {
+    int32_t kernel; /* PT_STAGE_* */
+    int32_t wave;   /* bounce index of the launch (0 for per-batch stages) */
+    float ms;
+} PtStageTime;
+int pt_enable_stage_timing(PtContext* ctx, int enable);
+int pt_get_stage_times(PtContext* ctx, PtStageTime* out, int max_entries, int* n_entries);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,6 +12,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <string>
+#include <vector>
 #include "pt_device.cuh"
 
 using namespace pt;
@@ -54,6 +55,12 @@ struct PtContext {
     int max_smem_optin = 0;
     bool count = false;
     DCounters* d_counters = nullptr;
+    // stage timing (pt_enable_stage_timing): events around every launch of the last render call
+    bool stage_timing = false;
+    std::vector<cudaEvent_t> ev_pool;
+    struct StageMark { int kernel, wave, ev_begin, ev_end; };
+    std::vector<StageMark> marks;
+    int ev_used = 0;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -299,10 +306,12 @@ __global__ void __launch_bounds__(256, 3) k_megakernel(const __grid_constant__ M
 // to slab[slot][pixel] and k_wf_resolve adds the slabs to the accumulation buffer in sample order,
 // so the sums are the ones the reference's one-sample-at-a-time loop produces.
 //
-// Ray record (48 B, three float4 planes): (o.xyz d.x) (d.yz thr.xy) (thr.z path_id rng depth)
+// Ray record (48 B): a 32-byte pair (o.xyz d.x)(d.yz thr.xy) -- what k_wf_extend reads, and one whole
+// sector for the gather of k_wf_shade -- plus a float4 plane (thr.z path_id rng depth)
 //   path_id = slot * N + local pixel.        Hit record (16 B): (t, ref, t_exit, exit_hit)
 struct WfQueues {
-    float4 *r0[2], *r1[2], *r2[2];
+    float4 *ra[2];           // [capacity][2]: (o.xyz d.x)(d.yz thr.xy), one 32-byte sector per ray
+    float4 *r2[2];           // [capacity]: (thr.z path_id rng depth)
     float4* hit;
     uint32_t* bins;          // kNumBins regions of `capacity` ray indices (material binning)
     int* bin_count;          // [kNumBins]
@@ -352,8 +361,8 @@ __global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ WfP
         uint32_t rng = ptm::rng_seed(P.seed, (uint32_t)pixel, (uint32_t)(P.sample_base + slot));
         f3 o, d;
         get_ray(P.cam, px, py, rng, o, d);                  // NOT normalised, kernels.py:1229-1233
-        P.Q.r0[0][id] = make_float4(o.x, o.y, o.z, d.x);
-        P.Q.r1[0][id] = make_float4(d.y, d.z, 1.0f, 1.0f);
+        P.Q.ra[0][2 * (size_t)id] = make_float4(o.x, o.y, o.z, d.x);
+        P.Q.ra[0][2 * (size_t)id + 1] = make_float4(d.y, d.z, 1.0f, 1.0f);
         P.Q.r2[0][id] = make_float4(1.0f, __int_as_float(id), __uint_as_float(rng), __int_as_float(0));
         P.Q.slab[3 * (size_t)id] = 0.0f;
         P.Q.slab[3 * (size_t)id + 1] = 0.0f;
@@ -420,8 +429,7 @@ __global__ void __launch_bounds__(256, MINB) k_wf_extend(const __grid_constant__
     LocalCounters lc;
     const unsigned lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const float4* __restrict__ q0 = P.Q.r0[cur];
-    const float4* __restrict__ q1 = P.Q.r1[cur];
+    const float4* __restrict__ qa = P.Q.ra[cur];
 
     // warp-uniform staging state
     int res_next = 0, res_end = 0;      // reserved, not yet staged ray indices
@@ -442,8 +450,8 @@ __global__ void __launch_bounds__(256, MINB) k_wf_extend(const __grid_constant__
         int n = res_end - res_next;
         n = n > 32 ? 32 : (n < 0 ? 0 : n);
         if ((int)lane < n) {
-            cp_async16(&s_ray[warp][b][lane][0], q0 + res_next + lane);
-            cp_async16(&s_ray[warp][b][lane][1], q1 + res_next + lane);
+            cp_async16(&s_ray[warp][b][lane][0], qa + 2 * (size_t)(res_next + lane));
+            cp_async16(&s_ray[warp][b][lane][1], qa + 2 * (size_t)(res_next + lane) + 1);
         }
         cp_async_commit();
         stg_base[b] = res_next;
@@ -537,13 +545,17 @@ __global__ void __launch_bounds__(256, MINB) k_wf_extend(const __grid_constant__
 // One ray of shade_miss_rays + shade_and_scatter (kernels.py:1266-1399): adds the ray's radiance
 // contribution (miss -> background, hit -> emission) to `sp` and returns true with the next ray
 // (origin, direction, throughput, depth) if the path goes on.
+// A path adds radiance exactly once, at the event that ends it (a miss, or an emissive hit --
+// emitters do not scatter, kernels.py:904-906), and its slab entry was zeroed when the path was
+// generated; so "slab += add" is written as "slab = 0 + add": same bits, but a plain store instead
+// of a scattered, latency-bound read-modify-write.
 template <bool FULL>
 __device__ __forceinline__ bool wf_shade_one(const DScene& S, f3 bg, int max_depth, float* sp, f3 o, f3 d, f3 thr,
                                              int depth, uint32_t& rng, float t, int ref, float t_exit_hit, bool exit_hit,
                                              f3& no, f3& nd, f3& nthr, int& ndepth, float time = 0.0f) {
     if (ref == kRefNone) {                           // shade_miss_rays, kernels.py:1266-1280
         f3 add = thr * bg;
-        sp[0] = sp[0] + add.x; sp[1] = sp[1] + add.y; sp[2] = sp[2] + add.z;
+        sp[0] = 0.0f + add.x; sp[1] = 0.0f + add.y; sp[2] = 0.0f + add.z;     // == slab + add, see above
         return false;
     }
     const int mid = mat_id_of(S, ref);               // shade_and_scatter, kernels.py:1289-1399
@@ -576,7 +588,11 @@ __device__ __forceinline__ bool wf_shade_one(const DScene& S, f3 bg, int max_dep
     }
     if (emit.x > 0.0f || emit.y > 0.0f || emit.z > 0.0f) {      // kernels.py:1368-1375
         f3 add = thr * emit;
-        sp[0] = sp[0] + add.x; sp[1] = sp[1] + add.y; sp[2] = sp[2] + add.z;
+        if (scattered) {                             // no such material today: keep the general form
+            sp[0] = sp[0] + add.x; sp[1] = sp[1] + add.y; sp[2] = sp[2] + add.z;
+        } else {
+            sp[0] = 0.0f + add.x; sp[1] = 0.0f + add.y; sp[2] = 0.0f + add.z;
+        }
     }
     if (scattered) {
         f3 new_thr = thr * atten;
@@ -683,7 +699,7 @@ __global__ void __launch_bounds__(256) k_wf_shade(const __grid_constant__ WfPara
                 for (int k = 1; k < kNumBins; k++) b += (j >= prefix[k]) ? 1 : 0;
                 i = (int)P.Q.bins[(size_t)b * P.Q.capacity + (j - prefix[b])];
             }
-            a = P.Q.r0[cur][i]; bq = P.Q.r1[cur][i]; c = P.Q.r2[cur][i]; h = P.Q.hit[i];
+            a = P.Q.ra[cur][2 * (size_t)i]; bq = P.Q.ra[cur][2 * (size_t)i + 1]; c = P.Q.r2[cur][i]; h = P.Q.hit[i];
         }
         bool emit_next = false;
         f3 no, nd, nthr;
@@ -697,11 +713,14 @@ __global__ void __launch_bounds__(256) k_wf_shade(const __grid_constant__ WfPara
                                      __float_as_int(h.y), h.z, (__float_as_int(h.w) & 1) != 0, no, nd, nthr, ndepth,
                                      wf_path_time<FULL>(P, path_id));
         }
-        // compaction: one atomic per warp (kernels.py:1345/:1394 use one per ray)
-        int pos = warp_agg_append(P.Q.qcount + nxt, 0, emit_next);
+        // compaction: one atomic per warp (kernels.py:1345/:1394 use one per ray).  Aggregating
+        // further, one atomic per CTA through shared memory and two barriers, measured slower
+        // (shade 5.11 vs 4.88 ms per batch): the barriers couple the warps of a CTA, and this kernel
+        // lives on its warps hiding each other's memory latency.
+        const int pos = warp_agg_append(P.Q.qcount + nxt, 0, emit_next);
         if (emit_next) {
-            P.Q.r0[nxt][pos] = make_float4(no.x, no.y, no.z, nd.x);
-            P.Q.r1[nxt][pos] = make_float4(nd.y, nd.z, nthr.x, nthr.y);
+            P.Q.ra[nxt][2 * (size_t)pos] = make_float4(no.x, no.y, no.z, nd.x);
+            P.Q.ra[nxt][2 * (size_t)pos + 1] = make_float4(nd.y, nd.z, nthr.x, nthr.y);
             P.Q.r2[nxt][pos] = make_float4(nthr.z, __int_as_float(path_id), __uint_as_float(rng), __int_as_float(ndepth));
         }
     }
@@ -790,8 +809,8 @@ __global__ void __launch_bounds__(256, 3) k_wf_primary(const __grid_constant__ W
         int pos = warp_agg_append(P.Q.qcount + qd, 0, emit_next);
         if (emit_next) {
             const int id2 = id;
-            P.Q.r0[qd][pos] = make_float4(no.x, no.y, no.z, nd.x);
-            P.Q.r1[qd][pos] = make_float4(nd.y, nd.z, nthr.x, nthr.y);
+            P.Q.ra[qd][2 * (size_t)pos] = make_float4(no.x, no.y, no.z, nd.x);
+            P.Q.ra[qd][2 * (size_t)pos + 1] = make_float4(nd.y, nd.z, nthr.x, nthr.y);
             P.Q.r2[qd][pos] = make_float4(nthr.z, __int_as_float(id2), __uint_as_float(rng), __int_as_float(ndepth));
         }
     }
@@ -824,7 +843,7 @@ __global__ void __launch_bounds__(256, 3) k_wf_tail(const __grid_constant__ WfPa
     const f3 bg = mk3(P.cam.background[0], P.cam.background[1], P.cam.background[2]);
     const int stride = gridDim.x * blockDim.x;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
-        const float4 a = P.Q.r0[cur][i], bq = P.Q.r1[cur][i], c = P.Q.r2[cur][i];
+        const float4 a = P.Q.ra[cur][2 * (size_t)i], bq = P.Q.ra[cur][2 * (size_t)i + 1], c = P.Q.r2[cur][i];
         f3 o = mk3(a.x, a.y, a.z), d = mk3(a.w, bq.x, bq.y), thr = mk3(bq.z, bq.w, c.x);
         const int path_id = __float_as_int(c.y);
         uint32_t rng = __float_as_uint(c.z);
@@ -1001,6 +1020,7 @@ int pt_destroy(PtContext* ctx) {
     if (!ctx) return PT_OK;
     cudaSetDevice(ctx->device);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
+    for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     delete ctx;
     return PT_OK;
 }
@@ -1137,6 +1157,31 @@ int pt_render_megakernel(PtContext* ctx, float* accum, int W, int H, int y0, int
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Stage timing: brackets a launch with two events on the launching stream (only when enabled; the
+// timed product path records nothing).
+static int stage_event(PtContext* ctx, cudaStream_t st) {
+    if (ctx->ev_used == (int)ctx->ev_pool.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return -1;
+        ctx->ev_pool.push_back(e);
+    }
+    const int id = ctx->ev_used++;
+    cudaEventRecord(ctx->ev_pool[id], st);
+    return id;
+}
+struct StageScope {
+    PtContext* ctx; cudaStream_t st; int kernel, wave, b;
+    StageScope(PtContext* c, cudaStream_t s, int k, int w) : ctx(c), st(s), kernel(k), wave(w), b(-1) {
+        if (ctx->stage_timing) b = stage_event(ctx, st);
+    }
+    ~StageScope() {
+        if (ctx->stage_timing && b >= 0) {
+            const int e = stage_event(ctx, st);
+            if (e >= 0) ctx->marks.push_back({kernel, wave, b, e});
+        }
+    }
+};
+
 // bytes of workspace one in-flight sample of an N-pixel window needs
 static size_t wf_bytes_per_sample(size_t n) {
     return 6 * n * 16      // two queues x three float4 planes
@@ -1176,8 +1221,7 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
     P.cam = ctx->cam;
     auto take = [&](size_t bytes) { char* q = p; p += align_up(bytes, 256); return q; };
     for (int q = 0; q < 2; q++) {
-        P.Q.r0[q] = reinterpret_cast<float4*>(take(cap * 16));
-        P.Q.r1[q] = reinterpret_cast<float4*>(take(cap * 16));
+        P.Q.ra[q] = reinterpret_cast<float4*>(take(cap * 32));
         P.Q.r2[q] = reinterpret_cast<float4*>(take(cap * 16));
     }
     P.Q.hit = reinterpret_cast<float4*>(take(cap * 16));
@@ -1222,6 +1266,8 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
     }
     if ((rc = set_smem(k_primary, smem)) || (rc = set_smem(k_extend, smem)) || (rc = set_smem(k_tail, smem))) return rc;
     const int max_depth = ctx->cam.max_depth;
+    ctx->marks.clear();
+    ctx->ev_used = 0;
     for (int s = sample_begin; s < sample_begin + sample_count; s += (int)B) {
         P.sample_base = s;
         P.batch = (int)B < sample_begin + sample_count - s ? (int)B : sample_begin + sample_count - s;
@@ -1235,25 +1281,25 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
         if (ctx->wf_fuse_primary && max_depth > 0) {
             // the first wave(s) in one kernel; survivors land in the queue the next wave reads
             P.fused_waves = ctx->wf_fuse_primary < waves ? ctx->wf_fuse_primary : waves;
-            k_wf_reset<<<1, 32, 0, st>>>(P);
-            k_primary<<<grid_wide, bt, smem, st>>>(P);
+            { StageScope t(ctx, st, PT_STAGE_RESET, 0); k_wf_reset<<<1, 32, 0, st>>>(P); }
+            { StageScope t(ctx, st, PT_STAGE_PRIMARY, 0); k_primary<<<grid_wide, bt, smem, st>>>(P); }
             first_wave = P.fused_waves;
         } else {
-            k_wf_generate<<<grid_wide, bt, 0, st>>>(P);
+            { StageScope t(ctx, st, PT_STAGE_GENERATE, 0); k_wf_generate<<<grid_wide, bt, 0, st>>>(P); }
         }
         for (int b = first_wave; b < waves; b++) {        // renderer.py:313; no host read-back of the ray count
             P.bounce = b;
-            k_extend<<<grid, bt, smem, st>>>(P);
-            if (P.sort) k_wf_bin<<<grid_wide, bt, 0, st>>>(P);
-            k_shade<<<grid_wide, bt, 0, st>>>(P);
+            { StageScope t(ctx, st, PT_STAGE_EXTEND, b); k_extend<<<grid, bt, smem, st>>>(P); }
+            if (P.sort) { StageScope t(ctx, st, PT_STAGE_BIN, b); k_wf_bin<<<grid_wide, bt, 0, st>>>(P); }
+            { StageScope t(ctx, st, PT_STAGE_SHADE, b); k_shade<<<grid_wide, bt, 0, st>>>(P); }
         }
         if (waves < max_depth) {                          // whatever is still alive: finish in one launch
             P.bounce = waves > first_wave ? waves : first_wave;
-            k_tail<<<grid_wide, bt, smem, st>>>(P);
+            { StageScope t(ctx, st, PT_STAGE_TAIL, P.bounce); k_tail<<<grid_wide, bt, smem, st>>>(P); }
         }
         int grid_res = (int)((n + bt - 1) / bt);
         if (grid_res > ctx->num_sms * 8) grid_res = ctx->num_sms * 8;
-        k_wf_resolve<<<grid_res, bt, 0, st>>>(P);
+        { StageScope t(ctx, st, PT_STAGE_RESOLVE, 0); k_wf_resolve<<<grid_res, bt, 0, st>>>(P); }
     }
     PT_CUDA(cudaGetLastError());
     return PT_OK;
@@ -1332,6 +1378,28 @@ int pt_get_counters(PtContext* ctx, PtCounters* out, int reset) {
     out->rays = h.rays; out->box_tests = h.box_tests; out->sphere_tests = h.sphere_tests;
     out->triangle_tests = h.triangle_tests; out->quad_tests = h.quad_tests; out->paths = h.paths; out->bounces = h.bounces;
     if (reset) PT_CUDA(cudaMemset(ctx->d_counters, 0, sizeof(DCounters)));
+    return PT_OK;
+}
+
+int pt_enable_stage_timing(PtContext* ctx, int enable) {
+    if (!ctx) return set_error(PT_ERR_INVALID_ARG, "pt_enable_stage_timing: NULL context");
+    ctx->stage_timing = enable != 0;
+    return PT_OK;
+}
+
+int pt_get_stage_times(PtContext* ctx, PtStageTime* out, int max_entries, int* n_entries) {
+    if (!ctx || !n_entries || (max_entries > 0 && !out)) return set_error(PT_ERR_INVALID_ARG, "pt_get_stage_times: NULL argument");
+    PT_CUDA(cudaSetDevice(ctx->device));
+    PT_CUDA(cudaDeviceSynchronize());
+    *n_entries = (int)ctx->marks.size();
+    for (int i = 0; i < (int)ctx->marks.size() && i < max_entries; i++) {
+        const PtContext::StageMark& m = ctx->marks[i];
+        float ms = 0.0f;
+        PT_CUDA(cudaEventElapsedTime(&ms, ctx->ev_pool[m.ev_begin], ctx->ev_pool[m.ev_end]));
+        out[i].kernel = m.kernel;
+        out[i].wave = m.wave;
+        out[i].ms = ms;
+    }
     return PT_OK;
 }
 

@@ -161,6 +161,19 @@ class Engine:
         return c.as_dict()
 
 
+    def enable_stage_timing(self, on: bool = True):
+        check(self.L.pt_enable_stage_timing(self.ctx, 1 if on else 0), "pt_enable_stage_timing")
+
+    def stage_times(self) -> list:
+        """[(stage name, wave, ms)] for every launch of the last render_wavefront call (synchronises)."""
+        from ._lib import PtStageTime, STAGE_NAMES
+        n = C.c_int(0)
+        check(self.L.pt_get_stage_times(self.ctx, None, 0, C.byref(n)), "pt_get_stage_times")
+        buf = (PtStageTime * max(1, n.value))()
+        check(self.L.pt_get_stage_times(self.ctx, buf, n.value, C.byref(n)), "pt_get_stage_times")
+        return [(STAGE_NAMES[buf[i].kernel], buf[i].wave, buf[i].ms) for i in range(n.value)]
+
+
 def algorithmic_bytes(counters: dict) -> int:
     """32 B per child-box test + primitive record bytes per leaf test."""
     return (32 * counters["box_tests"] + 16 * counters["sphere_tests"] + 48 * counters["triangle_tests"]

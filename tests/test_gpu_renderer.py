@@ -182,3 +182,30 @@ def test_results_do_not_depend_on_tuning_options(scene_name):
             acc = e.new_accum(W, H)
             e.render_wavefront(acc, 0, spp, seed)
             assert np.array_equal(acc.cpu().numpy(), out["accum_wavefront"]), (o, flight)
+
+
+def test_stage_timing_reports_every_launch():
+    """pt_enable_stage_timing / pt_get_stage_times: one record per kernel launch of the last wavefront
+    call, in launch order, and switching it on does not change the image."""
+    from path_tracer_python_b200 import scenes
+    from path_tracer_python_b200.engine import Engine
+    cs, meta, out = scenes.load_fixture("feature_zoo")
+    e = Engine(0)
+    e.set_scene(cs)
+    e.set_camera(meta["camera"], meta["background"], meta["max_depth"])
+    W, H, spp, seed = meta["width"], meta["height"], meta["spp"], meta["rng_seed"]
+    e.set_option("wf_waves", 4)
+    e.wavefront_samples_in_flight = 2
+    e.enable_stage_timing(True)
+    acc = e.new_accum(W, H)
+    e.render_wavefront(acc, 0, spp, seed)
+    t = e.stage_times()
+    assert np.array_equal(acc.cpu().numpy(), out["accum_wavefront"])
+    batches = (spp + 1) // 2
+    per_batch = ["reset", "primary"] + ["extend", "bin", "shade"] * 3 + ["tail", "resolve"]
+    assert [x[0] for x in t] == per_batch * batches
+    assert [x[1] for x in t if x[0] == "extend"] == [1, 2, 3] * batches
+    assert all(x[2] >= 0.0 for x in t) and sum(x[2] for x in t) > 0.0
+    e.enable_stage_timing(False)
+    e.render_wavefront(acc, 0, 1, seed)
+    assert e.stage_times() == []
