@@ -153,6 +153,18 @@ def run_reference(args, rank):
     print(json.dumps(line))
 
 
+def recorded_traffic(mode):
+    """dram__bytes_read + dram__bytes_write per launch of the dominant kernel, from the committed
+    `ncu --set full` capture of this workload (profiles/traffic.json; written by tools/ncu_traffic.py);
+    None when no capture is recorded."""
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f).get(mode, {}).get("dram_bytes_per_launch")
+    except (OSError, ValueError):
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -289,35 +301,64 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     other_value = paths_per_step / (float(t.item()) * 1e-3) / 1e6
 
-    # ---- roofline of the dominant kernel: algorithmic bytes from the counting instantiation on the
-    #      identical (seed, samples) launch, divided by the live CUDA-event duration above
+    # ---- roofline of the dominant kernel.  Algorithmic bytes come from the counting instantiation of
+    #      the same kernels on the identical (seed, samples) launch; durations are CUDA-event times
+    #      on the launching stream.  Megakernel: the one launch of the timed steps above.  Wavefront:
+    #      one extra, identical step with every launch bracketed by events (pt_enable_stage_timing),
+    #      summed over the launches of k_wf_extend (the kernel that owns >50 % of a step).
     roof = cpu = None
+    launches_per_step = 1
     if rank == 0:
+        peaks, which = measured_peaks()
+        k_ms = sum(kernel_ms) / len(kernel_ms)
+        scratch = eng.new_accum(W, H)
+        stage_ms = stage_cnt = None
+        if args.mode == "wavefront":
+            eng.enable_stage_timing(True)
+            flush.fill_(1)
+            render(scratch, s_begin, n_samples, SEED)
+            stage_ms = eng.stage_times()
+            launches_per_step = len(stage_ms)
         eng.enable_counters(True)
         eng.counters(reset=True)
-        scratch = eng.new_accum(W, H)
         render(scratch, s_begin, n_samples, SEED)
+        if args.mode == "wavefront":
+            stage_cnt = eng.stage_counters()
+            eng.enable_stage_timing(False)
         cnt = eng.counters(reset=True)
         eng.enable_counters(False)
-        peaks, which = measured_peaks()
         alg = algorithmic_bytes(cnt)
-        k_ms = sum(kernel_ms) / len(kernel_ms)
-        achieved = alg / (k_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": which,
-                "kernel": "k_megakernel" if args.mode == "megakernel" else "k_wf_extend (+k_wf_shade/generate/resolve: whole pipeline timed)",
-                "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg,
-                "note": "node/primitive fetches are served by shared memory + L1/L2 (scene = 2.5 MB); "
-                        "HBM traffic is compulsory only, see profiles/",
-                "counters": cnt, "mrays_per_s": cnt["rays"] / (k_ms * 1e-3) / 1e6,
-                "bytes_per_path": alg / max(1, W * H * n_samples)}
+        pipeline = {"kernel_ms": k_ms, "algorithmic_bytes": alg, "achieved_gbs": alg / (k_ms * 1e-3) / 1e9,
+                    "counters": cnt, "mrays_per_s": cnt["rays"] / (k_ms * 1e-3) / 1e6,
+                    "bytes_per_path": alg / max(1, W * H * n_samples)}
+        traffic = recorded_traffic(args.mode)
+        if args.mode == "megakernel":
+            roof = {"bound": "hbm", "achieved": pipeline["achieved_gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": pipeline["achieved_gbs"] / peaks["hbm_gbs"], "traffic": traffic, "peak_source": which,
+                    "kernel": "k_megakernel", "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg, "launches": 1}
+        else:
+            per = {}
+            for (name, wave, ms), c in zip(stage_ms, stage_cnt):
+                d = per.setdefault(name, {"ms": 0.0, "launches": 0, "bytes": 0, "rays": 0})
+                d["ms"] += ms; d["launches"] += 1; d["bytes"] += algorithmic_bytes(c); d["rays"] += c["rays"]
+            ext = per["extend"]
+            ach = ext["bytes"] / (ext["ms"] * 1e-3) / 1e9
+            stage_total = sum(d["ms"] for d in per.values())
+            roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                    "traffic": traffic, "peak_source": which, "kernel": "k_wf_extend",
+                    "launches": ext["launches"], "kernel_ms": ext["ms"] / ext["launches"],
+                    "algorithmic_bytes_per_launch": ext["bytes"] / ext["launches"],
+                    "share_of_step": ext["ms"] / stage_total, "grays_per_s": ext["rays"] / (ext["ms"] * 1e-3) / 1e9,
+                    "stages_ms_per_step": {k: round(v["ms"], 3) for k, v in per.items()},
+                    "stage_sum_over_step_ms": stage_total / k_ms}
+        roof["note"] = ("algorithmic = 32 B per child-box test + 16/48/64 B per sphere/triangle/quad test; those fetches are "
+                        "served by shared memory + L1/L2 (scene = 2.5 MB), so DRAM traffic << algorithmic: see profiles/")
+        roof["pipeline"] = pipeline
         if not args.no_cpu_baseline and world == 1:
             v, cores, sample = cpu_oracle_rate(cs)
             cpu = {"value": v, "unit": "Mpaths/s", "cores": cores, "kind": "port", "sample": sample}
 
     if rank == 0:
-        flight = max(1, min(eng.wavefront_samples_in_flight, n_samples))
-        launches_per_step = 1 if args.mode == "megakernel" else -(-n_samples // flight) * (2 + 2 * MAX_DEPTH)
         line = {
             "metric": METRIC, "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",

@@ -207,6 +207,9 @@ typedef struct PtStageTime {
 } PtStageTime;
 int pt_enable_stage_timing(PtContext* ctx, int enable);
 int pt_get_stage_times(PtContext* ctx, PtStageTime* out, int max_entries, int* n_entries);
+/* with counting AND stage timing enabled: the cumulative counters as they stood after each launch of
+ * the last call (same order as pt_get_stage_times); differences give per-launch ray / test counts. */
+int pt_get_stage_counters(PtContext* ctx, PtCounters* out, int max_entries, int* n_entries);
 
 #ifdef __cplusplus
 }

@@ -73,7 +73,7 @@ EXPORTS = [
     "pt_last_error", "pt_version", "pt_pack_scene_info", "pt_pack_scene", "pt_bvh_build_sah", "pt_create",
     "pt_destroy", "pt_set_option", "pt_set_scene", "pt_set_camera", "pt_render_megakernel",
     "pt_wavefront_workspace_bytes", "pt_wavefront_workspace_bytes_for", "pt_render_wavefront", "pt_generate_camera_rays", "pt_first_hit",
-    "pt_math_eval", "pt_tonemap", "pt_enable_counters", "pt_get_counters", "pt_enable_stage_timing", "pt_get_stage_times",
+    "pt_math_eval", "pt_tonemap", "pt_enable_counters", "pt_get_counters", "pt_enable_stage_timing", "pt_get_stage_times", "pt_get_stage_counters",
 ]
 
 _lib = None
@@ -120,6 +120,7 @@ def lib() -> C.CDLL:
     L.pt_get_counters.argtypes = [C.c_void_p, C.POINTER(PtCounters), C.c_int]
     L.pt_enable_stage_timing.argtypes = [C.c_void_p, C.c_int]
     L.pt_get_stage_times.argtypes = [C.c_void_p, C.POINTER(PtStageTime), C.c_int, C.POINTER(C.c_int)]
+    L.pt_get_stage_counters.argtypes = [C.c_void_p, C.POINTER(PtCounters), C.c_int, C.POINTER(C.c_int)]
     L.pt_bvh_build_sah.argtypes = [C.c_int32] + [C.c_void_p] * 12
     _lib = L
     return L

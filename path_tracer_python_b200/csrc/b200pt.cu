@@ -61,7 +61,9 @@ struct PtContext {
     struct StageMark { int kernel, wave, ev_begin, ev_end; };
     std::vector<StageMark> marks;
     int ev_used = 0;
+    DCounters* d_stage_snap = nullptr;      // counters after every timed launch (counting + timing both on)
 };
+static const int kMaxStageSnaps = 4096;
 
 // ------------------------------------------------------------------------------------------------
 // shared helpers
@@ -1021,6 +1023,7 @@ int pt_destroy(PtContext* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+    if (ctx->d_stage_snap) cudaFree(ctx->d_stage_snap);
     delete ctx;
     return PT_OK;
 }
@@ -1177,7 +1180,11 @@ struct StageScope {
     ~StageScope() {
         if (ctx->stage_timing && b >= 0) {
             const int e = stage_event(ctx, st);
-            if (e >= 0) ctx->marks.push_back({kernel, wave, b, e});
+            if (e < 0) return;
+            if (ctx->count && ctx->d_stage_snap && (int)ctx->marks.size() < kMaxStageSnaps)
+                cudaMemcpyAsync(ctx->d_stage_snap + ctx->marks.size(), ctx->d_counters, sizeof(DCounters),
+                                cudaMemcpyDeviceToDevice, st);
+            ctx->marks.push_back({kernel, wave, b, e});
         }
     }
 };
@@ -1384,6 +1391,31 @@ int pt_get_counters(PtContext* ctx, PtCounters* out, int reset) {
 int pt_enable_stage_timing(PtContext* ctx, int enable) {
     if (!ctx) return set_error(PT_ERR_INVALID_ARG, "pt_enable_stage_timing: NULL context");
     ctx->stage_timing = enable != 0;
+    if (enable && !ctx->d_stage_snap) {
+        PT_CUDA(cudaSetDevice(ctx->device));
+        PT_CUDA(cudaMalloc(&ctx->d_stage_snap, sizeof(DCounters) * kMaxStageSnaps));
+        PT_CUDA(cudaMemset(ctx->d_stage_snap, 0, sizeof(DCounters) * kMaxStageSnaps));
+    }
+    return PT_OK;
+}
+
+int pt_get_stage_counters(PtContext* ctx, PtCounters* out, int max_entries, int* n_entries) {
+    if (!ctx || !n_entries || (max_entries > 0 && !out)) return set_error(PT_ERR_INVALID_ARG, "pt_get_stage_counters: NULL argument");
+    PT_CUDA(cudaSetDevice(ctx->device));
+    PT_CUDA(cudaDeviceSynchronize());
+    int n = (ctx->count && ctx->d_stage_snap) ? (int)ctx->marks.size() : 0;
+    if (n > kMaxStageSnaps) n = kMaxStageSnaps;
+    *n_entries = n;
+    const int m = n < max_entries ? n : max_entries;
+    if (m > 0) {
+        std::vector<DCounters> h(m);
+        PT_CUDA(cudaMemcpy(h.data(), ctx->d_stage_snap, sizeof(DCounters) * m, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < m; i++) {
+            out[i].rays = h[i].rays; out[i].box_tests = h[i].box_tests; out[i].sphere_tests = h[i].sphere_tests;
+            out[i].triangle_tests = h[i].triangle_tests; out[i].quad_tests = h[i].quad_tests;
+            out[i].paths = h[i].paths; out[i].bounces = h[i].bounces;
+        }
+    }
     return PT_OK;
 }
 

@@ -174,6 +174,21 @@ class Engine:
         return [(STAGE_NAMES[buf[i].kernel], buf[i].wave, buf[i].ms) for i in range(n.value)]
 
 
+    def stage_counters(self) -> list:
+        """Per-launch counter increments of the last render_wavefront call (needs enable_counters and
+        enable_stage_timing); same order as stage_times()."""
+        n = C.c_int(0)
+        check(self.L.pt_get_stage_counters(self.ctx, None, 0, C.byref(n)), "pt_get_stage_counters")
+        buf = (PtCounters * max(1, n.value))()
+        check(self.L.pt_get_stage_counters(self.ctx, buf, n.value, C.byref(n)), "pt_get_stage_counters")
+        cum = [buf[i].as_dict() for i in range(n.value)]
+        out, prev = [], None
+        for c in cum:
+            out.append({k: c[k] - (prev[k] if prev else 0) for k in c})
+            prev = c
+        return out
+
+
 def algorithmic_bytes(counters: dict) -> int:
     """32 B per child-box test + primitive record bytes per leaf test."""
     return (32 * counters["box_tests"] + 16 * counters["sphere_tests"] + 48 * counters["triangle_tests"]

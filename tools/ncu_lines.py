@@ -89,7 +89,7 @@ if by_func:
             t = src.get(k)
             if t is None:
                 continue
-            m = fdef.match(t.strip())
+            m = fdef.match(re.sub(r"__launch_bounds__\([^)]*\)", "", t.strip()))
             if m:
                 return f"{f}:{m.group(1)}"
         return f
