@@ -166,7 +166,8 @@ __global__ void __launch_bounds__(256, 3) k_megakernel(const __grid_constant__ M
     // traversal state (persists across bursts)
     TravState T;
     T.cur = kRefNone;
-    StackEntry stack[kStackSize];
+    StackEntry stack[kStackSlots];
+    stack_init(stack);
     int st = (valid && s < s_end && max_depth > 0) ? LANE_NEED_PATH : LANE_DONE;
 
     for (;;) {
@@ -467,7 +468,8 @@ __global__ void __launch_bounds__(256, MINB) k_wf_extend(const __grid_constant__
 
     TravState T;
     T.cur = kRefNone;
-    StackEntry stack[kStackSize];
+    StackEntry stack[kStackSlots];
+    stack_init(stack);
     int st = LANE_NEED_PATH;     // NEED_PATH: wants a ray; TRAVERSING; HAVE_RESULT; DONE: queue exhausted
     int ray = 0, mode = 0, ref_entry = kRefNone;
     float t_entry = 0.0f;

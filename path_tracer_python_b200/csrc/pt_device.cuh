@@ -194,7 +194,7 @@ __device__ __forceinline__ float fmin3(float a, float b, float c) {
 
 typedef unsigned long long StackEntry;
 #ifndef PT_STACK_TOP
-#define PT_STACK_TOP 0      // see trav_push / trav_pop
+#define PT_STACK_TOP 1      // see trav_push / trav_pop
 #endif
 
 struct TravState {
@@ -232,17 +232,27 @@ __device__ __forceinline__ void trav_begin(TravState& T, const DScene& S, f3 o, 
 __device__ __forceinline__ StackEntry stack_pack(int ref, float t) {
     return ((StackEntry)__float_as_uint(t) << 32) | (StackEntry)(unsigned)ref;
 }
-// PT_STACK_TOP=1 keeps the newest entry in registers (T.top) and local memory holds the rest, so
-// that a pop hands out T.top and only *starts* the load of its successor.  Measured on config 2
-// (tools/ab.py, same box): wavefront +-0.0 %, megakernel -1.4 % (two more live registers at the
-// 80-register cap) -- so the default is the plain local-memory stack; the variant stays buildable.
+// PT_STACK_TOP=1 (default) keeps the newest entry in registers (T.top) and local memory holds the
+// rest, so that a pop hands out T.top and only *starts* the load of its successor: the local-memory
+// latency leaves the critical path of the pop.  It only pays if that load lands in T.top's own
+// registers -- with the natural code order the compiler loads into a temporary and copies, which
+// waits for the load on the spot (measured +-0 %); with the order below: wavefront +0.8 %,
+// megakernel +0.7 % on config 2 (tools/ab.py, same box).  PT_STACK_TOP=0 builds the plain stack.
 // Either way, entries whose slab entry distance is already beyond the closest hit are skipped on
 // pop (the box test would reject them anyway).
+// (PT_STACK_TOP=1) memory slots 1..T.sp hold the older entries and slot 0 a permanent sentinel
+// (stack_init), so that the refill of T.top after a pop is one unconditional load.
+constexpr int kStackSlots = kStackSize + PT_STACK_TOP;
+__device__ __forceinline__ void stack_init(StackEntry* stack) {
+#if PT_STACK_TOP
+    stack[0] = (StackEntry)(unsigned)kRefNone;
+#endif
+}
 __device__ __forceinline__ void trav_push(TravState& T, StackEntry* stack, StackEntry e) {
 #if PT_STACK_TOP
     if ((int)(unsigned)T.top != kRefNone && T.sp < kStackSize) {
-        stack[T.sp] = T.top;
         T.sp++;
+        stack[T.sp] = T.top;
     }
     T.top = e;
 #else
@@ -256,14 +266,14 @@ __device__ __forceinline__ int trav_pop(TravState& T, const StackEntry* stack) {
     int next = kRefNone;
 #if PT_STACK_TOP
     while ((int)(unsigned)T.top != kRefNone) {
-        const StackEntry e = T.top;
-        if (T.sp > 0) {
-            --T.sp;
-            T.top = stack[T.sp];
-        } else {
-            T.top = (StackEntry)(unsigned)kRefNone;
-        }
-        if (__uint_as_float((unsigned)(e >> 32)) <= T.best_t) { next = (int)(unsigned)e; break; }
+        const bool take = __uint_as_float((unsigned)(T.top >> 32)) <= T.best_t;
+        const int cand = (int)(unsigned)T.top;
+        // the old top is consumed above; the barrier keeps the compiler from hoisting the load over
+        // those uses, so it can land in T.top's own registers and nothing waits for it here
+        asm volatile("" ::: "memory");
+        T.top = stack[T.sp];                 // slot 0 = sentinel: no branch
+        T.sp = T.sp > 0 ? T.sp - 1 : 0;
+        if (take) { next = cand; break; }
     }
 #else
     while (T.sp > 0) {
@@ -326,8 +336,8 @@ __device__ __forceinline__ bool trav_run(TravState& T, const DScene& S, SNodeBas
             float rtmin = fmax3(fminf(r0x, r1x), fminf(r0y, r1y), fmaxf(fminf(r0z, r1z), t_min));
             float rtmax = fmin3(fmaxf(r0x, r1x), fmaxf(r0y, r1y), fminf(fmaxf(r0z, r1z), best_t));
             const int lref = __float_as_int(nc.x), rref = __float_as_int(nc.y);
-            const bool hl = (ltmax >= ltmin) && (lref != kRefNone);
-            const bool hr = (rtmax >= rtmin) && (rref != kRefNone);
+            const bool hl = ltmax >= ltmin;        // both children always exist (host packer)
+            const bool hr = rtmax >= rtmin;
             if (hl && hr) {
                 const bool left_first = ltmin <= rtmin;
                 trav_push(T, stack, stack_pack(left_first ? rref : lref, left_first ? rtmin : ltmin));
@@ -369,14 +379,16 @@ __device__ __forceinline__ void trav_run_vote(TravState& T, bool active, bool& d
                                               int min_active, int vote_num, LocalCounters& lc) {
     const f3 o = T.o, inv = T.inv;
     const float t_min = T.t_min;
+    // lanes that do not traverse look finished: one register carries "active and where"
+    int cur = active ? T.cur : kRefNone;
     bool progressed = false;     // at least one block is executed per call (no livelock whatever min_active is)
     for (;;) {
         // common case first: enough lanes want to descend -> one ballot, no further bookkeeping
-        const bool want_node = active && T.cur >= 0;
+        const bool want_node = cur >= 0;
         const unsigned m_node = __ballot_sync(0xffffffffu, want_node);
         bool do_node = __popc(m_node) >= vote_num && m_node != 0u;
         if (!do_node) {
-            const bool want_leaf = active && T.cur < 0 && T.cur != kRefNone;
+            const bool want_leaf = (unsigned)cur > (unsigned)kRefNone;      // negative, not kRefNone
             const unsigned m_leaf = __ballot_sync(0xffffffffu, want_leaf);
             const int n_all = __popc(m_node | m_leaf);
             if (n_all == 0 || (progressed && n_all < min_active)) break;
@@ -386,7 +398,7 @@ __device__ __forceinline__ void trav_run_vote(TravState& T, bool active, bool& d
         if (do_node) {
             if (want_node) {
                 float4 nx, ny, nz, nc;
-                load_node(S, s_nodes, n_snodes, T.cur, nx, ny, nz, nc);
+                load_node(S, s_nodes, n_snodes, cur, nx, ny, nz, nc);
                 if (COUNT) lc.box_tests += 2;
                 const float best_t = T.best_t;
                 float l0x = (nx.x - o.x) * inv.x, l1x = (nx.y - o.x) * inv.x;
@@ -400,34 +412,35 @@ __device__ __forceinline__ void trav_run_vote(TravState& T, bool active, bool& d
                 float rtmin = fmax3(fminf(r0x, r1x), fminf(r0y, r1y), fmaxf(fminf(r0z, r1z), t_min));
                 float rtmax = fmin3(fmaxf(r0x, r1x), fmaxf(r0y, r1y), fminf(fmaxf(r0z, r1z), best_t));
                 const int lref = __float_as_int(nc.x), rref = __float_as_int(nc.y);
-                const bool hl = (ltmax >= ltmin) && (lref != kRefNone);
-                const bool hr = (rtmax >= rtmin) && (rref != kRefNone);
+                const bool hl = ltmax >= ltmin;        // both children always exist (host packer)
+                const bool hr = rtmax >= rtmin;
                 if (hl && hr) {
                     const bool left_first = ltmin <= rtmin;
                     trav_push(T, stack, stack_pack(left_first ? rref : lref, left_first ? rtmin : ltmin));
-                    T.cur = left_first ? lref : rref;
+                    cur = left_first ? lref : rref;
                 } else if (hl) {
-                    T.cur = lref;
+                    cur = lref;
                 } else if (hr) {
-                    T.cur = rref;
+                    cur = rref;
                 } else {
-                    T.cur = trav_pop(T, stack);
+                    cur = trav_pop(T, stack);
                 }
             }
         } else {
-            if (active && T.cur < 0 && T.cur != kRefNone) {
-                const int type = ref_type(T.cur), idx = ref_index(T.cur);
+            if ((unsigned)cur > (unsigned)kRefNone) {
+                const int type = ref_type(cur), idx = ref_index(cur);
                 float t;
                 bool hit;
                 if (type == PT_PRIM_SPHERE) { if (COUNT) lc.sphere_tests++; hit = hit_sphere_t<FULL>(S, idx, T.o, T.d, t_min, T.best_t, t, T.time); }
                 else if (type == PT_PRIM_QUAD) { if (COUNT) lc.quad_tests++; hit = hit_quad_t(S, idx, T.o, T.d, t_min, T.best_t, t); }
                 else { if (COUNT) lc.triangle_tests++; hit = hit_triangle_t(S, idx, T.o, T.d, t_min, T.best_t, t); }
-                if (hit && t < T.best_t) { T.best_t = t; T.best_ref = T.cur; }   // kernels.py:691 (strict)
-                T.cur = trav_pop(T, stack);
+                if (hit && t < T.best_t) { T.best_t = t; T.best_ref = cur; }   // kernels.py:691 (strict)
+                cur = trav_pop(T, stack);
             }
         }
     }
-    done = active && T.cur == kRefNone;
+    if (active) T.cur = cur;
+    done = active && cur == kRefNone;
 }
 
 // One-shot traversal (probe / wavefront kernels).
@@ -435,7 +448,8 @@ template <bool COUNT, bool FULL = false>
 __device__ __forceinline__ void traverse(const DScene& S, SNodeBase s_nodes, int n_snodes, f3 o, f3 d,
                                          float t_min, float t_max, float& best_t, int& best_ref, LocalCounters& lc,
                                          float time = 0.0f) {
-    StackEntry stack[kStackSize];
+    StackEntry stack[kStackSlots];
+    stack_init(stack);
     TravState T;
     trav_begin<COUNT>(T, S, o, d, t_min, t_max, lc, time);
     trav_run<COUNT, FULL>(T, S, s_nodes, n_snodes, stack, 0, lc);

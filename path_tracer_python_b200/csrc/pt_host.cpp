@@ -138,6 +138,7 @@ int collapse(const PtHostScene* s, Collapsed& c) {
             c.new_index[ni] = (int)c.order.size();
             c.order.push_back(ni);
             const int ch[2] = {s->bvh_left[ni], s->bvh_right[ni]};
+            if (ch[0] < 0 && ch[1] < 0) { g_host_error = "BVH inner node without children"; return PT_ERR_INVALID_ARG; }
             for (int k = 0; k < 2; k++) {
                 if (ch[k] < 0) continue;
                 if (ch[k] >= n) { g_host_error = "BVH child index out of range"; return PT_ERR_INVALID_ARG; }
@@ -223,7 +224,12 @@ int pt_pack_scene(const PtHostScene* s, const PtPackedInfo* info, void* host_blo
         }
         return c.new_index[ref_node];
     };
+    // Every packed node has two real children, so the kernels' slab test needs no "child exists"
+    // check: a node with a single child (only a one-primitive scene's root in the reference's trees)
+    // references that child twice -- the second visit finds nothing closer (strict <, kernels.py:691).
     auto write_node = [&](int k, int lnode, int rnode) {
+        if (lnode < 0) lnode = rnode;
+        if (rnode < 0) rnode = lnode;
         float lmin[3], lmax[3], rmin[3], rmax[3];
         int lref = child(lnode, lmin, lmax), rref = child(rnode, rmin, rmax);
         float* p = nodes + 16 * (size_t)k;

@@ -73,6 +73,7 @@ def test_single_primitive_and_empty_scene():
     info, blob = _pack(one)
     assert info.num_inner == 1
     refs = blob[info.off_nodes + 48: info.off_nodes + 56].view(np.int32)
-    assert refs[0] == ~(2 << 2) and refs[1] == np.int32(-2 ** 31)       # leaf ref for sphere 0 (class 2 = Lambertian), "none" on the right
+    # leaf ref for sphere 0 (class 2 = Lambertian) in BOTH slots: every packed node has two real children
+    assert refs[0] == ~(2 << 2) and refs[1] == refs[0]
     info, blob = _pack({})
     assert info.num_inner == 0 and info.total_bytes >= 256
