@@ -286,9 +286,31 @@ __device__ __forceinline__ int trav_pop(TravState& T, const StackEntry* stack) {
 }
 
 // Fetch of one 64-byte node: the top n_snodes nodes (breadth-first order) are staged in shared
-// memory, the rest comes through L1.  The shared copy is addressed by its 32-bit shared-space
-// address, formed ONCE per kernel (snode_base): left to the compiler, the generic-pointer form has
-// the shared window base rebuilt (S2R CgaCtaId, shifts, adds) on every node visit.
+// memory, the rest comes through L1.  Default (PT_NODE_GENERIC=1): select the ADDRESS -- a generic
+// pointer into the shared copy or into global memory -- and issue one generic load sequence, so a
+// warp whose lanes sit on both sides of the boundary does not run two predicated sequences
+// (config 2, tools/ab.py: wavefront +1.4 %, megakernel +4 %).  PT_NODE_GENERIC=0 builds the
+// LDS / LDG.CONSTANT pair.  Either way the base address is formed ONCE per kernel (snode_base):
+// left to the compiler, it is rebuilt (S2R CgaCtaId, shifts, adds) on every node visit.
+#ifndef PT_NODE_GENERIC
+#define PT_NODE_GENERIC 1
+#endif
+#if PT_NODE_GENERIC
+typedef unsigned long long SNodeBase;
+__device__ __forceinline__ SNodeBase snode_base(const float4* s_node_mem) {
+    unsigned long long a = (unsigned long long)s_node_mem, r;
+    asm volatile("mov.u64 %0, %1;" : "=l"(r) : "l"(a));
+    return r;
+}
+__device__ __forceinline__ void load_node(const DScene& S, SNodeBase s_nodes, int n_snodes, int cur,
+                                          float4& nx, float4& ny, float4& nz, float4& nc) {
+    const unsigned long long base = cur < n_snodes ? s_nodes : (unsigned long long)S.nodes;
+    const float4* p = reinterpret_cast<const float4*>(base) + 4 * cur;
+    nx = p[0]; ny = p[1]; nz = p[2];
+    const float2 c2 = *reinterpret_cast<const float2*>(p + 3);
+    nc = make_float4(c2.x, c2.y, 0.0f, 0.0f);
+}
+#else
 typedef unsigned SNodeBase;
 __device__ __forceinline__ SNodeBase snode_base(const float4* s_node_mem) {
     unsigned a = (unsigned)__cvta_generic_to_shared(s_node_mem), r;
@@ -309,6 +331,7 @@ __device__ __forceinline__ void load_node(const DScene& S, SNodeBase s_nodes, in
         nx = __ldg(p); ny = __ldg(p + 1); nz = __ldg(p + 2); nc = __ldg(p + 3);
     }
 }
+#endif
 
 // Runs the traversal until it finishes (returns true) or, when min_active > 0, until fewer than
 // min_active lanes of the warp are still inside the loop (returns false; call again to resume).
