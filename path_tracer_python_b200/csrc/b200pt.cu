@@ -546,6 +546,34 @@ __global__ void __launch_bounds__(256, MINB) k_wf_extend(const __grid_constant__
     if (COUNT) flush_counters(P.counters, lc);
 }
 
+// Closest hit of a ray and, when that hit is a constant-medium boundary, the exit search behind it
+// (kernels.py:417-419) -- as ONE traversal loop run up to twice, so that the kernels that inline it
+// (k_wf_primary, k_wf_tail) carry one copy of the traversal code, not two (instruction cache).
+template <bool COUNT, bool FULL>
+__device__ __forceinline__ void closest_hit_and_exit(const DScene& S, SNodeBase s_nodes, int n_snodes, f3 o, f3 d, float time,
+                                                     float& t, int& ref, float& t_exit, int& eref, LocalCounters& lc) {
+    StackEntry stack[kStackSlots];
+    stack_init(stack);
+    TravState T;
+    float t_min = 0.001f;
+    t_exit = 0.0f;
+    eref = kRefNone;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+        trav_begin<COUNT>(T, S, o, d, t_min, 1e10f, lc, time);
+        trav_run<COUNT, FULL>(T, S, s_nodes, n_snodes, stack, 0, lc);
+        if (pass == 0) {
+            t = T.best_t;
+            ref = T.best_ref;
+            if (ref == kRefNone || !ref_is_medium(ref)) break;
+            t_min = t + 0.0001f;
+        } else {
+            t_exit = T.best_t;
+            eref = T.best_ref;
+        }
+    }
+}
+
 // One ray of shade_miss_rays + shade_and_scatter (kernels.py:1266-1399): adds the ray's radiance
 // contribution (miss -> background, hit -> emission) to `sp` and returns true with the next ray
 // (origin, direction, throughput, depth) if the path goes on.
@@ -762,8 +790,11 @@ __device__ __forceinline__ int tile_local_pixel(int local, int W, int rows) {
 // primary rays (kernels.py:1219-1399) in one kernel.  Camera rays are coherent, so nothing is gained
 // by sending them through the queues: the ray is generated in registers, traced, shaded, and only
 // the surviving bounce ray is appended (one atomic per warp) to queue 1, where wave 1 picks it up.
+#ifndef PT_PRIMARY_MINB
+#define PT_PRIMARY_MINB 3
+#endif
 template <bool COUNT, bool FULL>
-__global__ void __launch_bounds__(256, 3) k_wf_primary(const __grid_constant__ WfParams P) {
+__global__ void __launch_bounds__(256, PT_PRIMARY_MINB) k_wf_primary(const __grid_constant__ WfParams P) {
     extern __shared__ float4 s_node_mem[];
     const DScene& S = P.S;
     stage_nodes(s_node_mem, S, P.n_snodes);
@@ -801,9 +832,7 @@ __global__ void __launch_bounds__(256, 3) k_wf_primary(const __grid_constant__ W
                 float t, t_exit = 0.0f;
                 int ref, eref = kRefNone;
                 if (COUNT) lc.bounces++;
-                traverse<COUNT, FULL>(S, s_nodes, P.n_snodes, o, d, 0.001f, 1e10f, t, ref, lc, time);
-                if (ref != kRefNone && ref_is_medium(ref))
-                    traverse<COUNT, FULL>(S, s_nodes, P.n_snodes, o, d, t + 0.0001f, 1e10f, t_exit, eref, lc, time);
+                closest_hit_and_exit<COUNT, FULL>(S, s_nodes, P.n_snodes, o, d, time, t, ref, t_exit, eref, lc);
                 emit_next = wf_shade_one<FULL>(S, bg, max_depth, sp, o, d, thr, depth, rng, t, ref, t_exit, eref != kRefNone,
                                          no, nd, nthr, ndepth, time);
                 o = no; d = nd; thr = nthr; depth = ndepth;
@@ -858,9 +887,7 @@ __global__ void __launch_bounds__(256, 3) k_wf_tail(const __grid_constant__ WfPa
             float t, t_exit = 0.0f;
             int ref, eref = kRefNone;
             if (COUNT) lc.bounces++;
-            traverse<COUNT, FULL>(S, s_nodes, P.n_snodes, o, d, 0.001f, 1e10f, t, ref, lc, time);
-            if (ref != kRefNone && ref_is_medium(ref))
-                traverse<COUNT, FULL>(S, s_nodes, P.n_snodes, o, d, t + 0.0001f, 1e10f, t_exit, eref, lc, time);
+            closest_hit_and_exit<COUNT, FULL>(S, s_nodes, P.n_snodes, o, d, time, t, ref, t_exit, eref, lc);
             f3 no, nd, nthr;
             int ndepth;
             if (!wf_shade_one<FULL>(S, bg, max_depth, sp, o, d, thr, depth, rng, t, ref, t_exit, eref != kRefNone, no, nd, nthr, ndepth, time))
