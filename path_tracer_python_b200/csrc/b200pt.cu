@@ -287,14 +287,12 @@ __global__ void __launch_bounds__(256, 3) k_megakernel(const __grid_constant__ M
         }
         // leave the burst when fewer than burst_num/32 of the lanes that entered it still traverse
         const int min_active = (__popc(__ballot_sync(0xffffffffu, st == LANE_TRAVERSING)) * P.burst_num + 31) >> 5;
-        if (P.vote_num > 0) {
-            bool fin;
-            trav_run_vote<COUNT, FULL>(T, st == LANE_TRAVERSING, fin, S, s_nodes, P.n_snodes, stack,
-                                 min_active > 0 ? min_active : 1, P.vote_num, lc);
-            if (fin) st = LANE_HAVE_RESULT;
-        } else if (st == LANE_TRAVERSING) {
-            if (trav_run<COUNT, FULL>(T, S, s_nodes, P.n_snodes, stack, min_active, lc)) st = LANE_HAVE_RESULT;
-        }
+        // vote_num <= 0 ("no voting") is the vote with threshold 1: descend whenever any lane wants to,
+        // i.e. while-while order -- one copy of the traversal code in the kernel instead of two
+        bool fin;
+        trav_run_vote<COUNT, FULL>(T, st == LANE_TRAVERSING, fin, S, s_nodes, P.n_snodes, stack,
+                             min_active > 0 ? min_active : 1, P.vote_num > 0 ? P.vote_num : 1, lc);
+        if (fin) st = LANE_HAVE_RESULT;
     }
     if (valid) { ap[0] = acc.x; ap[1] = acc.y; ap[2] = acc.z; }
     if (COUNT) flush_counters(P.counters, lc);
@@ -533,14 +531,12 @@ __global__ void __launch_bounds__(256, MINB) k_wf_extend(const __grid_constant__
         const unsigned live = __ballot_sync(0xffffffffu, st != LANE_DONE);
         if (live == 0u) break;
         const int min_active = (__popc(live) * P.burst_num + 31) >> 5;
-        if (P.vote_num > 0) {
-            bool fin;
-            trav_run_vote<COUNT, FULL>(T, st == LANE_TRAVERSING, fin, S, s_nodes, P.n_snodes, stack,
-                                 min_active > 0 ? min_active : 1, P.vote_num, lc);
-            if (fin) st = LANE_HAVE_RESULT;
-        } else if (st == LANE_TRAVERSING) {
-            if (trav_run<COUNT, FULL>(T, S, s_nodes, P.n_snodes, stack, min_active, lc)) st = LANE_HAVE_RESULT;
-        }
+        // vote_num <= 0 ("no voting") is the vote with threshold 1: descend whenever any lane wants to,
+        // i.e. while-while order -- one copy of the traversal code in the kernel instead of two
+        bool fin;
+        trav_run_vote<COUNT, FULL>(T, st == LANE_TRAVERSING, fin, S, s_nodes, P.n_snodes, stack,
+                             min_active > 0 ? min_active : 1, P.vote_num > 0 ? P.vote_num : 1, lc);
+        if (fin) st = LANE_HAVE_RESULT;
     }
     cp_async_wait_all();
     if (COUNT) flush_counters(P.counters, lc);

@@ -1,6 +1,3 @@
 set -x
 timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_renderer.py tests/test_full_features.py -m gpu -x -q 2>&1 | tail -3
-timeout 900 env MODES=wavefront python tools/ab.py libb200pt_base.so libb200pt.so 2>&1 | tail -3
-for l in libb200pt_base.so libb200pt.so; do
-timeout 300 env PT_LIB_PATH=/root/repo/path_tracer_python_b200/$l python tools/stage_times.py 2>&1 | sed -n 1,2p
-done
+timeout 900 python tools/ab.py libb200pt_base.so libb200pt.so 2>&1 | tail -5
