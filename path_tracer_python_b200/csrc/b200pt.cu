@@ -129,7 +129,7 @@ struct MegaParams {
 };
 
 // Lane states of the persistent megakernel
-enum : int { LANE_NEED_PATH = 0, LANE_HAVE_RESULT = 1, LANE_TRAVERSING = 2, LANE_DONE = 3, LANE_WAIT = 4 };
+enum : int { LANE_NEED_PATH = 0, LANE_HAVE_RESULT = 1, LANE_TRAVERSING = 2, LANE_DONE = 3, LANE_WAIT = 4, LANE_BEGIN = 5 };
 
 template <bool COUNT, bool FULL>
 __global__ void __launch_bounds__(256, 3) k_megakernel(const __grid_constant__ MegaParams P) {
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(256, 3) k_megakernel(const __grid_constant__ M
                         mode = 1;                           // the exit search is simply the next traversal
                         t_entry = t;
                         ref_entry = ref;
-                        trav_begin<COUNT>(T, S, o, d, t + 0.0001f, 1e10f, lc, time);
+                        trav_restart<COUNT>(T, S, t + 0.0001f, 1e10f, lc);
                         restart = true;
                     } else {
                         do_shade = true;
@@ -252,8 +252,9 @@ __global__ void __launch_bounds__(256, 3) k_megakernel(const __grid_constant__ M
                                                                                                            : LANE_NEED_PATH;
                 } else {
                     if (COUNT) lc.bounces++;
-                    trav_begin<COUNT>(T, S, hp, sdir, 0.001f, 1e10f, lc, time);
-                    st = LANE_TRAVERSING;
+                    T.o = hp;
+                    T.d = sdir;
+                    st = LANE_BEGIN;
                 }
             } else {
                 st = LANE_TRAVERSING;
@@ -272,11 +273,18 @@ __global__ void __launch_bounds__(256, 3) k_megakernel(const __grid_constant__ M
                 depth = 0;
                 mode = 0;
                 if (COUNT) { lc.paths++; lc.bounces++; }
-                trav_begin<COUNT>(T, S, o, d, 0.001f, 1e10f, lc, time);
-                st = LANE_TRAVERSING;
+                T.o = o;
+                T.d = d;
+                st = LANE_BEGIN;
             } else {
                 st = LANE_DONE;
             }
+        }
+        // bounce rays and fresh camera rays start their traversal together (one copy of the set-up
+        // code, executed once per iteration by both groups of lanes)
+        if (st == LANE_BEGIN) {
+            trav_begin<COUNT>(T, S, T.o, T.d, 0.001f, 1e10f, lc, time);
+            st = LANE_TRAVERSING;
         }
         // ---- (c) traversal burst: leave when fewer than ~burst_frac of the live lanes still traverse
         const unsigned live = __ballot_sync(0xffffffffu, st != LANE_DONE);
@@ -483,7 +491,7 @@ __global__ void __launch_bounds__(256, MINB) k_wf_extend(const __grid_constant__
                     mode = 1;
                     t_entry = T.best_t;
                     ref_entry = ref;
-                    trav_begin<COUNT>(T, S, T.o, T.d, t_entry + 0.0001f, 1e10f, lc, T.time);
+                    trav_restart<COUNT>(T, S, t_entry + 0.0001f, 1e10f, lc);
                     st = LANE_TRAVERSING;
                 } else {
                     P.Q.hit[ray] = make_float4(T.best_t, __int_as_float(ref), 0.0f, __int_as_float(cls << 8));
@@ -554,9 +562,10 @@ __device__ __forceinline__ void closest_hit_and_exit(const DScene& S, SNodeBase 
     float t_min = 0.001f;
     t_exit = 0.0f;
     eref = kRefNone;
+    trav_begin<COUNT>(T, S, o, d, t_min, 1e10f, lc, time);
 #pragma unroll 1
     for (int pass = 0; pass < 2; pass++) {
-        trav_begin<COUNT>(T, S, o, d, t_min, 1e10f, lc, time);
+        if (pass) trav_restart<COUNT>(T, S, t_min, 1e10f, lc);
         trav_run<COUNT, FULL>(T, S, s_nodes, n_snodes, stack, 0, lc);
         if (pass == 0) {
             t = T.best_t;

@@ -227,6 +227,21 @@ __device__ __forceinline__ void trav_begin(TravState& T, const DScene& S, f3 o, 
     if (COUNT) lc.rays++;
 }
 
+// Second search along the SAME ray from a later t_min (the exit search behind a constant-medium
+// boundary, kernels.py:417-419): origin, direction and reciprocal direction stay as they are.
+template <bool COUNT>
+__device__ __forceinline__ void trav_restart(TravState& T, const DScene& S, float t_min, float t_max, LocalCounters& lc) {
+    T.t_min = t_min;
+    T.best_t = t_max;
+    T.best_ref = kRefNone;
+    T.cur = S.num_inner > 0 ? 0 : kRefNone;
+    T.sp = 0;
+#if PT_STACK_TOP
+    T.top = (unsigned long long)(unsigned)kRefNone;
+#endif
+    if (COUNT) lc.rays++;
+}
+
 // A stack entry packs the deferred child's reference and its slab entry distance into one 8-byte
 // word, so that a push / pop is a single local-memory instruction (STL.64 / LDL.64).
 __device__ __forceinline__ StackEntry stack_pack(int ref, float t) {
