@@ -142,9 +142,14 @@ int pt_bvh_build_sah(int32_t n_prims, const float* prim_bbox_min, const float* p
 /* ---- context */
 int pt_create(int device_ordinal, PtContext** out_ctx);   /* replaces ti.init (renderer.py:16) */
 int pt_destroy(PtContext* ctx);
-/* tuning knobs: "block_threads", "smem_nodes" (inner nodes staged in shared memory; -1 = auto),
- * "burst_num" / "wf_burst_num" (a warp leaves the traversal loop when fewer than n/32 of its live
- * lanes still traverse), "sync_samples", "wf_blocks_per_sm", "wavefront_sort" (0/1) */
+/* Scheduling knobs -- none of them changes a result bit (tests/test_gpu_renderer.py):
+ *   "block_threads" (megakernel CTA size), "smem_nodes" (inner nodes staged in shared memory; -1 = auto),
+ *   "burst_num" / "wf_burst_num" (a warp leaves the traversal loop when fewer than n/32 of the lanes
+ *   that entered it still traverse), "vote_num" / "wf_vote_num" (the warp visits a node when at least
+ *   n lanes want to, else it tests primitives; 0 = while-while order), "sync_samples",
+ *   "wf_blocks_per_sm", "wf_extend_minb" (4/5/6: register cap of k_wf_extend), "wf_waves" (full waves
+ *   before the tail kernel), "wf_fuse_primary" (leading waves run inside k_wf_primary), "wf_tile"
+ *   (8x4 pixel tiles in the primary wave), "wavefront_sort" (material binning, 0/1) */
 int pt_set_option(PtContext* ctx, const char* name, int64_t value);
 
 /* `device_blob` (device, info->total_bytes) stays owned by the caller and must outlive its use. */

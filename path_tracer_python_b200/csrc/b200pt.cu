@@ -42,9 +42,10 @@ struct PtContext {
     int block_threads = 256;
     int smem_nodes = -1;      // -1: auto
     int wavefront_sort = 1;
-    int burst_num = 16;
+    int burst_num = 12;      // megakernel: leave a burst when < 12/32 of the entering lanes still traverse
     int sync_samples = 0;
-    int vote_num = 16;
+    int vote_num = 12;       // megakernel: descend when >= 12 lanes want to (tools/sweep.py, config 2)
+    int wf_vote_num = 16;    // the same threshold for k_wf_extend (tools/sweep_wf.py)
     int wf_waves = 12;       // full waves per batch before the tail kernel takes over
     int wf_fuse_primary = 1; // wave 0 (camera rays) as one fused kernel
     int wf_burst_num = 20;
@@ -1076,6 +1077,9 @@ int pt_set_option(PtContext* ctx, const char* name, int64_t value) {
     } else if (k == "vote_num") {
         if (value < 0 || value > 32) return set_error(PT_ERR_INVALID_ARG, "vote_num must be in [0, 32]");
         ctx->vote_num = (int)value;
+    } else if (k == "wf_vote_num") {
+        if (value < 0 || value > 32) return set_error(PT_ERR_INVALID_ARG, "wf_vote_num must be in [0, 32]");
+        ctx->wf_vote_num = (int)value;
     } else if (k == "wf_fuse_primary") {
         ctx->wf_fuse_primary = value < 0 ? 0 : (int)value;   // number of leading waves run fused (0 = off)
     } else if (k == "wf_waves") {
@@ -1279,7 +1283,7 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
     P.seed = seed;
     P.sort = ctx->wavefront_sort;
     P.burst_num = ctx->wf_burst_num;
-    P.vote_num = ctx->vote_num;
+    P.vote_num = ctx->wf_vote_num;
     P.tile = ctx->wf_tile;
     P.counters = ctx->d_counters;
     P.n_snodes = pick_snodes(ctx, 4);

@@ -164,17 +164,17 @@ def test_results_do_not_depend_on_tuning_options(scene_name):
     mega_opts = [dict(burst_num=0, vote_num=0), dict(burst_num=32, vote_num=32), dict(burst_num=7, vote_num=3, smem_nodes=0),
                  dict(block_threads=64, smem_nodes=9), dict(block_threads=128, sync_samples=1), dict(sync_samples=3, smem_nodes=100000)]
     for o in mega_opts:
-        for k, v in dict(dict(burst_num=12, vote_num=10, smem_nodes=-1, block_threads=256, sync_samples=0), **o).items():
+        for k, v in dict(dict(burst_num=12, vote_num=12, smem_nodes=-1, block_threads=256, sync_samples=0), **o).items():
             e.set_option(k, v)
         acc = e.new_accum(W, H)
         e.render_megakernel(acc, 0, spp, seed)
         assert np.array_equal(acc.cpu().numpy(), out["accum_megakernel"]), o
     wf_opts = [dict(wf_waves=1), dict(wf_waves=2, wf_fuse_primary=0), dict(wf_waves=50, wf_fuse_primary=0, wavefront_sort=0),
-               dict(wf_fuse_primary=3, wf_waves=4), dict(wf_fuse_primary=7, wf_waves=3), dict(wf_burst_num=0, vote_num=0, wf_blocks_per_sm=1),
-               dict(wf_burst_num=32, vote_num=32, wf_blocks_per_sm=8, smem_nodes=0), dict(wf_tile=0, wf_extend_minb=5),
+               dict(wf_fuse_primary=3, wf_waves=4), dict(wf_fuse_primary=7, wf_waves=3), dict(wf_burst_num=0, wf_vote_num=0, wf_blocks_per_sm=1),
+               dict(wf_burst_num=32, wf_vote_num=32, wf_blocks_per_sm=8, smem_nodes=0), dict(wf_tile=0, wf_extend_minb=5),
                dict(wf_extend_minb=6, wf_blocks_per_sm=6)]
     for o in wf_opts:
-        for k, v in dict(dict(wf_waves=12, wf_fuse_primary=1, wavefront_sort=1, wf_burst_num=20, vote_num=12, wf_blocks_per_sm=6,
+        for k, v in dict(dict(wf_waves=12, wf_fuse_primary=1, wavefront_sort=1, wf_burst_num=20, wf_vote_num=16, wf_blocks_per_sm=6,
                               smem_nodes=-1, wf_tile=1, wf_extend_minb=4), **o).items():
             e.set_option(k, v)
         for flight in (1, 3, 32):
