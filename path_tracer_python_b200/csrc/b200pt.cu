@@ -768,10 +768,9 @@ __global__ void __launch_bounds__(256) k_wf_shade(const __grid_constant__ WfPara
 // rays of a warp span a compact patch (and so do the bounce rays they append, which the next wave
 // fetches 32 at a time); columns / rows that do not fill a tile follow in scanline order.  Any
 // bijection is allowed here: a path is keyed by its (pixel, sample), never by the lane that runs it.
-__device__ __forceinline__ int tile_local_pixel(int local, int W, int rows) {
+__device__ __forceinline__ void tile_local_pixel(int local, int W, int rows, int& px, int& py) {
     const int tw = W >> 3, th = rows >> 2;
     const int tiled = tw * th * 32;
-    int px, py;
     if (local < tiled) {
         const int t = local >> 5, in = local & 31;
         const int ty = t / tw, tx = t - ty * tw;
@@ -789,7 +788,6 @@ __device__ __forceinline__ int tile_local_pixel(int local, int W, int rows) {
             px = r - (r / W) * W;
         }
     }
-    return py * W + px;
 }
 
 // Wave 0 fused: generate_camera_rays + intersect_rays + shade_miss_rays + shade_and_scatter for the
@@ -820,10 +818,18 @@ __global__ void __launch_bounds__(256, PT_PRIMARY_MINB) k_wf_primary(const __gri
         uint32_t rng = 0;
         if (j < total) {
             const int slot = j / P.N;
-            const int local = P.tile ? tile_local_pixel(j - slot * P.N, P.W, P.y1 - P.y0) : j - slot * P.N;
+            int px, ly;                                         // column, row within the window
+            if (P.tile) {
+                tile_local_pixel(j - slot * P.N, P.W, P.y1 - P.y0, px, ly);
+            } else {
+                const int l = j - slot * P.N;
+                ly = l / P.W;
+                px = l - ly * P.W;
+            }
+            const int local = ly * P.W + px;
             id = slot * P.N + local;
             const int pixel = P.y0 * P.W + local;
-            const int py = pixel / P.W, px = pixel - py * P.W;
+            const int py = P.y0 + ly;
             rng = ptm::rng_seed(P.seed, (uint32_t)pixel, (uint32_t)(P.sample_base + slot));
             const float time = FULL ? ptm::path_time(rng) : 0.0f;
             f3 o, d;

@@ -1,4 +1,3 @@
 set -x
-timeout 400 env SPP=64 SNODES=-1 BURSTS=8,12,16,20,24 VOTES=8,12,16,20 python tools/sweep.py 2>&1 | tail -21
-timeout 300 env BURSTS=16,20,24 VOTES=12,16,20 python tools/sweep_wf.py 2>&1 | tail -9
-timeout 300 env SNODES=64,128,256,512 python tools/sweep_wf.py 2>&1 | tail -4
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 900 python tools/ab.py libb200pt_base.so libb200pt.so 2>&1 | tail -5
