@@ -46,7 +46,8 @@ struct PtContext {
     int sync_samples = 0;
     int vote_num = 12;       // megakernel: descend when >= 12 lanes want to (tools/sweep.py, config 2)
     int wf_vote_num = 16;    // the same threshold for k_wf_extend (tools/sweep_wf.py)
-    int wf_waves = 12;       // full waves per batch before the tail kernel takes over
+    int wf_waves = 8;        // full waves per batch before the tail kernel takes over (tools/sweep_wf.py)
+    int dbg_shade_smem = 0;  // experiment knob: dynamic shared memory reserved per k_wf_shade CTA (limits residency)
     int wf_fuse_primary = 1; // wave 0 (camera rays) as one fused kernel
     int wf_burst_num = 20;
     int wf_blocks_per_sm = 6;
@@ -1083,6 +1084,9 @@ int pt_set_option(PtContext* ctx, const char* name, int64_t value) {
     } else if (k == "vote_num") {
         if (value < 0 || value > 32) return set_error(PT_ERR_INVALID_ARG, "vote_num must be in [0, 32]");
         ctx->vote_num = (int)value;
+    } else if (k == "dbg_shade_smem") {
+        if (value < 0 || value > 200 * 1024) return set_error(PT_ERR_INVALID_ARG, "dbg_shade_smem must be in [0, 200 KiB]");
+        ctx->dbg_shade_smem = (int)value;
     } else if (k == "wf_vote_num") {
         if (value < 0 || value > 32) return set_error(PT_ERR_INVALID_ARG, "wf_vote_num must be in [0, 32]");
         ctx->wf_vote_num = (int)value;
@@ -1316,6 +1320,7 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
         k_tail = full ? k_wf_tail<false, true> : k_wf_tail<false, false>;
     }
     if ((rc = set_smem(k_primary, smem)) || (rc = set_smem(k_extend, smem)) || (rc = set_smem(k_tail, smem))) return rc;
+    if (ctx->dbg_shade_smem && (rc = set_smem(k_shade, (size_t)ctx->dbg_shade_smem))) return rc;
     const int max_depth = ctx->cam.max_depth;
     ctx->marks.clear();
     ctx->ev_used = 0;
@@ -1342,7 +1347,7 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
             P.bounce = b;
             { StageScope t(ctx, st, PT_STAGE_EXTEND, b); k_extend<<<grid, bt, smem, st>>>(P); }
             if (P.sort) { StageScope t(ctx, st, PT_STAGE_BIN, b); k_wf_bin<<<grid_wide, bt, 0, st>>>(P); }
-            { StageScope t(ctx, st, PT_STAGE_SHADE, b); k_shade<<<grid_wide, bt, 0, st>>>(P); }
+            { StageScope t(ctx, st, PT_STAGE_SHADE, b); k_shade<<<grid_wide, bt, ctx->dbg_shade_smem, st>>>(P); }
         }
         if (waves < max_depth) {                          // whatever is still alive: finish in one launch
             P.bounce = waves > first_wave ? waves : first_wave;
