@@ -47,6 +47,7 @@ struct PtContext {
     int vote_num = 12;       // megakernel: descend when >= 12 lanes want to (tools/sweep.py, config 2)
     int wf_vote_num = 16;    // the same threshold for k_wf_extend (tools/sweep_wf.py)
     int wf_waves = 8;        // full waves per batch before the tail kernel takes over (tools/sweep_wf.py)
+    int wf_grid_waves = 16;  // static-partition kernels launch this many full waves of resident CTAs
     int dbg_shade_smem = 0;  // experiment knob: dynamic shared memory reserved per k_wf_shade CTA (limits residency)
     int wf_fuse_primary = 1; // wave 0 (camera rays) as one fused kernel
     int wf_burst_num = 20;
@@ -1084,6 +1085,9 @@ int pt_set_option(PtContext* ctx, const char* name, int64_t value) {
     } else if (k == "vote_num") {
         if (value < 0 || value > 32) return set_error(PT_ERR_INVALID_ARG, "vote_num must be in [0, 32]");
         ctx->vote_num = (int)value;
+    } else if (k == "wf_grid_waves") {
+        if (value < 1 || value > 4096) return set_error(PT_ERR_INVALID_ARG, "wf_grid_waves must be in [1, 4096]");
+        ctx->wf_grid_waves = (int)value;
     } else if (k == "dbg_shade_smem") {
         if (value < 0 || value > 200 * 1024) return set_error(PT_ERR_INVALID_ARG, "dbg_shade_smem must be in [0, 200 KiB]");
         ctx->dbg_shade_smem = (int)value;
@@ -1321,6 +1325,14 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
     }
     if ((rc = set_smem(k_primary, smem)) || (rc = set_smem(k_extend, smem)) || (rc = set_smem(k_tail, smem))) return rc;
     if (ctx->dbg_shade_smem && (rc = set_smem(k_shade, (size_t)ctx->dbg_shade_smem))) return rc;
+    int occ_primary = 1, occ_shade = 1, occ_tail = 1;
+    PT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_primary, k_primary, bt, smem));
+    PT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_shade, k_shade, bt, (size_t)ctx->dbg_shade_smem));
+    PT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_tail, k_tail, bt, smem));
+    if (occ_primary < 1) occ_primary = 1;
+    if (occ_shade < 1) occ_shade = 1;
+    if (occ_tail < 1) occ_tail = 1;
+    if (ctx->wf_grid_waves > 1) { occ_primary *= ctx->wf_grid_waves; occ_shade *= ctx->wf_grid_waves; occ_tail *= ctx->wf_grid_waves; }
     const int max_depth = ctx->cam.max_depth;
     ctx->marks.clear();
     ctx->ev_used = 0;
@@ -1331,6 +1343,15 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
         int grid_full = (int)((total + bt - 1) / bt);
         int grid = grid_persist < grid_full ? grid_persist : grid_full;
         int grid_wide = ctx->num_sms * 8 < grid_full ? ctx->num_sms * 8 : grid_full;
+        // Kernels that split their work statically over the grid (primary, shade, tail) launch a
+        // whole number of waves of RESIDENT CTAs (occupancy x SMs).  Measured on config 2
+        // (tools/stage_times.py): 1 wave 6.07 / 6.44 ms (primary / shade per batch: per-CTA cost
+        // varies with the image region, the slowest CTA sets the time), 8/3 waves -- the former
+        // "8 CTAs per SM" with 3 resident -- 5.67 / 4.9, 16 waves 5.43 / 4.12, 1024 waves 5.91 / 6.02
+        // (per-CTA set-up dominates).
+        const int grid_primary = ctx->num_sms * occ_primary < grid_full ? ctx->num_sms * occ_primary : grid_full;
+        const int grid_shade = ctx->num_sms * occ_shade < grid_full ? ctx->num_sms * occ_shade : grid_full;
+        const int grid_tail = ctx->num_sms * occ_tail < grid_full ? ctx->num_sms * occ_tail : grid_full;
         const int waves = max_depth < ctx->wf_waves ? max_depth : ctx->wf_waves;
         int first_wave = 0;
         P.bounce = 0;
@@ -1338,7 +1359,7 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
             // the first wave(s) in one kernel; survivors land in the queue the next wave reads
             P.fused_waves = ctx->wf_fuse_primary < waves ? ctx->wf_fuse_primary : waves;
             { StageScope t(ctx, st, PT_STAGE_RESET, 0); k_wf_reset<<<1, 32, 0, st>>>(P); }
-            { StageScope t(ctx, st, PT_STAGE_PRIMARY, 0); k_primary<<<grid_wide, bt, smem, st>>>(P); }
+            { StageScope t(ctx, st, PT_STAGE_PRIMARY, 0); k_primary<<<grid_primary, bt, smem, st>>>(P); }
             first_wave = P.fused_waves;
         } else {
             { StageScope t(ctx, st, PT_STAGE_GENERATE, 0); k_wf_generate<<<grid_wide, bt, 0, st>>>(P); }
@@ -1347,11 +1368,11 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
             P.bounce = b;
             { StageScope t(ctx, st, PT_STAGE_EXTEND, b); k_extend<<<grid, bt, smem, st>>>(P); }
             if (P.sort) { StageScope t(ctx, st, PT_STAGE_BIN, b); k_wf_bin<<<grid_wide, bt, 0, st>>>(P); }
-            { StageScope t(ctx, st, PT_STAGE_SHADE, b); k_shade<<<grid_wide, bt, ctx->dbg_shade_smem, st>>>(P); }
+            { StageScope t(ctx, st, PT_STAGE_SHADE, b); k_shade<<<grid_shade, bt, ctx->dbg_shade_smem, st>>>(P); }
         }
         if (waves < max_depth) {                          // whatever is still alive: finish in one launch
             P.bounce = waves > first_wave ? waves : first_wave;
-            { StageScope t(ctx, st, PT_STAGE_TAIL, P.bounce); k_tail<<<grid_wide, bt, smem, st>>>(P); }
+            { StageScope t(ctx, st, PT_STAGE_TAIL, P.bounce); k_tail<<<grid_tail, bt, smem, st>>>(P); }
         }
         int grid_res = (int)((n + bt - 1) / bt);
         if (grid_res > ctx->num_sms * 8) grid_res = ctx->num_sms * 8;

@@ -1,5 +1,3 @@
 set -x
 timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-timeout 600 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_r01c.json 2> gpurun_out/bench_r01c.err || exit 1
-tail -c 1500 gpurun_out/bench_r01c.json
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r01c_launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; tail -2 gpurun_out/ncu_bench.log
+timeout 900 env MODES=wavefront python tools/ab.py libb200pt_base.so libb200pt.so 2>&1 | tail -3
