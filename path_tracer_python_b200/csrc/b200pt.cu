@@ -47,6 +47,10 @@ struct PtContext {
     int vote_num = 12;       // megakernel: descend when >= 12 lanes want to (tools/sweep.py, config 2)
     int wf_vote_num = 16;    // the same threshold for k_wf_extend (tools/sweep_wf.py)
     int wf_waves = 8;        // full waves per batch before the tail kernel takes over (tools/sweep_wf.py)
+    int wf_rel_primary = 1;  // camera rays without defocus: slab test against origin-relative node boxes
+    float4* d_nodes_rel = nullptr;
+    size_t rel_capacity = 0;     // nodes the buffer holds
+    bool rel_valid = false;      // matches the current scene and camera centre
     int wf_grid_waves = 16;  // static-partition kernels launch this many full waves of resident CTAs
     int dbg_shade_smem = 0;  // experiment knob: dynamic shared memory reserved per k_wf_shade CTA (limits residency)
     int wf_fuse_primary = 1; // wave 0 (camera rays) as one fused kernel
@@ -556,7 +560,7 @@ __global__ void __launch_bounds__(256, MINB) k_wf_extend(const __grid_constant__
 // Closest hit of a ray and, when that hit is a constant-medium boundary, the exit search behind it
 // (kernels.py:417-419) -- as ONE traversal loop run up to twice, so that the kernels that inline it
 // (k_wf_primary, k_wf_tail) carry one copy of the traversal code, not two (instruction cache).
-template <bool COUNT, bool FULL>
+template <bool COUNT, bool FULL, bool REL = false>
 __device__ __forceinline__ void closest_hit_and_exit(const DScene& S, SNodeBase s_nodes, int n_snodes, f3 o, f3 d, float time,
                                                      float& t, int& ref, float& t_exit, int& eref, LocalCounters& lc) {
     StackEntry stack[kStackSlots];
@@ -569,7 +573,7 @@ __device__ __forceinline__ void closest_hit_and_exit(const DScene& S, SNodeBase 
 #pragma unroll 1
     for (int pass = 0; pass < 2; pass++) {
         if (pass) trav_restart<COUNT>(T, S, t_min, 1e10f, lc);
-        trav_run<COUNT, FULL>(T, S, s_nodes, n_snodes, stack, 0, lc);
+        trav_run<COUNT, FULL, REL>(T, S, s_nodes, n_snodes, stack, 0, lc);
         if (pass == 0) {
             t = T.best_t;
             ref = T.best_ref;
@@ -799,7 +803,7 @@ __device__ __forceinline__ void tile_local_pixel(int local, int W, int rows, int
 #ifndef PT_PRIMARY_MINB
 #define PT_PRIMARY_MINB 3
 #endif
-template <bool COUNT, bool FULL>
+template <bool COUNT, bool FULL, bool REL>
 __global__ void __launch_bounds__(256, PT_PRIMARY_MINB) k_wf_primary(const __grid_constant__ WfParams P) {
     extern __shared__ float4 s_node_mem[];
     const DScene& S = P.S;
@@ -846,7 +850,7 @@ __global__ void __launch_bounds__(256, PT_PRIMARY_MINB) k_wf_primary(const __gri
                 float t, t_exit = 0.0f;
                 int ref, eref = kRefNone;
                 if (COUNT) lc.bounces++;
-                closest_hit_and_exit<COUNT, FULL>(S, s_nodes, P.n_snodes, o, d, time, t, ref, t_exit, eref, lc);
+                closest_hit_and_exit<COUNT, FULL, REL>(S, s_nodes, P.n_snodes, o, d, time, t, ref, t_exit, eref, lc);
                 emit_next = wf_shade_one<FULL>(S, bg, max_depth, sp, o, d, thr, depth, rng, t, ref, t_exit, eref != kRefNone,
                                          no, nd, nthr, ndepth, time);
                 o = no; d = nd; thr = nthr; depth = ndepth;
@@ -862,6 +866,20 @@ __global__ void __launch_bounds__(256, PT_PRIMARY_MINB) k_wf_primary(const __gri
         }
     }
     if (COUNT) flush_counters(P.counters, lc);
+}
+
+// Node boxes relative to one ray origin: (b - o) rounded once, exactly as the slab test would round
+// it; the child references ride along unchanged.
+__global__ void __launch_bounds__(256) k_make_rel_nodes(const float4* __restrict__ nodes, float4* __restrict__ rel, int num_inner,
+                                                        float ox, float oy, float oz) {
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 4 * num_inner; i += stride) {
+        float4 v = nodes[i];
+        const int row = i & 3;
+        const float o = row == 0 ? ox : (row == 1 ? oy : oz);
+        if (row < 3) v = make_float4(v.x - o, v.y - o, v.z - o, v.w - o);
+        rel[i] = v;
+    }
 }
 
 // zeroes the per-batch counters before k_wf_primary
@@ -1067,6 +1085,7 @@ int pt_destroy(PtContext* ctx) {
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->d_stage_snap) cudaFree(ctx->d_stage_snap);
+    if (ctx->d_nodes_rel) cudaFree(ctx->d_nodes_rel);
     delete ctx;
     return PT_OK;
 }
@@ -1085,6 +1104,8 @@ int pt_set_option(PtContext* ctx, const char* name, int64_t value) {
     } else if (k == "vote_num") {
         if (value < 0 || value > 32) return set_error(PT_ERR_INVALID_ARG, "vote_num must be in [0, 32]");
         ctx->vote_num = (int)value;
+    } else if (k == "wf_rel_primary") {
+        ctx->wf_rel_primary = value ? 1 : 0;
     } else if (k == "wf_grid_waves") {
         if (value < 1 || value > 4096) return set_error(PT_ERR_INVALID_ARG, "wf_grid_waves must be in [1, 4096]");
         ctx->wf_grid_waves = (int)value;
@@ -1152,6 +1173,7 @@ int pt_set_scene(PtContext* ctx, const void* device_blob, const PtPackedInfo* in
         return set_error(PT_ERR_CAPACITY, "pt_set_scene: BVH deeper than the 64-entry traversal stack (kernels.py:649)");
     ctx->info = *info;
     ctx->has_scene = true;
+    ctx->rel_valid = false;
     return PT_OK;
 }
 
@@ -1159,6 +1181,7 @@ int pt_set_camera(PtContext* ctx, const PtCamera* cam) {
     if (!ctx || !cam) return set_error(PT_ERR_INVALID_ARG, "pt_set_camera: NULL argument");
     ctx->cam = *cam;
     ctx->has_camera = true;
+    ctx->rel_valid = false;
     return PT_OK;
 }
 
@@ -1311,12 +1334,34 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
     void (*k_extend)(const WfParams) = nullptr;
     void (*k_tail)(const WfParams) = nullptr;
     void (*k_shade)(const WfParams) = full ? k_wf_shade<true> : k_wf_shade<false>;
+    // camera rays without defocus all start at the camera centre: the fused primary wave then tests
+    // origin-relative node boxes (one subtraction less per box coordinate).  Only when that kernel
+    // runs wave 0 alone -- later waves start elsewhere.
+    const bool rel = ctx->wf_rel_primary && ctx->wf_fuse_primary == 1 && !(ctx->cam.defocus_angle > 0.0f) &&
+                     ctx->scene.num_inner > 0 && ctx->cam.max_depth > 0;
+    if (rel && !ctx->rel_valid) {
+        const size_t need = (size_t)ctx->scene.num_inner;
+        if (ctx->rel_capacity < need) {
+            if (ctx->d_nodes_rel) cudaFree(ctx->d_nodes_rel);
+            ctx->d_nodes_rel = nullptr;
+            ctx->rel_capacity = 0;
+            PT_CUDA(cudaMalloc(&ctx->d_nodes_rel, need * 64));
+            ctx->rel_capacity = need;
+        }
+        int g = (int)((need * 4 + 255) / 256);
+        if (g > ctx->num_sms * 8) g = ctx->num_sms * 8;
+        k_make_rel_nodes<<<g, 256, 0, static_cast<cudaStream_t>(stream)>>>(ctx->scene.nodes, ctx->d_nodes_rel, ctx->scene.num_inner,
+                                                                          ctx->cam.center[0], ctx->cam.center[1], ctx->cam.center[2]);
+        PT_CUDA(cudaGetLastError());
+        ctx->rel_valid = true;
+    }
     if (ctx->count) {
-        k_primary = full ? k_wf_primary<true, true> : k_wf_primary<true, false>;
+        k_primary = full ? k_wf_primary<true, true, false> : k_wf_primary<true, false, false>;
         k_extend = full ? k_wf_extend<true, true, 4> : k_wf_extend<true, false, 4>;
         k_tail = full ? k_wf_tail<true, true> : k_wf_tail<true, false>;
     } else {
-        k_primary = full ? k_wf_primary<false, true> : k_wf_primary<false, false>;
+        if (rel) k_primary = full ? k_wf_primary<false, true, true> : k_wf_primary<false, false, true>;
+        else k_primary = full ? k_wf_primary<false, true, false> : k_wf_primary<false, false, false>;
         // MINB = resident CTAs per SM the register allocation is capped for (4: 64 regs, 5: 48, 6: 40)
         if (ctx->wf_extend_minb >= 6) k_extend = full ? k_wf_extend<false, true, 6> : k_wf_extend<false, false, 6>;
         else if (ctx->wf_extend_minb == 5) k_extend = full ? k_wf_extend<false, true, 5> : k_wf_extend<false, false, 5>;
@@ -1359,7 +1404,12 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
             // the first wave(s) in one kernel; survivors land in the queue the next wave reads
             P.fused_waves = ctx->wf_fuse_primary < waves ? ctx->wf_fuse_primary : waves;
             { StageScope t(ctx, st, PT_STAGE_RESET, 0); k_wf_reset<<<1, 32, 0, st>>>(P); }
-            { StageScope t(ctx, st, PT_STAGE_PRIMARY, 0); k_primary<<<grid_primary, bt, smem, st>>>(P); }
+            {
+                StageScope t(ctx, st, PT_STAGE_PRIMARY, 0);
+                WfParams Pp = P;
+                if (rel && !ctx->count) Pp.S.nodes = ctx->d_nodes_rel;     // this launch only
+                k_primary<<<grid_primary, bt, smem, st>>>(Pp);
+            }
             first_wave = P.fused_waves;
         } else {
             { StageScope t(ctx, st, PT_STAGE_GENERATE, 0); k_wf_generate<<<grid_wide, bt, 0, st>>>(P); }

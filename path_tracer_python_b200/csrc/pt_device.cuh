@@ -350,10 +350,14 @@ __device__ __forceinline__ void load_node(const DScene& S, SNodeBase s_nodes, in
 
 // Runs the traversal until it finishes (returns true) or, when min_active > 0, until fewer than
 // min_active lanes of the warp are still inside the loop (returns false; call again to resume).
-template <bool COUNT, bool FULL = false>
+// REL: S.nodes holds the node boxes with the ray origin already subtracted (every ray of the launch
+// shares that origin: camera rays without defocus; b200pt.cu k_make_rel_nodes).  fl(b - o) is the
+// same single rounding whoever performs it, so the slab test drops its 12 subtractions per node.
+template <bool COUNT, bool FULL = false, bool REL = false>
 __device__ __forceinline__ bool trav_run(TravState& T, const DScene& S, SNodeBase s_nodes, int n_snodes,
                                          StackEntry* stack, int min_active, LocalCounters& lc) {
-    const f3 o = T.o, inv = T.inv;
+    const f3 o = REL ? mk3(0.0f, 0.0f, 0.0f) : T.o;
+    const f3 inv = T.inv;
     const float t_min = T.t_min;
     while (T.cur != kRefNone) {
         while (T.cur >= 0) {
@@ -361,16 +365,20 @@ __device__ __forceinline__ bool trav_run(TravState& T, const DScene& S, SNodeBas
             load_node(S, s_nodes, n_snodes, T.cur, nx, ny, nz, nc);
             if (COUNT) lc.box_tests += 2;
             const float best_t = T.best_t;
-            // left child box
-            float l0x = (nx.x - o.x) * inv.x, l1x = (nx.y - o.x) * inv.x;
-            float l0y = (ny.x - o.y) * inv.y, l1y = (ny.y - o.y) * inv.y;
-            float l0z = (nz.x - o.z) * inv.z, l1z = (nz.y - o.z) * inv.z;
+            float l0x, l1x, l0y, l1y, l0z, l1z, r0x, r1x, r0y, r1y, r0z, r1z;
+            if (REL) {
+                l0x = nx.x * inv.x; l1x = nx.y * inv.x; l0y = ny.x * inv.y; l1y = ny.y * inv.y; l0z = nz.x * inv.z; l1z = nz.y * inv.z;
+                r0x = nx.z * inv.x; r1x = nx.w * inv.x; r0y = ny.z * inv.y; r1y = ny.w * inv.y; r0z = nz.z * inv.z; r1z = nz.w * inv.z;
+            } else {
+                l0x = (nx.x - o.x) * inv.x; l1x = (nx.y - o.x) * inv.x;
+                l0y = (ny.x - o.y) * inv.y; l1y = (ny.y - o.y) * inv.y;
+                l0z = (nz.x - o.z) * inv.z; l1z = (nz.y - o.z) * inv.z;
+                r0x = (nx.z - o.x) * inv.x; r1x = (nx.w - o.x) * inv.x;
+                r0y = (ny.z - o.y) * inv.y; r1y = (ny.w - o.y) * inv.y;
+                r0z = (nz.z - o.z) * inv.z; r1z = (nz.w - o.z) * inv.z;
+            }
             float ltmin = fmax3(fminf(l0x, l1x), fminf(l0y, l1y), fmaxf(fminf(l0z, l1z), t_min));
             float ltmax = fmin3(fmaxf(l0x, l1x), fmaxf(l0y, l1y), fminf(fmaxf(l0z, l1z), best_t));
-            // right child box
-            float r0x = (nx.z - o.x) * inv.x, r1x = (nx.w - o.x) * inv.x;
-            float r0y = (ny.z - o.y) * inv.y, r1y = (ny.w - o.y) * inv.y;
-            float r0z = (nz.z - o.z) * inv.z, r1z = (nz.w - o.z) * inv.z;
             float rtmin = fmax3(fminf(r0x, r1x), fminf(r0y, r1y), fmaxf(fminf(r0z, r1z), t_min));
             float rtmax = fmin3(fmaxf(r0x, r1x), fmaxf(r0y, r1y), fminf(fmaxf(r0z, r1z), best_t));
             const int lref = __float_as_int(nc.x), rref = __float_as_int(nc.y);
