@@ -32,6 +32,16 @@ static int set_error(int code, const std::string& msg) {
             return set_error(PT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
     } while (0)
 
+// launch bound of k_wf_primary: 128-thread CTAs x 7 per SM cap it at 72 registers = 28 warps per SM; the
+// kernel waits mostly on fixed-latency dependencies, which more warps hide (256 x 3 = 80 registers,
+// 24 warps: 5.08 ms per batch; 128 x 7: 4.94 ms with 28 B of spills; 256 x 4 = 64 registers: 212 B of spills)
+#ifndef PT_PRIMARY_MINB
+#define PT_PRIMARY_MINB 7
+#endif
+#ifndef PT_PRIMARY_THREADS
+#define PT_PRIMARY_THREADS 128
+#endif
+
 struct PtContext {
     int device = 0;
     bool has_scene = false;
@@ -47,6 +57,7 @@ struct PtContext {
     int vote_num = 12;       // megakernel: descend when >= 12 lanes want to (tools/sweep.py, config 2)
     int wf_vote_num = 16;    // the same threshold for k_wf_extend (tools/sweep_wf.py)
     int wf_waves = 8;        // full waves per batch before the tail kernel takes over (tools/sweep_wf.py)
+    int wf_primary_threads = PT_PRIMARY_THREADS;   // CTA size of k_wf_primary (<= its launch bound)
     int wf_rel_primary = 1;  // camera rays without defocus: slab test against origin-relative node boxes
     float4* d_nodes_rel = nullptr;
     size_t rel_capacity = 0;     // nodes the buffer holds
@@ -714,13 +725,17 @@ __global__ void __launch_bounds__(256) k_wf_bin(const __grid_constant__ WfParams
 
 // shade_miss_rays + shade_and_scatter (kernels.py:1266-1399) over the material bins; survivors are
 // appended to the other queue with one atomic per warp.
+#ifndef PT_SHADE_THREADS
+#define PT_SHADE_THREADS 256
+#define PT_SHADE_MINB 3
+#endif
 template <bool FULL>
-__global__ void __launch_bounds__(256) k_wf_shade(const __grid_constant__ WfParams P) {
+__global__ void __launch_bounds__(PT_SHADE_THREADS, PT_SHADE_MINB) k_wf_shade(const __grid_constant__ WfParams P) {
     const DScene& S = P.S;
     const int cur = P.bounce & 1, nxt = cur ^ 1;
     const int count = P.Q.qcount[cur];
     if (blockIdx.x == 0 && threadIdx.x == 0) P.Q.cursor[0] = 0;       // for the next k_wf_extend
-    if ((long long)blockIdx.x * 256 >= count) return;
+    if ((long long)blockIdx.x * blockDim.x >= count) return;
     int prefix[kNumBins + 1];
     if (P.sort) {
         prefix[0] = 0;
@@ -800,11 +815,8 @@ __device__ __forceinline__ void tile_local_pixel(int local, int W, int rows, int
 // primary rays (kernels.py:1219-1399) in one kernel.  Camera rays are coherent, so nothing is gained
 // by sending them through the queues: the ray is generated in registers, traced, shaded, and only
 // the surviving bounce ray is appended (one atomic per warp) to queue 1, where wave 1 picks it up.
-#ifndef PT_PRIMARY_MINB
-#define PT_PRIMARY_MINB 3
-#endif
 template <bool COUNT, bool FULL, bool REL>
-__global__ void __launch_bounds__(256, PT_PRIMARY_MINB) k_wf_primary(const __grid_constant__ WfParams P) {
+__global__ void __launch_bounds__(PT_PRIMARY_THREADS, PT_PRIMARY_MINB) k_wf_primary(const __grid_constant__ WfParams P) {
     extern __shared__ float4 s_node_mem[];
     const DScene& S = P.S;
     stage_nodes(s_node_mem, S, P.n_snodes);
@@ -900,7 +912,7 @@ __global__ void __launch_bounds__(256, 3) k_wf_tail(const __grid_constant__ WfPa
     const DScene& S = P.S;
     const int cur = P.bounce & 1;
     const int count = P.Q.qcount[cur];
-    if ((long long)blockIdx.x * 256 >= count) return;
+    if ((long long)blockIdx.x * blockDim.x >= count) return;
     stage_nodes(s_node_mem, S, P.n_snodes);
     const SNodeBase s_nodes = snode_base(s_node_mem);
     LocalCounters lc;
@@ -1104,6 +1116,10 @@ int pt_set_option(PtContext* ctx, const char* name, int64_t value) {
     } else if (k == "vote_num") {
         if (value < 0 || value > 32) return set_error(PT_ERR_INVALID_ARG, "vote_num must be in [0, 32]");
         ctx->vote_num = (int)value;
+    } else if (k == "wf_primary_threads") {
+        if ((value != 64 && value != 128 && value != 256) || value > PT_PRIMARY_THREADS)
+            return set_error(PT_ERR_INVALID_ARG, "wf_primary_threads must be 64, 128 or 256 and within the kernel's launch bound");
+        ctx->wf_primary_threads = (int)value;
     } else if (k == "wf_rel_primary") {
         ctx->wf_rel_primary = value ? 1 : 0;
     } else if (k == "wf_grid_waves") {
@@ -1371,8 +1387,10 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
     if ((rc = set_smem(k_primary, smem)) || (rc = set_smem(k_extend, smem)) || (rc = set_smem(k_tail, smem))) return rc;
     if (ctx->dbg_shade_smem && (rc = set_smem(k_shade, (size_t)ctx->dbg_shade_smem))) return rc;
     int occ_primary = 1, occ_shade = 1, occ_tail = 1;
-    PT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_primary, k_primary, bt, smem));
-    PT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_shade, k_shade, bt, (size_t)ctx->dbg_shade_smem));
+    const int bt_primary = ctx->wf_primary_threads;
+    PT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_primary, k_primary, bt_primary, smem));
+    const int bt_shade = PT_SHADE_THREADS;
+    PT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_shade, k_shade, bt_shade, (size_t)ctx->dbg_shade_smem));
     PT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_tail, k_tail, bt, smem));
     if (occ_primary < 1) occ_primary = 1;
     if (occ_shade < 1) occ_shade = 1;
@@ -1394,8 +1412,10 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
         // varies with the image region, the slowest CTA sets the time), 8/3 waves -- the former
         // "8 CTAs per SM" with 3 resident -- 5.67 / 4.9, 16 waves 5.43 / 4.12, 1024 waves 5.91 / 6.02
         // (per-CTA set-up dominates).
-        const int grid_primary = ctx->num_sms * occ_primary < grid_full ? ctx->num_sms * occ_primary : grid_full;
-        const int grid_shade = ctx->num_sms * occ_shade < grid_full ? ctx->num_sms * occ_shade : grid_full;
+        const int grid_full_primary = (int)((total + bt_primary - 1) / bt_primary);
+        const int grid_primary = ctx->num_sms * occ_primary < grid_full_primary ? ctx->num_sms * occ_primary : grid_full_primary;
+        const int grid_full_shade = (int)((total + bt_shade - 1) / bt_shade);
+        const int grid_shade = ctx->num_sms * occ_shade < grid_full_shade ? ctx->num_sms * occ_shade : grid_full_shade;
         const int grid_tail = ctx->num_sms * occ_tail < grid_full ? ctx->num_sms * occ_tail : grid_full;
         const int waves = max_depth < ctx->wf_waves ? max_depth : ctx->wf_waves;
         int first_wave = 0;
@@ -1408,7 +1428,7 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
                 StageScope t(ctx, st, PT_STAGE_PRIMARY, 0);
                 WfParams Pp = P;
                 if (rel && !ctx->count) Pp.S.nodes = ctx->d_nodes_rel;     // this launch only
-                k_primary<<<grid_primary, bt, smem, st>>>(Pp);
+                k_primary<<<grid_primary, bt_primary, smem, st>>>(Pp);
             }
             first_wave = P.fused_waves;
         } else {
@@ -1418,7 +1438,7 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
             P.bounce = b;
             { StageScope t(ctx, st, PT_STAGE_EXTEND, b); k_extend<<<grid, bt, smem, st>>>(P); }
             if (P.sort) { StageScope t(ctx, st, PT_STAGE_BIN, b); k_wf_bin<<<grid_wide, bt, 0, st>>>(P); }
-            { StageScope t(ctx, st, PT_STAGE_SHADE, b); k_shade<<<grid_shade, bt, ctx->dbg_shade_smem, st>>>(P); }
+            { StageScope t(ctx, st, PT_STAGE_SHADE, b); k_shade<<<grid_shade, bt_shade, ctx->dbg_shade_smem, st>>>(P); }
         }
         if (waves < max_depth) {                          // whatever is still alive: finish in one launch
             P.bounce = waves > first_wave ? waves : first_wave;
