@@ -32,6 +32,10 @@ static int set_error(int code, const std::string& msg) {
             return set_error(PT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
     } while (0)
 
+#ifndef PT_MEGA_THREADS
+#define PT_MEGA_THREADS 256
+#define PT_MEGA_MINB 3
+#endif
 // launch bound of k_wf_primary: 128-thread CTAs x 7 per SM cap it at 72 registers = 28 warps per SM; the
 // kernel waits mostly on fixed-latency dependencies, which more warps hide (256 x 3 = 80 registers,
 // 24 warps: 5.08 ms per batch; 128 x 7: 4.94 ms with 28 B of spills; 256 x 4 = 64 registers: 212 B of spills)
@@ -49,7 +53,7 @@ struct PtContext {
     DScene scene{};
     PtPackedInfo info{};
     PtCamera cam{};
-    int block_threads = 256;
+    int block_threads = PT_MEGA_THREADS;
     int smem_nodes = -1;      // -1: auto
     int wavefront_sort = 1;
     int burst_num = 12;      // megakernel: leave a burst when < 12/32 of the entering lanes still traverse
@@ -150,7 +154,7 @@ struct MegaParams {
 enum : int { LANE_NEED_PATH = 0, LANE_HAVE_RESULT = 1, LANE_TRAVERSING = 2, LANE_DONE = 3, LANE_WAIT = 4, LANE_BEGIN = 5 };
 
 template <bool COUNT, bool FULL>
-__global__ void __launch_bounds__(256, 3) k_megakernel(const __grid_constant__ MegaParams P) {
+__global__ void __launch_bounds__(PT_MEGA_THREADS, PT_MEGA_MINB) k_megakernel(const __grid_constant__ MegaParams P) {
     extern __shared__ float4 s_node_mem[];
     const DScene& S = P.S;
     stage_nodes(s_node_mem, S, P.n_snodes);
@@ -1106,7 +1110,8 @@ int pt_set_option(PtContext* ctx, const char* name, int64_t value) {
     if (!ctx || !name) return set_error(PT_ERR_INVALID_ARG, "pt_set_option: NULL argument");
     std::string k(name);
     if (k == "block_threads") {
-        if (value != 64 && value != 128 && value != 256) return set_error(PT_ERR_INVALID_ARG, "block_threads must be 64, 128 or 256");
+        if ((value != 64 && value != 128 && value != 256) || value > PT_MEGA_THREADS)
+            return set_error(PT_ERR_INVALID_ARG, "block_threads must be 64, 128 or 256 and within the kernel's launch bound");
         ctx->block_threads = (int)value;
     } else if (k == "smem_nodes") {
         ctx->smem_nodes = (int)value;
