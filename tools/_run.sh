@@ -1,2 +1,2 @@
 set -x
-timeout 600 env MODES=megakernel python tools/ab.py libb200pt.so libb200pt_m7.so 2>&1 | tail -2
+timeout 900 python tools/bench_configs.py > gpurun_out/r01d_configs.jsonl 2> gpurun_out/r01d_configs.err; cat gpurun_out/r01d_configs.jsonl | cut -c1-330; tail -3 gpurun_out/r01d_configs.err
