@@ -150,7 +150,18 @@ def run_reference(args, rank):
         "e2e": {"value": value, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+_RESULT_FD = None
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
 
 
 def recorded_traffic(mode):
@@ -177,6 +188,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version
+    # banner on the first collective), so everything except the result line goes to stderr.
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -374,7 +391,7 @@ def main():
             "roofline": roof, "cpu_baseline": cpu, "mean_radiance": mean_radiance,
             "modes": {args.mode: value, other_mode: other_value},
         }
-        print(json.dumps(line))
+        emit(line)
     if group is not None:
         dist.destroy_process_group()
 
