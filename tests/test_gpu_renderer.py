@@ -248,3 +248,27 @@ def test_origin_relative_nodes_follow_camera_and_scene_changes():
     e.set_option("wf_rel_primary", 0)
     c0 = e.new_accum(meta2["width"], meta2["height"]); e.render_wavefront(c0, 0, 2, seed)
     assert np.array_equal(c0.cpu().numpy(), c.cpu().numpy())
+
+
+@pytest.mark.parametrize("mode", ["megakernel", "wavefront"])
+def test_full_size_window_bit_exact_vs_oracle(oracle_mod, mode):
+    """Config 2 at BASELINE size (1920x1080): rows 500..564 of the full-size frame, 4 samples, are
+    bit-identical to the CPU oracle (a window the oracle finishes in seconds; the GPU renders it as
+    a row range of the full frame, with the wavefront's defaults -- tiles, origin-relative primary
+    nodes, 32 samples in flight)."""
+    from path_tracer_python_b200 import scenes
+    from path_tracer_python_b200.engine import Engine
+    O = oracle_mod
+    cs, meta = scenes.load_config("vol2_final_scene", 1920, 16 / 9)
+    W, H, y0, y1, spp, seed = 1920, meta["height"], 500, 564, 4, 2024
+    e = Engine(0)
+    e.set_scene(cs)
+    e.set_camera(meta["camera"], (0.7, 0.8, 1.0), 50)
+    acc = e.new_accum(W, H)
+    (e.render_megakernel if mode == "megakernel" else e.render_wavefront)(acc, 0, spp, seed, y0=y0, y1=y1)
+    got = acc.cpu().numpy()
+    S = O.OracleScene(cs)
+    cam = O.make_camera(meta["camera"], (0.7, 0.8, 1.0), 50)
+    ref, _ = O.render(S, cam, W, H, spp, seed=seed, mode=mode, y0=y0, y1=y1)
+    assert np.array_equal(got[y0:y1], ref[y0:y1])
+    assert not got[:y0].any() and not got[y1:].any()
