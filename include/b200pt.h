@@ -143,7 +143,7 @@ int pt_bvh_build_sah(int32_t n_prims, const float* prim_bbox_min, const float* p
 int pt_create(int device_ordinal, PtContext** out_ctx);   /* replaces ti.init (renderer.py:16) */
 int pt_destroy(PtContext* ctx);
 /* Scheduling knobs -- none of them changes a result bit (tests/test_gpu_renderer.py):
- *   "block_threads" (megakernel CTA size), "smem_nodes" (inner nodes staged in shared memory; -1 = auto),
+ *   "block_threads" (megakernel CTA size), "smem_nodes" (inner nodes staged in shared memory; only acts in builds with -DPT_SNODES=1: the default build fetches every node through L1, which measured faster),
  *   "burst_num" / "wf_burst_num" (a warp leaves the traversal loop when fewer than n/32 of the lanes
  *   that entered it still traverse), "vote_num" / "wf_vote_num" (the warp visits a node when at least
  *   n lanes want to, else it tests primitives; 0 = while-while order), "sync_samples",

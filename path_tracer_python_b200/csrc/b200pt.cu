@@ -1056,6 +1056,10 @@ __global__ void k_tonemap(const float* accum, int n, float scale, uint8_t* out) 
 // C ABI
 // ------------------------------------------------------------------------------------------------
 static int pick_snodes(const PtContext* ctx, int blocks_per_sm_hint) {
+#if !PT_SNODES
+    (void)ctx; (void)blocks_per_sm_hint;
+    return 0;                                   // no shared-memory node staging in this build (pt_device.cuh load_node)
+#endif
     int n = ctx->smem_nodes;
     const int cap_bytes = ctx->max_smem_optin / (blocks_per_sm_hint > 0 ? blocks_per_sm_hint : 1) - 1024;
     int cap = cap_bytes > 0 ? cap_bytes / 64 : 0;

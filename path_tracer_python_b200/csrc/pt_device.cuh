@@ -300,53 +300,42 @@ __device__ __forceinline__ int trav_pop(TravState& T, const StackEntry* stack) {
     return next;
 }
 
-// Fetch of one 64-byte node: the top n_snodes nodes (breadth-first order) are staged in shared
-// memory, the rest comes through L1.  Default (PT_NODE_GENERIC=1): select the ADDRESS -- a generic
-// pointer into the shared copy or into global memory -- and issue one generic load sequence, so a
-// warp whose lanes sit on both sides of the boundary does not run two predicated sequences
-// (config 2, tools/ab.py: wavefront +1.4 %, megakernel +4 %).  PT_NODE_GENERIC=0 builds the
-// LDS / LDG.CONSTANT pair.  Either way the base address is formed ONCE per kernel (snode_base):
-// left to the compiler, it is rebuilt (S2R CgaCtaId, shifts, adds) on every node visit.
-#ifndef PT_NODE_GENERIC
-#define PT_NODE_GENERIC 1
+// Fetch of one 64-byte node: four read-only loads through L1 (hit rate 70-75 % on config 2; the whole
+// tree is L2-resident).
+// History, all measured on config 2 with tools/ab.py: staging the top 256 nodes (breadth-first
+// order) in shared memory first paid (+1 % over none), and was refined twice -- shared-window base
+// formed once per kernel instead of per visit, then ONE generic load sequence through a selected
+// address instead of a predicated LDS/LDG pair (+1.4 % wavefront, +4 % megakernel).  With the rest
+// of the node visit trimmed, the address select alone (ISETP, 2 x SEL, shift) costs more than the
+// staged levels save: no staging at all is +3.0 % / +3.2 %, and returns 16 KB per CTA to L1.
+// PT_SNODES=1 rebuilds the staged variant (options "smem_nodes" then takes effect again).
+#ifndef PT_SNODES
+#define PT_SNODES 0
 #endif
-#if PT_NODE_GENERIC
 typedef unsigned long long SNodeBase;
 __device__ __forceinline__ SNodeBase snode_base(const float4* s_node_mem) {
+#if PT_SNODES
     unsigned long long a = (unsigned long long)s_node_mem, r;
-    asm volatile("mov.u64 %0, %1;" : "=l"(r) : "l"(a));
+    asm volatile("mov.u64 %0, %1;" : "=l"(r) : "l"(a));      // opaque: the generic address stays in a register
     return r;
+#else
+    return 0ull;
+#endif
 }
 __device__ __forceinline__ void load_node(const DScene& S, SNodeBase s_nodes, int n_snodes, int cur,
                                           float4& nx, float4& ny, float4& nz, float4& nc) {
+#if PT_SNODES
     const unsigned long long base = cur < n_snodes ? s_nodes : (unsigned long long)S.nodes;
     const float4* p = reinterpret_cast<const float4*>(base) + 4 * cur;
     nx = p[0]; ny = p[1]; nz = p[2];
     const float2 c2 = *reinterpret_cast<const float2*>(p + 3);
+#else
+    const float4* p = S.nodes + 4 * cur;
+    nx = __ldg(p); ny = __ldg(p + 1); nz = __ldg(p + 2);
+    const float2 c2 = __ldg(reinterpret_cast<const float2*>(p + 3));
+#endif
     nc = make_float4(c2.x, c2.y, 0.0f, 0.0f);
 }
-#else
-typedef unsigned SNodeBase;
-__device__ __forceinline__ SNodeBase snode_base(const float4* s_node_mem) {
-    unsigned a = (unsigned)__cvta_generic_to_shared(s_node_mem), r;
-    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(a));      // opaque: keeps the value in a register
-    return r;
-}
-__device__ __forceinline__ void load_node(const DScene& S, SNodeBase s_nodes, int n_snodes, int cur,
-                                          float4& nx, float4& ny, float4& nz, float4& nc) {
-    if (cur < n_snodes) {
-        const unsigned sa = s_nodes + (unsigned)cur * 64u;
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(nx.x), "=f"(nx.y), "=f"(nx.z), "=f"(nx.w) : "r"(sa));
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+16];" : "=f"(ny.x), "=f"(ny.y), "=f"(ny.z), "=f"(ny.w) : "r"(sa));
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+32];" : "=f"(nz.x), "=f"(nz.y), "=f"(nz.z), "=f"(nz.w) : "r"(sa));
-        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+48];" : "=f"(nc.x), "=f"(nc.y) : "r"(sa));
-        nc.z = 0.0f; nc.w = 0.0f;
-    } else {
-        const float4* p = S.nodes + 4 * cur;
-        nx = __ldg(p); ny = __ldg(p + 1); nz = __ldg(p + 2); nc = __ldg(p + 3);
-    }
-}
-#endif
 
 // Runs the traversal until it finishes (returns true) or, when min_active > 0, until fewer than
 // min_active lanes of the warp are still inside the loop (returns false; call again to resume).
