@@ -265,7 +265,7 @@ __device__ __forceinline__ void stack_init(StackEntry* stack) {
 }
 __device__ __forceinline__ void trav_push(TravState& T, StackEntry* stack, StackEntry e) {
 #if PT_STACK_TOP
-    if ((int)(unsigned)T.top != kRefNone && T.sp < kStackSize) {
+    if ((int)(unsigned)T.top != kRefNone) {      // cannot overflow: pt_set_scene rejects trees deeper than kStackSize
         T.sp++;
         stack[T.sp] = T.top;
     }
@@ -322,15 +322,16 @@ __device__ __forceinline__ SNodeBase snode_base(const float4* s_node_mem) {
     return 0ull;
 #endif
 }
-__device__ __forceinline__ void load_node(const DScene& S, SNodeBase s_nodes, int n_snodes, int cur,
+__device__ __forceinline__ void load_node(const float4* __restrict__ nodes, SNodeBase s_nodes, int n_snodes, int cur,
                                           float4& nx, float4& ny, float4& nz, float4& nc) {
 #if PT_SNODES
-    const unsigned long long base = cur < n_snodes ? s_nodes : (unsigned long long)S.nodes;
+    const unsigned long long base = cur < n_snodes ? s_nodes : (unsigned long long)nodes;
     const float4* p = reinterpret_cast<const float4*>(base) + 4 * cur;
     nx = p[0]; ny = p[1]; nz = p[2];
     const float2 c2 = *reinterpret_cast<const float2*>(p + 3);
 #else
-    const float4* p = S.nodes + 4 * cur;
+    // one IMAD.WIDE: the 64-byte stride applied in 64-bit arithmetic (4 * cur as an int costs a shift first)
+    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const char*>(nodes) + (unsigned long long)(unsigned)cur * 64ull);
     nx = __ldg(p); ny = __ldg(p + 1); nz = __ldg(p + 2);
     const float2 c2 = __ldg(reinterpret_cast<const float2*>(p + 3));
 #endif
@@ -348,10 +349,11 @@ __device__ __forceinline__ bool trav_run(TravState& T, const DScene& S, SNodeBas
     const f3 o = REL ? mk3(0.0f, 0.0f, 0.0f) : T.o;
     const f3 inv = T.inv;
     const float t_min = T.t_min;
+    const float4* const nodes = S.nodes;
     while (T.cur != kRefNone) {
         while (T.cur >= 0) {
             float4 nx, ny, nz, nc;
-            load_node(S, s_nodes, n_snodes, T.cur, nx, ny, nz, nc);
+            load_node(nodes, s_nodes, n_snodes, T.cur, nx, ny, nz, nc);
             if (COUNT) lc.box_tests += 2;
             const float best_t = T.best_t;
             float l0x, l1x, l0y, l1y, l0z, l1z, r0x, r1x, r0y, r1y, r0z, r1z;
@@ -414,6 +416,7 @@ __device__ __forceinline__ void trav_run_vote(TravState& T, bool active, bool& d
                                               int min_active, int vote_num, LocalCounters& lc) {
     const f3 o = T.o, inv = T.inv;
     const float t_min = T.t_min;
+    const float4* const nodes = S.nodes;
     // lanes that do not traverse look finished: one register carries "active and where"
     int cur = active ? T.cur : kRefNone;
     bool progressed = false;     // at least one block is executed per call (no livelock whatever min_active is)
@@ -433,7 +436,7 @@ __device__ __forceinline__ void trav_run_vote(TravState& T, bool active, bool& d
         if (do_node) {
             if (want_node) {
                 float4 nx, ny, nz, nc;
-                load_node(S, s_nodes, n_snodes, cur, nx, ny, nz, nc);
+                load_node(nodes, s_nodes, n_snodes, cur, nx, ny, nz, nc);
                 if (COUNT) lc.box_tests += 2;
                 const float best_t = T.best_t;
                 float l0x = (nx.x - o.x) * inv.x, l1x = (nx.y - o.x) * inv.x;
