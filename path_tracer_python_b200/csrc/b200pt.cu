@@ -70,8 +70,8 @@ struct PtContext {
     int dbg_shade_smem = 0;  // experiment knob: dynamic shared memory reserved per k_wf_shade CTA (limits residency)
     int wf_fuse_primary = 1; // wave 0 (camera rays) as one fused kernel
     int wf_burst_num = 20;
-    int wf_blocks_per_sm = 6;
-    int wf_extend_minb = 4;
+    int wf_blocks_per_sm = 7;
+    int wf_extend_minb = 5;  // 48 registers, 5 CTAs (40 warps) per SM: +1.3 % over 4 x 56 once node fetches all go through L1
     int wf_tile = 1;
     int num_sms = 148;
     int max_smem_optin = 0;
@@ -440,10 +440,15 @@ constexpr int kWfWarps = 8;       // warps per CTA of the wavefront kernels (256
 // the HBM latency of the queue read overlaps traversal), and hands staged rays to lanes as they
 // finish; the other lanes keep traversing (resumable warp-voting traversal).  Results go to the
 // hit-record array in ray order: no atomics, no binning here.
+#ifndef PT_EXT_WARPS
+#define PT_EXT_WARPS 6       // warps per CTA of k_wf_extend: 192 threads x 6 resident CTAs = 36 warps per SM at 56
+                             // registers without spills (256 x 4 = 32 warps; 256 x 5 = 40 warps at 48 registers with spills:
+                             // 2812 / 2846 / 2881 Mpaths/s on config 2)
+#endif
 template <bool COUNT, bool FULL, int MINB>
-__global__ void __launch_bounds__(256, MINB) k_wf_extend(const __grid_constant__ WfParams P) {
+__global__ void __launch_bounds__(PT_EXT_WARPS * 32, MINB) k_wf_extend(const __grid_constant__ WfParams P) {
     extern __shared__ float4 s_dyn[];
-    __shared__ float4 s_ray[kWfWarps][2][32][2];      // (o.xyz d.x)(d.yz ..) of staged rays, 16 KB
+    __shared__ float4 s_ray[PT_EXT_WARPS][2][32][2];      // (o.xyz d.x)(d.yz ..) of staged rays, 2 KB per warp
     float4* s_node_mem = s_dyn;
     const DScene& S = P.S;
     const int cur = P.bounce & 1;
@@ -454,7 +459,7 @@ __global__ void __launch_bounds__(256, MINB) k_wf_extend(const __grid_constant__
     if (blockIdx.x == 0 && threadIdx.x < kNumBins) P.Q.bin_count[threadIdx.x] = 0;   // for this wave's k_wf_bin
     // small waves: only as many CTAs as there are 256-ray slices take part (the rest would just
     // hammer the cursor with atomics and stage nodes for nothing)
-    if ((long long)blockIdx.x * 256 >= count) return;
+    if ((long long)blockIdx.x * (PT_EXT_WARPS * 32) >= count) return;
     stage_nodes(s_node_mem, S, P.n_snodes);
     const SNodeBase s_nodes = snode_base(s_node_mem);
     LocalCounters lc;
@@ -468,7 +473,7 @@ __global__ void __launch_bounds__(256, MINB) k_wf_extend(const __grid_constant__
     int stg_base[2] = {0, 0}, stg_n[2] = {0, 0};
     int buf = 0, stg_pos = 0;
     // small waves reserve 32 rays at a time so that the work spreads over all warps
-    const int reserve = (long long)count >= (long long)gridDim.x * kWfWarps * 2 * kWfReserve ? kWfReserve : 32;
+    const int reserve = (long long)count >= (long long)gridDim.x * PT_EXT_WARPS * 2 * kWfReserve ? kWfReserve : 32;
     auto stage = [&](int b) {           // start the async copy of up to 32 more rays into buffer b
         if (res_next >= res_end && !exhausted) {
             int base = 0;
@@ -1413,7 +1418,8 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
         P.batch = (int)B < sample_begin + sample_count - s ? (int)B : sample_begin + sample_count - s;
         const size_t total = n * (size_t)P.batch;
         int grid_full = (int)((total + bt - 1) / bt);
-        int grid = grid_persist < grid_full ? grid_persist : grid_full;
+        const int grid_full_extend = (int)((total + PT_EXT_WARPS * 32 - 1) / (PT_EXT_WARPS * 32));
+        const int grid_extend = grid_persist < grid_full_extend ? grid_persist : grid_full_extend;
         int grid_wide = ctx->num_sms * 8 < grid_full ? ctx->num_sms * 8 : grid_full;
         // Kernels that split their work statically over the grid (primary, shade, tail) launch a
         // whole number of waves of RESIDENT CTAs (occupancy x SMs).  Measured on config 2
@@ -1445,7 +1451,7 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
         }
         for (int b = first_wave; b < waves; b++) {        // renderer.py:313; no host read-back of the ray count
             P.bounce = b;
-            { StageScope t(ctx, st, PT_STAGE_EXTEND, b); k_extend<<<grid, bt, smem, st>>>(P); }
+            { StageScope t(ctx, st, PT_STAGE_EXTEND, b); k_extend<<<grid_extend, PT_EXT_WARPS * 32, smem, st>>>(P); }
             if (P.sort) { StageScope t(ctx, st, PT_STAGE_BIN, b); k_wf_bin<<<grid_wide, bt, 0, st>>>(P); }
             { StageScope t(ctx, st, PT_STAGE_SHADE, b); k_shade<<<grid_shade, bt_shade, ctx->dbg_shade_smem, st>>>(P); }
         }

@@ -17,7 +17,7 @@ def run():
     chk = int(acc.view(torch.int32).to(torch.int64).sum().item()) & 0xffffffff    # bit-level checksum: must not depend on the options
     return W * H * SPP / a.elapsed_time(b) / 1e3, chk
 L = lambda k, d: [int(x) for x in os.environ.get(k, d).split(",")]
-for fl, bn, bps, sn, so, vn, wv, fu, mb, tl in itertools.product(L("FLIGHT", "32"), L("BURSTS", "20"), L("BPS", "6"), L("SNODES", "256"), L("SORT", "1"), L("VOTES", "16"), L("WAVES", "12"), L("FUSE", "1"), L("MINB", "4"), L("TILE", "1")):
+for fl, bn, bps, sn, so, vn, wv, fu, mb, tl in itertools.product(L("FLIGHT", "32"), L("BURSTS", "20"), L("BPS", "7"), L("SNODES", "256"), L("SORT", "1"), L("VOTES", "16"), L("WAVES", "8"), L("FUSE", "1"), L("MINB", "5"), L("TILE", "1")):
     e.wavefront_samples_in_flight = fl
     e.set_option("wf_burst_num", bn); e.set_option("wf_blocks_per_sm", bps); e.set_option("smem_nodes", sn); e.set_option("wavefront_sort", so); e.set_option("wf_vote_num", vn); e.set_option("wf_waves", wv); e.set_option("wf_fuse_primary", fu); e.set_option("wf_extend_minb", mb); e.set_option("wf_tile", tl)
     v, chk = run()
