@@ -7,8 +7,21 @@ from path_tracer_python_b200.engine import Engine
 from path_tracer_python_b200 import scenes
 W = int(os.environ.get("W", 1920)); SPP = int(os.environ.get("SPP", 32))
 e = Engine(0)
-cs, meta = scenes.load_config(os.environ.get("SCENE", "vol2_final_scene"), W, 16 / 9)
-e.set_scene(cs); e.set_camera(meta["camera"], (0, 0, 0), 50)
+if os.environ.get("SCENE") == "cornell4":        # BASELINE config 4: Cornell + medium + glass + SSS-as-Lambert, 1024^2
+    from path_tracer_python_b200 import scene_compiler as SC, bvh
+    W = int(os.environ.get("W", 1024))
+    world, cam = scenes.cornell_config4(W, 64); cam.initialize()
+    cs = SC.compile_scene(world); cs.update(bvh.compile_bvh(cs)); cs.update(SC.perlin_tables())
+    v = lambda a: [a.x, a.y, a.z]
+    meta = {"height": cam.img_height,
+            "camera": {"cam_center": v(cam.center), "cam_pixel00": v(cam.pixel00_loc), "cam_delta_u": v(cam.delta_u), "cam_delta_v": v(cam.delta_v),
+                       "cam_defocus_disk_u": v(cam.defocus_disk_u), "cam_defocus_disk_v": v(cam.defocus_disk_v), "cam_defocus_angle": 0.0}}
+elif os.environ.get("SCENE") == "heightfield":  # BASELINE config 3: 1 M triangles
+    cs, meta = scenes.heightfield_scene()
+    W = meta["width"]
+else:
+    cs, meta = scenes.load_config(os.environ.get("SCENE", "vol2_final_scene"), W, 16 / 9)
+e.set_scene(cs); e.set_camera(meta["camera"], meta.get("background", (0, 0, 0)), meta.get("max_depth", 50))
 H = meta["height"]
 for k, v in [kv.split("=") for kv in os.environ.get("OPTS", "").split(",") if kv]:
     e.set_option(k, int(v))
@@ -27,5 +40,5 @@ for name, wave, ms in best:
 total = sum(tot.values())
 print(f"{W}x{H} spp={SPP}: sum of stages {total:.2f} ms = {W*H*SPP/total/1e3:.0f} Mpaths/s")
 print("  totals: " + "  ".join(f"{k} {v:.2f}" for k, v in tot.items()))
-for stage in ("extend", "bin", "shade"):
+for stage in ("extend", "bin", "shade", "tail"):
     print(f"  {stage:7s} per wave: " + " ".join(f"{ms:.2f}" for n, w, ms in best if n == stage))
