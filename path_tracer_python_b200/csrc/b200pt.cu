@@ -62,6 +62,7 @@ struct PtContext {
     int wf_vote_num = 16;    // the same threshold for k_wf_extend (tools/sweep_wf.py)
     int wf_waves = 8;        // full waves per batch before the tail kernel takes over (tools/sweep_wf.py)
     int wf_primary_threads = PT_PRIMARY_THREADS;   // CTA size of k_wf_primary (<= its launch bound)
+    int wf_tail_vote = 1;    // the tail as a persistent voting state machine (k_wf_tail_vote) instead of one lane per ray
     int wf_rel_primary = 1;  // camera rays without defocus: slab test against origin-relative node boxes
     float4* d_nodes_rel = nullptr;
     size_t rel_capacity = 0;     // nodes the buffer holds
@@ -403,6 +404,7 @@ __global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ WfP
         P.Q.qcount[0] = total;
         P.Q.qcount[1] = 0;
         P.Q.cursor[0] = 0;
+        P.Q.cursor[1] = 0;
     }
 }
 
@@ -906,7 +908,7 @@ __global__ void __launch_bounds__(256) k_make_rel_nodes(const float4* __restrict
 // zeroes the per-batch counters before k_wf_primary
 __global__ void k_wf_reset(const __grid_constant__ WfParams P) {
     if (threadIdx.x < kNumBins) P.Q.bin_count[threadIdx.x] = 0;
-    if (threadIdx.x == 0) { P.Q.qcount[0] = 0; P.Q.qcount[1] = 0; P.Q.cursor[0] = 0; }
+    if (threadIdx.x == 0) { P.Q.qcount[0] = 0; P.Q.qcount[1] = 0; P.Q.cursor[0] = 0; P.Q.cursor[1] = 0; }   // cursor[1]: k_wf_tail_vote's
 }
 
 // The tail of a batch: after `P.bounce` full waves only a small fraction of the paths is still
@@ -949,6 +951,112 @@ __global__ void __launch_bounds__(256, 3) k_wf_tail(const __grid_constant__ WfPa
         }
     }
     if (COUNT) { __syncwarp(); flush_counters(P.counters, lc); }
+}
+
+// The same tail as a persistent state machine (the megakernel's scheme applied to the queue): warps
+// pull the remaining rays from a cursor, lanes run traverse -> (exit search) -> wf_shade_one ->
+// next bounce independently, and the traversal is the resumable warp-voting one, so a lane whose
+// path has ended picks up the next ray while the others keep traversing.  Per-ray operations and
+// their order are those of k_wf_tail: identical results.
+template <bool COUNT, bool FULL>
+__global__ void __launch_bounds__(256, 3) k_wf_tail_vote(const __grid_constant__ WfParams P) {
+    const DScene& S = P.S;
+    const int cur = P.bounce & 1;
+    const int count = P.Q.qcount[cur];
+    if ((long long)blockIdx.x * blockDim.x >= count) return;
+    const SNodeBase s_nodes = 0;
+    LocalCounters lc;
+    const int max_depth = P.cam.max_depth;
+    const f3 bg = mk3(P.cam.background[0], P.cam.background[1], P.cam.background[2]);
+    const unsigned lane = threadIdx.x & 31;
+    TravState T;
+    T.cur = kRefNone;
+    StackEntry stack[kStackSlots];
+    stack_init(stack);
+    f3 thr = mk3(1.0f, 1.0f, 1.0f);
+    uint32_t rng = 0;
+    int path_id = 0, depth = 0, wave = 0, mode = 0, ref_entry = kRefNone;
+    float t_entry = 0.0f, time = 0.0f;
+    int st = LANE_NEED_PATH;
+    bool exhausted = false;                 // warp-uniform: the cursor ran past the end of the queue
+    for (;;) {
+        if (st == LANE_HAVE_RESULT) {
+            bool shade = true;
+            float t = T.best_t, t_exit = 0.0f;
+            int ref = T.best_ref;
+            bool exit_hit = false;
+            if (mode == 0) {
+                if (ref != kRefNone && ref_is_medium(ref)) {          // exit search behind a medium boundary
+                    mode = 1;
+                    t_entry = t;
+                    ref_entry = ref;
+                    trav_restart<COUNT>(T, S, t_entry + 0.0001f, 1e10f, lc);
+                    st = LANE_TRAVERSING;
+                    shade = false;
+                }
+            } else {
+                mode = 0;
+                t_exit = T.best_t;
+                exit_hit = T.best_ref != kRefNone;
+                t = t_entry;
+                ref = ref_entry;
+            }
+            if (shade) {
+                f3 no, nd, nthr;
+                int ndepth;
+                const bool go = wf_shade_one<FULL>(S, bg, max_depth, P.Q.slab + 3 * (size_t)path_id, T.o, T.d, thr, depth, rng, t, ref,
+                                                   t_exit, exit_hit, no, nd, nthr, ndepth, time);
+                wave++;
+                if (go && wave < max_depth) {
+                    thr = nthr;
+                    depth = ndepth;
+                    if (COUNT) lc.bounces++;
+                    trav_begin<COUNT>(T, S, no, nd, 0.001f, 1e10f, lc, time);
+                    st = LANE_TRAVERSING;
+                } else {
+                    st = LANE_NEED_PATH;
+                }
+            }
+        }
+        // ---- idle lanes take the next rays of the queue (one atomic per warp and round)
+        const unsigned want = __ballot_sync(0xffffffffu, st == LANE_NEED_PATH);
+        if (want && !exhausted) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(P.Q.cursor + 1, __popc(want));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= count) exhausted = true;
+            if (st == LANE_NEED_PATH) {
+                const int i = base + __popc(want & ((1u << lane) - 1));
+                if (i < count) {
+                    const float4 a = P.Q.ra[cur][2 * (size_t)i], bq = P.Q.ra[cur][2 * (size_t)i + 1], c = P.Q.r2[cur][i];
+                    thr = mk3(bq.z, bq.w, c.x);
+                    path_id = __float_as_int(c.y);
+                    rng = __float_as_uint(c.z);
+                    depth = __float_as_int(c.w);
+                    wave = P.bounce;
+                    time = wf_path_time<FULL>(P, path_id);
+                    mode = 0;
+                    if (wave < max_depth) {
+                        if (COUNT) lc.bounces++;
+                        trav_begin<COUNT>(T, S, mk3(a.x, a.y, a.z), mk3(a.w, bq.x, bq.y), 0.001f, 1e10f, lc, time);
+                        st = LANE_TRAVERSING;
+                    }
+                } else {
+                    st = LANE_DONE;
+                }
+            }
+        } else if (want && st == LANE_NEED_PATH) {
+            st = LANE_DONE;
+        }
+        const unsigned live = __ballot_sync(0xffffffffu, st != LANE_DONE);
+        if (live == 0u) break;
+        const int min_active = (__popc(__ballot_sync(0xffffffffu, st == LANE_TRAVERSING)) * P.burst_num + 31) >> 5;
+        bool fin;
+        trav_run_vote<COUNT, FULL>(T, st == LANE_TRAVERSING, fin, S, s_nodes, 0, stack, min_active > 0 ? min_active : 1,
+                             P.vote_num > 0 ? P.vote_num : 1, lc);
+        if (fin) st = LANE_HAVE_RESULT;
+    }
+    if (COUNT) flush_counters(P.counters, lc);
 }
 
 // accum[pixel] += slab[0][pixel]; += slab[1][pixel]; ... in sample order (kernels.py:1280/:1373)
@@ -1134,6 +1242,8 @@ int pt_set_option(PtContext* ctx, const char* name, int64_t value) {
         if ((value != 64 && value != 128 && value != 256) || value > PT_PRIMARY_THREADS)
             return set_error(PT_ERR_INVALID_ARG, "wf_primary_threads must be 64, 128 or 256 and within the kernel's launch bound");
         ctx->wf_primary_threads = (int)value;
+    } else if (k == "wf_tail_vote") {
+        ctx->wf_tail_vote = value ? 1 : 0;
     } else if (k == "wf_rel_primary") {
         ctx->wf_rel_primary = value ? 1 : 0;
     } else if (k == "wf_grid_waves") {
@@ -1388,7 +1498,8 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
     if (ctx->count) {
         k_primary = full ? k_wf_primary<true, true, false> : k_wf_primary<true, false, false>;
         k_extend = full ? k_wf_extend<true, true, 4> : k_wf_extend<true, false, 4>;
-        k_tail = full ? k_wf_tail<true, true> : k_wf_tail<true, false>;
+        if (ctx->wf_tail_vote) k_tail = full ? k_wf_tail_vote<true, true> : k_wf_tail_vote<true, false>;
+        else k_tail = full ? k_wf_tail<true, true> : k_wf_tail<true, false>;
     } else {
         if (rel) k_primary = full ? k_wf_primary<false, true, true> : k_wf_primary<false, false, true>;
         else k_primary = full ? k_wf_primary<false, true, false> : k_wf_primary<false, false, false>;
@@ -1396,7 +1507,8 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
         if (ctx->wf_extend_minb >= 6) k_extend = full ? k_wf_extend<false, true, 6> : k_wf_extend<false, false, 6>;
         else if (ctx->wf_extend_minb == 5) k_extend = full ? k_wf_extend<false, true, 5> : k_wf_extend<false, false, 5>;
         else k_extend = full ? k_wf_extend<false, true, 4> : k_wf_extend<false, false, 4>;
-        k_tail = full ? k_wf_tail<false, true> : k_wf_tail<false, false>;
+        if (ctx->wf_tail_vote) k_tail = full ? k_wf_tail_vote<false, true> : k_wf_tail_vote<false, false>;
+        else k_tail = full ? k_wf_tail<false, true> : k_wf_tail<false, false>;
     }
     if ((rc = set_smem(k_primary, smem)) || (rc = set_smem(k_extend, smem)) || (rc = set_smem(k_tail, smem))) return rc;
     if (ctx->dbg_shade_smem && (rc = set_smem(k_shade, (size_t)ctx->dbg_shade_smem))) return rc;
