@@ -747,11 +747,16 @@ __global__ void __launch_bounds__(PT_SHADE_THREADS, PT_SHADE_MINB) k_wf_shade(co
     const int count = P.Q.qcount[cur];
     if (blockIdx.x == 0 && threadIdx.x == 0) P.Q.cursor[0] = 0;       // for the next k_wf_extend
     if ((long long)blockIdx.x * blockDim.x >= count) return;
-    int prefix[kNumBins + 1];
+    // bin boundaries in shared memory: nine values that would otherwise sit in registers through the
+    // whole shading code of this register-bound kernel
+    __shared__ int prefix[kNumBins + 1];
     if (P.sort) {
-        prefix[0] = 0;
-#pragma unroll
-        for (int b = 0; b < kNumBins; b++) prefix[b + 1] = prefix[b] + P.Q.bin_count[b];
+        if (threadIdx.x == 0) {
+            int acc = 0;
+            prefix[0] = 0;
+            for (int b = 0; b < kNumBins; b++) { acc += P.Q.bin_count[b]; prefix[b + 1] = acc; }
+        }
+        __syncthreads();
     }
     const int max_depth = P.cam.max_depth;
     const f3 bg = mk3(P.cam.background[0], P.cam.background[1], P.cam.background[2]);
