@@ -62,6 +62,9 @@ struct PtContext {
     int wf_vote_num = 16;    // the same threshold for k_wf_extend (tools/sweep_wf.py)
     int wf_waves = 8;        // full waves per batch before the tail kernel takes over (tools/sweep_wf.py)
     int wf_primary_threads = PT_PRIMARY_THREADS;   // CTA size of k_wf_primary (<= its launch bound)
+    int wf_overlap = 1;      // tail + resolve of a batch run on a second stream, under the next batch's primary wave
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_waves[2] = {nullptr, nullptr}, ev_tail[2] = {nullptr, nullptr}, ev_resolve[2] = {nullptr, nullptr};
     int wf_tail_vote = 1;    // the tail as a persistent voting state machine (k_wf_tail_vote) instead of one lane per ray
     int wf_rel_primary = 1;  // camera rays without defocus: slab test against origin-relative node boxes
     float4* d_nodes_rel = nullptr;
@@ -1224,6 +1227,12 @@ int pt_destroy(PtContext* ctx) {
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->d_stage_snap) cudaFree(ctx->d_stage_snap);
     if (ctx->d_nodes_rel) cudaFree(ctx->d_nodes_rel);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->ev_waves[i]) cudaEventDestroy(ctx->ev_waves[i]);
+        if (ctx->ev_tail[i]) cudaEventDestroy(ctx->ev_tail[i]);
+        if (ctx->ev_resolve[i]) cudaEventDestroy(ctx->ev_resolve[i]);
+    }
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     delete ctx;
     return PT_OK;
 }
@@ -1247,6 +1256,8 @@ int pt_set_option(PtContext* ctx, const char* name, int64_t value) {
         if ((value != 64 && value != 128 && value != 256) || value > PT_PRIMARY_THREADS)
             return set_error(PT_ERR_INVALID_ARG, "wf_primary_threads must be 64, 128 or 256 and within the kernel's launch bound");
         ctx->wf_primary_threads = (int)value;
+    } else if (k == "wf_overlap") {
+        ctx->wf_overlap = value ? 1 : 0;
     } else if (k == "wf_tail_vote") {
         ctx->wf_tail_vote = value ? 1 : 0;
     } else if (k == "wf_rel_primary") {
@@ -1414,9 +1425,9 @@ static size_t wf_bytes_per_sample(size_t n) {
     return 6 * n * 16      // two queues x three float4 planes
            + n * 16        // hit records
            + (size_t)kNumBins * n * 4   // material bins
-           + n * 12;       // radiance slab
+           + 2 * n * 12;   // radiance slabs (two: a batch's tail/resolve overlap the next batch's primary wave)
 }
-static const size_t kWfFixedBytes = 4096 + 16 * 256;   // counters + per-section alignment slack
+static const size_t kWfFixedBytes = 4096 + 16 * 256;   // counter sets + per-section alignment slack
 
 size_t pt_wavefront_workspace_bytes(int W, int rows) { return pt_wavefront_workspace_bytes_for(W, rows, 1); }
 
@@ -1453,8 +1464,11 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
     }
     P.Q.hit = reinterpret_cast<float4*>(take(cap * 16));
     P.Q.bins = reinterpret_cast<uint32_t*>(take((size_t)kNumBins * cap * 4));
-    P.Q.slab = reinterpret_cast<float*>(take(cap * 12));
-    int* counters = reinterpret_cast<int*>(take(256));
+    float* slabs[2];
+    slabs[0] = reinterpret_cast<float*>(take(cap * 12));
+    slabs[1] = reinterpret_cast<float*>(take(cap * 12));
+    P.Q.slab = slabs[0];
+    int* counters = reinterpret_cast<int*>(take(512));       // two sets of 64 ints (one per batch parity)
     P.Q.qcount = counters;
     P.Q.bin_count = counters + 8;
     P.Q.cursor = counters + 32;
@@ -1488,6 +1502,12 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
         const size_t need = (size_t)ctx->scene.num_inner;
         if (ctx->rel_capacity < need) {
             if (ctx->d_nodes_rel) cudaFree(ctx->d_nodes_rel);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->ev_waves[i]) cudaEventDestroy(ctx->ev_waves[i]);
+        if (ctx->ev_tail[i]) cudaEventDestroy(ctx->ev_tail[i]);
+        if (ctx->ev_resolve[i]) cudaEventDestroy(ctx->ev_resolve[i]);
+    }
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
             ctx->d_nodes_rel = nullptr;
             ctx->rel_capacity = 0;
             PT_CUDA(cudaMalloc(&ctx->d_nodes_rel, need * 64));
@@ -1530,7 +1550,36 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
     const int max_depth = ctx->cam.max_depth;
     ctx->marks.clear();
     ctx->ev_used = 0;
-    for (int s = sample_begin; s < sample_begin + sample_count; s += (int)B) {
+    const int waves = max_depth < ctx->wf_waves ? max_depth : ctx->wf_waves;
+    const int fused = (ctx->wf_fuse_primary && max_depth > 0) ? (ctx->wf_fuse_primary < waves ? ctx->wf_fuse_primary : waves) : 0;
+    const int tail_bounce = waves > fused ? waves : fused;
+    const int n_batches = (sample_count + (int)B - 1) / (int)B;
+    // Two-stream schedule: the tail and the resolve of batch k run on a second stream while batch
+    // k+1's primary wave and first extend run on the caller's.  The tail is a latency chain (the few
+    // longest paths) that leaves the machine almost empty; the primary wave fills it.  Batches
+    // alternate between two radiance slabs and two counter sets; the queues are shared, which is
+    // safe when the tail reads the queue the fused primary wave does NOT write (parity check) and
+    // the first shade of batch k+1 -- the first kernel to write that queue again -- waits for tail k.
+    // Resolves stay in batch order on the second stream, so the sums are those of the serial schedule.
+    bool overlap = ctx->wf_overlap && !ctx->stage_timing && n_batches > 1 && fused > 0 && waves < max_depth &&
+                   ((tail_bounce & 1) != (fused & 1)) && fused < waves;
+    if (overlap && !ctx->aux_stream) {
+        if (cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) != cudaSuccess) { ctx->aux_stream = nullptr; overlap = false; }
+        for (int i = 0; i < 2 && overlap; i++)
+            if (cudaEventCreateWithFlags(&ctx->ev_waves[i], cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&ctx->ev_tail[i], cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&ctx->ev_resolve[i], cudaEventDisableTiming) != cudaSuccess) overlap = false;
+        (void)cudaGetLastError();
+    }
+    if (overlap && !ctx->aux_stream) overlap = false;
+    cudaStream_t st2 = overlap ? ctx->aux_stream : st;
+    int batch_index = 0;
+    for (int s = sample_begin; s < sample_begin + sample_count; s += (int)B, batch_index++) {
+        const int par = overlap ? (batch_index & 1) : 0;
+        P.Q.slab = slabs[par];
+        P.Q.qcount = counters + 64 * par;
+        P.Q.bin_count = counters + 64 * par + 8;
+        P.Q.cursor = counters + 64 * par + 32;
         P.sample_base = s;
         P.batch = (int)B < sample_begin + sample_count - s ? (int)B : sample_begin + sample_count - s;
         const size_t total = n * (size_t)P.batch;
@@ -1549,12 +1598,13 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
         const int grid_full_shade = (int)((total + bt_shade - 1) / bt_shade);
         const int grid_shade = ctx->num_sms * occ_shade < grid_full_shade ? ctx->num_sms * occ_shade : grid_full_shade;
         const int grid_tail = ctx->num_sms * occ_tail < grid_full ? ctx->num_sms * occ_tail : grid_full;
-        const int waves = max_depth < ctx->wf_waves ? max_depth : ctx->wf_waves;
         int first_wave = 0;
         P.bounce = 0;
-        if (ctx->wf_fuse_primary && max_depth > 0) {
+        // this batch's slab and counter set were last used by batch k-2: its resolve must be done
+        if (overlap && batch_index >= 2) PT_CUDA(cudaStreamWaitEvent(st, ctx->ev_resolve[par], 0));
+        if (fused > 0) {
             // the first wave(s) in one kernel; survivors land in the queue the next wave reads
-            P.fused_waves = ctx->wf_fuse_primary < waves ? ctx->wf_fuse_primary : waves;
+            P.fused_waves = fused;
             { StageScope t(ctx, st, PT_STAGE_RESET, 0); k_wf_reset<<<1, 32, 0, st>>>(P); }
             {
                 StageScope t(ctx, st, PT_STAGE_PRIMARY, 0);
@@ -1570,15 +1620,27 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
             P.bounce = b;
             { StageScope t(ctx, st, PT_STAGE_EXTEND, b); k_extend<<<grid_extend, PT_EXT_WARPS * 32, smem, st>>>(P); }
             if (P.sort) { StageScope t(ctx, st, PT_STAGE_BIN, b); k_wf_bin<<<grid_wide, bt, 0, st>>>(P); }
+            // the first shade of a batch is the first kernel to overwrite the queue the previous batch's tail reads
+            if (overlap && b == first_wave && batch_index >= 1) PT_CUDA(cudaStreamWaitEvent(st, ctx->ev_tail[par ^ 1], 0));
             { StageScope t(ctx, st, PT_STAGE_SHADE, b); k_shade<<<grid_shade, bt_shade, ctx->dbg_shade_smem, st>>>(P); }
         }
-        if (waves < max_depth) {                          // whatever is still alive: finish in one launch
-            P.bounce = waves > first_wave ? waves : first_wave;
-            { StageScope t(ctx, st, PT_STAGE_TAIL, P.bounce); k_tail<<<grid_tail, bt, smem, st>>>(P); }
+        if (overlap) {
+            PT_CUDA(cudaEventRecord(ctx->ev_waves[par], st));
+            PT_CUDA(cudaStreamWaitEvent(st2, ctx->ev_waves[par], 0));
         }
+        if (waves < max_depth) {                          // whatever is still alive: finish in one launch
+            P.bounce = tail_bounce;
+            { StageScope t(ctx, st2, PT_STAGE_TAIL, P.bounce); k_tail<<<grid_tail, bt, smem, st2>>>(P); }
+        }
+        if (overlap) PT_CUDA(cudaEventRecord(ctx->ev_tail[par], st2));
         int grid_res = (int)((n + bt - 1) / bt);
         if (grid_res > ctx->num_sms * 8) grid_res = ctx->num_sms * 8;
-        { StageScope t(ctx, st, PT_STAGE_RESOLVE, 0); k_wf_resolve<<<grid_res, bt, 0, st>>>(P); }
+        { StageScope t(ctx, st2, PT_STAGE_RESOLVE, 0); k_wf_resolve<<<grid_res, bt, 0, st2>>>(P); }
+        if (overlap) PT_CUDA(cudaEventRecord(ctx->ev_resolve[par], st2));
+    }
+    if (overlap) {                                         // join: the caller's stream continues after the last resolve
+        const int last = (batch_index - 1) & 1;
+        PT_CUDA(cudaStreamWaitEvent(st, ctx->ev_resolve[last], 0));
     }
     PT_CUDA(cudaGetLastError());
     return PT_OK;
