@@ -169,9 +169,10 @@ size_t pt_wavefront_workspace_bytes(int W, int rows);   /* minimum: one sample o
 /* workspace for `samples_in_flight` samples of every pixel in flight at once (bigger waves: fewer,
  * fuller launches).  pt_render_wavefront uses as many as the workspace it is given can hold. */
 size_t pt_wavefront_workspace_bytes_for(int W, int rows, int samples_in_flight);
-/* One context = one stream at a time: besides the caller's buffers the context owns a small device
- * cache (node boxes relative to the camera centre, rebuilt on `stream` after pt_set_scene /
- * pt_set_camera when the camera has no defocus) that successive calls on the same stream share. */
+/* Give the call 64 B per inner BVH node on top of that and the primary wave of a defocus-free camera
+ * runs against origin-relative node boxes (a per-call scratch copy; without the room the plain test
+ * is used).  With more than one batch per call the tail of each batch overlaps the next batch's
+ * primary wave on a second, context-owned stream that is joined before the call returns to `stream`. */
 int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int y1, int sample_begin,
                         int sample_count, uint32_t seed, void* workspace, size_t workspace_bytes, void* stream);
 

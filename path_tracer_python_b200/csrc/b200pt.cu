@@ -11,6 +11,8 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 #include "pt_device.cuh"
@@ -67,9 +69,6 @@ struct PtContext {
     cudaEvent_t ev_waves[2] = {nullptr, nullptr}, ev_tail[2] = {nullptr, nullptr}, ev_resolve[2] = {nullptr, nullptr};
     int wf_tail_vote = 1;    // the tail as a persistent voting state machine (k_wf_tail_vote) instead of one lane per ray
     int wf_rel_primary = 1;  // camera rays without defocus: slab test against origin-relative node boxes
-    float4* d_nodes_rel = nullptr;
-    size_t rel_capacity = 0;     // nodes the buffer holds
-    bool rel_valid = false;      // matches the current scene and camera centre
     int wf_grid_waves = 16;  // static-partition kernels launch this many full waves of resident CTAs
     int dbg_shade_smem = 0;  // experiment knob: dynamic shared memory reserved per k_wf_shade CTA (limits residency)
     int wf_fuse_primary = 1; // wave 0 (camera rays) as one fused kernel
@@ -1226,7 +1225,6 @@ int pt_destroy(PtContext* ctx) {
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->d_stage_snap) cudaFree(ctx->d_stage_snap);
-    if (ctx->d_nodes_rel) cudaFree(ctx->d_nodes_rel);
     for (int i = 0; i < 2; i++) {
         if (ctx->ev_waves[i]) cudaEventDestroy(ctx->ev_waves[i]);
         if (ctx->ev_tail[i]) cudaEventDestroy(ctx->ev_tail[i]);
@@ -1329,7 +1327,6 @@ int pt_set_scene(PtContext* ctx, const void* device_blob, const PtPackedInfo* in
         return set_error(PT_ERR_CAPACITY, "pt_set_scene: BVH deeper than the 64-entry traversal stack (kernels.py:649)");
     ctx->info = *info;
     ctx->has_scene = true;
-    ctx->rel_valid = false;
     return PT_OK;
 }
 
@@ -1337,7 +1334,6 @@ int pt_set_camera(PtContext* ctx, const PtCamera* cam) {
     if (!ctx || !cam) return set_error(PT_ERR_INVALID_ARG, "pt_set_camera: NULL argument");
     ctx->cam = *cam;
     ctx->has_camera = true;
-    ctx->rel_valid = false;
     return PT_OK;
 }
 
@@ -1445,8 +1441,13 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
     const size_t n = (size_t)W * rows;
     if (!workspace || workspace_bytes < pt_wavefront_workspace_bytes(W, rows))
         return set_error(PT_ERR_WORKSPACE, "pt_render_wavefront: workspace too small");
+    // The origin-relative node copy of the primary wave (64 B per inner node) comes out of the caller's
+    // workspace too, when that leaves room for at least one sample in flight; it is rebuilt by every
+    // call (microseconds), so the context owns no device memory besides its counters.
+    size_t rel_bytes = align_up((size_t)ctx->scene.num_inner * 64, 256);
+    if (workspace_bytes < kWfFixedBytes + rel_bytes + wf_bytes_per_sample(n)) rel_bytes = 0;
     // samples in flight: as many as the workspace holds (and the 31-bit path id allows)
-    size_t B = (workspace_bytes - kWfFixedBytes) / wf_bytes_per_sample(n);
+    size_t B = (workspace_bytes - kWfFixedBytes - rel_bytes) / wf_bytes_per_sample(n);
     if (B > (size_t)sample_count) B = (size_t)sample_count;
     if (B > 64) B = 64;
     while (B > 1 && B * n > (size_t)0x7fffffff) B--;
@@ -1454,6 +1455,8 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
     PT_CUDA(cudaSetDevice(ctx->device));
     const size_t cap = B * n;
     char* p = static_cast<char*>(workspace);
+    float4* rel_nodes = rel_bytes ? reinterpret_cast<float4*>(p) : nullptr;
+    p += rel_bytes;
     WfParams P;
     P.S = ctx->scene;
     P.cam = ctx->cam;
@@ -1496,29 +1499,14 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
     // camera rays without defocus all start at the camera centre: the fused primary wave then tests
     // origin-relative node boxes (one subtraction less per box coordinate).  Only when that kernel
     // runs wave 0 alone -- later waves start elsewhere.
-    const bool rel = ctx->wf_rel_primary && ctx->wf_fuse_primary == 1 && !(ctx->cam.defocus_angle > 0.0f) &&
-                     ctx->scene.num_inner > 0 && ctx->cam.max_depth > 0;
-    if (rel && !ctx->rel_valid) {
-        const size_t need = (size_t)ctx->scene.num_inner;
-        if (ctx->rel_capacity < need) {
-            if (ctx->d_nodes_rel) cudaFree(ctx->d_nodes_rel);
-    for (int i = 0; i < 2; i++) {
-        if (ctx->ev_waves[i]) cudaEventDestroy(ctx->ev_waves[i]);
-        if (ctx->ev_tail[i]) cudaEventDestroy(ctx->ev_tail[i]);
-        if (ctx->ev_resolve[i]) cudaEventDestroy(ctx->ev_resolve[i]);
-    }
-    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
-            ctx->d_nodes_rel = nullptr;
-            ctx->rel_capacity = 0;
-            PT_CUDA(cudaMalloc(&ctx->d_nodes_rel, need * 64));
-            ctx->rel_capacity = need;
-        }
-        int g = (int)((need * 4 + 255) / 256);
+    bool rel = ctx->wf_rel_primary && ctx->wf_fuse_primary == 1 && !(ctx->cam.defocus_angle > 0.0f) &&
+               ctx->scene.num_inner > 0 && ctx->cam.max_depth > 0 && !ctx->count && rel_nodes != nullptr;
+    if (rel) {
+        int g = (int)(((size_t)ctx->scene.num_inner * 4 + 255) / 256);
         if (g > ctx->num_sms * 8) g = ctx->num_sms * 8;
-        k_make_rel_nodes<<<g, 256, 0, static_cast<cudaStream_t>(stream)>>>(ctx->scene.nodes, ctx->d_nodes_rel, ctx->scene.num_inner,
+        k_make_rel_nodes<<<g, 256, 0, static_cast<cudaStream_t>(stream)>>>(ctx->scene.nodes, rel_nodes, ctx->scene.num_inner,
                                                                           ctx->cam.center[0], ctx->cam.center[1], ctx->cam.center[2]);
         PT_CUDA(cudaGetLastError());
-        ctx->rel_valid = true;
     }
     if (ctx->count) {
         k_primary = full ? k_wf_primary<true, true, false> : k_wf_primary<true, false, false>;
@@ -1609,7 +1597,7 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
             {
                 StageScope t(ctx, st, PT_STAGE_PRIMARY, 0);
                 WfParams Pp = P;
-                if (rel && !ctx->count) Pp.S.nodes = ctx->d_nodes_rel;     // this launch only
+                if (rel) Pp.S.nodes = rel_nodes;                           // this launch only
                 k_primary<<<grid_primary, bt_primary, smem, st>>>(Pp);
             }
             first_wave = P.fused_waves;

@@ -98,10 +98,11 @@ class Engine:
         assert accum.is_cuda and accum.dtype == torch.float32 and accum.is_contiguous()
         y1 = H if y1 is None else y1
         b = max(1, min(self.wavefront_samples_in_flight, sample_count))
-        need = int(self.L.pt_wavefront_workspace_bytes_for(W, y1 - y0, b))
+        extra = 64 * int(self.info.num_inner) + 256 if self.info is not None else 0     # origin-relative node copy
+        need = int(self.L.pt_wavefront_workspace_bytes_for(W, y1 - y0, b)) + extra
         while b > 1 and need > self.max_workspace_bytes:
             b -= 1
-            need = int(self.L.pt_wavefront_workspace_bytes_for(W, y1 - y0, b))
+            need = int(self.L.pt_wavefront_workspace_bytes_for(W, y1 - y0, b)) + extra
         if self._workspace is None or self._workspace.numel() < need:
             self._workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
         with torch.cuda.device(self.device):

@@ -6,6 +6,8 @@ import numpy as np
 import pytest
 import torch
 
+from conftest import GOLDEN_SCENES
+
 pytestmark = pytest.mark.gpu
 
 
@@ -274,3 +276,21 @@ def test_full_size_window_bit_exact_vs_oracle(oracle_mod, mode):
     ref, _ = O.render(S, cam, W, H, spp, seed=seed, mode=mode, y0=y0, y1=y1)
     assert np.array_equal(got[y0:y1], ref[y0:y1])
     assert not got[:y0].any() and not got[y1:].any()
+
+
+def test_one_context_many_scenes_with_batch_overlap():
+    """One context renders all fixture scenes back to back, twice, with several batches per call (so
+    the two-stream batch schedule and the per-call origin-relative node copy are exercised across
+    scene / camera / workspace changes): every image equals the reference's."""
+    from path_tracer_python_b200 import scenes
+    from path_tracer_python_b200.engine import Engine
+    e = Engine(0)
+    e.wavefront_samples_in_flight = 2
+    for _ in range(2):
+        for name in GOLDEN_SCENES:
+            cs, meta, out = scenes.load_fixture(name)
+            e.set_scene(cs)
+            e.set_camera(meta["camera"], meta["background"], meta["max_depth"])
+            acc = e.new_accum(meta["width"], meta["height"])
+            e.render_wavefront(acc, 0, meta["spp"], meta["rng_seed"])
+            assert np.array_equal(acc.cpu().numpy(), out["accum_wavefront"]), name
