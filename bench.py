@@ -186,6 +186,8 @@ def main():
     ap.add_argument("--width", type=int, default=WIDTH)
     ap.add_argument("--spp", type=int, default=SPP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
+                    help="scheduling option for the engine (pt_set_option); never changes a result bit")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version
@@ -232,6 +234,9 @@ def main():
     r._upload_camera()
     W, H = cam.img_width, cam.img_height
     eng = r.engine
+    for kv in args.opt:
+        k, v = kv.split("=")
+        eng.set_option(k, int(v))
     render = eng.render_megakernel if args.mode == "megakernel" else eng.render_wavefront
     s_begin, s_end = r._sample_range()
     n_samples = s_end - s_begin
