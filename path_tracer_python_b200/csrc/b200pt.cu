@@ -1449,9 +1449,14 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
     // samples in flight: as many as the workspace holds (and the 31-bit path id allows)
     size_t B = (workspace_bytes - kWfFixedBytes - rel_bytes) / wf_bytes_per_sample(n);
     if (B > (size_t)sample_count) B = (size_t)sample_count;
-    if (B > 64) B = 64;
+    if (B > 256) B = 256;
     while (B > 1 && B * n > (size_t)0x7fffffff) B--;
     if (B * n > (size_t)0x7fffffff) return set_error(PT_ERR_CAPACITY, "pt_render_wavefront: window too large");
+    // equal batches: 64 samples with room for 63 in flight run as 32 + 32, not 63 + 1
+    if (B > 0) {
+        const size_t nb = ((size_t)sample_count + B - 1) / B;
+        B = ((size_t)sample_count + nb - 1) / nb;
+    }
     PT_CUDA(cudaSetDevice(ctx->device));
     const size_t cap = B * n;
     char* p = static_cast<char*>(workspace);

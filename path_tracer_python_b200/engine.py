@@ -33,7 +33,7 @@ class Engine:
         self._pinned_blob = None
         self._workspace = None
         self.h2d_bytes = 0
-        self.wavefront_samples_in_flight = 32   # bigger waves = fewer, fuller launches; bounded by max_workspace_bytes
+        self.wavefront_samples_in_flight = None  # None = auto (about 66 M paths per batch); bounded by max_workspace_bytes
         self.max_workspace_bytes = 12 << 30
 
     def close(self):
@@ -97,7 +97,14 @@ class Engine:
         H, W, _ = accum.shape
         assert accum.is_cuda and accum.dtype == torch.float32 and accum.is_contiguous()
         y1 = H if y1 is None else y1
-        b = max(1, min(self.wavefront_samples_in_flight, sample_count))
+        if self.wavefront_samples_in_flight is None:
+            # auto: about 66 M paths in flight per batch (32 samples of a 1080p frame; fewer paths leave
+            # the later waves too small to fill the GPU, more gain nothing), in equal batches
+            target = 66.4e6 / max(1, W * (y1 - y0))
+            n_batches = max(1, round(sample_count / target))
+            b = min(256, -(-sample_count // n_batches))
+        else:
+            b = max(1, min(self.wavefront_samples_in_flight, sample_count))
         extra = 64 * int(self.info.num_inner) + 256 if self.info is not None else 0     # origin-relative node copy
         need = int(self.L.pt_wavefront_workspace_bytes_for(W, y1 - y0, b)) + extra
         while b > 1 and need > self.max_workspace_bytes:
@@ -108,7 +115,7 @@ class Engine:
         with torch.cuda.device(self.device):
             check(self.L.pt_render_wavefront(self.ctx, C.c_void_p(accum.data_ptr()), W, H, y0, y1, sample_begin,
                                              sample_count, C.c_uint32(seed & 0xFFFFFFFF),
-                                             C.c_void_p(self._workspace.data_ptr()), C.c_size_t(self._workspace.numel()),
+                                             C.c_void_p(self._workspace.data_ptr()), C.c_size_t(need),
                                              self._stream_ptr()), "pt_render_wavefront")
 
     # ------------------------------------------------------------------ probes

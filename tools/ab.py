@@ -13,11 +13,15 @@ if os.environ.get("AB_CHILD"):
     import torch
     from path_tracer_python_b200.engine import Engine
     from path_tracer_python_b200 import scenes
-    W = int(os.environ.get("W", 1920)); SPP = int(os.environ.get("SPP", 64))
+    sys.path.insert(0, HERE)
+    import _scenes
+    SPP = int(os.environ.get("SPP", 64))
     e = Engine(0)
-    cs, meta = scenes.load_config(os.environ.get("SCENE", "vol2_final_scene"), W, 16 / 9)
-    e.set_scene(cs); e.set_camera(meta["camera"], (0, 0, 0), 50)
+    cs, meta, W = _scenes.load()
+    e.set_scene(cs); e.set_camera(meta["camera"], meta["background"], meta["max_depth"])
     H = meta["height"]
+    if os.environ.get("FLIGHT"):
+        e.wavefront_samples_in_flight = int(os.environ["FLIGHT"])
     for k, v in [kv.split("=") for kv in os.environ.get("OPTS", "").split(",") if kv]:
         e.set_option(k, int(v))
     out = []
