@@ -98,11 +98,7 @@ class Engine:
         assert accum.is_cuda and accum.dtype == torch.float32 and accum.is_contiguous()
         y1 = H if y1 is None else y1
         if self.wavefront_samples_in_flight is None:
-            # auto: about 66 M paths in flight per batch (32 samples of a 1080p frame; fewer paths leave
-            # the later waves too small to fill the GPU, more gain nothing), in equal batches
-            target = 66.4e6 / max(1, W * (y1 - y0))
-            n_batches = max(1, round(sample_count / target))
-            b = min(256, -(-sample_count // n_batches))
+            b = auto_samples_in_flight(W, y1 - y0, sample_count)
         else:
             b = max(1, min(self.wavefront_samples_in_flight, sample_count))
         extra = 64 * int(self.info.num_inner) + 256 if self.info is not None else 0     # origin-relative node copy
@@ -195,6 +191,15 @@ class Engine:
             out.append({k: c[k] - (prev[k] if prev else 0) for k in c})
             prev = c
         return out
+
+
+def auto_samples_in_flight(W: int, rows: int, sample_count: int, target_paths: float = 66.4e6) -> int:
+    """Samples of every pixel the wavefront pipeline keeps in flight per batch: about `target_paths`
+    paths (32 samples of a 1080p frame -- fewer leave the later waves too small to fill the GPU, more
+    gain nothing), split into equal batches, at most 256 (the library's limit)."""
+    per_batch = target_paths / max(1, W * rows)
+    n_batches = max(1, round(sample_count / per_batch))
+    return max(1, min(256, -(-sample_count // n_batches)))
 
 
 def algorithmic_bytes(counters: dict) -> int:

@@ -70,3 +70,16 @@ def test_gloo_world2_spp_split_reduces_to_single_gpu_result(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "RANK0" in r.stdout and "RANK1" in r.stdout and "ok=True" in r.stdout
+
+
+def test_auto_samples_in_flight_sizes_batches_by_paths():
+    """Engine batch sizing (host logic): ~66 M paths per batch, equal batches, library limit 256."""
+    from path_tracer_python_b200.engine import auto_samples_in_flight as f
+    assert f(1920, 1080, 256) == 32          # BASELINE config 2: 8 batches of 32
+    assert f(1920, 1080, 16) == 16           # fewer samples than one batch holds
+    assert f(1024, 1024, 64) == 64           # one batch
+    assert f(3840, 2160, 32) == 8
+    assert f(400, 225, 16) == 16
+    assert f(64, 64, 100000) == 256          # tiny window: the library's limit
+    assert f(1920, 1080, 100) == 34          # 3 equal batches (34 + 34 + 32), not 32 + 32 + 32 + 4
+    assert f(8192, 8192, 4) == 1
