@@ -1,3 +1,6 @@
+"""One context renders a sequence of scenes (vol2 / hf / cornell ...), two calls each, with several
+batches per call -- the stress sequence that exposed the device-allocation problem described in
+DESIGN.md section 5.2 (development aid).    python tools/repro_overlap.py vol2 hf vol2 cornell"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
