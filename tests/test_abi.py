@@ -43,6 +43,11 @@ def test_errors_are_reported_without_a_gpu(L):
     assert rc == -1 and b"NULL" in L.pt_last_error()
     assert L.pt_wavefront_workspace_bytes(0, 10) == 0
     assert L.pt_wavefront_workspace_bytes(1920, 1080) > 1920 * 1080 * (6 * 16 + 16 + 12)
+    # per in-flight sample and pixel: two queues (2 x 48 B), hit record 16 B, 8 bin entries 32 B, two slabs 24 B
+    n = 1920 * 1080
+    one, many = L.pt_wavefront_workspace_bytes_for(1920, 1080, 1), L.pt_wavefront_workspace_bytes_for(1920, 1080, 32)
+    assert one == L.pt_wavefront_workspace_bytes(1920, 1080)
+    assert many - one == 31 * n * 168 and 0 < one - n * 168 <= 64 * 1024
     assert b"sm_100a" in L.pt_version()
 
 
