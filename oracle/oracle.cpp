@@ -111,7 +111,7 @@ inline float fmin2(float a, float b) { return a < b ? a : b; }   /* ti.min / ti.
 inline float fmax2(float a, float b) { return a > b ? a : b; }
 
 struct Rng {
-    uint32_t s;
+    ORng s;          /* (position, stride) of the path's stream, oracle_math.h */
     float next() { return o_rng_next(&s); }
 };
 
@@ -691,9 +691,28 @@ void o_math_eval(int fn, int n, const float* a, const float* b, float* out) {
     }
 }
 
-uint32_t o_rng_seed_state(uint32_t seed, uint32_t pixel, uint32_t sample) { return o_rng_seed(seed, pixel, sample); }
-void o_rng_draw(uint32_t* state, int n, float* out) {
-    for (int i = 0; i < n; i++) out[i] = o_rng_next(state);
+/* a stream's state crosses the C ABI as one 64-bit word: position in the low half, stride in the high half */
+uint64_t o_rng_seed_state(uint32_t seed, uint32_t pixel, uint32_t sample) {
+    ORng r = o_rng_seed(seed, pixel, sample);
+    return ((uint64_t)r.inc << 32) | r.s;
+}
+/* batch form for the stream-uniqueness tests: states of n (pixel, sample) keys */
+void o_rng_seed_states(uint32_t seed, int64_t n, const uint32_t* pixels, const uint32_t* samples, uint64_t* out) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; i++) out[i] = o_rng_seed_state(seed, pixels[i], samples[i]);
+}
+/* first draw of each of n streams (u32 before the float conversion), same purpose */
+void o_rng_first_draws(int64_t n, const uint64_t* states, int k, uint32_t* out) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; i++) {
+        uint32_t s = (uint32_t)states[i], inc = (uint32_t)(states[i] >> 32);
+        for (int j = 0; j < k; j++) { s += inc; out[i * k + j] = o_mix32(s); }
+    }
+}
+void o_rng_draw(uint64_t* state, int n, float* out) {
+    ORng r = {(uint32_t)*state, (uint32_t)(*state >> 32)};
+    for (int i = 0; i < n; i++) out[i] = o_rng_next(&r);
+    *state = ((uint64_t)r.inc << 32) | r.s;
 }
 
 /* get_ray for sample `sample` of every pixel (kernels.py:176-201; generate_camera_rays :1219-1239).
@@ -708,7 +727,7 @@ void o_generate_camera_rays(const OCamera* cam, int W, int H, uint32_t seed, int
             get_ray(cam, px, py, rng, &o, &d);
             out_o[3 * idx] = o.x; out_o[3 * idx + 1] = o.y; out_o[3 * idx + 2] = o.z;
             out_d[3 * idx] = d.x; out_d[3 * idx + 1] = d.y; out_d[3 * idx + 2] = d.z;
-            if (out_rng) out_rng[idx] = rng.s;
+            if (out_rng) out_rng[idx] = rng.s.s;
         }
 }
 

@@ -77,7 +77,7 @@ def lib():
         if not os.path.exists(_LIB_PATH):
             build()
         _lib = C.CDLL(_LIB_PATH)
-        _lib.o_rng_seed_state.restype = C.c_uint32
+        _lib.o_rng_seed_state.restype = C.c_uint64
         _lib.o_rng_seed_state.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
         _lib.o_num_threads.restype = C.c_int
     return _lib
@@ -233,14 +233,33 @@ def math_eval(fn: str, a, b=None):
 
 
 def rng_seed(seed, pixel, sample) -> int:
+    """Initial state of the path's random stream as one 64-bit word: stride << 32 | position."""
     return int(lib().o_rng_seed_state(C.c_uint32(seed), C.c_uint32(pixel), C.c_uint32(sample)))
 
 
 def rng_draw(state: int, n: int):
-    st = C.c_uint32(state)
+    st = C.c_uint64(state)
     out = np.empty(n, np.float32)
     lib().o_rng_draw(C.byref(st), C.c_int(n), out.ctypes.data_as(C.c_void_p))
     return out, int(st.value)
+
+
+def rng_seed_states(seed, pixels, samples):
+    """Vectorised rng_seed: uint64 stream states of the (pixel, sample) keys."""
+    px = np.ascontiguousarray(pixels, np.uint32)
+    sm = np.ascontiguousarray(samples, np.uint32)
+    out = np.empty(px.size, np.uint64)
+    lib().o_rng_seed_states(C.c_uint32(seed), C.c_int64(px.size), px.ctypes.data_as(C.c_void_p),
+                            sm.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def rng_first_draws(states, k):
+    """The first k raw 32-bit outputs of each stream: (n, k) uint32."""
+    st = np.ascontiguousarray(states, np.uint64)
+    out = np.empty((st.size, k), np.uint32)
+    lib().o_rng_first_draws(C.c_int64(st.size), st.ctypes.data_as(C.c_void_p), C.c_int(k), out.ctypes.data_as(C.c_void_p))
+    return out
 
 
 def buffer_to_image(accum, sample_count):

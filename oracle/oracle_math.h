@@ -188,26 +188,32 @@ static inline float o_pow5f(float x) {
 /* PT-F32 contract, part 2: the per-path random stream that stands in for `ti.random()`
  * (kernels.py:21, :33, :47, :184, :441, :894, :1150, :1388; Taichi's own generator is an
  * un-seeded, backend-specific per-thread xorshift and is not reproducible).
- * state += golden; output = 2-round multiply-xorshift finaliser; f32 = top 24 bits * 2^-24. */
+ * A stream = a Weyl sequence on 32 bits with its own odd increment: s += inc; output = 2-round
+ * multiply-xorshift finaliser of s; f32 = top 24 bits * 2^-24.  (start, increment) come from
+ * (seed, pixel, sample) through three Feistel steps, each a bijection on 32 x 31 bits: for one seed
+ * no two (pixel, sample) pairs share a stream (63 bits of stream identity). */
 static inline uint32_t o_mix32(uint32_t z) {
     z ^= z >> 16; z *= 0x21f0aaadu;
     z ^= z >> 15; z *= 0x735a2d97u;
     z ^= z >> 15;
     return z;
 }
-static inline uint32_t o_rng_seed(uint32_t seed, uint32_t pixel_index, uint32_t sample_index) {
-    uint32_t h = o_mix32(seed ^ 0xa511e9b3u);
-    h = o_mix32(h + pixel_index);
-    h = o_mix32(h + sample_index);
-    return h;
+typedef struct ORng { uint32_t s, inc; } ORng;
+static inline ORng o_rng_seed(uint32_t seed, uint32_t pixel_index, uint32_t sample_index) {
+    ORng r;
+    uint32_t a1 = o_mix32(pixel_index ^ o_mix32(seed ^ 0xa511e9b3u));
+    uint32_t b1 = (sample_index + (o_mix32(a1 ^ 0x3c6ef372u) >> 1)) & 0x7fffffffu;
+    r.s = a1 + o_mix32(b1 ^ 0xdaa66d2bu);
+    r.inc = 2u * b1 + 1u;
+    return r;
 }
 /* full-feature mode: a path's shutter time (camera.py:136 `ray_time = random()`) is a pure function
  * of the path key, so that both kernel architectures can recompute it without carrying it */
-static inline float o_path_time(uint32_t key) {
-    return (float)(o_mix32(key ^ 0x7157a3d1u) >> 8) * 5.9604644775390625e-8f;
+static inline float o_path_time(ORng key) {
+    return (float)(o_mix32(key.s ^ 0x7157a3d1u ^ (key.inc * 0x9e3779b9u)) >> 8) * 5.9604644775390625e-8f;
 }
-static inline float o_rng_next(uint32_t* state) {
-    *state += 0x9e3779b9u;
-    return (float)(o_mix32(*state) >> 8) * 5.9604644775390625e-8f; /* 2^-24, exact */
+static inline float o_rng_next(ORng* r) {
+    r->s += r->inc;
+    return (float)(o_mix32(r->s) >> 8) * 5.9604644775390625e-8f; /* 2^-24, exact */
 }
 #endif

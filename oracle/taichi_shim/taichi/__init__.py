@@ -73,7 +73,7 @@ class _Runtime:
         self.sample_counter = 0      # launches since last clear
         self.current_sample = 0
         self.current_pixel = None
-        self.states = {}             # pixel -> u32 state for current sample
+        self.states = {}             # pixel -> u64 stream state (stride << 32 | position) for current sample
         self.image_width = None      # set by the driver (needed to turn (py,px) into a pixel index)
         self.draws = 0
 
@@ -89,10 +89,10 @@ class _Runtime:
         p = self.current_pixel
         s = self.states.get(p)
         if s is None:
-            s = _oracle.rng_seed(self.seed, p, self.current_sample)
-        s = (s + 0x9E3779B9) & 0xFFFFFFFF
+            s = _oracle.rng_seed(self.seed, p, self.current_sample)      # stride << 32 | position
+        s = (s & 0xFFFFFFFF00000000) | ((s + (s >> 32)) & 0xFFFFFFFF)   # position += stride
         self.states[p] = s
-        z = s
+        z = s & 0xFFFFFFFF
         z ^= z >> 16
         z = (z * 0x21F0AAAD) & 0xFFFFFFFF
         z ^= z >> 15

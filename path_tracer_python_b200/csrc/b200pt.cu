@@ -115,7 +115,7 @@ __device__ __forceinline__ void flush_counters(DCounters* dc, const LocalCounter
 // The constant-medium decision once the exit search is done (kernels.py:421-448). Returns true if
 // the ray scatters inside the medium (t_scatter valid).
 __device__ __forceinline__ bool medium_sample(bool hit_exit, float t_exit_hit, float t_entry, f3 d, float density,
-                                              uint32_t& rng, float& t_exit, float& t_scatter) {
+                                              ptm::Rng& rng, float& t_exit, float& t_scatter) {
     t_exit = 0.0f;
     t_scatter = 0.0f;
     if (!hit_exit) return false;
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(PT_MEGA_THREADS, PT_MEGA_MINB) k_megakernel(co
 
     // per-path state
     f3 thr = mk3(1.0f, 1.0f, 1.0f), col = mk3(0.0f, 0.0f, 0.0f);
-    uint32_t rng = 0;
+    ptm::Rng rng{0u, 1u};
     float time = 0.0f;       // shutter time of the current path (full feature mode)
     int depth = 0;
     int mode = 0;            // 0: closest-hit search, 1: medium-exit search (kernels.py:417)
@@ -363,6 +363,7 @@ struct WfParams {
     float* accum;
     int W, H, y0, y1;
     int N;                   // W * (y1 - y0)
+    float inv_N;             // 1.0f / N (wf_path_key)
     int sample_base;         // first sample index of this batch
     int batch;               // samples in this batch (<= B)
     uint32_t seed;
@@ -376,13 +377,22 @@ struct WfParams {
     DCounters* counters;
 };
 
-// full feature mode: the shutter time of the path that owns a queue entry, recomputed from its id
+// The key of the path that owns a queue entry -- (start, stride) of its random stream -- recomputed from
+// its id: the ray record carries only the stream position, the stride is a pure function of
+// (seed, pixel, sample).  path_id = slot * N + local pixel with slot <= 256, so the quotient comes
+// from one float multiply and an exact fix-up instead of an integer division.
+__device__ __forceinline__ ptm::Rng wf_path_key(const WfParams& P, int path_id) {
+    int slot = (int)((float)path_id * P.inv_N);
+    int local = path_id - slot * P.N;
+    if (local < 0) { slot--; local += P.N; }
+    else if (local >= P.N) { slot++; local -= P.N; }
+    return ptm::rng_seed(P.seed, (uint32_t)(P.y0 * P.W + local), (uint32_t)(P.sample_base + slot));
+}
+// full feature mode: the shutter time of that path
 template <bool FULL>
 __device__ __forceinline__ float wf_path_time(const WfParams& P, int path_id) {
     if (!FULL) return 0.0f;
-    const int slot = path_id / P.N;
-    const int pixel = P.y0 * P.W + (path_id - slot * P.N);
-    return ptm::path_time(ptm::rng_seed(P.seed, (uint32_t)pixel, (uint32_t)(P.sample_base + slot)));
+    return ptm::path_time(wf_path_key(P, path_id));
 }
 
 __global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ WfParams P) {
@@ -392,12 +402,12 @@ __global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ WfP
         const int slot = id / P.N;
         const int pixel = P.y0 * P.W + (id - slot * P.N);
         const int py = pixel / P.W, px = pixel - py * P.W;
-        uint32_t rng = ptm::rng_seed(P.seed, (uint32_t)pixel, (uint32_t)(P.sample_base + slot));
+        ptm::Rng rng = ptm::rng_seed(P.seed, (uint32_t)pixel, (uint32_t)(P.sample_base + slot));
         f3 o, d;
         get_ray(P.cam, px, py, rng, o, d);                  // NOT normalised, kernels.py:1229-1233
         P.Q.ra[0][2 * (size_t)id] = make_float4(o.x, o.y, o.z, d.x);
         P.Q.ra[0][2 * (size_t)id + 1] = make_float4(d.y, d.z, 1.0f, 1.0f);
-        P.Q.r2[0][id] = make_float4(1.0f, __int_as_float(id), __uint_as_float(rng), __int_as_float(0));
+        P.Q.r2[0][id] = make_float4(1.0f, __int_as_float(id), __uint_as_float(rng.s), __int_as_float(0));
         P.Q.slab[3 * (size_t)id] = 0.0f;
         P.Q.slab[3 * (size_t)id + 1] = 0.0f;
         P.Q.slab[3 * (size_t)id + 2] = 0.0f;
@@ -619,7 +629,7 @@ __device__ __forceinline__ void closest_hit_and_exit(const DScene& S, SNodeBase 
 // of a scattered, latency-bound read-modify-write.
 template <bool FULL>
 __device__ __forceinline__ bool wf_shade_one(const DScene& S, f3 bg, int max_depth, float* sp, f3 o, f3 d, f3 thr,
-                                             int depth, uint32_t& rng, float t, int ref, float t_exit_hit, bool exit_hit,
+                                             int depth, ptm::Rng& rng, float t, int ref, float t_exit_hit, bool exit_hit,
                                              f3& no, f3& nd, f3& nthr, int& ndepth, float time = 0.0f) {
     if (ref == kRefNone) {                           // shade_miss_rays, kernels.py:1266-1280
         f3 add = thr * bg;
@@ -781,14 +791,16 @@ __global__ void __launch_bounds__(PT_SHADE_THREADS, PT_SHADE_MINB) k_wf_shade(co
         bool emit_next = false;
         f3 no, nd, nthr;
         int path_id = 0, ndepth = 0;
-        uint32_t rng = 0;
+        ptm::Rng rng{0u, 1u};
         if (active) {
             path_id = __float_as_int(c.y);
-            rng = __float_as_uint(c.z);
+            const ptm::Rng key = wf_path_key(P, path_id);
+            rng.s = __float_as_uint(c.z);
+            rng.inc = key.inc;
             emit_next = wf_shade_one<FULL>(S, bg, max_depth, P.Q.slab + 3 * (size_t)path_id, mk3(a.x, a.y, a.z),
                                      mk3(a.w, bq.x, bq.y), mk3(bq.z, bq.w, c.x), __float_as_int(c.w), rng, h.x,
                                      __float_as_int(h.y), h.z, (__float_as_int(h.w) & 1) != 0, no, nd, nthr, ndepth,
-                                     wf_path_time<FULL>(P, path_id));
+                                     FULL ? ptm::path_time(key) : 0.0f);
         }
         // compaction: one atomic per warp (kernels.py:1345/:1394 use one per ray).  Aggregating
         // further, one atomic per CTA through shared memory and two barriers, measured slower
@@ -798,7 +810,7 @@ __global__ void __launch_bounds__(PT_SHADE_THREADS, PT_SHADE_MINB) k_wf_shade(co
         if (emit_next) {
             P.Q.ra[nxt][2 * (size_t)pos] = make_float4(no.x, no.y, no.z, nd.x);
             P.Q.ra[nxt][2 * (size_t)pos + 1] = make_float4(nd.y, nd.z, nthr.x, nthr.y);
-            P.Q.r2[nxt][pos] = make_float4(nthr.z, __int_as_float(path_id), __uint_as_float(rng), __int_as_float(ndepth));
+            P.Q.r2[nxt][pos] = make_float4(nthr.z, __int_as_float(path_id), __uint_as_float(rng.s), __int_as_float(ndepth));
         }
     }
 }
@@ -851,7 +863,7 @@ __global__ void __launch_bounds__(PT_PRIMARY_THREADS, PT_PRIMARY_MINB) k_wf_prim
         bool emit_next = false;
         f3 no, nd, nthr;
         int ndepth = 0;
-        uint32_t rng = 0;
+        ptm::Rng rng{0u, 1u};
         if (j < total) {
             const int slot = j / P.N;
             int px, ly;                                         // column, row within the window
@@ -892,7 +904,7 @@ __global__ void __launch_bounds__(PT_PRIMARY_THREADS, PT_PRIMARY_MINB) k_wf_prim
             const int id2 = id;
             P.Q.ra[qd][2 * (size_t)pos] = make_float4(no.x, no.y, no.z, nd.x);
             P.Q.ra[qd][2 * (size_t)pos + 1] = make_float4(nd.y, nd.z, nthr.x, nthr.y);
-            P.Q.r2[qd][pos] = make_float4(nthr.z, __int_as_float(id2), __uint_as_float(rng), __int_as_float(ndepth));
+            P.Q.r2[qd][pos] = make_float4(nthr.z, __int_as_float(id2), __uint_as_float(rng.s), __int_as_float(ndepth));
         }
     }
     if (COUNT) flush_counters(P.counters, lc);
@@ -941,10 +953,11 @@ __global__ void __launch_bounds__(256, 3) k_wf_tail(const __grid_constant__ WfPa
         const float4 a = P.Q.ra[cur][2 * (size_t)i], bq = P.Q.ra[cur][2 * (size_t)i + 1], c = P.Q.r2[cur][i];
         f3 o = mk3(a.x, a.y, a.z), d = mk3(a.w, bq.x, bq.y), thr = mk3(bq.z, bq.w, c.x);
         const int path_id = __float_as_int(c.y);
-        uint32_t rng = __float_as_uint(c.z);
+        const ptm::Rng key = wf_path_key(P, path_id);
+        ptm::Rng rng{__float_as_uint(c.z), key.inc};
         int depth = __float_as_int(c.w);
         float* sp = P.Q.slab + 3 * (size_t)path_id;
-        const float time = wf_path_time<FULL>(P, path_id);
+        const float time = FULL ? ptm::path_time(key) : 0.0f;
         for (int wave = P.bounce; wave < max_depth; wave++) {
             float t, t_exit = 0.0f;
             int ref, eref = kRefNone;
@@ -981,7 +994,7 @@ __global__ void __launch_bounds__(256, 3) k_wf_tail_vote(const __grid_constant__
     StackEntry stack[kStackSlots];
     stack_init(stack);
     f3 thr = mk3(1.0f, 1.0f, 1.0f);
-    uint32_t rng = 0;
+    ptm::Rng rng{0u, 1u};
     int path_id = 0, depth = 0, wave = 0, mode = 0, ref_entry = kRefNone;
     float t_entry = 0.0f, time = 0.0f;
     int st = LANE_NEED_PATH;
@@ -1038,10 +1051,12 @@ __global__ void __launch_bounds__(256, 3) k_wf_tail_vote(const __grid_constant__
                     const float4 a = P.Q.ra[cur][2 * (size_t)i], bq = P.Q.ra[cur][2 * (size_t)i + 1], c = P.Q.r2[cur][i];
                     thr = mk3(bq.z, bq.w, c.x);
                     path_id = __float_as_int(c.y);
-                    rng = __float_as_uint(c.z);
+                    const ptm::Rng key = wf_path_key(P, path_id);
+                    rng.s = __float_as_uint(c.z);
+                    rng.inc = key.inc;
                     depth = __float_as_int(c.w);
                     wave = P.bounce;
-                    time = wf_path_time<FULL>(P, path_id);
+                    time = FULL ? ptm::path_time(key) : 0.0f;
                     mode = 0;
                     if (wave < max_depth) {
                         if (COUNT) lc.bounces++;
@@ -1087,7 +1102,7 @@ __global__ void k_generate_rays(PtCamera cam, int W, int H, uint32_t seed, int s
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= W * H) return;
     int py = i / W, px = i - py * W;
-    uint32_t rng = ptm::rng_seed(seed, (uint32_t)i, (uint32_t)sample);
+    ptm::Rng rng = ptm::rng_seed(seed, (uint32_t)i, (uint32_t)sample);
     f3 o, d;
     get_ray(cam, px, py, rng, o, d);
     o_out[3 * i] = o.x; o_out[3 * i + 1] = o.y; o_out[3 * i + 2] = o.z;
@@ -1141,7 +1156,7 @@ __global__ void k_math_eval(int fn, int n, const float* a, const float* b, float
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (fn == 6) {
         if (i == 0) {
-            uint32_t s = __float_as_uint(a[0]);
+            ptm::Rng s{__float_as_uint(a[0]), __float_as_uint(a[1])};      // (position, stride) of the stream
             for (int k = 0; k < n; k++) out[k] = ptm::rng_next(s);
         }
         return;
@@ -1484,6 +1499,7 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
     P.accum = accum;
     P.W = W; P.H = H; P.y0 = y0; P.y1 = y1;
     P.N = (int)n;
+    P.inv_N = 1.0f / (float)n;
     P.seed = seed;
     P.sort = ctx->wavefront_sort;
     P.burst_num = ctx->wf_burst_num;

@@ -496,7 +496,7 @@ __device__ __forceinline__ void traverse(const DScene& S, SNodeBase s_nodes, int
 }
 
 // ---- samplers (kernels.py:16-71)
-__device__ __forceinline__ f3 random_in_unit_disk(uint32_t& rng) {
+__device__ __forceinline__ f3 random_in_unit_disk(ptm::Rng& rng) {
     for (;;) {
         float px = ptm::rng_next(rng) * 2.0f - 1.0f;
         float py = ptm::rng_next(rng) * 2.0f - 1.0f;
@@ -504,7 +504,7 @@ __device__ __forceinline__ f3 random_in_unit_disk(uint32_t& rng) {
         if (dot(p, p) < 1.0f) return p;
     }
 }
-__device__ __forceinline__ f3 random_unit_vector(uint32_t& rng) {
+__device__ __forceinline__ f3 random_unit_vector(ptm::Rng& rng) {
     for (;;) {
         float px = ptm::rng_next(rng) * 2.0f - 1.0f;
         float py = ptm::rng_next(rng) * 2.0f - 1.0f;
@@ -514,7 +514,7 @@ __device__ __forceinline__ f3 random_unit_vector(uint32_t& rng) {
         if (l < 1.0f && l > 1e-20f) return normalized(p);
     }
 }
-__device__ __forceinline__ f3 random_cosine_direction(f3 normal, uint32_t& rng) {
+__device__ __forceinline__ f3 random_cosine_direction(f3 normal, ptm::Rng& rng) {
     float r1 = ptm::rng_next(rng);
     float r2 = ptm::rng_next(rng);
     float z = ptm::fsqrt(1.0f - r2);
@@ -534,7 +534,7 @@ __device__ __forceinline__ f3 random_cosine_direction(f3 normal, uint32_t& rng) 
 }
 
 // ---- camera (kernels.py:176-201)
-__device__ __forceinline__ void get_ray(const PtCamera& cam, int px, int py, uint32_t& rng, f3& o, f3& d) {
+__device__ __forceinline__ void get_ray(const PtCamera& cam, int px, int py, ptm::Rng& rng, f3& o, f3& d) {
     float ox = ptm::rng_next(rng) - 0.5f;
     float oy = ptm::rng_next(rng) - 0.5f;
     f3 p00 = mk3(cam.pixel00[0], cam.pixel00[1], cam.pixel00[2]);
@@ -664,7 +664,7 @@ __device__ __forceinline__ float reflectance(float cosine, float ref_idx) {
 }
 
 // core/material.py:258-276 _sample_henyey_greenstein (full feature mode)
-__device__ __noinline__ f3 sample_henyey_greenstein(f3 incident, float g, uint32_t& rng) {
+__device__ __noinline__ f3 sample_henyey_greenstein(f3 incident, float g, ptm::Rng& rng) {
     if (fabsf(g) < 1e-3f) return random_unit_vector(rng);
     float sqr_term = ptm::fdiv(1.0f - g * g, 1.0f - g + 2.0f * g * ptm::rng_next(rng));
     float cos_theta = ptm::fdiv(1.0f + g * g - sqr_term * sqr_term, 2.0f * g);
@@ -681,7 +681,7 @@ __device__ __noinline__ f3 sample_henyey_greenstein(f3 incident, float g, uint32
 
 // subsurface_simple / subsurface_volumetric (core/material.py:144-256), full feature mode only.
 // `hp` is replaced by the (possibly displaced) origin of the scattered ray.
-__device__ __noinline__ bool shade_subsurface(const Mat& m, f3 ray_dir, f3& hp, f3 normal, uint32_t& rng,
+__device__ __noinline__ bool shade_subsurface(const Mat& m, f3 ray_dir, f3& hp, f3 normal, ptm::Rng& rng,
                                               f3& scatter_dir, f3& attenuation) {
     const f3 nf = dot(ray_dir, normal) < 0.0f ? normal : -normal;     // face-forwarded, core/hittable.py:17-22
     const f3 albedo = m.c1;
@@ -732,7 +732,7 @@ __device__ __noinline__ bool shade_subsurface(const Mat& m, f3 ray_dir, f3& hp, 
 // scattered ray starts at the hit point, except for the full-mode subsurface materials.
 template <bool FULL = false>
 __device__ __forceinline__ bool shade_surface(const DScene& S, const Mat& m, int ref, f3 ray_dir, f3& hp, f3 normal,
-                                              uint32_t& rng, f3& emit, f3& scatter_dir, f3& attenuation) {
+                                              ptm::Rng& rng, f3& emit, f3& scatter_dir, f3& attenuation) {
     int mt = mat_type(m.header);
     emit = mk3(0.0f, 0.0f, 0.0f);
     scatter_dir = mk3(0.0f, 0.0f, 0.0f);

@@ -59,11 +59,10 @@ def test_traversal_reciprocal_bit_exact(engine):
 
 
 def test_random_stream_bit_exact(engine, oracle_mod):
-    for key in [(1234, 0, 0), (1234, 2073599, 255), (0xFFFFFFFF, 17, 3)]:
-        s0 = oracle_mod.rng_seed(*key)
+    for key in [(1234, 0, 0), (1234, 2073599, 255), (0xFFFFFFFF, 17, 3), (7, 8294399, 1023)]:
+        s0 = oracle_mod.rng_seed(*key)                          # stride << 32 | position
         ref, _ = oracle_mod.rng_draw(s0, 4096)
-        a = torch.zeros(4096, dtype=torch.float32)
-        a[0] = torch.tensor([s0], dtype=torch.int64).to(torch.int32).view(torch.float32)[0] if s0 < 2 ** 31 else \
-            torch.tensor([s0 - 2 ** 32], dtype=torch.int64).to(torch.int32).view(torch.float32)[0]
-        got = engine.math_eval(6, a).cpu().numpy()
+        a = np.zeros(4096, np.uint32)
+        a[0], a[1] = s0 & 0xFFFFFFFF, s0 >> 32
+        got = engine.math_eval(6, torch.from_numpy(a.view(np.float32))).cpu().numpy()
         assert np.array_equal(got, ref)

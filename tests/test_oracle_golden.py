@@ -89,3 +89,35 @@ def test_rng_stream_uniform(oracle_mod):
     assert v.min() >= 0.0 and v.max() < 1.0
     assert abs(v.mean() - 0.5) < 3e-3 and abs(v.var() - 1 / 12) < 2e-3
     assert O.rng_seed(1234, 77, 3) != O.rng_seed(1234, 77, 4) != O.rng_seed(1234, 78, 3)
+
+
+def test_rng_no_two_paths_share_a_stream(oracle_mod):
+    """Config 5 has 3840*2160*1024 = 8.5e9 paths > 2^32: the stream identity must be wider than 32
+    bits.  (start, stride) is a bijective function of (pixel, sample) for one seed; checked here on
+    1.7e7 keys of config 5's domain: no duplicate stream state, no duplicate 2-draw (64-bit) prefix."""
+    O = oracle_mod
+
+    def n_distinct(a):                                                     # (np.unique is slow on 1e7 uint64)
+        b = np.sort(np.ascontiguousarray(a).ravel())
+        return int(1 + np.count_nonzero(b[1:] != b[:-1]))
+
+    npix = 3840 * 2160
+    g = np.random.default_rng(5)
+    groups = [(np.arange(npix, dtype=np.uint32), np.zeros(npix, np.uint32)),                     # one sample of every pixel
+              (g.integers(0, npix, npix, dtype=np.uint32), g.integers(1, 1024, npix, dtype=np.uint32)),
+              (np.full(1 << 20, 12345, np.uint32), np.arange(1024, 1024 + (1 << 20), dtype=np.uint32))]   # one pixel, 2^20 samples
+    px, sm = (np.concatenate(c) for c in zip(*groups))
+    keys = (px.astype(np.uint64) << np.uint64(32)) | sm.astype(np.uint64)
+    st = O.rng_seed_states(1234, px, sm)
+    assert keys.size > 1.7e7 and n_distinct(st) == n_distinct(keys)   # distinct keys <=> distinct streams
+    assert np.all((st >> np.uint64(32)) & np.uint64(1) == 1)                 # strides are odd: full 2^32 period
+    # every pixel of one sample starts somewhere else; every sample of one pixel has its own stride
+    assert n_distinct(st[:npix] & np.uint64(0xFFFFFFFF)) > 0.99 * npix
+    one_pixel = st[-(1 << 20):]
+    assert n_distinct(one_pixel >> np.uint64(32)) == one_pixel.size
+    d = O.rng_first_draws(st, 2)
+    prefix = np.ascontiguousarray(d).view(np.uint64).ravel()                 # the first two raw draws of every stream
+    assert n_distinct(prefix) == n_distinct(keys)
+    # neighbouring streams are uncorrelated draw by draw
+    u = d[:npix].astype(np.float64) / 2.0 ** 32
+    assert abs(np.corrcoef(u[:-1, 0], u[1:, 0])[0, 1]) < 2e-3 and abs(np.corrcoef(u[:, 0], u[:, 1])[0, 1]) < 2e-3
