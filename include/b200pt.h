@@ -156,6 +156,13 @@ int pt_set_option(PtContext* ctx, const char* name, int64_t value);
 int pt_set_scene(PtContext* ctx, const void* device_blob, const PtPackedInfo* info);
 int pt_set_camera(PtContext* ctx, const PtCamera* cam);  /* replaces _upload_camera, renderer.py:230 */
 
+/* Row-interleaved windows for the multi-GPU tile split (no reference counterpart; SURVEY.md 8e "use
+ * interleaved row blocks"): after pt_set_row_interleave(ctx, B, S) the window [y0, y1) of the render
+ * calls means y1 - y0 LOCAL rows (a multiple of B), local row ly being image row
+ * y0 + (ly / B) * S + ly % B -- rank r of N passes y0 = r * B, S = N * B and renders blocks r, r + N, ...
+ * in ONE call.  Rows beyond H are skipped.  B: power of two >= 4; block_rows <= 0 switches it off. */
+int pt_set_row_interleave(PtContext* ctx, int block_rows, int stride_rows);
+
 /* ---- megakernel: replaces `render_sample` (kernels.py:1177-1187) launched once per sample by
  *      render() (renderer.py:405-409).  Adds samples [sample_begin, sample_begin+sample_count) of
  *      rows [y0,y1) to accum (device, H*W*3 f32, row-major like fields.accum_buffer). */
@@ -188,6 +195,15 @@ int pt_first_hit(PtContext* ctx, const float* o, const float* d, int n, float t_
  * fn 7 exp; fn 8 the slab test's reciprocal direction (|x| > 1e-8 ? 1/x : 1e8) of a[i] (even i) or
  * b[i] (odd i) */
 int pt_math_eval(PtContext* ctx, int fn, int n, const float* a, const float* b, float* out, void* stream);
+
+/* ---- roofline probe (no reference counterpart: SURVEY.md section 8d asks for the measured L2 /
+ *      L1 roof of the node-fetch stream).  Issues the traversal kernels' node-fetch sequence -- four
+ *      16-byte read-only loads of one 64-byte record -- at full rate, every lane active, from `buffer`
+ *      (device, `bytes` bytes, finite floats): pattern 0 = every lane its own pseudo-random record,
+ *      1 = one record per warp.  4 * iters records per lane per launch, `repeats` timed launches after
+ *      one warm-up; returns the best gathered GB/s.  Synchronises `stream`. */
+int pt_probe_gather(PtContext* ctx, const void* buffer, size_t bytes, int pattern, int iters, int repeats,
+                    double* out_gbytes_per_s, void* stream);
 
 /* ---- output: replaces LivePreview.buffer_to_image (preview.py:117-132) on the device */
 int pt_tonemap(PtContext* ctx, const float* accum, int n_floats, int sample_count, uint8_t* out_rgb, void* stream);

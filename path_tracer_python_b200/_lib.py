@@ -9,6 +9,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PT_LIB_PATH") or os.path.join(_HERE, "libb200pt.so")   # PT_LIB_PATH: A/B builds
+# numerics="fast": the same sources built with -DPT_FAST=1 --fmad=true (build.py); never the parity build
+LIB_PATHS = {"strict": LIB_PATH, "fast": os.environ.get("PT_FAST_LIB_PATH") or os.path.join(_HERE, "libb200pt_fast.so")}
 
 PT_MAX_IMAGES = 16
 PRIM_SPHERE, PRIM_TRIANGLE, PRIM_QUAD = 0, 1, 2
@@ -71,28 +73,35 @@ class PtCounters(C.Structure):
 # every symbol include/b200pt.h declares (tests/test_abi.py checks the library exports them all)
 EXPORTS = [
     "pt_last_error", "pt_version", "pt_pack_scene_info", "pt_pack_scene", "pt_bvh_build_sah", "pt_create",
-    "pt_destroy", "pt_set_option", "pt_set_scene", "pt_set_camera", "pt_render_megakernel",
+    "pt_destroy", "pt_set_option", "pt_set_row_interleave", "pt_set_scene", "pt_set_camera", "pt_render_megakernel",
     "pt_wavefront_workspace_bytes", "pt_wavefront_workspace_bytes_for", "pt_render_wavefront", "pt_generate_camera_rays", "pt_first_hit",
-    "pt_math_eval", "pt_tonemap", "pt_enable_counters", "pt_get_counters", "pt_enable_stage_timing", "pt_get_stage_times", "pt_get_stage_counters",
+    "pt_math_eval", "pt_probe_gather", "pt_tonemap", "pt_enable_counters", "pt_get_counters", "pt_enable_stage_timing", "pt_get_stage_times", "pt_get_stage_counters",
 ]
 
-_lib = None
+_libs = {}
 
 
 class B200PTError(RuntimeError):
     pass
 
 
-def lib() -> C.CDLL:
-    """Load libb200pt.so.  Raises if it has not been built (python -m path_tracer_python_b200.build)."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
+def has_numerics(numerics: str) -> bool:
+    return numerics in LIB_PATHS and os.path.exists(LIB_PATHS[numerics])
+
+
+def lib(numerics: str = "strict") -> C.CDLL:
+    """Load libb200pt.so (or the fast-numerics variant).  Raises if it has not been built
+    (python -m path_tracer_python_b200.build)."""
+    if numerics in _libs:
+        return _libs[numerics]
+    if numerics not in LIB_PATHS:
+        raise B200PTError(f"unknown numerics {numerics!r} (strict | fast)")
+    path = LIB_PATHS[numerics]
+    if not os.path.exists(path):
         raise B200PTError(
-            f"{LIB_PATH} not found: the CUDA extension is not built. Run `python -m path_tracer_python_b200.build` "
+            f"{path} not found: the CUDA extension is not built. Run `python -m path_tracer_python_b200.build` "
             "(there is no CPU fallback).")
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(path)
     L.pt_last_error.restype = C.c_char_p
     L.pt_version.restype = C.c_char_p
     L.pt_wavefront_workspace_bytes.restype = C.c_size_t
@@ -102,6 +111,7 @@ def lib() -> C.CDLL:
     L.pt_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
     L.pt_destroy.argtypes = [C.c_void_p]
     L.pt_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
+    L.pt_set_row_interleave.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.pt_set_scene.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(PtPackedInfo)]
     L.pt_set_camera.argtypes = [C.c_void_p, C.POINTER(PtCamera)]
     L.pt_pack_scene_info.argtypes = [C.POINTER(PtHostScene), C.POINTER(PtPackedInfo)]
@@ -115,6 +125,8 @@ def lib() -> C.CDLL:
     L.pt_first_hit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p,
                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pt_math_eval.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pt_probe_gather.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double),
+                                  C.c_void_p]
     L.pt_tonemap.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.pt_enable_counters.argtypes = [C.c_void_p, C.c_int]
     L.pt_get_counters.argtypes = [C.c_void_p, C.POINTER(PtCounters), C.c_int]
@@ -122,13 +134,13 @@ def lib() -> C.CDLL:
     L.pt_get_stage_times.argtypes = [C.c_void_p, C.POINTER(PtStageTime), C.c_int, C.POINTER(C.c_int)]
     L.pt_get_stage_counters.argtypes = [C.c_void_p, C.POINTER(PtCounters), C.c_int, C.POINTER(C.c_int)]
     L.pt_bvh_build_sah.argtypes = [C.c_int32] + [C.c_void_p] * 12
-    _lib = L
+    _libs[numerics] = L
     return L
 
 
-def check(rc: int, what: str = ""):
+def check(rc: int, what: str = "", L: C.CDLL | None = None):
     if rc != 0:
-        msg = lib().pt_last_error()
+        msg = (L or lib()).pt_last_error()       # the error slot lives in the library that failed
         raise B200PTError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
 
 
@@ -136,63 +148,76 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
 
 
+_MATERIAL_KEYS = (("material_type", "i", ()), ("material_albedo", "f", (3,)), ("material_fuzz", "f", ()),
+                  ("material_ir", "f", ()), ("material_emit_color", "f", (3,)), ("texture_type", "i", ()),
+                  ("texture_scale", "f", ()), ("texture_color1", "f", (3,)), ("texture_color2", "f", (3,)),
+                  ("texture_image_idx", "i", ()), ("is_constant_medium", "i", ()), ("medium_density", "f", ()),
+                  ("medium_albedo", "f", (3,)))
+_MATERIAL_FIELDS = ("material_type", "albedo", "fuzz", "ir", "emit", "texture_type", "texture_scale", "color1", "color2",
+                    "image_idx", "is_medium", "medium_density", "medium_albedo")
+
+
 class HostScene:
-    """Contiguous typed copies of a CompiledScene dict + the PtHostScene view over them."""
+    """Contiguous typed copies of a CompiledScene dict + the PtHostScene view over them.
+
+    The dict is the flat form scene_compiler.compile_scene + bvh.compile_bvh produce (the reference's
+    compile_scene returns the same arrays as a tuple of per-type dicts, scene_compiler.py:931-965).
+    A primitive type that is present must come with ALL of its arrays, each with one row per
+    primitive: a missing key or a short array raises here instead of handing the C packer a NULL or
+    an out-of-bounds pointer (the packer re-checks pointers and index ranges: PT_ERR_INVALID_ARG)."""
 
     def __init__(self, cs: dict):
         self._keep = []
         s = PtHostScene()
 
-        def f32(key, tail=()):
-            a = np.ascontiguousarray(cs.get(key, np.zeros((0,) + tail)), dtype=np.float32)
+        def arr(key, kind, tail, rows=None):
+            if key not in cs:
+                if rows:
+                    raise B200PTError(f"compiled scene lacks '{key}' ({rows} primitives of that type need it)")
+                a = np.zeros((0,) + tail, np.float32 if kind == "f" else np.int32)
+            else:
+                a = np.ascontiguousarray(cs[key], dtype=np.float32 if kind == "f" else np.int32)
+                if a.shape[1:] != tail and not (tail == () and a.ndim == 1):
+                    raise B200PTError(f"compiled scene: '{key}' has shape {a.shape}, expected (n,{','.join(map(str, tail))})")
+                if rows is not None and a.shape[0] != rows:
+                    raise B200PTError(f"compiled scene: '{key}' has {a.shape[0]} rows for {rows} primitives")
             self._keep.append(a)
             return a
 
-        def i32(key):
-            a = np.ascontiguousarray(cs.get(key, np.zeros((0,))), dtype=np.int32)
-            self._keep.append(a)
-            return a
-
-        sd = f32("sphere_data", (4,))
+        sd = arr("sphere_data", "f", (4,))
+        nq = len(cs["quad_Q"]) if "quad_Q" in cs else 0
+        nt = len(cs["triangle_v0"]) if "triangle_v0" in cs else 0
         s.num_spheres, s.sphere_data = sd.shape[0], _ptr(sd)
+        s.num_quads, s.num_triangles = nq, nt
         for k in ("quad_Q", "quad_u", "quad_v", "quad_normal", "quad_D", "quad_w"):
-            a = f32(k, () if k == "quad_D" else (3,))
-            setattr(s, k, _ptr(a))
-            if k == "quad_Q":
-                s.num_quads = a.shape[0]
+            setattr(s, k, _ptr(arr(k, "f", () if k == "quad_D" else (3,), nq)))
         for k, dst in (("triangle_v0", "tri_v0"), ("triangle_edge1", "tri_edge1"), ("triangle_edge2", "tri_edge2"),
                        ("triangle_normal", "tri_normal")):
-            a = f32(k, (3,))
-            setattr(s, dst, _ptr(a))
-            if dst == "tri_v0":
-                s.num_triangles = a.shape[0]
+            setattr(s, dst, _ptr(arr(k, "f", (3,), nt)))
+        counts = {PRIM_SPHERE: sd.shape[0], PRIM_TRIANGLE: nt, PRIM_QUAD: nq}
         for pt, prefix in PRIM_PREFIX.items():
             m = s.mat[pt]
-            m.material_type = _ptr(i32(f"{prefix}_material_type"))
-            m.albedo = _ptr(f32(f"{prefix}_material_albedo", (3,)))
-            m.fuzz = _ptr(f32(f"{prefix}_material_fuzz"))
-            m.ir = _ptr(f32(f"{prefix}_material_ir"))
-            m.emit = _ptr(f32(f"{prefix}_material_emit_color", (3,)))
-            m.texture_type = _ptr(i32(f"{prefix}_texture_type"))
-            m.texture_scale = _ptr(f32(f"{prefix}_texture_scale"))
-            m.color1 = _ptr(f32(f"{prefix}_texture_color1", (3,)))
-            m.color2 = _ptr(f32(f"{prefix}_texture_color2", (3,)))
-            m.image_idx = _ptr(i32(f"{prefix}_texture_image_idx"))
-            m.is_medium = _ptr(i32(f"{prefix}_is_constant_medium"))
-            m.medium_density = _ptr(f32(f"{prefix}_medium_density"))
-            m.medium_albedo = _ptr(f32(f"{prefix}_medium_albedo", (3,)))
-        bmin = f32("bvh_bbox_min", (3,))
-        s.num_nodes, s.bvh_bbox_min = bmin.shape[0], _ptr(bmin)
-        s.bvh_bbox_max = _ptr(f32("bvh_bbox_max", (3,)))
-        s.bvh_left = _ptr(i32("bvh_left_child"))
-        s.bvh_right = _ptr(i32("bvh_right_child"))
-        s.bvh_prim_type = _ptr(i32("bvh_prim_type"))
-        s.bvh_prim_idx = _ptr(i32("bvh_prim_idx"))
+            for (key, kind, tail), field in zip(_MATERIAL_KEYS, _MATERIAL_FIELDS):
+                setattr(m, field, _ptr(arr(f"{prefix}_{key}", kind, tail, counts[pt])))
+        bmin = arr("bvh_bbox_min", "f", (3,))
+        nn = bmin.shape[0]
+        if nn == 0 and sum(counts.values()) > 0:
+            raise B200PTError("compiled scene has primitives but no BVH arrays (run bvh.compile_bvh)")
+        s.num_nodes, s.bvh_bbox_min = nn, _ptr(bmin)
+        s.bvh_bbox_max = _ptr(arr("bvh_bbox_max", "f", (3,), nn))
+        s.bvh_left = _ptr(arr("bvh_left_child", "i", (), nn))
+        s.bvh_right = _ptr(arr("bvh_right_child", "i", (), nn))
+        s.bvh_prim_type = _ptr(arr("bvh_prim_type", "i", (), nn))
+        s.bvh_prim_idx = _ptr(arr("bvh_prim_idx", "i", (), nn))
         rv = np.ascontiguousarray(cs["perlin_randvec"] if "perlin_randvec" in cs else np.zeros((256, 3)), np.float32)
+        if rv.shape != (256, 3):
+            raise B200PTError(f"compiled scene: perlin_randvec has shape {rv.shape}, expected (256, 3)")
         self._keep.append(rv)
         s.perlin_randvec = _ptr(rv)
         for k, dst in (("perlin_perm_x", "perm_x"), ("perlin_perm_y", "perm_y"), ("perlin_perm_z", "perm_z")):
             a = np.ascontiguousarray(cs[k] if k in cs else np.arange(256), np.int32)
+            if a.shape != (256,):
+                raise B200PTError(f"compiled scene: {k} has shape {a.shape}, expected (256,)")
             self._keep.append(a)
             setattr(s, dst, _ptr(a))
         n_img = int(cs.get("num_images", 0))
@@ -200,13 +225,19 @@ class HostScene:
             raise B200PTError(f"{n_img} image textures > {PT_MAX_IMAGES}")
         s.num_images = n_img
         for i in range(n_img):
+            if f"image_{i}" not in cs:
+                raise B200PTError(f"compiled scene lacks 'image_{i}' (num_images = {n_img})")
             img = np.ascontiguousarray(cs[f"image_{i}"], dtype=np.uint8)
+            if img.ndim != 3 or img.shape[2] != 3:
+                raise B200PTError(f"compiled scene: image_{i} has shape {img.shape}, expected (h, w, 3) uint8")
             self._keep.append(img)
             s.images[i] = img.ctypes.data
             s.image_h[i], s.image_w[i] = img.shape[0], img.shape[1]
         s.full_features = int(cs.get("full_features", 0))
         if s.full_features:
             mo = np.ascontiguousarray(cs["sphere_motion"] if "sphere_motion" in cs else np.zeros((sd.shape[0], 3)), np.float32)
+            if mo.shape != (sd.shape[0], 3):
+                raise B200PTError(f"compiled scene: sphere_motion has shape {mo.shape} for {sd.shape[0]} spheres")
             self._keep.append(mo)
             s.sphere_motion = _ptr(mo)
         self.c = s

@@ -1,9 +1,11 @@
-"""Builds libb200pt.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+"""Builds libb200pt.so (strict numerics, the parity build) and libb200pt_fast.so (production numerics)
+in-tree with nvcc for sm_100a (cross-compiles without a GPU).
 
-    python -m path_tracer_python_b200.build [--force] [--verbose]
+    python -m path_tracer_python_b200.build [--force] [--verbose] [--only=strict|fast]
 
-Flags that matter: ``--fmad=false`` (PT-F32 contract: no FFMA contraction), ``-lineinfo`` (ncu source
-page), ``-gencode arch=compute_100a,code=sm_100a`` (B200 only; no other architectures, no PTX JIT).
+Flags that matter: ``--fmad=false`` (PT-F32 contract: no FFMA contraction; the fast variant is the same
+sources with ``-DPT_FAST=1 --fmad=true``), ``-lineinfo`` (ncu source page),
+``-gencode arch=compute_100a,code=sm_100a`` (B200 only; no other architectures, no PTX JIT).
 """
 from __future__ import annotations
 
@@ -14,6 +16,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libb200pt.so")
+FAST_LIB_PATH = os.path.join(HERE, "libb200pt_fast.so")
+FAST_DEFINES = ("PT_FAST=1",)
 SOURCES = ["b200pt.cu", "pt_host.cpp"]
 HEADERS = ["pt_device.cuh", "pt_math.cuh", os.path.join("..", "..", "include", "b200pt.h")]
 
@@ -32,10 +36,10 @@ def _nvcc() -> str:
     return "nvcc"
 
 
-def needs_build() -> bool:
-    if not os.path.exists(LIB_PATH):
+def needs_build(lib_path: str = LIB_PATH) -> bool:
+    if not os.path.exists(lib_path):
         return True
-    t = os.path.getmtime(LIB_PATH)
+    t = os.path.getmtime(lib_path)
     deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps)
 
@@ -47,7 +51,10 @@ def build_native(force: bool = False, verbose: bool = False, defines=(), out: st
         if not force and not needs_build():
             return LIB_PATH
     out = out or LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else [])
+    flags = list(NVCC_FLAGS)
+    if any(d.split("=")[0] == "PT_FAST" and not d.endswith("=0") for d in defines):
+        flags[flags.index("--fmad=false")] = "--fmad=true"
+    cmd = [_nvcc()] + flags + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else [])
     if os.path.exists("/usr/bin/g++"):
         cmd += ["-ccbin", "/usr/bin/g++"]
     cmd += ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
@@ -59,8 +66,22 @@ def build_native(force: bool = False, verbose: bool = False, defines=(), out: st
     return out
 
 
+def build_fast(force: bool = False, verbose: bool = False) -> str:
+    """The production-numerics variant (PT_FAST: FMA slab test, approximate reciprocals) next to the strict library."""
+    if not force and not needs_build(FAST_LIB_PATH):
+        return FAST_LIB_PATH
+    return build_native(force=True, verbose=verbose, defines=FAST_DEFINES, out=FAST_LIB_PATH)
+
+
 if __name__ == "__main__":
     defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
     outs = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")]
-    path = build_native(force="--force" in sys.argv, verbose="--verbose" in sys.argv, defines=defs, out=outs[0] if outs else None)
-    print(path)
+    only = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--only=")]
+    force, verbose = "--force" in sys.argv, "--verbose" in sys.argv
+    if defs or outs:
+        print(build_native(force=force, verbose=verbose, defines=defs, out=outs[0] if outs else None))
+    else:
+        if not only or only[0] == "strict":
+            print(build_native(force=force, verbose=verbose))
+        if not only or only[0] == "fast":
+            print(build_fast(force=force, verbose=verbose))

@@ -76,6 +76,7 @@ struct PtContext {
     int wf_blocks_per_sm = 7;
     int wf_extend_minb = 5;  // 48 registers, 5 CTAs (40 warps) per SM: +1.3 % over 4 x 56 once node fetches all go through L1
     int wf_tile = 1;
+    int row_shift = -1, row_stride = 0;   // pt_set_row_interleave
     int num_sms = 148;
     int max_smem_optin = 0;
     bool count = false;
@@ -138,11 +139,20 @@ __device__ __forceinline__ bool medium_sample(bool hit_exit, float t_exit_hit, f
 // ------------------------------------------------------------------------------------------------
 // megakernel
 // ------------------------------------------------------------------------------------------------
+// Row-interleaved windows (the multi-GPU tile split, distributed.py): the window's local row ly is the
+// image row  y0 + (ly >> row_shift) * row_stride + (ly & (block - 1)),  block = 1 << row_shift rows, so
+// that rank r of N renders blocks r, r + N, r + 2N, ... (row_stride = N * block) with ONE call; rows
+// that fall beyond the image are skipped.  row_shift < 0: the plain contiguous window [y0, y1).
+__device__ __forceinline__ int win_row(int y0, int row_shift, int row_stride, int ly) {
+    return row_shift < 0 ? y0 + ly : y0 + (ly >> row_shift) * row_stride + (ly & ((1 << row_shift) - 1));
+}
+
 struct MegaParams {
     DScene S;
     PtCamera cam;
     float* accum;
     int W, H, y0, y1;
+    int row_shift, row_stride;   // row interleave (win_row); row_shift < 0 = contiguous window
     int sample_begin, sample_count;
     uint32_t seed;
     int n_snodes;
@@ -168,8 +178,9 @@ __global__ void __launch_bounds__(PT_MEGA_THREADS, PT_MEGA_MINB) k_megakernel(co
     const int lane = threadIdx.x & 31;
     const int tx = gwarp % P.tiles_x, ty = gwarp / P.tiles_x;
     const int px = tx * 8 + (lane & 7);
-    const int py = P.y0 + ty * 4 + (lane >> 3);
-    const bool valid = (px < P.W) && (py < P.y1);
+    const int ly = ty * 4 + (lane >> 3);
+    const int py = win_row(P.y0, P.row_shift, P.row_stride, ly);
+    const bool valid = (px < P.W) && (ly < P.y1 - P.y0) && (py < P.H);
     const int pixel = py * P.W + px;
     float* ap = P.accum + 3 * (size_t)(valid ? pixel : 0);
     LocalCounters lc;
@@ -354,6 +365,7 @@ struct WfQueues {
     int* cursor;             // dynamic-fetch cursor of k_wf_extend
     int capacity;            // B * N
 };
+constexpr int kNodeBytes = 64;   // one packed inner node (both children's boxes + two references)
 constexpr int kNumBins = 8;  // 0 miss, 1 medium boundary, 2.. = 2 + material type (0..4)
 
 struct WfParams {
@@ -362,6 +374,8 @@ struct WfParams {
     WfQueues Q;
     float* accum;
     int W, H, y0, y1;
+    int row_shift, row_stride;   // row interleave (win_row); row_shift < 0 = contiguous window
+    float inv_W;             // 1.0f / W (win_pixel)
     int N;                   // W * (y1 - y0)
     float inv_N;             // 1.0f / N (wf_path_key)
     int sample_base;         // first sample index of this batch
@@ -377,6 +391,16 @@ struct WfParams {
     DCounters* counters;
 };
 
+// Image pixel index of the window's local pixel (row-major within the window).
+__device__ __forceinline__ int win_pixel(const WfParams& P, int local) {
+    if (P.row_shift < 0) return P.y0 * P.W + local;
+    int ly = (int)((float)local * P.inv_W);          // local / W by one float multiply + exact fix-up
+    int px = local - ly * P.W;
+    if (px < 0) { ly--; px += P.W; }
+    else if (px >= P.W) { ly++; px -= P.W; }
+    return win_row(P.y0, P.row_shift, P.row_stride, ly) * P.W + px;
+}
+
 // The key of the path that owns a queue entry -- (start, stride) of its random stream -- recomputed from
 // its id: the ray record carries only the stream position, the stride is a pure function of
 // (seed, pixel, sample).  path_id = slot * N + local pixel with slot <= 256, so the quotient comes
@@ -386,7 +410,7 @@ __device__ __forceinline__ ptm::Rng wf_path_key(const WfParams& P, int path_id) 
     int local = path_id - slot * P.N;
     if (local < 0) { slot--; local += P.N; }
     else if (local >= P.N) { slot++; local -= P.N; }
-    return ptm::rng_seed(P.seed, (uint32_t)(P.y0 * P.W + local), (uint32_t)(P.sample_base + slot));
+    return ptm::rng_seed(P.seed, (uint32_t)win_pixel(P, local), (uint32_t)(P.sample_base + slot));
 }
 // full feature mode: the shutter time of that path
 template <bool FULL>
@@ -400,7 +424,7 @@ __global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ WfP
     const int stride = gridDim.x * blockDim.x;
     for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < total; id += stride) {
         const int slot = id / P.N;
-        const int pixel = P.y0 * P.W + (id - slot * P.N);
+        const int pixel = win_pixel(P, id - slot * P.N);
         const int py = pixel / P.W, px = pixel - py * P.W;
         ptm::Rng rng = ptm::rng_seed(P.seed, (uint32_t)pixel, (uint32_t)(P.sample_base + slot));
         f3 o, d;
@@ -876,8 +900,8 @@ __global__ void __launch_bounds__(PT_PRIMARY_THREADS, PT_PRIMARY_MINB) k_wf_prim
             }
             const int local = ly * P.W + px;
             id = slot * P.N + local;
-            const int pixel = P.y0 * P.W + local;
-            const int py = P.y0 + ly;
+            const int py = win_row(P.y0, P.row_shift, P.row_stride, ly);
+            const int pixel = py * P.W + px;
             rng = ptm::rng_seed(P.seed, (uint32_t)pixel, (uint32_t)(P.sample_base + slot));
             const float time = FULL ? ptm::path_time(rng) : 0.0f;
             f3 o, d;
@@ -887,7 +911,7 @@ __global__ void __launch_bounds__(PT_PRIMARY_THREADS, PT_PRIMARY_MINB) k_wf_prim
             if (COUNT) lc.paths++;
             f3 thr = mk3(1.0f, 1.0f, 1.0f);
             int depth = 0;
-            emit_next = max_depth > 0;
+            emit_next = max_depth > 0 && py < P.H;          // rows of an interleaved window beyond the image: no path
             for (int w = 0; w < P.fused_waves && emit_next; w++) {
                 float t, t_exit = 0.0f;
                 int ref, eref = kRefNone;
@@ -1085,7 +1109,9 @@ __global__ void __launch_bounds__(256, 3) k_wf_tail_vote(const __grid_constant__
 __global__ void __launch_bounds__(256) k_wf_resolve(const __grid_constant__ WfParams P) {
     const int stride = gridDim.x * blockDim.x;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.N; i += stride) {
-        float* ap = P.accum + 3 * ((size_t)P.y0 * P.W + i);
+        const int pixel = win_pixel(P, i);
+        if (pixel >= P.W * P.H) continue;               // interleaved window: row beyond the image
+        float* ap = P.accum + 3 * (size_t)pixel;
         f3 acc = mk3(ap[0], ap[1], ap[2]);
         for (int s = 0; s < P.batch; s++) {
             const float* sp = P.Q.slab + 3 * ((size_t)s * P.N + i);
@@ -1176,6 +1202,38 @@ __global__ void k_math_eval(int fn, int n, const float* a, const float* b, float
     out[i] = r;
 }
 
+// Roofline probe: the node-fetch instruction sequence of the traversal kernels (four 16-byte read-only
+// loads of one 64-byte record, load_node) issued at full rate with every lane active -- no stack, no
+// arithmetic beyond a checksum, four independent records in flight per lane.  pattern 0: every lane
+// its own pseudo-random record (what incoherent bounce rays do at the leaves of the tree); pattern 1:
+// one record per warp (what coherent rays do at the top of the tree).  The measured GB/s over a
+// working set that fits L1, L2 or neither are the memory roofs the traversal kernels sit under
+// ("report against L2 bandwidth ... microbenchmark it on the box").
+__global__ void __launch_bounds__(PT_EXT_WARPS * 32, 6) k_probe_gather(const float4* __restrict__ buf, unsigned n_records, int iters,
+                                                                      int pattern, float* __restrict__ sink) {
+    const unsigned gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned who = pattern == 1 ? (gtid >> 5) : gtid;
+    unsigned h = ptm::mix32(who * 0x9e3779b9u + 0x85ebca6bu);
+    float acc = 0.0f;
+    for (int i = 0; i < iters; i++) {
+        unsigned idx[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            h = h * 0x915f77f5u + 0x6a09e667u;
+            idx[k] = (unsigned)(((unsigned long long)(h ^ (h >> 15)) * n_records) >> 32);
+        }
+        float4 v[4][4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const char*>(buf) + (unsigned long long)idx[k] * 64ull);
+            v[k][0] = __ldg(p); v[k][1] = __ldg(p + 1); v[k][2] = __ldg(p + 2); v[k][3] = __ldg(p + 3);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) acc += (v[k][0].x + v[k][1].y) + (v[k][2].z + v[k][3].w);
+    }
+    if (acc == 123.456f) sink[0] = acc;          // keeps the loads alive; never true for the zero/finite test buffer
+}
+
 // preview.py:117-132: u8 = clip(sqrt(max(0, accum * (1/spp))) * 255.999, 0, 255)
 __global__ void k_tonemap(const float* accum, int n, float scale, uint8_t* out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1214,7 +1272,13 @@ static int set_smem(K kernel, size_t bytes) {
 extern "C" {
 
 const char* pt_last_error(void) { return pt_error_slot()->c_str(); }
-const char* pt_version(void) { return "b200pt 0.1 (sm_100a, PT-F32 strict)"; }
+const char* pt_version(void) {
+#if PT_FAST
+    return "b200pt 0.2 (sm_100a, PT-F32 fast: FMA + approximate reciprocal)";
+#else
+    return "b200pt 0.2 (sm_100a, PT-F32 strict)";
+#endif
+}
 
 int pt_create(int device_ordinal, PtContext** out_ctx) {
     if (!out_ctx) return set_error(PT_ERR_INVALID_ARG, "pt_create: out_ctx is NULL");
@@ -1313,8 +1377,27 @@ int pt_set_option(PtContext* ctx, const char* name, int64_t value) {
 int pt_set_scene(PtContext* ctx, const void* device_blob, const PtPackedInfo* info) {
     if (!ctx || !info) return set_error(PT_ERR_INVALID_ARG, "pt_set_scene: NULL argument");
     if (!device_blob && info->total_bytes) return set_error(PT_ERR_INVALID_ARG, "pt_set_scene: NULL blob");
+    // Validate everything before touching the context: a rejected scene leaves the previous one
+    // (and has_scene) exactly as they were.
+    if (info->max_depth_tree > kStackSize)
+        return set_error(PT_ERR_CAPACITY, "pt_set_scene: BVH deeper than the 64-entry traversal stack (kernels.py:649)");
+    if (info->num_inner < 0 || info->num_spheres < 0 || info->num_quads < 0 || info->num_triangles < 0 ||
+        info->num_materials < 0 || info->num_images < 0 || info->num_images > PT_MAX_IMAGES)
+        return set_error(PT_ERR_INVALID_ARG, "pt_set_scene: bad counts in PtPackedInfo");
+    const uint64_t total = info->total_bytes;
+    auto inside = [&](uint64_t off, uint64_t bytes) { return off <= total && bytes <= total - off; };
+    const uint64_t n_prims = (uint64_t)info->num_spheres + (uint64_t)info->num_triangles + (uint64_t)info->num_quads;
+    bool ok = inside(info->off_nodes, (uint64_t)info->num_inner * kNodeBytes) && inside(info->off_spheres, (uint64_t)info->num_spheres * 16) &&
+              inside(info->off_quads, (uint64_t)info->num_quads * 64) && inside(info->off_tris, (uint64_t)info->num_triangles * 48) &&
+              inside(info->off_prim_mat, n_prims * 4) && inside(info->off_materials, (uint64_t)info->num_materials * 48) &&
+              inside(info->off_perlin, 256 * 16 + 768) &&
+              (!info->full_features || inside(info->off_sphere_motion, (uint64_t)info->num_spheres * 16));
+    for (int i = 0; i < info->num_images && ok; i++)
+        ok = info->image_w[i] > 0 && info->image_h[i] > 0 && inside(info->off_images, info->image_off[i]) &&
+             inside(info->off_images + info->image_off[i], (uint64_t)info->image_w[i] * info->image_h[i] * 4);
+    if (!ok) return set_error(PT_ERR_INVALID_ARG, "pt_set_scene: a section of PtPackedInfo lies outside the blob");
     const char* base = static_cast<const char*>(device_blob);
-    DScene& S = ctx->scene;
+    DScene S;
     memset(&S, 0, sizeof S);
     S.nodes = reinterpret_cast<const float4*>(base + info->off_nodes);
     S.spheres = reinterpret_cast<const float4*>(base + info->off_spheres);
@@ -1324,12 +1407,10 @@ int pt_set_scene(PtContext* ctx, const void* device_blob, const PtPackedInfo* in
     S.materials = reinterpret_cast<const float4*>(base + info->off_materials);
     S.perlin_vec = reinterpret_cast<const float4*>(base + info->off_perlin);
     S.perlin_perm = reinterpret_cast<const uint8_t*>(base + info->off_perlin + 256 * 16);
-    for (int i = 0; i < PT_MAX_IMAGES; i++) {
-        if (i < info->num_images) {
-            S.image[i] = reinterpret_cast<const uchar4*>(base + info->off_images + info->image_off[i]);
-            S.image_w[i] = info->image_w[i];
-            S.image_h[i] = info->image_h[i];
-        }
+    for (int i = 0; i < info->num_images; i++) {
+        S.image[i] = reinterpret_cast<const uchar4*>(base + info->off_images + info->image_off[i]);
+        S.image_w[i] = info->image_w[i];
+        S.image_h[i] = info->image_h[i];
     }
     S.num_inner = info->num_inner;
     S.mat_base[PT_PRIM_SPHERE] = 0;
@@ -1338,8 +1419,7 @@ int pt_set_scene(PtContext* ctx, const void* device_blob, const PtPackedInfo* in
     S.has_media = info->has_media;
     S.full_features = info->full_features;
     S.sphere_motion = reinterpret_cast<const float4*>(base + info->off_sphere_motion);
-    if (info->max_depth_tree > kStackSize)
-        return set_error(PT_ERR_CAPACITY, "pt_set_scene: BVH deeper than the 64-entry traversal stack (kernels.py:649)");
+    ctx->scene = S;
     ctx->info = *info;
     ctx->has_scene = true;
     return PT_OK;
@@ -1355,8 +1435,29 @@ int pt_set_camera(PtContext* ctx, const PtCamera* cam) {
 static int check_render_args(PtContext* ctx, const float* accum, int W, int H, int y0, int y1, int sample_count) {
     if (!ctx || !accum) return set_error(PT_ERR_INVALID_ARG, "render: NULL argument");
     if (!ctx->has_scene || !ctx->has_camera) return set_error(PT_ERR_NO_SCENE, "render: scene or camera not set");
-    if (W <= 0 || H <= 0 || y0 < 0 || y1 > H || y0 > y1 || sample_count < 0)
+    if (W <= 0 || H <= 0 || y0 < 0 || y0 > y1 || sample_count < 0 || (long long)W * H > 0x7fffffffll)
         return set_error(PT_ERR_INVALID_ARG, "render: bad image window / sample range");
+    if (ctx->row_shift < 0) {
+        if (y1 > H) return set_error(PT_ERR_INVALID_ARG, "render: window rows beyond the image");
+    } else {
+        // interleaved window: y1 - y0 local rows, mapped by win_row; the last block may stick out of the image
+        // (those rows are skipped), but not by a whole block
+        const int rows = y1 - y0, blk = 1 << ctx->row_shift;
+        if (rows > 0 && (rows % blk != 0 || y0 + (long long)(rows / blk - 1) * ctx->row_stride >= H))
+            return set_error(PT_ERR_INVALID_ARG, "render: interleaved window needs whole blocks that start inside the image");
+    }
+    return PT_OK;
+}
+
+int pt_set_row_interleave(PtContext* ctx, int block_rows, int stride_rows) {
+    if (!ctx) return set_error(PT_ERR_INVALID_ARG, "pt_set_row_interleave: NULL context");
+    if (block_rows <= 0) { ctx->row_shift = -1; ctx->row_stride = 0; return PT_OK; }
+    int sh = 0;
+    while ((1 << sh) < block_rows) sh++;
+    if ((1 << sh) != block_rows || block_rows < 4 || stride_rows < block_rows)
+        return set_error(PT_ERR_INVALID_ARG, "pt_set_row_interleave: block_rows must be a power of two >= 4 and stride_rows >= block_rows");
+    ctx->row_shift = sh;
+    ctx->row_stride = stride_rows;
     return PT_OK;
 }
 
@@ -1371,6 +1472,7 @@ int pt_render_megakernel(PtContext* ctx, float* accum, int W, int H, int y0, int
     P.cam = ctx->cam;
     P.accum = accum;
     P.W = W; P.H = H; P.y0 = y0; P.y1 = y1;
+    P.row_shift = ctx->row_shift; P.row_stride = ctx->row_stride;
     P.sample_begin = sample_begin; P.sample_count = sample_count;
     P.seed = seed;
     P.tiles_x = (W + 7) / 8;
@@ -1423,7 +1525,9 @@ struct StageScope {
         if (ctx->stage_timing && b >= 0) {
             const int e = stage_event(ctx, st);
             if (e < 0) return;
-            if (ctx->count && ctx->d_stage_snap && (int)ctx->marks.size() < kMaxStageSnaps)
+            // marks and counter snapshots stay in step: once the snapshot buffer is full nothing more is recorded
+            if ((int)ctx->marks.size() >= kMaxStageSnaps) return;
+            if (ctx->count && ctx->d_stage_snap)
                 cudaMemcpyAsync(ctx->d_stage_snap + ctx->marks.size(), ctx->d_counters, sizeof(DCounters),
                                 cudaMemcpyDeviceToDevice, st);
             ctx->marks.push_back({kernel, wave, b, e});
@@ -1438,6 +1542,7 @@ static size_t wf_bytes_per_sample(size_t n) {
            + (size_t)kNumBins * n * 4   // material bins
            + 2 * n * 12;   // radiance slabs (two: a batch's tail/resolve overlap the next batch's primary wave)
 }
+static const size_t kMaxPathsInFlight = 0x78000000;
 static const size_t kWfFixedBytes = 4096 + 16 * 256;   // counter sets + per-section alignment slack
 
 size_t pt_wavefront_workspace_bytes(int W, int rows) { return pt_wavefront_workspace_bytes_for(W, rows, 1); }
@@ -1465,8 +1570,10 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
     size_t B = (workspace_bytes - kWfFixedBytes - rel_bytes) / wf_bytes_per_sample(n);
     if (B > (size_t)sample_count) B = (size_t)sample_count;
     if (B > 256) B = 256;
-    while (B > 1 && B * n > (size_t)0x7fffffff) B--;
-    if (B * n > (size_t)0x7fffffff) return set_error(PT_ERR_CAPACITY, "pt_render_wavefront: window too large");
+    // paths in flight are indexed with 32-bit ints; the grid-stride loops overshoot `total` by up to one
+    // grid (< 2^26 threads) before their bounds test, so the cap leaves that much headroom
+    while (B > 1 && B * n > kMaxPathsInFlight) B--;
+    if (B * n > kMaxPathsInFlight) return set_error(PT_ERR_CAPACITY, "pt_render_wavefront: window too large");
     // equal batches: 64 samples with room for 63 in flight run as 32 + 32, not 63 + 1
     if (B > 0) {
         const size_t nb = ((size_t)sample_count + B - 1) / B;
@@ -1498,6 +1605,8 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
     P.Q.capacity = (int)cap;
     P.accum = accum;
     P.W = W; P.H = H; P.y0 = y0; P.y1 = y1;
+    P.row_shift = ctx->row_shift; P.row_stride = ctx->row_stride;
+    P.inv_W = 1.0f / (float)W;
     P.N = (int)n;
     P.inv_N = 1.0f / (float)n;
     P.seed = seed;
@@ -1520,7 +1629,7 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
     // camera rays without defocus all start at the camera centre: the fused primary wave then tests
     // origin-relative node boxes (one subtraction less per box coordinate).  Only when that kernel
     // runs wave 0 alone -- later waves start elsewhere.
-    bool rel = ctx->wf_rel_primary && ctx->wf_fuse_primary == 1 && !(ctx->cam.defocus_angle > 0.0f) &&
+    bool rel = !PT_FAST && ctx->wf_rel_primary && ctx->wf_fuse_primary == 1 && !(ctx->cam.defocus_angle > 0.0f) &&
                ctx->scene.num_inner > 0 && ctx->cam.max_depth > 0 && !ctx->count && rel_nodes != nullptr;
     if (rel) {
         int g = (int)(((size_t)ctx->scene.num_inner * 4 + 255) / 256);
@@ -1710,6 +1819,37 @@ int pt_tonemap(PtContext* ctx, const float* accum, int n_floats, int sample_coun
     const float scale = 1.0f / (float)(sample_count > 1 ? sample_count : 1);
     k_tonemap<<<(n_floats + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(accum, n_floats, scale, out_rgb);
     PT_CUDA(cudaGetLastError());
+    return PT_OK;
+}
+
+int pt_probe_gather(PtContext* ctx, const void* buffer, size_t bytes, int pattern, int iters, int repeats,
+                    double* out_gbytes_per_s, void* stream) {
+    if (!ctx || !buffer || !out_gbytes_per_s) return set_error(PT_ERR_INVALID_ARG, "pt_probe_gather: NULL argument");
+    if (bytes < 64 || bytes / 64 > 0xffffffffull || iters <= 0 || repeats <= 0 || pattern < 0 || pattern > 1)
+        return set_error(PT_ERR_INVALID_ARG, "pt_probe_gather: bad size / pattern / iteration count");
+    PT_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int threads = PT_EXT_WARPS * 32, grid = ctx->num_sms * 6;           // the launch shape of k_wf_extend
+    cudaEvent_t e0, e1;
+    PT_CUDA(cudaEventCreate(&e0));
+    PT_CUDA(cudaEventCreate(&e1));
+    float best_ms = 0.0f;
+    for (int r = 0; r < repeats + 1; r++) {                                    // first pass warms the caches
+        cudaEventRecord(e0, st);
+        k_probe_gather<<<grid, threads, 0, st>>>(static_cast<const float4*>(buffer), (unsigned)(bytes / 64), iters, pattern,
+                                                 reinterpret_cast<float*>(ctx->d_counters));
+        cudaEventRecord(e1, st);
+        cudaError_t e = cudaEventSynchronize(e1);
+        float ms = 0.0f;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+        if (e != cudaSuccess) { cudaEventDestroy(e0); cudaEventDestroy(e1); return set_error(PT_ERR_CUDA, cudaGetErrorString(e)); }
+        if (r > 0 && (best_ms == 0.0f || ms < best_ms)) best_ms = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    PT_CUDA(cudaGetLastError());
+    const double gathered = (double)grid * threads * (double)iters * 4.0 * 64.0;
+    *out_gbytes_per_s = gathered / (best_ms * 1e-3) / 1e9;
     return PT_OK;
 }
 

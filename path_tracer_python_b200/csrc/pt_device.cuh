@@ -192,6 +192,14 @@ __device__ __forceinline__ float fmin3(float a, float b, float c) {
     return d;
 }
 
+// One plane of the slab test, hit_aabb_optimized (kernels.py:609-614): (b - o) * inv, two roundings
+// (strict) -- or one FFMA against the precomputed -(o * inv) in the fast-numerics build.
+#if PT_FAST
+#define PT_SLAB(b, o_, inv_, noi_) __fmaf_rn((b), (inv_), (noi_))
+#else
+#define PT_SLAB(b, o_, inv_, noi_) (((b) - (o_)) * (inv_))
+#endif
+
 typedef unsigned long long StackEntry;
 #ifndef PT_STACK_TOP
 #define PT_STACK_TOP 1      // see trav_push / trav_pop
@@ -199,6 +207,9 @@ typedef unsigned long long StackEntry;
 
 struct TravState {
     f3 o, d, inv;
+#if PT_FAST
+    f3 noi;              // -(o * inv): the slab test is fma(b, inv, noi) per plane (fast numerics only)
+#endif
     float time;          // shutter time of the path (full feature mode; 0 otherwise)
     float t_min, best_t;
     int best_ref;
@@ -216,6 +227,9 @@ __device__ __forceinline__ void trav_begin(TravState& T, const DScene& S, f3 o, 
     T.d = d;
     T.time = time;
     ptm::inv_dir3(d.x, d.y, d.z, T.inv.x, T.inv.y, T.inv.z);
+#if PT_FAST
+    T.noi = mk3(-(o.x * T.inv.x), -(o.y * T.inv.y), -(o.z * T.inv.z));
+#endif
     T.t_min = t_min;
     T.best_t = t_max;
     T.best_ref = kRefNone;
@@ -348,6 +362,11 @@ __device__ __forceinline__ bool trav_run(TravState& T, const DScene& S, SNodeBas
                                          StackEntry* stack, int min_active, LocalCounters& lc) {
     const f3 o = REL ? mk3(0.0f, 0.0f, 0.0f) : T.o;
     const f3 inv = T.inv;
+#if PT_FAST
+    const f3 noi = T.noi;
+#else
+    const f3 noi = mk3(0.0f, 0.0f, 0.0f);
+#endif
     const float t_min = T.t_min;
     const float4* const nodes = S.nodes;
     while (T.cur != kRefNone) {
@@ -361,12 +380,12 @@ __device__ __forceinline__ bool trav_run(TravState& T, const DScene& S, SNodeBas
                 l0x = nx.x * inv.x; l1x = nx.y * inv.x; l0y = ny.x * inv.y; l1y = ny.y * inv.y; l0z = nz.x * inv.z; l1z = nz.y * inv.z;
                 r0x = nx.z * inv.x; r1x = nx.w * inv.x; r0y = ny.z * inv.y; r1y = ny.w * inv.y; r0z = nz.z * inv.z; r1z = nz.w * inv.z;
             } else {
-                l0x = (nx.x - o.x) * inv.x; l1x = (nx.y - o.x) * inv.x;
-                l0y = (ny.x - o.y) * inv.y; l1y = (ny.y - o.y) * inv.y;
-                l0z = (nz.x - o.z) * inv.z; l1z = (nz.y - o.z) * inv.z;
-                r0x = (nx.z - o.x) * inv.x; r1x = (nx.w - o.x) * inv.x;
-                r0y = (ny.z - o.y) * inv.y; r1y = (ny.w - o.y) * inv.y;
-                r0z = (nz.z - o.z) * inv.z; r1z = (nz.w - o.z) * inv.z;
+                l0x = PT_SLAB(nx.x, o.x, inv.x, noi.x); l1x = PT_SLAB(nx.y, o.x, inv.x, noi.x);
+                l0y = PT_SLAB(ny.x, o.y, inv.y, noi.y); l1y = PT_SLAB(ny.y, o.y, inv.y, noi.y);
+                l0z = PT_SLAB(nz.x, o.z, inv.z, noi.z); l1z = PT_SLAB(nz.y, o.z, inv.z, noi.z);
+                r0x = PT_SLAB(nx.z, o.x, inv.x, noi.x); r1x = PT_SLAB(nx.w, o.x, inv.x, noi.x);
+                r0y = PT_SLAB(ny.z, o.y, inv.y, noi.y); r1y = PT_SLAB(ny.w, o.y, inv.y, noi.y);
+                r0z = PT_SLAB(nz.z, o.z, inv.z, noi.z); r1z = PT_SLAB(nz.w, o.z, inv.z, noi.z);
             }
             float ltmin = fmax3(fminf(l0x, l1x), fminf(l0y, l1y), fmaxf(fminf(l0z, l1z), t_min));
             float ltmax = fmin3(fmaxf(l0x, l1x), fmaxf(l0y, l1y), fminf(fmaxf(l0z, l1z), best_t));
@@ -415,6 +434,11 @@ __device__ __forceinline__ void trav_run_vote(TravState& T, bool active, bool& d
                                               SNodeBase s_nodes, int n_snodes, StackEntry* stack,
                                               int min_active, int vote_num, LocalCounters& lc) {
     const f3 o = T.o, inv = T.inv;
+#if PT_FAST
+    const f3 noi = T.noi;
+#else
+    const f3 noi = mk3(0.0f, 0.0f, 0.0f);
+#endif
     const float t_min = T.t_min;
     const float4* const nodes = S.nodes;
     // lanes that do not traverse look finished: one register carries "active and where"
@@ -439,14 +463,14 @@ __device__ __forceinline__ void trav_run_vote(TravState& T, bool active, bool& d
                 load_node(nodes, s_nodes, n_snodes, cur, nx, ny, nz, nc);
                 if (COUNT) lc.box_tests += 2;
                 const float best_t = T.best_t;
-                float l0x = (nx.x - o.x) * inv.x, l1x = (nx.y - o.x) * inv.x;
-                float l0y = (ny.x - o.y) * inv.y, l1y = (ny.y - o.y) * inv.y;
-                float l0z = (nz.x - o.z) * inv.z, l1z = (nz.y - o.z) * inv.z;
+                float l0x = PT_SLAB(nx.x, o.x, inv.x, noi.x), l1x = PT_SLAB(nx.y, o.x, inv.x, noi.x);
+                float l0y = PT_SLAB(ny.x, o.y, inv.y, noi.y), l1y = PT_SLAB(ny.y, o.y, inv.y, noi.y);
+                float l0z = PT_SLAB(nz.x, o.z, inv.z, noi.z), l1z = PT_SLAB(nz.y, o.z, inv.z, noi.z);
                 float ltmin = fmax3(fminf(l0x, l1x), fminf(l0y, l1y), fmaxf(fminf(l0z, l1z), t_min));
                 float ltmax = fmin3(fmaxf(l0x, l1x), fmaxf(l0y, l1y), fminf(fmaxf(l0z, l1z), best_t));
-                float r0x = (nx.z - o.x) * inv.x, r1x = (nx.w - o.x) * inv.x;
-                float r0y = (ny.z - o.y) * inv.y, r1y = (ny.w - o.y) * inv.y;
-                float r0z = (nz.z - o.z) * inv.z, r1z = (nz.w - o.z) * inv.z;
+                float r0x = PT_SLAB(nx.z, o.x, inv.x, noi.x), r1x = PT_SLAB(nx.w, o.x, inv.x, noi.x);
+                float r0y = PT_SLAB(ny.z, o.y, inv.y, noi.y), r1y = PT_SLAB(ny.w, o.y, inv.y, noi.y);
+                float r0z = PT_SLAB(nz.z, o.z, inv.z, noi.z), r1z = PT_SLAB(nz.w, o.z, inv.z, noi.z);
                 float rtmin = fmax3(fminf(r0x, r1x), fminf(r0y, r1y), fmaxf(fminf(r0z, r1z), t_min));
                 float rtmax = fmin3(fmaxf(r0x, r1x), fmaxf(r0y, r1y), fminf(fmaxf(r0z, r1z), best_t));
                 const int lref = __float_as_int(nc.x), rref = __float_as_int(nc.y);

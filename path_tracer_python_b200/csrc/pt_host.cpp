@@ -152,6 +152,48 @@ int collapse(const PtHostScene* s, Collapsed& c) {
     return PT_OK;
 }
 
+// Everything the packer dereferences, checked once up front: a caller-built scene (the public
+// `compiled_scene=` path, or any C caller) must come back as PT_ERR_INVALID_ARG, not as a crash.
+int validate_scene(const PtHostScene* s) {
+    auto fail = [](const char* msg) { g_host_error = std::string("scene: ") + msg; return (int)PT_ERR_INVALID_ARG; };
+    if (s->num_spheres < 0 || s->num_quads < 0 || s->num_triangles < 0 || s->num_nodes < 0 || s->num_images < 0)
+        return fail("negative count");
+    if (s->num_spheres > 0 && !s->sphere_data) return fail("sphere_data is NULL");
+    if (s->num_quads > 0 && (!s->quad_Q || !s->quad_u || !s->quad_v || !s->quad_normal || !s->quad_D || !s->quad_w))
+        return fail("a quad array is NULL");
+    if (s->num_triangles > 0 && (!s->tri_v0 || !s->tri_edge1 || !s->tri_edge2 || !s->tri_normal))
+        return fail("a triangle array is NULL");
+    if (s->full_features && s->num_spheres > 0 && !s->sphere_motion) return fail("full feature mode without sphere_motion");
+    for (int i = 0; i < s->num_images; i++)
+        if (!s->images[i] || s->image_w[i] <= 0 || s->image_h[i] <= 0) return fail("image texture without pixels");
+    const int counts[3] = {s->num_spheres, s->num_triangles, s->num_quads};
+    for (int pt = 0; pt < 3; pt++) {
+        const PtHostMaterials& m = s->mat[pt];
+        if (counts[pt] == 0) continue;
+        if (!m.material_type || !m.albedo || !m.fuzz || !m.ir || !m.emit || !m.texture_type || !m.texture_scale ||
+            !m.color1 || !m.color2 || !m.image_idx || !m.is_medium || !m.medium_density || !m.medium_albedo)
+            return fail("a material array is NULL (every per-primitive material array is required)");
+        for (int i = 0; i < counts[pt]; i++) {
+            if (m.material_type[i] < 0 || m.material_type[i] > 6) return fail("material_type outside 0..6");
+            if (m.texture_type[i] < 0 || m.texture_type[i] > 3) return fail("texture_type outside 0..3");
+            if ((m.material_type[i] == 0 || m.material_type[i] == 4) && m.texture_type[i] == 2 &&
+                (m.image_idx[i] < -1 || m.image_idx[i] >= s->num_images))
+                return fail("texture_image_idx outside the image table");
+        }
+    }
+    if (s->num_nodes > 0) {
+        if (!s->bvh_bbox_min || !s->bvh_bbox_max || !s->bvh_left || !s->bvh_right || !s->bvh_prim_type || !s->bvh_prim_idx)
+            return fail("a BVH array is NULL");
+        for (int i = 0; i < s->num_nodes; i++) {
+            if (s->bvh_prim_idx[i] < 0) continue;
+            const int pt = s->bvh_prim_type[i];
+            if (pt < 0 || pt > 2) return fail("bvh_prim_type outside 0..2");
+            if (s->bvh_prim_idx[i] >= counts[pt]) return fail("bvh_prim_idx beyond the primitive count");
+        }
+    }
+    return PT_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -167,8 +209,10 @@ int pt_pack_scene_info(const PtHostScene* s, PtPackedInfo* info) {
         return PT_ERR_CAPACITY;
     }
     memset(info, 0, sizeof *info);
+    int rc = validate_scene(s);
+    if (rc) return rc;
     Collapsed c;
-    int rc = collapse(s, c);
+    rc = collapse(s, c);
     if (rc) return rc;
     MatTable mt;
     build_materials(s, mt);
@@ -208,9 +252,11 @@ int pt_pack_scene_info(const PtHostScene* s, PtPackedInfo* info) {
 int pt_pack_scene(const PtHostScene* s, const PtPackedInfo* info, void* host_blob) {
     if (!s || !info || !host_blob) { g_host_error = "pt_pack_scene: NULL argument"; return PT_ERR_INVALID_ARG; }
     char* base = static_cast<char*>(host_blob);
+    int rc = validate_scene(s);
+    if (rc) return rc;
     memset(base, 0, info->total_bytes);
     Collapsed c;
-    int rc = collapse(s, c);
+    rc = collapse(s, c);
     if (rc) return rc;
 
     // ---- nodes: (lmin.x lmax.x rmin.x rmax.x) (..y) (..z) (left_ref right_ref 0 0)

@@ -1,10 +1,17 @@
-"""Multi-GPU: one process per GPU (torchrun), the scene replicated, samples split across ranks.
+"""Multi-GPU: one process per GPU (torchrun), the scene replicated, the frame sharded two ways.
 
 The path shards perfectly: paths are independent and the device random stream is keyed by
-(seed, pixel, sample), so rank r rendering samples [r*S/N, (r+1)*S/N) produces exactly the
-per-sample radiances the single-GPU run would.  The only exchange step is one sum of the fp32
-accumulation buffer (24.9 MB at 1080p, 99.5 MB at 2160p) -- NCCL all-reduce / reduce over
-NVLink 5 / NVSwitch.  (The reference has no multi-GPU path)
+(seed, pixel, sample), so any partition of the (pixel, sample) set reproduces exactly the per-sample
+radiances of the single-GPU run.  (The reference has no multi-GPU path)
+
+* **sample split** (default): rank r renders samples [r*S/N, (r+1)*S/N) of every pixel; the only
+  exchange step is one sum of the fp32 accumulation buffer (24.9 MB at 1080p, 99.5 MB at 2160p) --
+  NCCL reduce / all-reduce over NVLink 5 / NVSwitch.  Perfectly balanced; equal to the 1-GPU frame up to
+  fp32 summation order.
+* **tile split**: rank r renders all samples of the interleaved row blocks r, r+N, r+2N, ... in ONE call
+  (Engine.set_row_interleave -> pt_set_row_interleave); the exchange step is a gather of each rank's own
+  rows (1/N of the buffer per rank, nothing is summed), so the result is bit-identical to the 1-GPU
+  frame.  Balance depends on the block size (8 rows: sky and sphere cluster are shared out evenly).
 """
 from __future__ import annotations
 
@@ -23,15 +30,31 @@ def sample_slice(spp: int, group=None, rank: int | None = None, world: int | Non
 
 
 def row_slice(height: int, rank: int, world: int, block: int = 4):
-    """Row-block tile split (alternative to the sample split): rows [y0,y1) in units of `block`."""
+    """Contiguous row range of a rank (plain [y0, y1) windows, no interleave): rows in units of `block`."""
     nb = (height + block - 1) // block
     y0 = min(height, ((rank * nb) // world) * block)
     y1 = min(height, (((rank + 1) * nb) // world) * block)
     return y0, y1
 
 
+def row_blocks(height: int, rank: int, world: int, block: int = 8):
+    """The image-row ranges [(y0, y1), ...] of the interleaved blocks rank, rank + world, ... (clipped to
+    the image).  Each can be rendered by its own contiguous-window call; interleaved_window() renders
+    them all in one."""
+    nb = (height + block - 1) // block
+    return [(b * block, min(height, (b + 1) * block)) for b in range(rank, nb, world)]
+
+
+def interleaved_window(height: int, rank: int, world: int, block: int = 8):
+    """-> (y0, y1, stride_rows): after Engine.set_row_interleave(block, stride_rows), a render call with
+    y0=y0, y1=y1 covers exactly row_blocks(height, rank, world, block).  block: power of two >= 4."""
+    n_mine = len(row_blocks(height, rank, world, block))
+    return rank * block, rank * block + n_mine * block, world * block
+
+
 def reduce_accum(accum: torch.Tensor, group=None, dst: int | None = None):
-    """Sum the per-rank accumulation buffers in place (all ranks get the total unless dst is given)."""
+    """Sample split epilogue: sum the per-rank accumulation buffers in place (every rank gets the total
+    unless dst names the one rank that needs it)."""
     if dist.get_world_size(group) == 1:
         return accum
     if dst is None:
@@ -41,6 +64,35 @@ def reduce_accum(accum: torch.Tensor, group=None, dst: int | None = None):
     return accum
 
 
-def gather_rows(accum: torch.Tensor, height: int, group=None, block: int = 4):
-    """Tile split epilogue: every rank owns rows row_slice(...); sum works because the others are 0."""
-    return reduce_accum(accum, group)
+def _own_rows(height, rank, world, block, device):
+    rows = [torch.arange(y0, y1, device=device) for y0, y1 in row_blocks(height, rank, world, block)]
+    return torch.cat(rows) if rows else torch.zeros(0, dtype=torch.long, device=device)
+
+
+def gather_rows(accum: torch.Tensor, height: int, group=None, block: int = 8, dst: int | None = None):
+    """Tile split epilogue: every rank owns the rows of row_blocks(height, rank, world, block) of its
+    (H, W, 3) buffer; they are packed, exchanged (each rank sends only its own 1/world of the frame) and
+    written into place on `dst` (or on every rank when dst is None).  Nothing is added: the assembled
+    frame is bit-identical to the one a single GPU renders."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return accum
+    rank = dist.get_rank(group)
+    nb = (height + block - 1) // block
+    per = (nb + world - 1) // world * block                     # rows in the largest share
+    mine = _own_rows(height, rank, world, block, accum.device)
+    send = torch.zeros((per,) + tuple(accum.shape[1:]), dtype=accum.dtype, device=accum.device)
+    send[: mine.numel()] = accum.index_select(0, mine)
+    want = dst is None or rank == dst
+    parts = [torch.empty_like(send) for _ in range(world)] if want else None
+    if dst is None:
+        dist.all_gather(parts, send, group=group)
+    else:
+        dist.gather(send, parts, dst=dst, group=group)
+    if want:
+        for r in range(world):
+            if r == rank:
+                continue
+            rows = _own_rows(height, r, world, block, accum.device)
+            accum.index_copy_(0, rows, parts[r][: rows.numel()])
+    return accum

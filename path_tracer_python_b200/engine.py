@@ -20,21 +20,27 @@ def _require_cuda():
 
 
 class Engine:
-    def __init__(self, device: int | None = None):
+    def __init__(self, device: int | None = None, numerics: str = "strict"):
+        """numerics: "strict" = the PT-F32 contract (bit-exact against the reference's kernels; the parity
+        build) or "fast" = the production build of the same sources (FMA contraction, FFMA slab test,
+        approximate reciprocal / division / square root; first hits within 1e-5 relative of strict)."""
         _require_cuda()
-        self.L = _lib.lib()
+        self.numerics = numerics
+        self.L = _lib.lib(numerics)
         self.device_index = torch.cuda.current_device() if device is None else int(device)
         self.device = torch.device("cuda", self.device_index)
         ctx = C.c_void_p()
-        check(self.L.pt_create(self.device_index, C.byref(ctx)), "pt_create")
+        self._check(self.L.pt_create(self.device_index, C.byref(ctx)), "pt_create")
         self.ctx = ctx
         self.info: PtPackedInfo | None = None
         self.scene_blob = None          # device uint8 tensor (owned here, borrowed by the library)
         self._pinned_blob = None
+        self._upload_done = None         # event: the last pinned -> device scene copy has finished
         self._workspace = None
         self.h2d_bytes = 0
         self.wavefront_samples_in_flight = None  # None = auto (about 66 M paths per batch); bounded by max_workspace_bytes
         self.max_workspace_bytes = 12 << 30
+        self.wavefront_min_batches = 1           # auto sizing: split a render call into at least this many batches
 
     def close(self):
         if getattr(self, "ctx", None):
@@ -47,9 +53,22 @@ class Engine:
         except Exception:
             pass
 
+    def _check(self, rc: int, what: str = ""):
+        check(rc, what, self.L)
+
+    @staticmethod
+    def has_numerics(numerics: str) -> bool:
+        return _lib.has_numerics(numerics)
+
     # ------------------------------------------------------------------ configuration
     def set_option(self, name: str, value: int):
-        check(self.L.pt_set_option(self.ctx, name.encode(), int(value)), f"pt_set_option({name})")
+        self._check(self.L.pt_set_option(self.ctx, name.encode(), int(value)), f"pt_set_option({name})")
+
+    def set_row_interleave(self, block_rows: int = 0, stride_rows: int = 0):
+        """Interleaved row blocks for the multi-GPU tile split (pt_set_row_interleave): afterwards
+        render_*(…, y0=rank * block_rows, y1=y0 + local_rows) renders this rank's blocks in one call.
+        block_rows = 0 switches back to contiguous windows."""
+        self._check(self.L.pt_set_row_interleave(self.ctx, int(block_rows), int(stride_rows)), "pt_set_row_interleave")
 
     def _stream_ptr(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -59,23 +78,30 @@ class Engine:
         """cs: CompiledScene dict (reference layout).  Packs on the host (C++), one pinned->device copy."""
         hs = HostScene(cs)
         info = PtPackedInfo()
-        check(self.L.pt_pack_scene_info(C.byref(hs.c), C.byref(info)), "pt_pack_scene_info")
+        self._check(self.L.pt_pack_scene_info(C.byref(hs.c), C.byref(info)), "pt_pack_scene_info")
+        if int(info.max_depth_tree) > 64:      # what pt_set_scene would refuse: do not upload, keep the current scene
+            raise _lib.B200PTError(f"BVH depth {int(info.max_depth_tree)} exceeds the 64-entry traversal stack (kernels.py:649)")
         nbytes = int(info.total_bytes)
+        # the pinned staging buffer is reused: the previous upload must have left it before it is rewritten
+        if self._upload_done is not None:
+            self._upload_done.synchronize()
         if self._pinned_blob is None or self._pinned_blob.numel() < nbytes:
             self._pinned_blob = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
         pinned = self._pinned_blob[:nbytes]
-        check(self.L.pt_pack_scene(C.byref(hs.c), C.byref(info), C.c_void_p(pinned.data_ptr())), "pt_pack_scene")
+        self._check(self.L.pt_pack_scene(C.byref(hs.c), C.byref(info), C.c_void_p(pinned.data_ptr())), "pt_pack_scene")
         with torch.cuda.device(self.device):
             blob = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
             blob.copy_(pinned, non_blocking=True)
-        check(self.L.pt_set_scene(self.ctx, C.c_void_p(blob.data_ptr()), C.byref(info)), "pt_set_scene")
+            self._upload_done = torch.cuda.Event()
+            self._upload_done.record()
+        self._check(self.L.pt_set_scene(self.ctx, C.c_void_p(blob.data_ptr()), C.byref(info)), "pt_set_scene")
         self.scene_blob, self.info = blob, info
         self.h2d_bytes = nbytes
         return info
 
     def set_camera(self, cam: dict | PtCamera, background=(0.7, 0.8, 1.0), max_depth=50):
         pc = cam if isinstance(cam, PtCamera) else make_camera(cam, background, max_depth)
-        check(self.L.pt_set_camera(self.ctx, C.byref(pc)), "pt_set_camera")
+        self._check(self.L.pt_set_camera(self.ctx, C.byref(pc)), "pt_set_camera")
         self.camera = pc
 
     # ------------------------------------------------------------------ rendering
@@ -88,7 +114,7 @@ class Engine:
         assert accum.is_cuda and accum.dtype == torch.float32 and accum.is_contiguous()
         y1 = H if y1 is None else y1
         with torch.cuda.device(self.device):
-            check(self.L.pt_render_megakernel(self.ctx, C.c_void_p(accum.data_ptr()), W, H, y0, y1, sample_begin,
+            self._check(self.L.pt_render_megakernel(self.ctx, C.c_void_p(accum.data_ptr()), W, H, y0, y1, sample_begin,
                                               sample_count, C.c_uint32(seed & 0xFFFFFFFF), self._stream_ptr()),
                   "pt_render_megakernel")
 
@@ -98,7 +124,7 @@ class Engine:
         assert accum.is_cuda and accum.dtype == torch.float32 and accum.is_contiguous()
         y1 = H if y1 is None else y1
         if self.wavefront_samples_in_flight is None:
-            b = auto_samples_in_flight(W, y1 - y0, sample_count)
+            b = auto_samples_in_flight(W, y1 - y0, sample_count, min_batches=self.wavefront_min_batches)
         else:
             b = max(1, min(self.wavefront_samples_in_flight, sample_count))
         extra = 64 * int(self.info.num_inner) + 256 if self.info is not None else 0     # origin-relative node copy
@@ -109,7 +135,7 @@ class Engine:
         if self._workspace is None or self._workspace.numel() < need:
             self._workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
         with torch.cuda.device(self.device):
-            check(self.L.pt_render_wavefront(self.ctx, C.c_void_p(accum.data_ptr()), W, H, y0, y1, sample_begin,
+            self._check(self.L.pt_render_wavefront(self.ctx, C.c_void_p(accum.data_ptr()), W, H, y0, y1, sample_begin,
                                              sample_count, C.c_uint32(seed & 0xFFFFFFFF),
                                              C.c_void_p(self._workspace.data_ptr()), C.c_size_t(need),
                                              self._stream_ptr()), "pt_render_wavefront")
@@ -119,7 +145,7 @@ class Engine:
         o = torch.empty((H * W, 3), dtype=torch.float32, device=self.device)
         d = torch.empty_like(o)
         with torch.cuda.device(self.device):
-            check(self.L.pt_generate_camera_rays(self.ctx, W, H, C.c_uint32(seed & 0xFFFFFFFF), sample,
+            self._check(self.L.pt_generate_camera_rays(self.ctx, W, H, C.c_uint32(seed & 0xFFFFFFFF), sample,
                                                  C.c_void_p(o.data_ptr()), C.c_void_p(d.data_ptr()), self._stream_ptr()),
                   "pt_generate_camera_rays")
         return o, d
@@ -133,7 +159,7 @@ class Engine:
         p = torch.empty((n, 3), dtype=torch.float32, device=self.device) if want_pn else None
         nn = torch.empty((n, 3), dtype=torch.float32, device=self.device) if want_pn else None
         with torch.cuda.device(self.device):
-            check(self.L.pt_first_hit(self.ctx, C.c_void_p(o.data_ptr()), C.c_void_p(d.data_ptr()), n, t_min, t_max,
+            self._check(self.L.pt_first_hit(self.ctx, C.c_void_p(o.data_ptr()), C.c_void_p(d.data_ptr()), n, t_min, t_max,
                                       C.c_void_p(t.data_ptr()), C.c_void_p(prim.data_ptr()),
                                       C.c_void_p(p.data_ptr()) if want_pn else None,
                                       C.c_void_p(nn.data_ptr()) if want_pn else None, self._stream_ptr()), "pt_first_hit")
@@ -144,37 +170,48 @@ class Engine:
         b = a if b is None else b.to(self.device, torch.float32).contiguous()
         out = torch.empty_like(a)
         with torch.cuda.device(self.device):
-            check(self.L.pt_math_eval(self.ctx, fn, a.numel(), C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()),
+            self._check(self.L.pt_math_eval(self.ctx, fn, a.numel(), C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()),
                                       C.c_void_p(out.data_ptr()), self._stream_ptr()), "pt_math_eval")
         return out
+
+    def probe_gather(self, working_set_bytes: int, pattern: int = 0, iters: int = 64, repeats: int = 5) -> float:
+        """Measured GB/s of 64-byte record gathers (the node-fetch instruction sequence, all lanes
+        active) over a zero-filled working set of that size: the memory roof of the traversal kernels
+        for a scene of that size.  pattern 0 = random record per lane, 1 = one record per warp."""
+        buf = torch.zeros(max(64, int(working_set_bytes)) // 64 * 64, dtype=torch.uint8, device=self.device)
+        out = C.c_double(0.0)
+        with torch.cuda.device(self.device):
+            self._check(self.L.pt_probe_gather(self.ctx, C.c_void_p(buf.data_ptr()), C.c_size_t(buf.numel()), int(pattern),
+                                         int(iters), int(repeats), C.byref(out), self._stream_ptr()), "pt_probe_gather")
+        return float(out.value)
 
     def tonemap(self, accum: torch.Tensor, sample_count: int) -> torch.Tensor:
         out = torch.empty(accum.shape, dtype=torch.uint8, device=self.device)
         with torch.cuda.device(self.device):
-            check(self.L.pt_tonemap(self.ctx, C.c_void_p(accum.data_ptr()), accum.numel(), int(sample_count),
+            self._check(self.L.pt_tonemap(self.ctx, C.c_void_p(accum.data_ptr()), accum.numel(), int(sample_count),
                                     C.c_void_p(out.data_ptr()), self._stream_ptr()), "pt_tonemap")
         return out
 
     # ------------------------------------------------------------------ statistics
     def enable_counters(self, on: bool = True):
-        check(self.L.pt_enable_counters(self.ctx, 1 if on else 0), "pt_enable_counters")
+        self._check(self.L.pt_enable_counters(self.ctx, 1 if on else 0), "pt_enable_counters")
 
     def counters(self, reset: bool = True) -> dict:
         c = PtCounters()
-        check(self.L.pt_get_counters(self.ctx, C.byref(c), 1 if reset else 0), "pt_get_counters")
+        self._check(self.L.pt_get_counters(self.ctx, C.byref(c), 1 if reset else 0), "pt_get_counters")
         return c.as_dict()
 
 
     def enable_stage_timing(self, on: bool = True):
-        check(self.L.pt_enable_stage_timing(self.ctx, 1 if on else 0), "pt_enable_stage_timing")
+        self._check(self.L.pt_enable_stage_timing(self.ctx, 1 if on else 0), "pt_enable_stage_timing")
 
     def stage_times(self) -> list:
         """[(stage name, wave, ms)] for every launch of the last render_wavefront call (synchronises)."""
         from ._lib import PtStageTime, STAGE_NAMES
         n = C.c_int(0)
-        check(self.L.pt_get_stage_times(self.ctx, None, 0, C.byref(n)), "pt_get_stage_times")
+        self._check(self.L.pt_get_stage_times(self.ctx, None, 0, C.byref(n)), "pt_get_stage_times")
         buf = (PtStageTime * max(1, n.value))()
-        check(self.L.pt_get_stage_times(self.ctx, buf, n.value, C.byref(n)), "pt_get_stage_times")
+        self._check(self.L.pt_get_stage_times(self.ctx, buf, n.value, C.byref(n)), "pt_get_stage_times")
         return [(STAGE_NAMES[buf[i].kernel], buf[i].wave, buf[i].ms) for i in range(n.value)]
 
 
@@ -182,9 +219,9 @@ class Engine:
         """Per-launch counter increments of the last render_wavefront call (needs enable_counters and
         enable_stage_timing); same order as stage_times()."""
         n = C.c_int(0)
-        check(self.L.pt_get_stage_counters(self.ctx, None, 0, C.byref(n)), "pt_get_stage_counters")
+        self._check(self.L.pt_get_stage_counters(self.ctx, None, 0, C.byref(n)), "pt_get_stage_counters")
         buf = (PtCounters * max(1, n.value))()
-        check(self.L.pt_get_stage_counters(self.ctx, buf, n.value, C.byref(n)), "pt_get_stage_counters")
+        self._check(self.L.pt_get_stage_counters(self.ctx, buf, n.value, C.byref(n)), "pt_get_stage_counters")
         cum = [buf[i].as_dict() for i in range(n.value)]
         out, prev = [], None
         for c in cum:
@@ -193,12 +230,14 @@ class Engine:
         return out
 
 
-def auto_samples_in_flight(W: int, rows: int, sample_count: int, target_paths: float = 66.4e6) -> int:
+def auto_samples_in_flight(W: int, rows: int, sample_count: int, target_paths: float = 66.4e6, min_batches: int = 1) -> int:
     """Samples of every pixel the wavefront pipeline keeps in flight per batch: about `target_paths`
     paths (32 samples of a 1080p frame -- fewer leave the later waves too small to fill the GPU, more
-    gain nothing), split into equal batches, at most 256 (the library's limit)."""
+    gain nothing), split into equal batches, at most 256 (the library's limit).  `min_batches` > 1
+    keeps the two-stream overlap (a batch's tail under the next batch's primary wave) alive when a
+    rank's share of the samples would fit one batch."""
     per_batch = target_paths / max(1, W * rows)
-    n_batches = max(1, round(sample_count / per_batch))
+    n_batches = max(1, round(sample_count / per_batch), min(int(min_batches), max(1, sample_count)))
     return max(1, min(256, -(-sample_count // n_batches)))
 
 

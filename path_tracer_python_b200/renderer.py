@@ -11,7 +11,8 @@ no per-sample host synchronisation, no CPU fallback.
 Extra (keyword-only) knobs: ``seed`` (device RNG key), ``device`` (GPU ordinal),
 ``spp_per_launch`` (samples folded into one megakernel launch; None = all), ``process_group``
 (torch.distributed group: samples are split across ranks and the accumulation buffer is summed
-with NCCL, see distributed.py), ``features`` ("taichi_compat" = exactly what the reference's Taichi
+with NCCL, see distributed.py; ``reduce_dst`` = the one rank that needs the frame, default all),
+``numerics`` ("strict" = bit-exact parity build, "fast" = FMA / approximate-reciprocal build), ``features`` ("taichi_compat" = exactly what the reference's Taichi
 path renders; "full" = additionally motion blur and the subsurface materials, which only the
 reference's pure-Python tracer has).
 """
@@ -37,7 +38,8 @@ def _color_tuple(c):
 class TaichiRenderer:
     def __init__(self, world, cam, img_path: str, *, seed: int = 0, device: int | None = None,
                  spp_per_launch: int | None = None, process_group=None, compiled_scene: dict | None = None,
-                 quiet: bool = False, features: str = "taichi_compat"):
+                 quiet: bool = False, features: str = "taichi_compat", numerics: str = "strict",
+                 reduce_dst: int | None = None):
         self.timing = {k: 0.0 for k in ("taichi_init", "scene_compile", "bvh_compile", "bvh_flatten", "camera_upload",
                                         "gpu_upload", "kernel_warmup", "total_setup")}
         self.sample_times = []
@@ -54,9 +56,10 @@ class TaichiRenderer:
         self.seed = int(seed)
         self.spp_per_launch = spp_per_launch
         self.process_group = process_group
+        self.reduce_dst = reduce_dst         # None: every rank gets the summed frame (all-reduce); r: only rank r (reduce)
 
         t0 = time.time()
-        self.engine = Engine(device)
+        self.engine = Engine(device, numerics)
         self.timing["taichi_init"] = time.time() - t0
 
         # Perlin tables are drawn first, like the reference (renderer.py:78-80), so that a seeded
@@ -149,7 +152,7 @@ class TaichiRenderer:
                 preview.process_events()
         if self.process_group is not None:
             from .distributed import reduce_accum
-            reduce_accum(self._accum, self.process_group)
+            reduce_accum(self._accum, self.process_group, self.reduce_dst)
         self.current_sample = int(self.cam.samples_per_pixel)
         if self.process_group is None or torch.distributed.get_rank(self.process_group) == 0:
             self._write_image()
@@ -180,7 +183,7 @@ class TaichiRenderer:
         fn(self._accum, s_begin, s_end - s_begin, self.seed)
         if self.process_group is not None:
             from .distributed import reduce_accum
-            reduce_accum(self._accum, self.process_group)
+            reduce_accum(self._accum, self.process_group, self.reduce_dst)
         if getattr(self, "_host_accum", None) is None:
             self._host_accum = torch.empty(self._accum.shape, dtype=torch.float32, pin_memory=True)
         self._host_accum.copy_(self._accum, non_blocking=True)

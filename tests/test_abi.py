@@ -10,10 +10,11 @@ from path_tracer_python_b200 import _lib, build
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.fixture(scope="module")
-def L():
-    build.build_native()
-    return _lib.lib()
+@pytest.fixture(scope="module", params=["strict", "fast"])
+def L(request):
+    """Both builds of the library: the strict (parity) one and the fast-numerics variant of the same sources."""
+    build.build_native() if request.param == "strict" else build.build_fast()
+    return _lib.lib(request.param)
 
 
 def _declared():
@@ -48,14 +49,17 @@ def test_errors_are_reported_without_a_gpu(L):
     one, many = L.pt_wavefront_workspace_bytes_for(1920, 1080, 1), L.pt_wavefront_workspace_bytes_for(1920, 1080, 32)
     assert one == L.pt_wavefront_workspace_bytes(1920, 1080)
     assert many - one == 31 * n * 168 and 0 < one - n * 168 <= 64 * 1024
-    assert b"sm_100a" in L.pt_version()
+    assert b"sm_100a" in L.pt_version() and (b"strict" in L.pt_version()) != (b"fast" in L.pt_version())
 
 
 def test_no_cpu_fallback_when_library_missing(monkeypatch, tmp_path):
-    monkeypatch.setattr(_lib, "_lib", None)
-    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
-    with pytest.raises(_lib.B200PTError):
-        _lib.lib()
+    monkeypatch.setattr(_lib, "_libs", {})
+    monkeypatch.setattr(_lib, "LIB_PATHS", {"strict": str(tmp_path / "nope.so"), "fast": str(tmp_path / "nope_fast.so")})
+    for numerics in ("strict", "fast"):
+        with pytest.raises(_lib.B200PTError, match="not built"):
+            _lib.lib(numerics)
+    with pytest.raises(_lib.B200PTError, match="unknown numerics"):
+        _lib.lib("sloppy")
 
 
 def test_product_never_imports_the_oracle():

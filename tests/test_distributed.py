@@ -6,7 +6,7 @@ import sys
 
 import numpy as np
 
-from path_tracer_python_b200.distributed import row_slice, sample_slice
+from path_tracer_python_b200.distributed import interleaved_window, row_blocks, row_slice, sample_slice
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -32,12 +32,28 @@ def test_row_slices_partition_rows():
             assert rows == list(range(h))
 
 
+def test_interleaved_row_blocks_partition_rows():
+    for world in (1, 2, 3, 8):
+        for h in (1, 18, 225, 1080, 2160):
+            for block in (4, 8, 32):
+                rows = []
+                for r in range(world):
+                    blocks = row_blocks(h, r, world, block)
+                    rows += [y for y0, y1 in blocks for y in range(y0, y1)]
+                    # the one-call window maps onto the same rows: local row ly -> y0 + (ly // block) * stride + ly % block
+                    y0, y1, stride = interleaved_window(h, r, world, block)
+                    assert (y1 - y0) % block == 0 and stride == world * block
+                    mapped = [y0 + (ly // block) * stride + ly % block for ly in range(y1 - y0)]
+                    assert [y for y in mapped if y < h] == [y for a, b in blocks for y in range(a, b)]
+                assert sorted(rows) == list(range(h))
+
+
 _WORKER = r'''
 import os, sys
 sys.path.insert(0, %(repo)r); sys.path.insert(0, os.path.join(%(repo)r, "oracle"))
 import numpy as np, torch, torch.distributed as dist
 from path_tracer_python_b200 import scenes
-from path_tracer_python_b200.distributed import sample_slice, reduce_accum
+from path_tracer_python_b200.distributed import sample_slice, reduce_accum, row_blocks, gather_rows
 import oracle as O
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
@@ -52,6 +68,16 @@ reduce_accum(acc)
 ref = out["accum_megakernel"]
 err = float(np.abs(acc.numpy() - ref).max())
 ok = np.allclose(acc.numpy(), ref, rtol=1e-5, atol=1e-5)
+# tile split: every rank renders all samples of its interleaved row blocks; gather_rows assembles the
+# frame without adding anything -> bit-identical to the single-process result
+for dst in (None, 0):
+    tile = np.zeros((H, W, 3), np.float32)
+    for y0, y1 in row_blocks(H, rank, world, 4):
+        O.render(S, cam, W, H, spp, seed=seed, accum=tile, y0=y0, y1=y1, nthreads=1)
+    tt = torch.from_numpy(tile)
+    gather_rows(tt, H, block=4, dst=dst)
+    if dst is None or rank == dst:
+        ok = ok and np.array_equal(tt.numpy(), ref)
 print(f"RANK{rank} slice=({b},{e}) maxerr={err:.3e} ok={ok}")
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

@@ -1,0 +1,80 @@
+"""numerics="fast": the production build of the same sources (-DPT_FAST=1 --fmad=true: FMA contraction, one
+FFMA per slab plane, approximate reciprocal / division / square root).  It is NOT the parity build; it is
+gated by north_star's own tolerance against the strict build: primary-ray first-hit primitive equal and
+|dt|/t <= 1e-5 on configs 1-3, and images equal within Monte-Carlo error."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _engines():
+    from path_tracer_python_b200.engine import Engine
+    if not Engine.has_numerics("fast"):
+        pytest.fail("libb200pt_fast.so is not built (python -m path_tracer_python_b200.build)")
+    return Engine(0, "strict"), Engine(0, "fast")
+
+
+def _scene(name):
+    from path_tracer_python_b200 import scenes
+    if name == "heightfield":
+        cs, meta = scenes.heightfield_scene(img_width=960)
+        return cs, meta, meta["background"], meta["max_depth"]
+    width, bg = (400, (0.7, 0.8, 1.0)) if name == "wavefront_comparison" else (1920, (0, 0, 0))
+    cs, meta = scenes.load_config(name, width, 16 / 9)
+    meta["width"] = width
+    return cs, meta, bg, 50
+
+
+@pytest.mark.parametrize("name", ["wavefront_comparison", "vol2_final_scene", "heightfield"])
+def test_fast_first_hit_within_north_star_tolerance(name):
+    strict, fast = _engines()
+    assert b"strict" in strict.L.pt_version() and b"fast" in fast.L.pt_version()
+    cs, meta, bg, depth = _scene(name)
+    W, H = meta["width"], meta["height"]
+    for e in (strict, fast):
+        e.set_scene(cs)
+        e.set_camera(meta["camera"], bg, depth)
+    o, d = strict.generate_camera_rays(W, H, 9, 0)
+    o2, d2 = fast.generate_camera_rays(W, H, 9, 0)
+    assert torch.allclose(d, d2, rtol=1e-6, atol=1e-6)
+    ts, ps, _, _ = strict.first_hit(o, d, want_pn=False)
+    tf, pf, _, _ = fast.first_hit(o, d, want_pn=False)           # the same rays through both builds
+    ts, ps, tf, pf = (x.cpu().numpy() for x in (ts, ps, tf, pf))
+    hit = ps >= 0
+    assert np.array_equal(hit, pf >= 0), f"{np.count_nonzero(hit != (pf >= 0))} rays hit in one build only"
+    rel = np.abs(tf[hit].astype(np.float64) - ts[hit]) / ts[hit]
+    # equal-t ties between coincident surfaces may resolve to either primitive (SURVEY.md 8a note vi)
+    differ = ps[hit] != pf[hit]
+    print(f"{name}: {hit.sum()} hits, max |dt|/t = {rel.max():.2e}, primitive differs on {differ.sum()} rays")
+    assert rel.max() <= 1e-5
+    assert np.all(rel[differ] <= 1e-6) and differ.mean() < 2e-3
+
+
+def test_fast_image_matches_strict_within_mc_error():
+    """Config 2 at 480x270 x 256 spp: fast vs strict (same seed: most paths identical, a few fork at
+    borderline decisions) against the spread of two strict seeds."""
+    strict, fast = _engines()
+    from path_tracer_python_b200 import scenes
+    cs, meta = scenes.load_config("vol2_final_scene", 480, 16 / 9)
+    W, H, spp = 480, meta["height"], 256
+    imgs = {}
+    for key, e, seed in (("s1", strict, 1), ("s2", strict, 2), ("f1", fast, 1)):
+        e.set_scene(cs)
+        e.set_camera(meta["camera"], (0, 0, 0), 50)
+        acc = e.new_accum(W, H)
+        e.render_wavefront(acc, 0, spp, seed)
+        imgs[key] = acc.cpu().numpy().astype(np.float64) / spp
+    lum = lambda x: 0.2126 * x[..., 0] + 0.7152 * x[..., 1] + 0.0722 * x[..., 2]
+    se = np.sqrt(np.mean((lum(imgs["s1"]) - lum(imgs["s2"])) ** 2) / 2.0)       # per-pixel standard error of one render
+    rmse = np.sqrt(np.mean((lum(imgs["f1"]) - lum(imgs["s1"])) ** 2))
+    print(f"fast vs strict: rmse {rmse:.5f}; per-pixel MC standard error {se:.5f}; "
+          f"mean luminance {lum(imgs['f1']).mean():.5f} vs {lum(imgs['s1']).mean():.5f}")
+    assert rmse <= 3.0 * se * np.sqrt(2.0)
+    assert abs(lum(imgs["f1"]).mean() / lum(imgs["s1"]).mean() - 1.0) < 0.005
+    # megakernel of the fast build agrees with its wavefront statistically too
+    acc = fast.new_accum(W, H)
+    fast.render_megakernel(acc, 0, spp, 1)
+    m = acc.cpu().numpy().astype(np.float64) / spp
+    assert abs(lum(m).mean() / lum(imgs["f1"]).mean() - 1.0) < 0.01

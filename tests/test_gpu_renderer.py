@@ -294,3 +294,31 @@ def test_one_context_many_scenes_with_batch_overlap():
             acc = e.new_accum(meta["width"], meta["height"])
             e.render_wavefront(acc, 0, meta["spp"], meta["rng_seed"])
             assert np.array_equal(acc.cpu().numpy(), out["accum_wavefront"]), name
+
+
+@pytest.mark.parametrize("mode", ["megakernel", "wavefront"])
+def test_interleaved_row_windows_compose_to_the_full_frame(mode):
+    """The multi-GPU tile split on one GPU: three 'ranks' render their interleaved row blocks (one call
+    each, pt_set_row_interleave) into one buffer -- the union is bit-identical to the full-frame render.
+    270 rows / 8-row blocks = 33.75 blocks: the last block sticks out of the image (rows skipped)."""
+    from path_tracer_python_b200 import scenes
+    from path_tracer_python_b200.distributed import interleaved_window
+    from path_tracer_python_b200.engine import Engine
+    e = Engine(0)
+    cs, meta = scenes.load_config("vol2_final_scene", 480, 16 / 9)
+    e.set_scene(cs)
+    e.set_camera(meta["camera"], (0, 0, 0), 50)
+    W, H, spp, seed = 480, meta["height"], 8, 3
+    fn = e.render_megakernel if mode == "megakernel" else e.render_wavefront
+    full = e.new_accum(W, H)
+    fn(full, 0, spp, seed)
+    for block, world in ((8, 3), (4, 2), (32, 5)):
+        tiles = e.new_accum(W, H)
+        for rank in range(world):
+            y0, y1, stride = interleaved_window(H, rank, world, block)
+            e.set_row_interleave(block, stride)
+            fn(tiles, 0, spp, seed, y0=y0, y1=y1)
+        e.set_row_interleave(0)
+        assert torch.equal(tiles, full), (block, world)
+    with pytest.raises(Exception, match="power of two"):
+        e.set_row_interleave(6, 12)

@@ -77,3 +77,40 @@ def test_single_primitive_and_empty_scene():
     assert refs[0] == ~(2 << 2) and refs[1] == refs[0]
     info, blob = _pack({})
     assert info.num_inner == 0 and info.total_bytes >= 256
+
+
+def test_malformed_scenes_are_rejected_not_dereferenced():
+    """`compiled_scene=` is public API.  A missing key or a short per-primitive array
+    raises in HostScene; index ranges the Python side cannot see are rejected by the C packer with
+    PT_ERR_INVALID_ARG (never a NULL / out-of-bounds dereference)."""
+    cs, _, _ = scenes.load_fixture("wavefront_comparison")
+    for drop in ("sphere_material_type", "sphere_is_constant_medium", "bvh_prim_type", "bvh_left_child"):
+        bad = {k: v for k, v in cs.items() if k != drop}
+        with pytest.raises(_lib.B200PTError, match=drop):
+            _lib.HostScene(bad)
+    bad = dict(cs, sphere_material_fuzz=cs["sphere_material_fuzz"][:-1])
+    with pytest.raises(_lib.B200PTError, match="rows"):
+        _lib.HostScene(bad)
+    bad = dict(cs, sphere_material_albedo=cs["sphere_material_albedo"][:, :2])
+    with pytest.raises(_lib.B200PTError, match="shape"):
+        _lib.HostScene(bad)
+    L = _lib.lib()
+    leaf = int(np.where(cs["bvh_prim_idx"] >= 0)[0][0])
+    for key, value, msg in (("bvh_prim_type", 3, "bvh_prim_type"), ("bvh_prim_idx", 10 ** 6, "bvh_prim_idx"),
+                            ("bvh_prim_type", 2, "bvh_prim_idx")):          # type 2 = quad: the scene has none
+        a = cs[key].copy()
+        a[leaf] = value
+        hs = _lib.HostScene(dict(cs, **{key: a}))
+        info = _lib.PtPackedInfo()
+        assert L.pt_pack_scene_info(C.byref(hs.c), C.byref(info)) == -1      # PT_ERR_INVALID_ARG
+        assert msg in L.pt_last_error().decode()
+    mt = cs["sphere_material_type"].copy()
+    mt[0] = 9
+    hs = _lib.HostScene(dict(cs, sphere_material_type=mt))
+    assert L.pt_pack_scene_info(C.byref(hs.c), C.byref(_lib.PtPackedInfo())) == -1
+    # an image-textured Lambertian whose image index points past the image table
+    z, _, _ = scenes.load_fixture("feature_zoo")
+    idx = z["sphere_texture_image_idx"].copy()
+    idx[z["sphere_texture_type"] == 2] = 5
+    hs = _lib.HostScene(dict(z, sphere_texture_image_idx=idx))
+    assert L.pt_pack_scene_info(C.byref(hs.c), C.byref(_lib.PtPackedInfo())) == -1
