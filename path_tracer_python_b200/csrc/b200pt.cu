@@ -74,8 +74,12 @@ struct PtContext {
     int wf_fuse_primary = 1; // wave 0 (camera rays) as one fused kernel
     int wf_burst_num = 20;
     int wf_blocks_per_sm = 7;
-    int wf_extend_minb = 5;  // 48 registers, 5 CTAs (40 warps) per SM: +1.3 % over 4 x 56 once node fetches all go through L1
+    int wf_extend_minb = PT_FAST ? 6 : 5;  // launch bound of k_wf_extend: the one that compiles to <= 56 registers without spills, so
+                                           // that six 192-thread CTAs (36 warps) are resident per SM (strict: 5 -> 56; fast: 6 -> 55, 5 -> 61)
     int wf_tile = 1;
+    int wf_shade_split = 0;  // 1: k_wf_shade_cls<KIND> per class run instead of one k_wf_shade for all classes (measured slower:
+                             // 5.99 vs 5.12 ms per config-2 batch -- three dependent launches, each with its own ramp and tail,
+                             // where one kernel lets warps of different classes hide each other's memory latency)
     int row_shift = -1, row_stride = 0;   // pt_set_row_interleave
     int num_sms = 148;
     int max_smem_optin = 0;
@@ -366,7 +370,7 @@ struct WfQueues {
     int capacity;            // B * N
 };
 constexpr int kNodeBytes = 64;   // one packed inner node (both children's boxes + two references)
-constexpr int kNumBins = 8;  // 0 miss, 1 medium boundary, 2.. = 2 + material type (0..4)
+constexpr int kNumBins = 8;  // one bin per shading class (pt_device.cuh PT_CLS_*)
 
 struct WfParams {
     DScene S;
@@ -550,9 +554,9 @@ __global__ void __launch_bounds__(PT_EXT_WARPS * 32, MINB) k_wf_extend(const __g
         if (st == LANE_HAVE_RESULT) {
             if (mode == 0) {
                 const int ref = T.best_ref;
-                // 0 miss, 1 medium boundary, 2 + material type (subsurface materials share the last bin)
+                // shading class of the hit = its material bin (0 = miss)
                 const int cls = ref != kRefNone ? ref_class(ref) : 0;
-                if (cls == 1) {
+                if (cls == PT_CLS_MEDIUM) {
                     mode = 1;
                     t_entry = T.best_t;
                     ref_entry = ref;
@@ -565,7 +569,7 @@ __global__ void __launch_bounds__(PT_EXT_WARPS * 32, MINB) k_wf_extend(const __g
             } else {
                 mode = 0;
                 P.Q.hit[ray] = make_float4(t_entry, __int_as_float(ref_entry), T.best_t,
-                                           __int_as_float((T.best_ref != kRefNone ? 1 : 0) | (1 << 8)));
+                                           __int_as_float((T.best_ref != kRefNone ? 1 : 0) | (PT_CLS_MEDIUM << 8)));
                 st = LANE_NEED_PATH;
             }
         }
@@ -835,6 +839,108 @@ __global__ void __launch_bounds__(PT_SHADE_THREADS, PT_SHADE_MINB) k_wf_shade(co
             P.Q.ra[nxt][2 * (size_t)pos] = make_float4(no.x, no.y, no.z, nd.x);
             P.Q.ra[nxt][2 * (size_t)pos + 1] = make_float4(nd.y, nd.z, nthr.x, nthr.y);
             P.Q.r2[nxt][pos] = make_float4(nthr.z, __int_as_float(path_id), __uint_as_float(rng.s), __int_as_float(ndepth));
+        }
+    }
+}
+
+// The same work split by shading class: the bins are class-sorted, so each of three kernels owns a
+// contiguous run of the index space and is compiled for what that run needs --
+//   KIND 0  miss + emissive: the path ends here; one multiply and one 12-byte store per ray, no next ray,
+//           no random numbers (reads 32 of the ray's 48 bytes and, for emitters, the hit's primitive);
+//   KIND 1  Lambert with a solid colour (the bulk of every scene): hit point, normal, cosine-weighted
+//           direction, Russian roulette;
+//   KIND 2  everything else through the general code (textures with Perlin noise / image lookups, metal,
+//           dielectric, medium boundaries, full-mode subsurface).
+// One kernel for all classes runs the trivial bins at the register budget of the worst one (80 registers,
+// 3 CTAs per SM); split, the terminal kernel is a pure streaming pass at full occupancy.  Per-ray arithmetic
+// is wf_shade_one's, operation for operation (bit-identical; options test "wf_shade_split").
+template <bool FULL, int KIND>
+__global__ void __launch_bounds__(256, KIND == 0 ? 8 : (KIND == 1 ? 4 : 3)) k_wf_shade_cls(const __grid_constant__ WfParams P) {
+    constexpr int c_lo = KIND == 0 ? PT_CLS_MISS : (KIND == 1 ? PT_CLS_LAMBERT_SOLID : PT_CLS_LAMBERT_TEX);
+    constexpr int c_hi = KIND == 0 ? PT_CLS_LAMBERT_SOLID : (KIND == 1 ? PT_CLS_LAMBERT_TEX : kNumBins);
+    const DScene& S = P.S;
+    const int cur = P.bounce & 1, nxt = cur ^ 1;
+    if (KIND == 0 && blockIdx.x == 0 && threadIdx.x == 0) P.Q.cursor[0] = 0;       // for the next k_wf_extend
+    __shared__ int prefix[c_hi - c_lo + 1];       // starts of this kernel's classes within its own run
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        prefix[0] = 0;
+        for (int b = c_lo; b < c_hi; b++) { acc += P.Q.bin_count[b]; prefix[b - c_lo + 1] = acc; }
+    }
+    __syncthreads();
+    const int count = prefix[c_hi - c_lo];
+    if ((long long)blockIdx.x * blockDim.x >= count) return;
+    const int max_depth = P.cam.max_depth;
+    const f3 bg = mk3(P.cam.background[0], P.cam.background[1], P.cam.background[2]);
+    const int stride = gridDim.x * blockDim.x;
+    const int rounds = (count + stride - 1) / stride;
+    for (int r = 0; r < rounds; r++) {
+        const int j = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        const bool active = j < count;
+        bool emit_next = false;
+        f3 no, nd, nthr;
+        int path_id = 0, ndepth = 0;
+        ptm::Rng rng{0u, 1u};
+        if (active) {
+            int b = 0;
+#pragma unroll
+            for (int k = 1; k < c_hi - c_lo; k++) b += (j >= prefix[k]) ? 1 : 0;
+            const int i = (int)P.Q.bins[(size_t)(c_lo + b) * P.Q.capacity + (j - prefix[b])];
+            const float4 bq = P.Q.ra[cur][2 * (size_t)i + 1], c = P.Q.r2[cur][i];
+            const f3 thr = mk3(bq.z, bq.w, c.x);
+            path_id = __float_as_int(c.y);
+            float* sp = P.Q.slab + 3 * (size_t)path_id;
+            if (KIND == 0) {
+                f3 add;
+                bool store = true;
+                if (b == 0) {                                    // shade_miss_rays, kernels.py:1266-1280
+                    add = thr * bg;
+                } else {                                         // emitter: emitted() on both faces, no scatter (:904-906)
+                    const int ref = __float_as_int(P.Q.hit[i].y);
+                    const Mat m = load_mat(S, mat_id_of(S, ref));
+                    const f3 emit = m.c1;
+                    store = emit.x > 0.0f || emit.y > 0.0f || emit.z > 0.0f;      // kernels.py:1368
+                    add = thr * emit;
+                }
+                if (store) { sp[0] = 0.0f + add.x; sp[1] = 0.0f + add.y; sp[2] = 0.0f + add.z; }   // == slab + add (wf_shade_one)
+            } else {
+                const float4 a = P.Q.ra[cur][2 * (size_t)i], h = P.Q.hit[i];
+                const f3 o = mk3(a.x, a.y, a.z), d = mk3(a.w, bq.x, bq.y);
+                const int depth = __float_as_int(c.w);
+                const ptm::Rng key = wf_path_key(P, path_id);
+                rng.s = __float_as_uint(c.z);
+                rng.inc = key.inc;
+                const float time = FULL ? ptm::path_time(key) : 0.0f;
+                if (KIND == 1) {
+                    const int ref = __float_as_int(h.y);
+                    const Mat m = load_mat(S, mat_id_of(S, ref));
+                    f3 hp, n;
+                    finalize_hit<FULL>(S, ref, o, d, h.x, hp, n, time);
+                    const f3 sdir = random_cosine_direction(n, rng);       // scatter(), Lambertian: kernels.py:833-838
+                    f3 new_thr = thr * m.c1;                                // eval_texture, solid colour (:931)
+                    const int new_depth = depth + 1;
+                    if (new_depth < max_depth) {
+                        bool cont = true;
+                        if (new_depth >= 5) {                               // Russian roulette, :1379-1391
+                            const float survival = min2(max2(max2(new_thr.x, new_thr.y), new_thr.z), 0.95f);
+                            if (ptm::rng_next(rng) > survival) cont = false;
+                            else new_thr = vdiv(new_thr, survival);
+                        }
+                        if (cont) { no = hp; nd = sdir; nthr = new_thr; ndepth = new_depth; emit_next = true; }
+                    }
+                } else {
+                    emit_next = wf_shade_one<FULL>(S, bg, max_depth, sp, o, d, thr, depth, rng, h.x, __float_as_int(h.y), h.z,
+                                                   (__float_as_int(h.w) & 1) != 0, no, nd, nthr, ndepth, time);
+                }
+            }
+        }
+        if (KIND != 0) {
+            const int pos = warp_agg_append(P.Q.qcount + nxt, 0, emit_next);       // one atomic per warp
+            if (emit_next) {
+                P.Q.ra[nxt][2 * (size_t)pos] = make_float4(no.x, no.y, no.z, nd.x);
+                P.Q.ra[nxt][2 * (size_t)pos + 1] = make_float4(nd.y, nd.z, nthr.x, nthr.y);
+                P.Q.r2[nxt][pos] = make_float4(nthr.z, __int_as_float(path_id), __uint_as_float(rng.s), __int_as_float(ndepth));
+            }
         }
     }
 }
@@ -1356,6 +1462,8 @@ int pt_set_option(PtContext* ctx, const char* name, int64_t value) {
     } else if (k == "wf_burst_num") {
         if (value < 0 || value > 32) return set_error(PT_ERR_INVALID_ARG, "wf_burst_num must be in [0, 32]");
         ctx->wf_burst_num = (int)value;
+    } else if (k == "wf_shade_split") {
+        ctx->wf_shade_split = value ? 1 : 0;
     } else if (k == "wf_tile") {
         ctx->wf_tile = value ? 1 : 0;
     } else if (k == "wf_extend_minb") {
@@ -1626,6 +1734,11 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
     void (*k_extend)(const WfParams) = nullptr;
     void (*k_tail)(const WfParams) = nullptr;
     void (*k_shade)(const WfParams) = full ? k_wf_shade<true> : k_wf_shade<false>;
+    const bool split = ctx->wf_shade_split && ctx->wavefront_sort && !ctx->dbg_shade_smem;
+    void (*k_shade_cls[3])(const WfParams) = {full ? k_wf_shade_cls<true, 0> : k_wf_shade_cls<false, 0>,
+                                              full ? k_wf_shade_cls<true, 1> : k_wf_shade_cls<false, 1>,
+                                              full ? k_wf_shade_cls<true, 2> : k_wf_shade_cls<false, 2>};
+    int occ_cls[3] = {1, 1, 1};
     // camera rays without defocus all start at the camera centre: the fused primary wave then tests
     // origin-relative node boxes (one subtraction less per box coordinate).  Only when that kernel
     // runs wave 0 alone -- later waves start elsewhere.
@@ -1661,6 +1774,11 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
     const int bt_shade = PT_SHADE_THREADS;
     PT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_shade, k_shade, bt_shade, (size_t)ctx->dbg_shade_smem));
     PT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_tail, k_tail, bt, smem));
+    for (int k = 0; k < 3; k++) {
+        PT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cls[k], k_shade_cls[k], 256, 0));
+        if (occ_cls[k] < 1) occ_cls[k] = 1;
+        if (ctx->wf_grid_waves > 1) occ_cls[k] *= ctx->wf_grid_waves;
+    }
     if (occ_primary < 1) occ_primary = 1;
     if (occ_shade < 1) occ_shade = 1;
     if (occ_tail < 1) occ_tail = 1;
@@ -1740,7 +1858,16 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
             if (P.sort) { StageScope t(ctx, st, PT_STAGE_BIN, b); k_wf_bin<<<grid_wide, bt, 0, st>>>(P); }
             // the first shade of a batch is the first kernel to overwrite the queue the previous batch's tail reads
             if (overlap && b == first_wave && batch_index >= 1) PT_CUDA(cudaStreamWaitEvent(st, ctx->ev_tail[par ^ 1], 0));
-            { StageScope t(ctx, st, PT_STAGE_SHADE, b); k_shade<<<grid_shade, bt_shade, ctx->dbg_shade_smem, st>>>(P); }
+            if (split) {
+                for (int k = 0; k < 3; k++) {
+                    const int g = ctx->num_sms * occ_cls[k] < grid_full ? ctx->num_sms * occ_cls[k] : grid_full;
+                    StageScope t(ctx, st, PT_STAGE_SHADE, b);
+                    k_shade_cls[k]<<<g, 256, 0, st>>>(P);
+                }
+            } else {
+                StageScope t(ctx, st, PT_STAGE_SHADE, b);
+                k_shade<<<grid_shade, bt_shade, ctx->dbg_shade_smem, st>>>(P);
+            }
         }
         if (overlap) {
             PT_CUDA(cudaEventRecord(ctx->ev_waves[par], st));

@@ -70,13 +70,34 @@ struct LocalCounters {
 
 __device__ __forceinline__ int ref_type(int ref) { return (~ref) & 3; }
 __device__ __forceinline__ int ref_index(int ref) { return (~ref) >> 5; }
-// shading class packed into the reference by the host packer: 1 = constant-medium boundary,
-// 2 + material type otherwise (capped at 7)
+// Shading class packed into the reference by the host packer (pt_host.cpp shading_class); 0 is what the
+// wavefront kernels use for a miss.  The order is the order of the material bins, chosen so that each
+// specialised shade kernel owns a contiguous run: [miss, emissive] end the path with one store,
+// [Lambert with a solid colour] is the bulk of every scene, the rest needs the general code.
+enum : int { PT_CLS_MISS = 0, PT_CLS_EMISSIVE = 1, PT_CLS_LAMBERT_SOLID = 2, PT_CLS_LAMBERT_TEX = 3, PT_CLS_METAL = 4,
+             PT_CLS_DIELECTRIC = 5, PT_CLS_MEDIUM = 6, PT_CLS_OTHER = 7 };
 __device__ __forceinline__ int ref_class(int ref) { return ((~ref) >> 2) & 7; }
-__device__ __forceinline__ bool ref_is_medium(int ref) { return ref_class(ref) == 1; }
+__device__ __forceinline__ bool ref_is_medium(int ref) { return ref_class(ref) == PT_CLS_MEDIUM; }
 
 // ---- primitive tests: arithmetic identical to hit_sphere / hit_triangle / hit_quad; they return
 //      only t (the caller keeps t and the primitive reference).
+//      They are written with the explicitly rounded intrinsics (__fmul_rn / __fadd_rn / __fsub_rn / __fdiv_rn /
+//      __fsqrt_rn: never contracted, never approximated), so BOTH builds of the library evaluate them
+//      bit-identically: the reference's formulas are ill-conditioned where it matters (|oc|^2 - r^2 for a
+//      radius-1000 ground sphere, D - n.o for a far plane), and any other rounding of them moves t by 1e-5 ..
+//      1e-4 relative -- more than north_star's tolerance.  The fast build therefore keeps the strict
+//      primitive tests and spends its freedom on the slab test and the shading arithmetic.
+namespace sx {
+__device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ f3 sub(f3 a, f3 b) { return f3{sub(a.x, b.x), sub(a.y, b.y), sub(a.z, b.z)}; }
+__device__ __forceinline__ float dot(f3 a, f3 b) { return add(add(mul(a.x, b.x), mul(a.y, b.y)), mul(a.z, b.z)); }
+__device__ __forceinline__ f3 cross(f3 a, f3 b) {
+    return f3{sub(mul(a.y, b.z), mul(a.z, b.y)), sub(mul(a.z, b.x), mul(a.x, b.z)), sub(mul(a.x, b.y), mul(a.y, b.x))};
+}
+}  // namespace sx
 // kernels.py:208-248
 // centre(time) = centre(0) + time * motion (core/sphere.py:36); time is only used in full mode
 template <bool FULL>
@@ -84,7 +105,7 @@ __device__ __forceinline__ f3 sphere_center(const DScene& S, int idx, float4 s, 
     f3 c = mk3(s.x, s.y, s.z);
     if (FULL) {
         float4 m = __ldg(S.sphere_motion + idx);
-        c = c + time * mk3(m.x, m.y, m.z);
+        c = mk3(sx::add(c.x, sx::mul(time, m.x)), sx::add(c.y, sx::mul(time, m.y)), sx::add(c.z, sx::mul(time, m.z)));
     }
     return c;
 }
@@ -92,15 +113,15 @@ template <bool FULL>
 __device__ __forceinline__ bool hit_sphere_t(const DScene& S, int idx, f3 o, f3 d, float t_min, float t_max, float& t,
                                              float time) {
     float4 s = __ldg(S.spheres + idx);
-    f3 oc = sphere_center<FULL>(S, idx, s, time) - o;
-    float a = dot(d, d);
-    float h = dot(d, oc);
-    float c = dot(oc, oc) - s.w * s.w;
-    float disc = h * h - a * c;
+    f3 oc = sx::sub(sphere_center<FULL>(S, idx, s, time), o);
+    float a = sx::dot(d, d);
+    float h = sx::dot(d, oc);
+    float c = sx::sub(sx::dot(oc, oc), sx::mul(s.w, s.w));
+    float disc = sx::sub(sx::mul(h, h), sx::mul(a, c));
     if (disc >= 0.0f) {
-        float sq = ptm::fsqrt(disc);
-        float root = ptm::fdiv(h - sq, a);
-        if (root < t_min || root > t_max) root = ptm::fdiv(h + sq, a);
+        float sq = __fsqrt_rn(disc);
+        float root = sx::div(sx::sub(h, sq), a);
+        if (root < t_min || root > t_max) root = sx::div(sx::add(h, sq), a);
         if (root >= t_min && root <= t_max) { t = root; return true; }
     }
     return false;
@@ -110,17 +131,17 @@ __device__ __forceinline__ bool hit_triangle_t(const DScene& S, int idx, f3 o, f
     const float4* p = S.tris + 3 * idx;
     float4 a0 = __ldg(p), a1 = __ldg(p + 1), a2 = __ldg(p + 2);
     f3 v0 = mk3(a0.x, a0.y, a0.z), e1 = mk3(a1.x, a1.y, a1.z), e2 = mk3(a2.x, a2.y, a2.z);
-    f3 h = cross(d, e2);
-    float det = dot(e1, h);
+    f3 h = sx::cross(d, e2);
+    float det = sx::dot(e1, h);
     if (fabsf(det) >= 1e-8f) {
-        float inv_det = ptm::frcp(det);
-        f3 s = o - v0;
-        float u = inv_det * dot(s, h);
+        float inv_det = __frcp_rn(det);
+        f3 s = sx::sub(o, v0);
+        float u = sx::mul(inv_det, sx::dot(s, h));
         if (u >= 0.0f && u <= 1.0f) {
-            f3 q = cross(s, e1);
-            float v = inv_det * dot(d, q);
-            if (v >= 0.0f && u + v <= 1.0f) {
-                float tt = inv_det * dot(e2, q);
+            f3 q = sx::cross(s, e1);
+            float v = sx::mul(inv_det, sx::dot(d, q));
+            if (v >= 0.0f && sx::add(u, v) <= 1.0f) {
+                float tt = sx::mul(inv_det, sx::dot(e2, q));
                 if (tt >= t_min && tt <= t_max) { t = tt; return true; }
             }
         }
@@ -132,16 +153,16 @@ __device__ __forceinline__ bool hit_quad_t(const DScene& S, int idx, f3 o, f3 d,
     const float4* p = S.quads + 4 * idx;
     float4 q0 = __ldg(p);
     f3 n = mk3(q0.x, q0.y, q0.z);
-    float denom = dot(n, d);
+    float denom = sx::dot(n, d);
     if (fabsf(denom) >= 1e-8f) {
-        float tt = ptm::fdiv(q0.w - dot(n, o), denom);
+        float tt = sx::div(sx::sub(q0.w, sx::dot(n, o)), denom);
         if (tt >= t_min && tt <= t_max) {
             float4 q1 = __ldg(p + 1), q2 = __ldg(p + 2), q3 = __ldg(p + 3);
-            f3 isect = o + tt * d;
-            f3 ph = isect - mk3(q1.x, q1.y, q1.z);
+            f3 isect = mk3(sx::add(o.x, sx::mul(tt, d.x)), sx::add(o.y, sx::mul(tt, d.y)), sx::add(o.z, sx::mul(tt, d.z)));
+            f3 ph = sx::sub(isect, mk3(q1.x, q1.y, q1.z));
             f3 u = mk3(q2.x, q2.y, q2.z), v = mk3(q3.x, q3.y, q3.z), w = mk3(q1.w, q2.w, q3.w);
-            float alpha = dot(w, cross(ph, v));
-            float beta = dot(w, cross(u, ph));
+            float alpha = sx::dot(w, sx::cross(ph, v));
+            float beta = sx::dot(w, sx::cross(u, ph));
             if (alpha >= 0.0f && alpha <= 1.0f && beta >= 0.0f && beta <= 1.0f) { t = tt; return true; }
         }
     }
@@ -196,8 +217,14 @@ __device__ __forceinline__ float fmin3(float a, float b, float c) {
 // (strict) -- or one FFMA against the precomputed -(o * inv) in the fast-numerics build.
 #if PT_FAST
 #define PT_SLAB(b, o_, inv_, noi_) __fmaf_rn((b), (inv_), (noi_))
+// fl(b * inv - fl(o * inv)) is off by up to eps * (|o * inv| + |t|) from the exact plane distance, which for a
+// ray that starts far from a thin box (|o * inv| >> thickness * inv) is enough to make the box vanish.  The
+// fast build therefore tests  tmax * (1 + 2^-20) + slack >= tmin  with slack = 2^-21 * max |o * inv| per
+// ray: never culls a box the strict test keeps (one FFMA per box; the result is a superset traversal).
+#define PT_BOX_HIT(tmax, tmin, slack) (__fmaf_rn((tmax), 1.00000095f, (slack)) >= (tmin))
 #else
 #define PT_SLAB(b, o_, inv_, noi_) (((b) - (o_)) * (inv_))
+#define PT_BOX_HIT(tmax, tmin, slack) ((tmax) >= (tmin))
 #endif
 
 typedef unsigned long long StackEntry;
@@ -209,6 +236,7 @@ struct TravState {
     f3 o, d, inv;
 #if PT_FAST
     f3 noi;              // -(o * inv): the slab test is fma(b, inv, noi) per plane (fast numerics only)
+    float slack;         // 2^-21 * max |o * inv| (PT_BOX_HIT)
 #endif
     float time;          // shutter time of the path (full feature mode; 0 otherwise)
     float t_min, best_t;
@@ -229,6 +257,7 @@ __device__ __forceinline__ void trav_begin(TravState& T, const DScene& S, f3 o, 
     ptm::inv_dir3(d.x, d.y, d.z, T.inv.x, T.inv.y, T.inv.z);
 #if PT_FAST
     T.noi = mk3(-(o.x * T.inv.x), -(o.y * T.inv.y), -(o.z * T.inv.z));
+    T.slack = 4.76837158e-7f * fmaxf(fmaxf(fabsf(T.noi.x), fabsf(T.noi.y)), fabsf(T.noi.z));
 #endif
     T.t_min = t_min;
     T.best_t = t_max;
@@ -364,8 +393,10 @@ __device__ __forceinline__ bool trav_run(TravState& T, const DScene& S, SNodeBas
     const f3 inv = T.inv;
 #if PT_FAST
     const f3 noi = T.noi;
+    const float slack = T.slack;
 #else
     const f3 noi = mk3(0.0f, 0.0f, 0.0f);
+    const float slack = 0.0f;
 #endif
     const float t_min = T.t_min;
     const float4* const nodes = S.nodes;
@@ -392,8 +423,8 @@ __device__ __forceinline__ bool trav_run(TravState& T, const DScene& S, SNodeBas
             float rtmin = fmax3(fminf(r0x, r1x), fminf(r0y, r1y), fmaxf(fminf(r0z, r1z), t_min));
             float rtmax = fmin3(fmaxf(r0x, r1x), fmaxf(r0y, r1y), fminf(fmaxf(r0z, r1z), best_t));
             const int lref = __float_as_int(nc.x), rref = __float_as_int(nc.y);
-            const bool hl = ltmax >= ltmin;        // both children always exist (host packer)
-            const bool hr = rtmax >= rtmin;
+            const bool hl = PT_BOX_HIT(ltmax, ltmin, slack);        // both children always exist (host packer)
+            const bool hr = PT_BOX_HIT(rtmax, rtmin, slack);
             if (hl && hr) {
                 const bool left_first = ltmin <= rtmin;
                 trav_push(T, stack, stack_pack(left_first ? rref : lref, left_first ? rtmin : ltmin));
@@ -436,8 +467,10 @@ __device__ __forceinline__ void trav_run_vote(TravState& T, bool active, bool& d
     const f3 o = T.o, inv = T.inv;
 #if PT_FAST
     const f3 noi = T.noi;
+    const float slack = T.slack;
 #else
     const f3 noi = mk3(0.0f, 0.0f, 0.0f);
+    const float slack = 0.0f;
 #endif
     const float t_min = T.t_min;
     const float4* const nodes = S.nodes;
@@ -474,8 +507,8 @@ __device__ __forceinline__ void trav_run_vote(TravState& T, bool active, bool& d
                 float rtmin = fmax3(fminf(r0x, r1x), fminf(r0y, r1y), fmaxf(fminf(r0z, r1z), t_min));
                 float rtmax = fmin3(fmaxf(r0x, r1x), fmaxf(r0y, r1y), fminf(fmaxf(r0z, r1z), best_t));
                 const int lref = __float_as_int(nc.x), rref = __float_as_int(nc.y);
-                const bool hl = ltmax >= ltmin;        // both children always exist (host packer)
-                const bool hr = rtmax >= rtmin;
+                const bool hl = PT_BOX_HIT(ltmax, ltmin, slack);        // both children always exist (host packer)
+                const bool hr = PT_BOX_HIT(rtmax, rtmin, slack);
                 if (hl && hr) {
                     const bool left_first = ltmin <= rtmin;
                     trav_push(T, stack, stack_pack(left_first ? rref : lref, left_first ? rtmin : ltmin));

@@ -16,15 +16,22 @@ thread_local std::string g_host_error_storage;
 #define g_host_error (g_host_error_storage)
 
 constexpr int kRefNone = (int)0x80000000;
-// Leaf reference: ~(prim_idx << 5 | shading_class << 2 | prim_type).  The shading class (1 = medium
-// boundary, 2 + material type otherwise, capped at 7) rides along so that the kernels can tell a
-// medium boundary and pick the material bin of a hit without touching the material tables.
+// Leaf reference: ~(prim_idx << 5 | shading_class << 2 | prim_type).  The shading class rides along so
+// that the kernels can tell a medium boundary and pick the material bin of a hit without touching the
+// material tables: 1 emissive, 2 Lambert with a solid colour, 3 Lambert with a checker / image / noise
+// texture, 4 metal, 5 dielectric, 6 constant-medium boundary, 7 everything else (isotropic, subsurface);
+// 0 is reserved for "miss" (pt_device.cuh PT_CLS_*).
 constexpr int kMaxPrimsPerType = 1 << 26;
 inline int leaf_ref(int prim_type, int prim_idx, int cls) { return ~((prim_idx << 5) | ((cls & 7) << 2) | prim_type); }
 inline int shading_class(const PtHostMaterials& m, int i) {
-    if (m.is_medium[i] > 0) return 1;
-    const int c = 2 + (m.material_type[i] & 15);
-    return c > 7 ? 7 : c;
+    if (m.is_medium[i] > 0) return 6;
+    switch (m.material_type[i]) {
+        case 0: return m.texture_type[i] == 0 ? 2 : 3;
+        case 1: return 4;
+        case 2: return 5;
+        case 3: return 1;
+        default: return 7;
+    }
 }
 inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 

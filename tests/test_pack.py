@@ -31,11 +31,13 @@ def test_pack_covers_every_primitive_once(name):
     assert sorted(inner.tolist()) == list(range(1, info.num_inner))      # every inner node referenced once, BFS ids
     k = ~leaves
     got = sorted(zip((k & 3).tolist(), (k >> 5).tolist()))
-    # bits 2..4: shading class (1 = medium boundary, else 2 + material type)
+    # bits 2..4: shading class = material bin (6 medium boundary; else 1 emissive, 2 Lambert solid, 3 Lambert textured,
+    # 4 metal, 5 dielectric, 7 other; 0 is the kernels' "miss")
     pre = {0: "sphere", 1: "triangle", 2: "quad"}
     for t, i, c in zip((k & 3).tolist(), (k >> 5).tolist(), ((k >> 2) & 7).tolist()):
         med = cs[f"{pre[t]}_is_constant_medium"][i] > 0
-        assert c == (1 if med else min(7, 2 + int(cs[f"{pre[t]}_material_type"][i])))
+        mt, tt = int(cs[f"{pre[t]}_material_type"][i]), int(cs[f"{pre[t]}_texture_type"][i])
+        assert c == (6 if med else {0: 2 if tt == 0 else 3, 1: 4, 2: 5, 3: 1}.get(mt, 7))
     want = sorted(zip(cs["bvh_prim_type"][cs["bvh_prim_idx"] >= 0].tolist(), cs["bvh_prim_idx"][cs["bvh_prim_idx"] >= 0].tolist()))
     assert got == want
     # child boxes are the reference's node boxes: root children = nodes 1 and right(0)
@@ -73,7 +75,7 @@ def test_single_primitive_and_empty_scene():
     info, blob = _pack(one)
     assert info.num_inner == 1
     refs = blob[info.off_nodes + 48: info.off_nodes + 56].view(np.int32)
-    # leaf ref for sphere 0 (class 2 = Lambertian) in BOTH slots: every packed node has two real children
+    # leaf ref for sphere 0 (class 2 = Lambertian, solid colour) in BOTH slots: every packed node has two real children
     assert refs[0] == ~(2 << 2) and refs[1] == refs[0]
     info, blob = _pack({})
     assert info.num_inner == 0 and info.total_bytes >= 256
