@@ -103,9 +103,13 @@ def test_auto_samples_in_flight_sizes_batches_by_paths():
     from path_tracer_python_b200.engine import auto_samples_in_flight as f
     assert f(1920, 1080, 256) == 32          # BASELINE config 2: 8 batches of 32
     assert f(1920, 1080, 16) == 16           # fewer samples than one batch holds
-    assert f(1024, 1024, 64) == 64           # one batch
+    assert f(1024, 1024, 64) == 32           # would fit one batch: split in two (tail / primary overlap)
     assert f(3840, 2160, 32) == 8
     assert f(400, 225, 16) == 16
     assert f(64, 64, 100000) == 256          # tiny window: the library's limit
     assert f(1920, 1080, 100) == 34          # 3 equal batches (34 + 34 + 32), not 32 + 32 + 32 + 4
     assert f(8192, 8192, 4) == 1
+    # one rank's share of config 2 on 8 GPUs (32 samples): two batches of 16, so that the first batch's tail
+    # overlaps the second batch's primary wave; small jobs are not split
+    assert f(1920, 1080, 32) == 16 and f(1920, 1080, 24) == 24 and f(1920, 1080, 30) == 15
+    assert f(1920, 1080, 32, min_batches=4) == 8 and f(400, 225, 16, min_batches=2) == 8

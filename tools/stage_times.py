@@ -1,5 +1,5 @@
 """Per-stage device times of one wavefront batch on config 2 (pt_enable_stage_timing), no profiler.
-    python tools/stage_times.py            env: SPP (default 32), W, PT_LIB_PATH, OPTS=k=v,..."""
+    python tools/stage_times.py            env: SPP (default 32), W, FLIGHT (samples per batch), PT_LIB_PATH, OPTS=k=v,..."""
 import os, sys, collections
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -25,6 +25,8 @@ e.set_scene(cs); e.set_camera(meta["camera"], meta.get("background", (0, 0, 0)),
 H = meta["height"]
 for k, v in [kv.split("=") for kv in os.environ.get("OPTS", "").split(",") if kv]:
     e.set_option(k, int(v))
+if os.environ.get("FLIGHT"):
+    e.wavefront_samples_in_flight = int(os.environ["FLIGHT"])      # samples of every pixel per batch (default: auto)
 acc = e.new_accum(W, H)
 e.render_wavefront(acc, 0, SPP, 7); torch.cuda.synchronize()
 e.enable_stage_timing(True)
