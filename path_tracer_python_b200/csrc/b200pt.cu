@@ -206,7 +206,8 @@ __global__ void __launch_bounds__(PT_MEGA_THREADS, PT_MEGA_MINB) k_megakernel(co
     // traversal state (persists across bursts)
     TravState T;
     T.cur = kRefNone;
-    StackEntry stack[kStackSlots];
+    StackEntry stack_mem[kStackSlots];
+    const LocalStack stack{stack_mem};
     stack_init(stack);
     int st = (valid && s < s_end && max_depth > 0) ? LANE_NEED_PATH : LANE_DONE;
 
@@ -487,10 +488,18 @@ constexpr int kWfWarps = 8;       // warps per CTA of the wavefront kernels (256
                              // registers without spills (256 x 4 = 32 warps; 256 x 5 = 40 warps at 48 registers with spills:
                              // 2812 / 2846 / 2881 Mpaths/s on config 2)
 #endif
+// Traversal-stack slots per lane that k_wf_extend keeps in shared memory (slot 0 = sentinel; HybridStack,
+// pt_device.cuh).  Measured on config 2, extend per 32-sample frame: 1 slot 13.81 ms, 4: 13.12, 8: 13.26, 12: 13.60,
+// 16: 14.04 (more slots take L1 capacity away from the node fetches); the all-local stack of round 1: 13.25.
+#ifndef PT_EXT_SMEM_SLOTS
+#define PT_EXT_SMEM_SLOTS 4
+#endif
+constexpr int kExtSmemSlots = PT_EXT_SMEM_SLOTS;
 template <bool COUNT, bool FULL, int MINB>
 __global__ void __launch_bounds__(PT_EXT_WARPS * 32, MINB) k_wf_extend(const __grid_constant__ WfParams P) {
     extern __shared__ float4 s_dyn[];
     __shared__ float4 s_ray[PT_EXT_WARPS][2][32][2];      // (o.xyz d.x)(d.yz ..) of staged rays, 2 KB per warp
+    __shared__ StackEntry s_stack[kExtSmemSlots][PT_EXT_WARPS * 32];
     float4* s_node_mem = s_dyn;
     const DScene& S = P.S;
     const int cur = P.bounce & 1;
@@ -543,7 +552,9 @@ __global__ void __launch_bounds__(PT_EXT_WARPS * 32, MINB) k_wf_extend(const __g
 
     TravState T;
     T.cur = kRefNone;
-    StackEntry stack[kStackSlots];
+    // stack: the first kExtSmemSlots slots of every lane in shared memory, the rest in local memory
+    StackEntry stack_mem[kStackSlots - kExtSmemSlots > 0 ? kStackSlots - kExtSmemSlots : 1];
+    const HybridStack<kExtSmemSlots> stack{&s_stack[0][threadIdx.x], PT_EXT_WARPS * 32, stack_mem};
     stack_init(stack);
     int st = LANE_NEED_PATH;     // NEED_PATH: wants a ray; TRAVERSING; HAVE_RESULT; DONE: queue exhausted
     int ray = 0, mode = 0, ref_entry = kRefNone;
@@ -625,7 +636,8 @@ __global__ void __launch_bounds__(PT_EXT_WARPS * 32, MINB) k_wf_extend(const __g
 template <bool COUNT, bool FULL, bool REL = false>
 __device__ __forceinline__ void closest_hit_and_exit(const DScene& S, SNodeBase s_nodes, int n_snodes, f3 o, f3 d, float time,
                                                      float& t, int& ref, float& t_exit, int& eref, LocalCounters& lc) {
-    StackEntry stack[kStackSlots];
+    StackEntry stack_mem[kStackSlots];
+    const LocalStack stack{stack_mem};
     stack_init(stack);
     TravState T;
     float t_min = 0.001f;
@@ -1121,7 +1133,8 @@ __global__ void __launch_bounds__(256, 3) k_wf_tail_vote(const __grid_constant__
     const unsigned lane = threadIdx.x & 31;
     TravState T;
     T.cur = kRefNone;
-    StackEntry stack[kStackSlots];
+    StackEntry stack_mem[kStackSlots];
+    const LocalStack stack{stack_mem};
     stack_init(stack);
     f3 thr = mk3(1.0f, 1.0f, 1.0f);
     ptm::Rng rng{0u, 1u};

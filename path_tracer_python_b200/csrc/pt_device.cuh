@@ -301,26 +301,52 @@ __device__ __forceinline__ StackEntry stack_pack(int ref, float t) {
 // (PT_STACK_TOP=1) memory slots 1..T.sp hold the older entries and slot 0 a permanent sentinel
 // (stack_init), so that the refill of T.top after a pop is one unconditional load.
 constexpr int kStackSlots = kStackSize + PT_STACK_TOP;
-__device__ __forceinline__ void stack_init(StackEntry* stack) {
+// Where the stack slots live.  LocalStack: the per-lane array in local memory (every kernel but k_wf_extend).
+// HybridStack<S>: slots 0..S-1 in shared memory, one column per thread (entry i of thread t at s[i * stride + t]:
+// the bank depends on t only, so lanes at different depths never conflict), deeper slots in local memory.
+// A push or pop in shared memory is two conflict-free wavefronts whatever the lanes' depths; the same access
+// to the lane-interleaved local array touches one 256-byte line per distinct depth in the warp and competes
+// with the node fetches for L1's tag stage (ncu round 1: 262 M local-memory sectors against 397 M global-load
+// sectors per wave-1 launch of k_wf_extend).
+struct LocalStack {
+    StackEntry* p;
+    __device__ __forceinline__ StackEntry load(int i) const { return p[i]; }
+    __device__ __forceinline__ void store(int i, StackEntry e) const { p[i] = e; }
+};
+template <int S>
+struct HybridStack {
+    StackEntry* s;       // this thread's column of the CTA's shared-memory slots
+    int stride;          // threads per CTA
+    StackEntry* l;       // local-memory overflow, slots S..
+    __device__ __forceinline__ StackEntry load(int i) const { return i < S ? s[i * stride] : l[i - S]; }
+    __device__ __forceinline__ void store(int i, StackEntry e) const {
+        if (i < S) s[i * stride] = e;
+        else l[i - S] = e;
+    }
+};
+template <class STK>
+__device__ __forceinline__ void stack_init(const STK& stack) {
 #if PT_STACK_TOP
-    stack[0] = (StackEntry)(unsigned)kRefNone;
+    stack.store(0, (StackEntry)(unsigned)kRefNone);
 #endif
 }
-__device__ __forceinline__ void trav_push(TravState& T, StackEntry* stack, StackEntry e) {
+template <class STK>
+__device__ __forceinline__ void trav_push(TravState& T, const STK& stack, StackEntry e) {
 #if PT_STACK_TOP
     if ((int)(unsigned)T.top != kRefNone) {      // cannot overflow: pt_set_scene rejects trees deeper than kStackSize
         T.sp++;
-        stack[T.sp] = T.top;
+        stack.store(T.sp, T.top);
     }
     T.top = e;
 #else
     if (T.sp < kStackSize) {
-        stack[T.sp] = e;
+        stack.store(T.sp, e);
         T.sp++;
     }
 #endif
 }
-__device__ __forceinline__ int trav_pop(TravState& T, const StackEntry* stack) {
+template <class STK>
+__device__ __forceinline__ int trav_pop(TravState& T, const STK& stack) {
     int next = kRefNone;
 #if PT_STACK_TOP
     while ((int)(unsigned)T.top != kRefNone) {
@@ -329,14 +355,14 @@ __device__ __forceinline__ int trav_pop(TravState& T, const StackEntry* stack) {
         // the old top is consumed above; the barrier keeps the compiler from hoisting the load over
         // those uses, so it can land in T.top's own registers and nothing waits for it here
         asm volatile("" ::: "memory");
-        T.top = stack[T.sp];                 // slot 0 = sentinel: no branch
+        T.top = stack.load(T.sp);            // slot 0 = sentinel: no branch
         T.sp = T.sp > 0 ? T.sp - 1 : 0;
         if (take) { next = cand; break; }
     }
 #else
     while (T.sp > 0) {
         --T.sp;
-        const StackEntry e = stack[T.sp];
+        const StackEntry e = stack.load(T.sp);
         if (__uint_as_float((unsigned)(e >> 32)) <= T.best_t) { next = (int)(unsigned)e; break; }
     }
 #endif
@@ -386,9 +412,9 @@ __device__ __forceinline__ void load_node(const float4* __restrict__ nodes, SNod
 // REL: S.nodes holds the node boxes with the ray origin already subtracted (every ray of the launch
 // shares that origin: camera rays without defocus; b200pt.cu k_make_rel_nodes).  fl(b - o) is the
 // same single rounding whoever performs it, so the slab test drops its 12 subtractions per node.
-template <bool COUNT, bool FULL = false, bool REL = false>
+template <bool COUNT, bool FULL = false, bool REL = false, class STK = LocalStack>
 __device__ __forceinline__ bool trav_run(TravState& T, const DScene& S, SNodeBase s_nodes, int n_snodes,
-                                         StackEntry* stack, int min_active, LocalCounters& lc) {
+                                         const STK& stack, int min_active, LocalCounters& lc) {
     const f3 o = REL ? mk3(0.0f, 0.0f, 0.0f) : T.o;
     const f3 inv = T.inv;
 #if PT_FAST
@@ -460,9 +486,9 @@ __device__ __forceinline__ bool trav_run(TravState& T, const DScene& S, SNodeBas
 // model of this policy predicts ~25).  Returns when fewer than min_active lanes still traverse.
 // `done` is set for a lane when its traversal has finished.  Visiting order per lane is unchanged,
 // so results are bit-identical to trav_run.
-template <bool COUNT, bool FULL = false>
+template <bool COUNT, bool FULL = false, class STK = LocalStack>
 __device__ __forceinline__ void trav_run_vote(TravState& T, bool active, bool& done, const DScene& S,
-                                              SNodeBase s_nodes, int n_snodes, StackEntry* stack,
+                                              SNodeBase s_nodes, int n_snodes, const STK& stack,
                                               int min_active, int vote_num, LocalCounters& lc) {
     const f3 o = T.o, inv = T.inv;
 #if PT_FAST
@@ -543,7 +569,8 @@ template <bool COUNT, bool FULL = false>
 __device__ __forceinline__ void traverse(const DScene& S, SNodeBase s_nodes, int n_snodes, f3 o, f3 d,
                                          float t_min, float t_max, float& best_t, int& best_ref, LocalCounters& lc,
                                          float time = 0.0f) {
-    StackEntry stack[kStackSlots];
+    StackEntry stack_mem[kStackSlots];
+    const LocalStack stack{stack_mem};
     stack_init(stack);
     TravState T;
     trav_begin<COUNT>(T, S, o, d, t_min, t_max, lc, time);

@@ -99,6 +99,18 @@ class Engine:
         self.h2d_bytes = nbytes
         return info
 
+    def reupload_scene(self):
+        """Copy the already packed scene from pinned host memory to the device again (the per-frame
+        host -> device input copy of `render_frame`; packing happened once in set_scene)."""
+        if self.info is None or self._pinned_blob is None:
+            raise _lib.B200PTError("reupload_scene: no scene has been set")
+        nbytes = int(self.info.total_bytes)
+        with torch.cuda.device(self.device):
+            self.scene_blob.copy_(self._pinned_blob[:nbytes], non_blocking=True)
+            self._upload_done = torch.cuda.Event()
+            self._upload_done.record()
+        return nbytes
+
     def set_camera(self, cam: dict | PtCamera, background=(0.7, 0.8, 1.0), max_depth=50):
         pc = cam if isinstance(cam, PtCamera) else make_camera(cam, background, max_depth)
         self._check(self.L.pt_set_camera(self.ctx, C.byref(pc)), "pt_set_camera")

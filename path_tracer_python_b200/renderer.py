@@ -170,12 +170,12 @@ class TaichiRenderer:
         self._render("wavefront", enable_preview)
 
     def render_frame(self, mode: str = "megakernel", reupload_scene: bool = True) -> np.ndarray:
-        """Host buffers in, host buffer out: (re-)upload the packed scene from pinned host memory,
+        """Host buffers in, host buffer out: copy the packed scene from pinned host memory to the device,
         upload the camera, render every sample of this rank, sum across ranks if distributed, and
         copy the float32 accumulation buffer back into pinned host memory.  Returns an (H, W, 3)
         float32 numpy view of that pinned buffer.  This is the call bench.py times as `e2e`."""
         if reupload_scene:
-            self.info = self.engine.set_scene(self.compiled)
+            self.engine.reupload_scene()       # pinned host blob (packed once, at construction) -> device
         self._upload_camera()
         self._accum.zero_()
         s_begin, s_end = self._sample_range()

@@ -39,7 +39,7 @@ per = {}
 for i in ids:
     if i < first:
         continue
-    k = re.sub(r"<.*", "", launches[i]["kernel"].split("(")[0]).strip()
+    k = re.sub(r"<.*", "", launches[i]["kernel"].split("(")[0]).replace("void ", "").strip()
     m = launches[i]["m"]
     d = per.setdefault(k, {"launches": 0, "thread_inst": 0.0, "warp_inst": 0.0, "dram_bytes": 0.0, "l1tex_t_bytes": 0.0,
                            "lts_t_bytes": 0.0, "ns_under_ncu": 0.0})
