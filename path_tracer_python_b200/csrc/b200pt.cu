@@ -987,7 +987,10 @@ __device__ __forceinline__ void tile_local_pixel(int local, int W, int rows, int
 // primary rays (kernels.py:1219-1399) in one kernel.  Camera rays are coherent, so nothing is gained
 // by sending them through the queues: the ray is generated in registers, traced, shaded, and only
 // the surviving bounce ray is appended (one atomic per warp) to queue 1, where wave 1 picks it up.
-template <bool COUNT, bool FULL, bool REL>
+// ONE: exactly one fused wave (the default schedule) -- throughput (1,1,1) and depth 0 are then compile-time
+// constants, the wave loop disappears and with it the Russian-roulette code (depth + 1 < 5) and several
+// registers that were live across the traversal.
+template <bool COUNT, bool FULL, bool REL, bool ONE>
 __global__ void __launch_bounds__(PT_PRIMARY_THREADS, PT_PRIMARY_MINB) k_wf_primary(const __grid_constant__ WfParams P) {
     extern __shared__ float4 s_node_mem[];
     const DScene& S = P.S;
@@ -1030,7 +1033,9 @@ __global__ void __launch_bounds__(PT_PRIMARY_THREADS, PT_PRIMARY_MINB) k_wf_prim
             f3 thr = mk3(1.0f, 1.0f, 1.0f);
             int depth = 0;
             emit_next = max_depth > 0 && py < P.H;          // rows of an interleaved window beyond the image: no path
-            for (int w = 0; w < P.fused_waves && emit_next; w++) {
+            const int fused_waves = ONE ? 1 : P.fused_waves;
+#pragma unroll 1
+            for (int w = 0; w < fused_waves && emit_next; w++) {
                 float t, t_exit = 0.0f;
                 int ref, eref = kRefNone;
                 if (COUNT) lc.bounces++;
@@ -1040,7 +1045,7 @@ __global__ void __launch_bounds__(PT_PRIMARY_THREADS, PT_PRIMARY_MINB) k_wf_prim
                 o = no; d = nd; thr = nthr; depth = ndepth;
             }
         }
-        const int qd = P.fused_waves & 1;               // the queue wave `fused_waves` reads from
+        const int qd = ONE ? 1 : (P.fused_waves & 1);   // the queue wave `fused_waves` reads from
         int pos = warp_agg_append(P.Q.qcount + qd, 0, emit_next);
         if (emit_next) {
             const int id2 = id;
@@ -1765,13 +1770,15 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
         PT_CUDA(cudaGetLastError());
     }
     if (ctx->count) {
-        k_primary = full ? k_wf_primary<true, true, false> : k_wf_primary<true, false, false>;
+        k_primary = full ? k_wf_primary<true, true, false, false> : k_wf_primary<true, false, false, false>;
         k_extend = full ? k_wf_extend<true, true, 4> : k_wf_extend<true, false, 4>;
         if (ctx->wf_tail_vote) k_tail = full ? k_wf_tail_vote<true, true> : k_wf_tail_vote<true, false>;
         else k_tail = full ? k_wf_tail<true, true> : k_wf_tail<true, false>;
     } else {
-        if (rel) k_primary = full ? k_wf_primary<false, true, true> : k_wf_primary<false, false, true>;
-        else k_primary = full ? k_wf_primary<false, true, false> : k_wf_primary<false, false, false>;
+        const bool one = ctx->wf_fuse_primary == 1 && ctx->cam.max_depth > 0;   // then fused == 1 below
+        if (rel) k_primary = full ? k_wf_primary<false, true, true, true> : k_wf_primary<false, false, true, true>;
+        else if (one) k_primary = full ? k_wf_primary<false, true, false, true> : k_wf_primary<false, false, false, true>;
+        else k_primary = full ? k_wf_primary<false, true, false, false> : k_wf_primary<false, false, false, false>;
         // MINB = resident CTAs per SM the register allocation is capped for (4: 64 regs, 5: 48, 6: 40)
         if (ctx->wf_extend_minb >= 6) k_extend = full ? k_wf_extend<false, true, 6> : k_wf_extend<false, false, 6>;
         else if (ctx->wf_extend_minb == 5) k_extend = full ? k_wf_extend<false, true, 5> : k_wf_extend<false, false, 5>;
