@@ -64,9 +64,9 @@ struct PtContext {
     int wf_vote_num = 16;    // the same threshold for k_wf_extend (tools/sweep_wf.py)
     int wf_waves = 8;        // full waves per batch before the tail kernel takes over (tools/sweep_wf.py)
     int wf_primary_threads = PT_PRIMARY_THREADS;   // CTA size of k_wf_primary (<= its launch bound)
-    int wf_overlap = 1;      // tail + resolve of a batch run on a second stream, under the next batch's primary wave
+    int wf_overlap = 1;      // two pipelines: consecutive batches on two streams with their own queue sets (pt_render_wavefront)
     cudaStream_t aux_stream = nullptr;
-    cudaEvent_t ev_waves[2] = {nullptr, nullptr}, ev_tail[2] = {nullptr, nullptr}, ev_resolve[2] = {nullptr, nullptr};
+    cudaEvent_t ev_resolve[2] = {nullptr, nullptr}, ev_start = nullptr;
     int wf_tail_vote = 1;    // the tail as a persistent voting state machine (k_wf_tail_vote) instead of one lane per ray
     int wf_rel_primary = 1;  // camera rays without defocus: slab test against origin-relative node boxes
     int wf_grid_waves = 16;  // static-partition kernels launch this many full waves of resident CTAs
@@ -1429,10 +1429,9 @@ int pt_destroy(PtContext* ctx) {
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->d_stage_snap) cudaFree(ctx->d_stage_snap);
     for (int i = 0; i < 2; i++) {
-        if (ctx->ev_waves[i]) cudaEventDestroy(ctx->ev_waves[i]);
-        if (ctx->ev_tail[i]) cudaEventDestroy(ctx->ev_tail[i]);
         if (ctx->ev_resolve[i]) cudaEventDestroy(ctx->ev_resolve[i]);
     }
+    if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     delete ctx;
     return PT_OK;
@@ -1666,10 +1665,11 @@ static size_t wf_bytes_per_sample(size_t n) {
     return 6 * n * 16      // two queues x three float4 planes
            + n * 16        // hit records
            + (size_t)kNumBins * n * 4   // material bins
-           + 2 * n * 12;   // radiance slabs (two: a batch's tail/resolve overlap the next batch's primary wave)
+           + n * 12        // radiance slab
+           + n * 12;       // spare (round 1 kept a second slab here; the size formula is part of the ABI)
 }
 static const size_t kMaxPathsInFlight = 0x78000000;
-static const size_t kWfFixedBytes = 4096 + 16 * 256;   // counter sets + per-section alignment slack
+static const size_t kWfFixedBytes = 4096 + 32 * 256;   // counter sets + per-section alignment slack
 
 size_t pt_wavefront_workspace_bytes(int W, int rows) { return pt_wavefront_workspace_bytes_for(W, rows, 1); }
 
@@ -1693,18 +1693,28 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
     size_t rel_bytes = align_up((size_t)ctx->scene.num_inner * 64, 256);
     if (workspace_bytes < kWfFixedBytes + rel_bytes + wf_bytes_per_sample(n)) rel_bytes = 0;
     // samples in flight: as many as the workspace holds (and the 31-bit path id allows)
-    size_t B = (workspace_bytes - kWfFixedBytes - rel_bytes) / wf_bytes_per_sample(n);
-    if (B > (size_t)sample_count) B = (size_t)sample_count;
+    const size_t S_cap = (workspace_bytes - kWfFixedBytes - rel_bytes) / wf_bytes_per_sample(n);
+    // Two pipelines: the workspace is split into two complete sets of queues and consecutive batches run
+    // on two streams (the caller's and a context-owned one).  Every stage of a batch depends only on the
+    // stage before it, so the two batches are independent until their resolves, which are chained in
+    // batch order.  What this buys: the small launches of a batch -- late waves that cannot fill 148 SMs,
+    // the tail's latency chain, bin / resolve passes -- run in the shadow of the other batch's big ones,
+    // and the block scheduler back-fills every kernel's ramp-down with the other stream's CTAs.
+    int n_pipe = (ctx->wf_overlap && !ctx->stage_timing && S_cap >= 2 && sample_count >= 2) ? 2 : 1;
+    size_t B = S_cap / (size_t)n_pipe;
+    if (B > ((size_t)sample_count + n_pipe - 1) / n_pipe) B = ((size_t)sample_count + n_pipe - 1) / n_pipe;
     if (B > 256) B = 256;
     // paths in flight are indexed with 32-bit ints; the grid-stride loops overshoot `total` by up to one
     // grid (< 2^26 threads) before their bounds test, so the cap leaves that much headroom
     while (B > 1 && B * n > kMaxPathsInFlight) B--;
-    if (B * n > kMaxPathsInFlight) return set_error(PT_ERR_CAPACITY, "pt_render_wavefront: window too large");
+    if (B == 0 || B * n > kMaxPathsInFlight) return set_error(PT_ERR_CAPACITY, "pt_render_wavefront: window too large");
     // equal batches: 64 samples with room for 63 in flight run as 32 + 32, not 63 + 1
-    if (B > 0) {
+    {
         const size_t nb = ((size_t)sample_count + B - 1) / B;
         B = ((size_t)sample_count + nb - 1) / nb;
     }
+    const int n_batches = (sample_count + (int)B - 1) / (int)B;
+    if (n_batches < 2) n_pipe = 1;
     PT_CUDA(cudaSetDevice(ctx->device));
     const size_t cap = B * n;
     char* p = static_cast<char*>(workspace);
@@ -1714,21 +1724,24 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
     P.S = ctx->scene;
     P.cam = ctx->cam;
     auto take = [&](size_t bytes) { char* q = p; p += align_up(bytes, 256); return q; };
-    for (int q = 0; q < 2; q++) {
-        P.Q.ra[q] = reinterpret_cast<float4*>(take(cap * 32));
-        P.Q.r2[q] = reinterpret_cast<float4*>(take(cap * 16));
+    WfQueues sets[2];
+    for (int k = 0; k < n_pipe; k++) {
+        WfQueues& Q = sets[k];
+        for (int q = 0; q < 2; q++) {
+            Q.ra[q] = reinterpret_cast<float4*>(take(cap * 32));
+            Q.r2[q] = reinterpret_cast<float4*>(take(cap * 16));
+        }
+        Q.hit = reinterpret_cast<float4*>(take(cap * 16));
+        Q.bins = reinterpret_cast<uint32_t*>(take((size_t)kNumBins * cap * 4));
+        Q.slab = reinterpret_cast<float*>(take(cap * 12));
+        int* counters = reinterpret_cast<int*>(take(256));       // 64 ints
+        Q.qcount = counters;
+        Q.bin_count = counters + 8;
+        Q.cursor = counters + 32;
+        Q.capacity = (int)cap;
     }
-    P.Q.hit = reinterpret_cast<float4*>(take(cap * 16));
-    P.Q.bins = reinterpret_cast<uint32_t*>(take((size_t)kNumBins * cap * 4));
-    float* slabs[2];
-    slabs[0] = reinterpret_cast<float*>(take(cap * 12));
-    slabs[1] = reinterpret_cast<float*>(take(cap * 12));
-    P.Q.slab = slabs[0];
-    int* counters = reinterpret_cast<int*>(take(512));       // two sets of 64 ints (one per batch parity)
-    P.Q.qcount = counters;
-    P.Q.bin_count = counters + 8;
-    P.Q.cursor = counters + 32;
-    P.Q.capacity = (int)cap;
+    if (n_pipe == 1) sets[1] = sets[0];
+    P.Q = sets[0];
     P.accum = accum;
     P.W = W; P.H = H; P.y0 = y0; P.y1 = y1;
     P.row_shift = ctx->row_shift; P.row_stride = ctx->row_stride;
@@ -1809,33 +1822,25 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
     const int waves = max_depth < ctx->wf_waves ? max_depth : ctx->wf_waves;
     const int fused = (ctx->wf_fuse_primary && max_depth > 0) ? (ctx->wf_fuse_primary < waves ? ctx->wf_fuse_primary : waves) : 0;
     const int tail_bounce = waves > fused ? waves : fused;
-    const int n_batches = (sample_count + (int)B - 1) / (int)B;
-    // Two-stream schedule: the tail and the resolve of batch k run on a second stream while batch
-    // k+1's primary wave and first extend run on the caller's.  The tail is a latency chain (the few
-    // longest paths) that leaves the machine almost empty; the primary wave fills it.  Batches
-    // alternate between two radiance slabs and two counter sets; the queues are shared, which is
-    // safe when the tail reads the queue the fused primary wave does NOT write (parity check) and
-    // the first shade of batch k+1 -- the first kernel to write that queue again -- waits for tail k.
-    // Resolves stay in batch order on the second stream, so the sums are those of the serial schedule.
-    bool overlap = ctx->wf_overlap && !ctx->stage_timing && n_batches > 1 && fused > 0 && waves < max_depth &&
-                   ((tail_bounce & 1) != (fused & 1)) && fused < waves;
-    if (overlap && !ctx->aux_stream) {
-        if (cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) != cudaSuccess) { ctx->aux_stream = nullptr; overlap = false; }
-        for (int i = 0; i < 2 && overlap; i++)
-            if (cudaEventCreateWithFlags(&ctx->ev_waves[i], cudaEventDisableTiming) != cudaSuccess ||
-                cudaEventCreateWithFlags(&ctx->ev_tail[i], cudaEventDisableTiming) != cudaSuccess ||
-                cudaEventCreateWithFlags(&ctx->ev_resolve[i], cudaEventDisableTiming) != cudaSuccess) overlap = false;
-        (void)cudaGetLastError();
+    if (n_pipe == 2 && !ctx->aux_stream) {
+        bool ok = cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) == cudaSuccess;
+        for (int i = 0; i < 2 && ok; i++) ok = cudaEventCreateWithFlags(&ctx->ev_resolve[i], cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) {
+            (void)cudaGetLastError();
+            return set_error(PT_ERR_CUDA, "pt_render_wavefront: cannot create the second stream / its events");
+        }
     }
-    if (overlap && !ctx->aux_stream) overlap = false;
-    cudaStream_t st2 = overlap ? ctx->aux_stream : st;
+    cudaStream_t streams[2] = {st, n_pipe == 2 ? ctx->aux_stream : st};
+    if (n_pipe == 2) {            // the second stream starts after everything the caller queued before this call (and the node copy)
+        PT_CUDA(cudaEventRecord(ctx->ev_start, st));
+        PT_CUDA(cudaStreamWaitEvent(streams[1], ctx->ev_start, 0));
+    }
     int batch_index = 0;
     for (int s = sample_begin; s < sample_begin + sample_count; s += (int)B, batch_index++) {
-        const int par = overlap ? (batch_index & 1) : 0;
-        P.Q.slab = slabs[par];
-        P.Q.qcount = counters + 64 * par;
-        P.Q.bin_count = counters + 64 * par + 8;
-        P.Q.cursor = counters + 64 * par + 32;
+        const int pipe = n_pipe == 2 ? (batch_index & 1) : 0;
+        cudaStream_t bs = streams[pipe];
+        P.Q = sets[pipe];
         P.sample_base = s;
         P.batch = (int)B < sample_begin + sample_count - s ? (int)B : sample_begin + sample_count - s;
         const size_t total = n * (size_t)P.batch;
@@ -1856,57 +1861,50 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
         const int grid_tail = ctx->num_sms * occ_tail < grid_full ? ctx->num_sms * occ_tail : grid_full;
         int first_wave = 0;
         P.bounce = 0;
-        // this batch's slab and counter set were last used by batch k-2: its resolve must be done
-        if (overlap && batch_index >= 2) PT_CUDA(cudaStreamWaitEvent(st, ctx->ev_resolve[par], 0));
         if (fused > 0) {
             // the first wave(s) in one kernel; survivors land in the queue the next wave reads
             P.fused_waves = fused;
-            { StageScope t(ctx, st, PT_STAGE_RESET, 0); k_wf_reset<<<1, 32, 0, st>>>(P); }
+            { StageScope t(ctx, bs, PT_STAGE_RESET, 0); k_wf_reset<<<1, 32, 0, bs>>>(P); }
             {
-                StageScope t(ctx, st, PT_STAGE_PRIMARY, 0);
+                StageScope t(ctx, bs, PT_STAGE_PRIMARY, 0);
                 WfParams Pp = P;
                 if (rel) Pp.S.nodes = rel_nodes;                           // this launch only
-                k_primary<<<grid_primary, bt_primary, smem, st>>>(Pp);
+                k_primary<<<grid_primary, bt_primary, smem, bs>>>(Pp);
             }
             first_wave = P.fused_waves;
         } else {
-            { StageScope t(ctx, st, PT_STAGE_GENERATE, 0); k_wf_generate<<<grid_wide, bt, 0, st>>>(P); }
+            { StageScope t(ctx, bs, PT_STAGE_GENERATE, 0); k_wf_generate<<<grid_wide, bt, 0, bs>>>(P); }
         }
         for (int b = first_wave; b < waves; b++) {        // renderer.py:313; no host read-back of the ray count
             P.bounce = b;
-            { StageScope t(ctx, st, PT_STAGE_EXTEND, b); k_extend<<<grid_extend, PT_EXT_WARPS * 32, smem, st>>>(P); }
-            if (P.sort) { StageScope t(ctx, st, PT_STAGE_BIN, b); k_wf_bin<<<grid_wide, bt, 0, st>>>(P); }
-            // the first shade of a batch is the first kernel to overwrite the queue the previous batch's tail reads
-            if (overlap && b == first_wave && batch_index >= 1) PT_CUDA(cudaStreamWaitEvent(st, ctx->ev_tail[par ^ 1], 0));
+            { StageScope t(ctx, bs, PT_STAGE_EXTEND, b); k_extend<<<grid_extend, PT_EXT_WARPS * 32, smem, bs>>>(P); }
+            if (P.sort) { StageScope t(ctx, bs, PT_STAGE_BIN, b); k_wf_bin<<<grid_wide, bt, 0, bs>>>(P); }
             if (split) {
                 for (int k = 0; k < 3; k++) {
                     const int g = ctx->num_sms * occ_cls[k] < grid_full ? ctx->num_sms * occ_cls[k] : grid_full;
-                    StageScope t(ctx, st, PT_STAGE_SHADE, b);
-                    k_shade_cls[k]<<<g, 256, 0, st>>>(P);
+                    StageScope t(ctx, bs, PT_STAGE_SHADE, b);
+                    k_shade_cls[k]<<<g, 256, 0, bs>>>(P);
                 }
             } else {
-                StageScope t(ctx, st, PT_STAGE_SHADE, b);
-                k_shade<<<grid_shade, bt_shade, ctx->dbg_shade_smem, st>>>(P);
+                StageScope t(ctx, bs, PT_STAGE_SHADE, b);
+                k_shade<<<grid_shade, bt_shade, ctx->dbg_shade_smem, bs>>>(P);
             }
-        }
-        if (overlap) {
-            PT_CUDA(cudaEventRecord(ctx->ev_waves[par], st));
-            PT_CUDA(cudaStreamWaitEvent(st2, ctx->ev_waves[par], 0));
         }
         if (waves < max_depth) {                          // whatever is still alive: finish in one launch
             P.bounce = tail_bounce;
-            { StageScope t(ctx, st2, PT_STAGE_TAIL, P.bounce); k_tail<<<grid_tail, bt, smem, st2>>>(P); }
+            { StageScope t(ctx, bs, PT_STAGE_TAIL, P.bounce); k_tail<<<grid_tail, bt, smem, bs>>>(P); }
         }
-        if (overlap) PT_CUDA(cudaEventRecord(ctx->ev_tail[par], st2));
+        // resolves add to the accumulation buffer in batch order, whichever stream their batch ran on: the
+        // sums are those of the serial schedule (bit-identical, options test wf_overlap=0/1)
+        if (n_pipe == 2 && batch_index >= 1) PT_CUDA(cudaStreamWaitEvent(bs, ctx->ev_resolve[pipe ^ 1], 0));
         int grid_res = (int)((n + bt - 1) / bt);
         if (grid_res > ctx->num_sms * 8) grid_res = ctx->num_sms * 8;
-        { StageScope t(ctx, st2, PT_STAGE_RESOLVE, 0); k_wf_resolve<<<grid_res, bt, 0, st2>>>(P); }
-        if (overlap) PT_CUDA(cudaEventRecord(ctx->ev_resolve[par], st2));
+        { StageScope t(ctx, bs, PT_STAGE_RESOLVE, 0); k_wf_resolve<<<grid_res, bt, 0, bs>>>(P); }
+        if (n_pipe == 2) PT_CUDA(cudaEventRecord(ctx->ev_resolve[pipe], bs));
     }
-    if (overlap) {                                         // join: the caller's stream continues after the last resolve
-        const int last = (batch_index - 1) & 1;
-        PT_CUDA(cudaStreamWaitEvent(st, ctx->ev_resolve[last], 0));
-    }
+    // join: the caller's stream continues after the last resolve (which follows every other resolve, and each
+    // stream's last kernel is a resolve)
+    if (n_pipe == 2 && ((batch_index - 1) & 1) == 1) PT_CUDA(cudaStreamWaitEvent(st, ctx->ev_resolve[1], 0));
     PT_CUDA(cudaGetLastError());
     return PT_OK;
 }

@@ -39,7 +39,7 @@ class Engine:
         self._workspace = None
         self.h2d_bytes = 0
         self.wavefront_samples_in_flight = None  # None = auto (about 66 M paths per batch); bounded by max_workspace_bytes
-        self.max_workspace_bytes = 12 << 30
+        self.max_workspace_bytes = 24 << 30        # two pipelines x ~66 M paths x 168 B
         self.wavefront_min_batches = 1           # auto sizing: split a render call into at least this many batches
 
     def close(self):
@@ -136,7 +136,10 @@ class Engine:
         assert accum.is_cuda and accum.dtype == torch.float32 and accum.is_contiguous()
         y1 = H if y1 is None else y1
         if self.wavefront_samples_in_flight is None:
+            # per-batch samples, times the two pipelines the library runs consecutive batches on (two queue sets)
             b = auto_samples_in_flight(W, y1 - y0, sample_count, min_batches=self.wavefront_min_batches)
+            if b < sample_count:
+                b *= 2
         else:
             b = max(1, min(self.wavefront_samples_in_flight, sample_count))
         extra = 64 * int(self.info.num_inner) + 256 if self.info is not None else 0     # origin-relative node copy
