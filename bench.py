@@ -207,6 +207,7 @@ def main():
     ap.add_argument("--width", type=int, default=WIDTH)
     ap.add_argument("--spp", type=int, default=SPP)
     ap.add_argument("--min-batches", type=int, default=None, help="wavefront: at least this many batches per render call")
+    ap.add_argument("--flight", type=int, default=None, help="wavefront: samples of every pixel in flight (all pipelines together)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-config5", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the other mode / numerics, probes and config 5")
@@ -264,6 +265,9 @@ def main():
             r.engine.set_option(k, int(v))
         if args.min_batches:
             r.engine.wavefront_min_batches = args.min_batches
+        if args.flight:
+            r.engine.wavefront_samples_in_flight = args.flight
+            r.engine.max_workspace_bytes = 80 << 30
         return r, cs
 
     # strong scaling: the frame's 256 samples are shared out; weak: every rank renders 256 of its own

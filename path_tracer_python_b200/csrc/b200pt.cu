@@ -48,6 +48,7 @@ static int set_error(int code, const std::string& msg) {
 #define PT_PRIMARY_THREADS 128
 #endif
 
+constexpr int kMaxPipes = 4;
 struct PtContext {
     int device = 0;
     bool has_scene = false;
@@ -65,8 +66,9 @@ struct PtContext {
     int wf_waves = 8;        // full waves per batch before the tail kernel takes over (tools/sweep_wf.py)
     int wf_primary_threads = PT_PRIMARY_THREADS;   // CTA size of k_wf_primary (<= its launch bound)
     int wf_overlap = 1;      // two pipelines: consecutive batches on two streams with their own queue sets (pt_render_wavefront)
-    cudaStream_t aux_stream = nullptr;
-    cudaEvent_t ev_resolve[2] = {nullptr, nullptr}, ev_start = nullptr;
+    int wf_pipelines = 2;    // batches in flight at once when wf_overlap is on (each with its own stream and queue set)
+    cudaStream_t aux_stream[kMaxPipes] = {};          // [0] unused: pipeline 0 runs on the caller's stream
+    cudaEvent_t ev_resolve[kMaxPipes] = {}, ev_start = nullptr;
     int wf_tail_vote = 1;    // the tail as a persistent voting state machine (k_wf_tail_vote) instead of one lane per ray
     int wf_rel_primary = 1;  // camera rays without defocus: slab test against origin-relative node boxes
     int wf_grid_waves = 16;  // static-partition kernels launch this many full waves of resident CTAs
@@ -1428,11 +1430,11 @@ int pt_destroy(PtContext* ctx) {
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->d_stage_snap) cudaFree(ctx->d_stage_snap);
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < kMaxPipes; i++) {
         if (ctx->ev_resolve[i]) cudaEventDestroy(ctx->ev_resolve[i]);
+        if (ctx->aux_stream[i]) cudaStreamDestroy(ctx->aux_stream[i]);
     }
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
-    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     delete ctx;
     return PT_OK;
 }
@@ -1458,6 +1460,9 @@ int pt_set_option(PtContext* ctx, const char* name, int64_t value) {
         ctx->wf_primary_threads = (int)value;
     } else if (k == "wf_overlap") {
         ctx->wf_overlap = value ? 1 : 0;
+    } else if (k == "wf_pipelines") {
+        if (value < 1 || value > kMaxPipes) return set_error(PT_ERR_INVALID_ARG, "wf_pipelines must be in [1, 4]");
+        ctx->wf_pipelines = (int)value;
     } else if (k == "wf_tail_vote") {
         ctx->wf_tail_vote = value ? 1 : 0;
     } else if (k == "wf_rel_primary") {
@@ -1700,7 +1705,9 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
     // batch order.  What this buys: the small launches of a batch -- late waves that cannot fill 148 SMs,
     // the tail's latency chain, bin / resolve passes -- run in the shadow of the other batch's big ones,
     // and the block scheduler back-fills every kernel's ramp-down with the other stream's CTAs.
-    int n_pipe = (ctx->wf_overlap && !ctx->stage_timing && S_cap >= 2 && sample_count >= 2) ? 2 : 1;
+    int n_pipe = (ctx->wf_overlap && !ctx->stage_timing) ? ctx->wf_pipelines : 1;
+    if ((size_t)n_pipe > S_cap) n_pipe = (int)S_cap;
+    if (n_pipe > sample_count) n_pipe = sample_count;
     size_t B = S_cap / (size_t)n_pipe;
     if (B > ((size_t)sample_count + n_pipe - 1) / n_pipe) B = ((size_t)sample_count + n_pipe - 1) / n_pipe;
     if (B > 256) B = 256;
@@ -1714,7 +1721,7 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
         B = ((size_t)sample_count + nb - 1) / nb;
     }
     const int n_batches = (sample_count + (int)B - 1) / (int)B;
-    if (n_batches < 2) n_pipe = 1;
+    if (n_batches < n_pipe) n_pipe = n_batches;
     PT_CUDA(cudaSetDevice(ctx->device));
     const size_t cap = B * n;
     char* p = static_cast<char*>(workspace);
@@ -1724,7 +1731,7 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
     P.S = ctx->scene;
     P.cam = ctx->cam;
     auto take = [&](size_t bytes) { char* q = p; p += align_up(bytes, 256); return q; };
-    WfQueues sets[2];
+    WfQueues sets[kMaxPipes];
     for (int k = 0; k < n_pipe; k++) {
         WfQueues& Q = sets[k];
         for (int q = 0; q < 2; q++) {
@@ -1740,7 +1747,6 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
         Q.cursor = counters + 32;
         Q.capacity = (int)cap;
     }
-    if (n_pipe == 1) sets[1] = sets[0];
     P.Q = sets[0];
     P.accum = accum;
     P.W = W; P.H = H; P.y0 = y0; P.y1 = y1;
@@ -1822,23 +1828,27 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
     const int waves = max_depth < ctx->wf_waves ? max_depth : ctx->wf_waves;
     const int fused = (ctx->wf_fuse_primary && max_depth > 0) ? (ctx->wf_fuse_primary < waves ? ctx->wf_fuse_primary : waves) : 0;
     const int tail_bounce = waves > fused ? waves : fused;
-    if (n_pipe == 2 && !ctx->aux_stream) {
-        bool ok = cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) == cudaSuccess;
-        for (int i = 0; i < 2 && ok; i++) ok = cudaEventCreateWithFlags(&ctx->ev_resolve[i], cudaEventDisableTiming) == cudaSuccess;
-        ok = ok && cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming) == cudaSuccess;
+    cudaStream_t streams[kMaxPipes] = {st, st, st, st};
+    if (n_pipe > 1) {
+        bool ok = ctx->ev_start || cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming) == cudaSuccess;
+        for (int i = 0; i < n_pipe && ok; i++) {
+            if (i > 0 && !ctx->aux_stream[i]) ok = cudaStreamCreateWithFlags(&ctx->aux_stream[i], cudaStreamNonBlocking) == cudaSuccess;
+            if (ok && !ctx->ev_resolve[i]) ok = cudaEventCreateWithFlags(&ctx->ev_resolve[i], cudaEventDisableTiming) == cudaSuccess;
+        }
         if (!ok) {
             (void)cudaGetLastError();
-            return set_error(PT_ERR_CUDA, "pt_render_wavefront: cannot create the second stream / its events");
+            return set_error(PT_ERR_CUDA, "pt_render_wavefront: cannot create the pipeline streams / events");
         }
-    }
-    cudaStream_t streams[2] = {st, n_pipe == 2 ? ctx->aux_stream : st};
-    if (n_pipe == 2) {            // the second stream starts after everything the caller queued before this call (and the node copy)
+        // the other streams start after everything the caller queued before this call (and the node copy)
         PT_CUDA(cudaEventRecord(ctx->ev_start, st));
-        PT_CUDA(cudaStreamWaitEvent(streams[1], ctx->ev_start, 0));
+        for (int i = 1; i < n_pipe; i++) {
+            streams[i] = ctx->aux_stream[i];
+            PT_CUDA(cudaStreamWaitEvent(streams[i], ctx->ev_start, 0));
+        }
     }
     int batch_index = 0;
     for (int s = sample_begin; s < sample_begin + sample_count; s += (int)B, batch_index++) {
-        const int pipe = n_pipe == 2 ? (batch_index & 1) : 0;
+        const int pipe = batch_index % n_pipe;
         cudaStream_t bs = streams[pipe];
         P.Q = sets[pipe];
         P.sample_base = s;
@@ -1896,15 +1906,15 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
         }
         // resolves add to the accumulation buffer in batch order, whichever stream their batch ran on: the
         // sums are those of the serial schedule (bit-identical, options test wf_overlap=0/1)
-        if (n_pipe == 2 && batch_index >= 1) PT_CUDA(cudaStreamWaitEvent(bs, ctx->ev_resolve[pipe ^ 1], 0));
+        if (n_pipe > 1 && batch_index >= 1) PT_CUDA(cudaStreamWaitEvent(bs, ctx->ev_resolve[(batch_index - 1) % n_pipe], 0));
         int grid_res = (int)((n + bt - 1) / bt);
         if (grid_res > ctx->num_sms * 8) grid_res = ctx->num_sms * 8;
         { StageScope t(ctx, bs, PT_STAGE_RESOLVE, 0); k_wf_resolve<<<grid_res, bt, 0, bs>>>(P); }
-        if (n_pipe == 2) PT_CUDA(cudaEventRecord(ctx->ev_resolve[pipe], bs));
+        if (n_pipe > 1) PT_CUDA(cudaEventRecord(ctx->ev_resolve[pipe], bs));
     }
     // join: the caller's stream continues after the last resolve (which follows every other resolve, and each
     // stream's last kernel is a resolve)
-    if (n_pipe == 2 && ((batch_index - 1) & 1) == 1) PT_CUDA(cudaStreamWaitEvent(st, ctx->ev_resolve[1], 0));
+    if (n_pipe > 1 && (batch_index - 1) % n_pipe != 0) PT_CUDA(cudaStreamWaitEvent(st, ctx->ev_resolve[(batch_index - 1) % n_pipe], 0));
     PT_CUDA(cudaGetLastError());
     return PT_OK;
 }

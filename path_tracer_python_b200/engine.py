@@ -40,6 +40,7 @@ class Engine:
         self.h2d_bytes = 0
         self.wavefront_samples_in_flight = None  # None = auto (about 66 M paths per batch); bounded by max_workspace_bytes
         self.max_workspace_bytes = 24 << 30        # two pipelines x ~66 M paths x 168 B
+        self.wavefront_pipelines = 2             # batches in flight at once (option "wf_pipelines"): each has its own queue set
         self.wavefront_min_batches = 1           # auto sizing: split a render call into at least this many batches
 
     def close(self):
@@ -62,6 +63,8 @@ class Engine:
 
     # ------------------------------------------------------------------ configuration
     def set_option(self, name: str, value: int):
+        if name == "wf_pipelines":
+            self.wavefront_pipelines = int(value)
         self._check(self.L.pt_set_option(self.ctx, name.encode(), int(value)), f"pt_set_option({name})")
 
     def set_row_interleave(self, block_rows: int = 0, stride_rows: int = 0):
@@ -139,7 +142,7 @@ class Engine:
             # per-batch samples, times the two pipelines the library runs consecutive batches on (two queue sets)
             b = auto_samples_in_flight(W, y1 - y0, sample_count, min_batches=self.wavefront_min_batches)
             if b < sample_count:
-                b *= 2
+                b *= self.wavefront_pipelines
         else:
             b = max(1, min(self.wavefront_samples_in_flight, sample_count))
         extra = 64 * int(self.info.num_inner) + 256 if self.info is not None else 0     # origin-relative node copy
