@@ -139,7 +139,7 @@ def run_reference(args, rank):
     from path_tracer_python_b200 import scenes
     O.build()
     nthreads = host_cores()
-    cs, meta = scenes.load_config("vol2_final_scene", WIDTH, ASPECT)
+    cs = scenes.compile_world(scenes.vol2_final_scene(WIDTH, ASPECT, SPP, seed=SEED)[0])
     sw = 480
     cam_s, sh = scenes.camera_vectors(img_width=sw, aspect_ratio=ASPECT, **scenes._CAMERAS["vol2_final_scene"])
     S = O.OracleScene(cs)
@@ -236,7 +236,6 @@ def main():
     from path_tracer_python_b200 import scenes
     from path_tracer_python_b200.engine import Engine, algorithmic_bytes
     from path_tracer_python_b200.renderer import TaichiRenderer
-    from path_tracer_python_b200.scene import camera, point3, vec3
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (there is no CPU path; use --impl reference for the CPU arm)")
@@ -250,14 +249,12 @@ def main():
     strong = world > 1 and args.scaling != "weak"
 
     def make_renderer(width, spp_total, numerics):
-        cs, _meta = scenes.load_config("vol2_final_scene", width, ASPECT)
-        cam = camera()
-        cam.aspect_ratio, cam.img_width = ASPECT, width
-        cam.samples_per_pixel = spp_total
-        c = scenes._CAMERAS["vol2_final_scene"]
-        cam.vfov, cam.lookfrom, cam.lookat, cam.vup = c["vfov"], point3(*c["lookfrom"]), point3(*c["lookat"]), vec3(*c["vup"])
-        r = TaichiRenderer(None, cam, os.path.join("/tmp", f"bench_{rank}.png"), seed=SEED, device=local_rank,
-                           process_group=group, compiled_scene=cs, quiet=True, numerics=numerics, reduce_dst=0)
+        # the scene goes through the package's own classes, compiler and native SAH builder, like a user's would
+        # (scenes.vol2_final_scene follows src/scenes.py:1152-1244; seed 1234 = the reference's geometry)
+        world, cam = scenes.vol2_final_scene(width, ASPECT, spp_total, seed=SEED)
+        r = TaichiRenderer(world, cam, os.path.join("/tmp", f"bench_{rank}.png"), seed=SEED, device=local_rank,
+                           process_group=group, quiet=True, numerics=numerics, reduce_dst=0)
+        cs = r.compiled
         r.background_color, r.max_depth = BG, MAX_DEPTH
         r._upload_camera()
         for kv in args.opt:
@@ -566,7 +563,8 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"vol2_final_scene {W}x{H} {spp_total}spp depth{MAX_DEPTH}" + (f" ({n_samples} spp per GPU)" if world > 1 else ""),
                        "mode": args.mode,
-                       "scene": "1007 spheres + 2401 quads, 6815-node SAH BVH (reference compile, seed 1234)",
+                       "scene": "1007 spheres + 2401 quads, 6815-node SAH BVH (own scene classes -> compile_scene -> native SAH builder, seed 1234)",
+                       "setup_ms": {k: round(v * 1e3, 2) for k, v in r.timing.items() if k in ("scene_compile", "bvh_compile", "gpu_upload", "total_setup")},
                        "l2": "flushed between timed steps (256 MiB fill)",
                        "parallelism": f"spp-split x{world}" + (", one NCCL reduce(sum) of the fp32 accumulation buffer onto rank 0 per step" if world > 1 else ""),
                        "numerics": "PT-F32 strict (bit-exact vs reference kernels)" if args.numerics == "strict" else

@@ -100,10 +100,16 @@ static const int kMaxStageSnaps = 4096;
 // ------------------------------------------------------------------------------------------------
 // shared helpers
 // ------------------------------------------------------------------------------------------------
+// (PT_SNODES=1 builds only: copies the top n_snodes nodes into the CTA's shared memory; the default build
+// fetches every node through L1 and this is a no-op without a barrier.)
 __device__ __forceinline__ void stage_nodes(float4* s_node_mem, const DScene& S, int n_snodes) {
+#if PT_SNODES
     const int n4 = n_snodes * 4;
     for (int i = threadIdx.x; i < n4; i += blockDim.x) s_node_mem[i] = __ldg(S.nodes + i);
     __syncthreads();
+#else
+    (void)s_node_mem; (void)S; (void)n_snodes;
+#endif
 }
 
 __device__ __forceinline__ void flush_counters(DCounters* dc, const LocalCounters& lc) {

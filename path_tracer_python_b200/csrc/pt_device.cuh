@@ -2,9 +2,10 @@
 // BVH traversal, primitive tests, material evaluation.  Semantics follow the reference's Taichi
 // functions (src/render_server/taichi_renderer/kernels.py, cited per function); the structure does
 // not: nodes hold both children's boxes (one 64-byte fetch per visit instead of three 44-byte
-// fetches, kernels.py:664,707-708), leaves are folded into child references, the top of the tree
-// is served from shared memory, hit point / normal are reconstructed after the loop instead of
-// being carried through it, and materials are de-duplicated records behind a per-primitive id.
+// fetches, kernels.py:664,707-708), leaves are folded into child references (which also carry the
+// shading class), every node is fetched through L1 (the whole tree is L2-resident), hit point / normal
+// are reconstructed after the loop instead of being carried through it, and materials are de-duplicated
+// records behind a per-primitive id.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

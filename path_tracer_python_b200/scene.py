@@ -91,6 +91,11 @@ class checker_texture:
 
 class noise_texture:
     def __init__(self, scale=1.0):
+        # the reference's noise_texture owns a perlin() (core/texture.py:80-84), whose constructor draws its
+        # gradient vectors and permutations from Python's `random`: the same draws are made here so that a
+        # seeded scene script continues with the same stream (the Taichi path itself uses the renderer's tables)
+        from .scene_compiler import perlin_tables
+        self.noise = perlin_tables()
         self.scale = scale
 
 
@@ -285,6 +290,29 @@ class hittable_list:
 
     def add(self, obj):
         self.objects.append(obj)
+
+
+class bvh_node:
+    """Container with the reference's constructor shape (core/bvh_node.py:13-46: `from_objects(objects, start,
+    end)`).  The reference sorts the span along its longest axis and splits it in the middle to make a
+    traversable object tree; the Taichi path never traverses that tree -- its compiler only walks it to collect
+    the primitives (scene_compiler.py:28-146) and then builds its own SAH tree -- so here the span is split in
+    the middle as it stands.  Same primitives, same SAH input set; only their order (hence their indices) differs."""
+
+    def __init__(self, left=None, right=None):
+        self.left, self.right = left, right
+
+    @classmethod
+    def from_objects(cls, objects, start: int, end: int):
+        span = end - start
+        if span <= 0:
+            return cls(None, None)
+        if span == 1:
+            return cls(objects[start], None)
+        if span == 2:
+            return cls(objects[start], objects[start + 1])
+        mid = start + span // 2
+        return cls(cls.from_objects(objects, start, mid), cls.from_objects(objects, mid, end))
 
 
 class constant_medium:

@@ -1,10 +1,10 @@
-"""Benchmark / test scenes as compiled arrays.
-
-`/root/reference` (and therefore src/scenes.py + src/core) does not exist on the GPU box, so the
-scenes BASELINE.json names are shipped as the arrays the reference's own `compile_scene` +
-`compile_bvh` produced for them (tests/golden/*.npz, written by oracle/gen_golden.py, seed 1234).
-Resolution / spp / depth are re-targeted here by recomputing the camera vectors with the
-reference's formulas (src/core/camera.py:34-72).
+"""The scenes BASELINE.json names, built with this package's own scene classes (scene.py) and compiled by
+its own compiler + native SAH builder -- `/root/reference` (src/scenes.py, src/core) does not exist on the GPU
+box.  Scene definitions follow the reference's (src/scenes.py, cited per function): same objects, same
+parameters, same draws from Python's `random` stream, so seed 1234 yields the same geometry.  Camera vectors
+come from the reference's formulas (src/core/camera.py:34-72).  The only asset is the earth texture
+(data/earthmap_u8.npz).  (Golden fixtures -- the reference's own compiled arrays and outputs -- live under
+tests/golden and are read by tests/golden_fixtures.py, never by this package.)
 """
 from __future__ import annotations
 
@@ -13,31 +13,13 @@ import os
 
 import numpy as np
 
-REPO_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-GOLDEN_DIR = os.path.join(REPO_ROOT, "tests", "golden")
+DATA_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
 
 
-def load_fixture(name: str):
-    """-> (compiled_scene dict, meta dict, golden outputs dict)"""
-    path = os.path.join(GOLDEN_DIR, f"{name}.npz")
-    g = np.load(path)
-    cs, out = {}, {}
-    for k in g.files:
-        if k.startswith("in_"):
-            cs[k[3:]] = g[k]
-        elif k.startswith("out_"):
-            out[k[4:]] = g[k]
-    for k in [k for k in cs if k.endswith("_ref")]:
-        cs[k[:-4]] = np.load(os.path.join(GOLDEN_DIR, str(cs.pop(k)) + ".npz"))["image"]
-    cs["num_images"] = int(cs.get("num_images", 0))
-    meta = {
-        "width": int(cs.pop("img_width")), "height": int(cs.pop("img_height")), "spp": int(cs.pop("spp")),
-        "background": tuple(float(x) for x in cs.pop("bg")), "max_depth": int(cs.pop("max_depth")),
-        "rng_seed": int(cs.pop("rng_seed")),
-    }
-    cam = {k: cs.pop(k) for k in list(cs) if k.startswith("cam_")}
-    meta["camera"] = cam
-    return cs, meta, out
+def earth_texture() -> np.ndarray:
+    """The earth map the reference's scenes use (src/assets/images/earthmap.jpg) as 8-bit RGB, shipped as
+    package data: texel = u8 / 255.0f reproduces the reference's float32 image bit for bit."""
+    return np.load(os.path.join(DATA_DIR, "earthmap_u8.npz"))["image"]
 
 
 def camera_vectors(lookfrom, lookat, vup, vfov, img_width, aspect_ratio, defocus_angle=0.0, focus_distance=10.0):
@@ -80,14 +62,6 @@ _CAMERAS = {
     "wavefront_comparison": dict(lookfrom=(13, 2, 3), lookat=(0, 0, 0), vup=(0, 1, 0), vfov=20),
     "cornell_smoke": dict(lookfrom=(278, 278, -800), lookat=(278, 278, 0), vup=(0, 1, 0), vfov=40),
 }
-
-
-def load_config(name: str, img_width: int, aspect_ratio: float):
-    """Scene arrays of a golden fixture with the camera re-targeted to another resolution."""
-    cs, meta, _ = load_fixture(name)
-    cam, h = camera_vectors(img_width=img_width, aspect_ratio=aspect_ratio, **_CAMERAS[name])
-    meta = dict(meta, width=img_width, height=h, camera=cam)
-    return cs, meta
 
 
 # ---------------------------------------------------------------------------------------------
@@ -174,3 +148,109 @@ def cornell_config4(img_width: int = 1024, spp: int = 4096):
     cam.vfov, cam.lookfrom, cam.lookat, cam.vup = 40, P(278, 278, -800), P(278, 278, 0), V(0, 1, 0)
     cam.defocus_angle = 0
     return w, cam
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json configs 1 and 2 / 5, through the scene classes.
+# ---------------------------------------------------------------------------------------------
+def vol2_final_scene(img_width: int = 1920, aspect_ratio: float = 16 / 9, spp: int = 256, seed: int | None = 1234):
+    """Configs 2 and 5: `vol2_final_scene` (src/scenes.py:1152-1244): 20 x 20 ground boxes of random height
+    (2400 quads), a light quad, a moving / a glass / a metal sphere, a glass sphere doubling as a medium
+    boundary, the r = 5000 'fog' sphere around everything, the earth, a Perlin sphere and 1000 small spheres
+    in a cube.  Returns (world, camera); `seed` re-seeds Python's `random` first (the reference's scenes draw
+    from the global stream, and so do the Perlin tables the renderer makes afterwards)."""
+    import random
+
+    from . import scene as sc
+    if seed is not None:
+        random.seed(seed)
+    P, V, C = sc.point3, sc.vec3, sc.color
+    ground = sc.lambertian.from_color(C(0.48, 0.83, 0.53))
+    boxes = sc.hittable_list()
+    for i in range(20):
+        for j in range(20):
+            x0, z0 = -1000.0 + i * 100.0, -1000.0 + j * 100.0
+            boxes.add(sc.box(P(x0, 0.0, z0), P(x0 + 100.0, random.uniform(1, 101), z0 + 100.0), ground))
+    world = sc.hittable_list()
+    world.add(sc.bvh_node.from_objects(boxes.objects, 0, len(boxes.objects)))
+    world.add(sc.quad(P(123, 554, 147), V(300, 0, 0), V(0, 0, 265), sc.diffuse_light.from_color(C(7, 7, 7))))
+    c1 = P(400, 400, 200)
+    world.add(sc.Sphere.moving(c1, c1 + V(30, 0, 0), 50, sc.lambertian.from_color(C(0.7, 0.3, 0.1))))
+    world.add(sc.Sphere.stationary(P(260, 150, 45), 50, sc.dielectric(1.5)))
+    world.add(sc.Sphere.stationary(P(0, 150, 145), 50, sc.metal(C(0.8, 0.8, 0.9), 1.0)))
+    boundary = sc.Sphere.stationary(P(360, 150, 145), 70, sc.dielectric(1.5))
+    world.add(boundary)
+    world.add(sc.constant_medium.from_color(boundary, C(0.2, 0.4, 0.9), 0.2))
+    world.add(sc.constant_medium.from_color(sc.Sphere.stationary(P(0, 0, 0), 5000, sc.dielectric(1.5)), C(1, 1, 1), 0.0001))
+    world.add(sc.Sphere.stationary(P(400, 200, 400), 100, sc.lambertian.from_texture(sc.image_texture(earth_texture()))))
+    world.add(sc.Sphere.stationary(P(220, 280, 300), 80, sc.lambertian.from_texture(sc.noise_texture(0.2))))
+    white = sc.lambertian.from_color(C(0.73, 0.73, 0.73))
+    cube = sc.hittable_list()
+    for _ in range(1000):
+        cube.add(sc.Sphere.stationary(P(random.uniform(0, 165), random.uniform(0, 165), random.uniform(0, 165)) + V(-100, 270, 395), 10, white))
+    world.add(sc.bvh_node.from_objects(cube.objects, 0, len(cube.objects)))
+    top = sc.hittable_list([sc.bvh_node.from_objects(world.objects, 0, len(world.objects))])
+    cam = sc.camera()
+    cam.aspect_ratio, cam.img_width, cam.samples_per_pixel = aspect_ratio, img_width, spp
+    c = _CAMERAS["vol2_final_scene"]
+    cam.vfov, cam.lookfrom, cam.lookat, cam.vup, cam.defocus_angle = c["vfov"], P(*c["lookfrom"]), P(*c["lookat"]), V(*c["vup"]), 0
+    return top, cam
+
+
+def wavefront_comparison(img_width: int = 400, aspect_ratio: float = 16 / 9, spp: int = 16, seed: int | None = 1234):
+    """Config 1: `wavefront_comparison` (src/scenes.py:1433-1503): a ground sphere, a 6 x 6 grid of small
+    diffuse / metal / glass spheres, three large ones and a spherical light.  Returns (world, camera)."""
+    import random
+
+    from . import scene as sc
+    if seed is not None:
+        random.seed(seed)
+    P, V, C = sc.point3, sc.vec3, sc.color
+    rnd3 = lambda lo=0.0, hi=1.0: C(random.uniform(lo, hi), random.uniform(lo, hi), random.uniform(lo, hi))
+    world = sc.hittable_list()
+    world.add(sc.Sphere.stationary(P(0, -1000, 0), 1000, sc.lambertian.from_color(C(0.5, 0.5, 0.5))))
+    for a in range(-3, 3):
+        for b in range(-3, 3):
+            choose = random.random()
+            center = P(a + 0.9 * random.random(), 0.2, b + 0.9 * random.random())
+            if (center - P(4, 0.2, 0)).length() > 0.9:
+                if choose < 0.6:
+                    c1, c2 = rnd3(), rnd3()
+                    world.add(sc.Sphere.stationary(center, 0.2, sc.lambertian.from_color(C(c1.x * c2.x, c1.y * c2.y, c1.z * c2.z))))
+                elif choose < 0.85:
+                    albedo = rnd3(0.5, 1)
+                    world.add(sc.Sphere.stationary(center, 0.2, sc.metal(albedo, random.uniform(0, 0.5))))
+                else:
+                    world.add(sc.Sphere.stationary(center, 0.2, sc.dielectric(1.5)))
+    world.add(sc.Sphere.stationary(P(0, 1, 0), 1.0, sc.dielectric(1.5)))
+    world.add(sc.Sphere.stationary(P(-4, 1, 0), 1.0, sc.lambertian.from_color(C(0.4, 0.2, 0.1))))
+    world.add(sc.Sphere.stationary(P(4, 1, 0), 1.0, sc.metal(C(0.7, 0.6, 0.5), 0.0)))
+    world.add(sc.Sphere.stationary(P(0, 5, 0), 1.5, sc.diffuse_light.from_color(C(4, 4, 4))))
+    top = sc.hittable_list([sc.bvh_node.from_objects(world.objects, 0, len(world.objects))])
+    cam = sc.camera()
+    cam.aspect_ratio, cam.img_width, cam.samples_per_pixel = aspect_ratio, img_width, spp
+    c = _CAMERAS["wavefront_comparison"]
+    cam.vfov, cam.lookfrom, cam.lookat, cam.vup, cam.defocus_angle = c["vfov"], P(*c["lookfrom"]), P(*c["lookat"]), V(*c["vup"]), 0.0
+    return top, cam
+
+
+def camera_dict(cam) -> dict:
+    """The seven camera vectors of an initialised scene.camera as the dict Engine.set_camera takes."""
+    cam.initialize()
+    v = lambda a: np.array([a.x, a.y, a.z], np.float64)
+    return {"cam_center": v(cam.center), "cam_pixel00": v(cam.pixel00_loc), "cam_delta_u": v(cam.delta_u),
+            "cam_delta_v": v(cam.delta_v), "cam_defocus_disk_u": v(cam.defocus_disk_u),
+            "cam_defocus_disk_v": v(cam.defocus_disk_v), "cam_defocus_angle": np.float64(cam.defocus_angle)}
+
+
+def compile_world(world, features: str = "taichi_compat", with_perlin: bool = True) -> dict:
+    """scene graph -> the flat compiled-scene dict the engine consumes: Perlin tables, compile_scene, native SAH
+    build -- in the order TaichiRenderer.__init__ makes them (the Perlin tables draw from `random` first)."""
+    from . import bvh as _bvh
+    from . import scene_compiler as _sc
+    perlin = _sc.perlin_tables() if with_perlin else {}
+    cs = _sc.compile_scene(world, features)
+    cs.update(_bvh.compile_bvh(cs))
+    for k, v in perlin.items():
+        cs.setdefault(k, v)
+    return cs

@@ -70,3 +70,15 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(root, f)).read()
                 assert "import oracle" not in src and "liboracle" not in src and "oracle/" not in src.replace(
                     "oracle/oracle_math.h", "").replace("oracle/gen_golden.py", ""), f
+
+
+def test_product_never_reads_the_test_fixtures():
+    """The package builds its scenes from its own classes + package data (path_tracer_python_b200/data); the
+    golden fixtures under tests/golden are test inputs, loaded only by tests/golden_fixtures.py."""
+    pkg = os.path.join(REPO, "path_tracer_python_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(root, f)).read()
+                assert "import golden_fixtures" not in src and "GOLDEN_DIR" not in src and "load_fixture" not in src, f
+    assert os.path.exists(os.path.join(pkg, "data", "earthmap_u8.npz"))

@@ -4,6 +4,7 @@ import pytest
 
 from conftest import GOLDEN_SCENES
 from path_tracer_python_b200 import bvh, scenes
+import golden_fixtures
 
 KEYS = ["bvh_bbox_min", "bvh_bbox_max", "bvh_left_child", "bvh_right_child", "bvh_parent", "bvh_prim_type",
         "bvh_prim_idx"]
@@ -11,7 +12,7 @@ KEYS = ["bvh_bbox_min", "bvh_bbox_max", "bvh_left_child", "bvh_right_child", "bv
 
 @pytest.mark.parametrize("name", GOLDEN_SCENES)
 def test_matches_reference_tree(name):
-    cs, meta, _ = scenes.load_fixture(name)
+    cs, meta, _ = golden_fixtures.load_fixture(name)
     mine = bvh.compile_bvh(cs)
     for k in KEYS:
         assert mine[k].dtype == cs[k].dtype

@@ -50,14 +50,15 @@ def test_interleaved_row_blocks_partition_rows():
 
 _WORKER = r'''
 import os, sys
-sys.path.insert(0, %(repo)r); sys.path.insert(0, os.path.join(%(repo)r, "oracle"))
+sys.path.insert(0, %(repo)r); sys.path.insert(0, os.path.join(%(repo)r, "oracle")); sys.path.insert(0, os.path.join(%(repo)r, "tests"))
 import numpy as np, torch, torch.distributed as dist
 from path_tracer_python_b200 import scenes
+import golden_fixtures
 from path_tracer_python_b200.distributed import sample_slice, reduce_accum, row_blocks, gather_rows
 import oracle as O
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
-cs, meta, out = scenes.load_fixture("wavefront_comparison")
+cs, meta, out = golden_fixtures.load_fixture("wavefront_comparison")
 S = O.OracleScene(cs); cam = O.make_camera(meta["camera"], meta["background"], meta["max_depth"])
 W, H, spp, seed = meta["width"], meta["height"], meta["spp"], meta["rng_seed"]
 b, e = sample_slice(spp)

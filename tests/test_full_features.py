@@ -10,10 +10,11 @@ import numpy as np
 import pytest
 
 from path_tracer_python_b200 import scenes
+import golden_fixtures
 
 
 def _load():
-    cs, meta, out = scenes.load_fixture("full_features")
+    cs, meta, out = golden_fixtures.load_fixture("full_features")
     return cs, meta, out["radiance_pure_python"]
 
 

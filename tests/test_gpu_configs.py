@@ -18,6 +18,7 @@ def test_config3_million_triangles_first_hit_bit_exact(engine, oracle_mod):
     """~1 M triangles: native SAH build, then first-hit parity (bit-exact t / point / normal, ids equal
     up to exact-t ties between neighbouring triangles) on primary and on incoherent bounce rays."""
     from path_tracer_python_b200 import scenes
+    import golden_fixtures
     O = oracle_mod
     t0 = time.time()
     cs, meta = scenes.heightfield_scene(img_width=480)
@@ -53,6 +54,7 @@ def test_config3_million_triangles_first_hit_bit_exact(engine, oracle_mod):
 
 def test_config3_paths_megakernel_equals_oracle_on_a_window(engine, oracle_mod):
     from path_tracer_python_b200 import scenes
+    import golden_fixtures
     O = oracle_mod
     cs, meta = scenes.heightfield_scene(img_width=96)
     engine.set_scene(cs)
@@ -67,6 +69,7 @@ def test_config3_paths_megakernel_equals_oracle_on_a_window(engine, oracle_mod):
 
 def _config4(width, spp):
     from path_tracer_python_b200 import scenes
+    import golden_fixtures
     from path_tracer_python_b200.renderer import TaichiRenderer
     world, cam = scenes.cornell_config4(width, spp)
     return world, cam, TaichiRenderer
@@ -113,8 +116,9 @@ def test_config1_full_size_bit_exact_vs_oracle(engine, oracle_mod):
     oracle, both architectures, whole accumulation buffer bit for bit (the golden
     fixture only covers 48x27x4)."""
     from path_tracer_python_b200 import scenes
+    import golden_fixtures
     O = oracle_mod
-    cs, meta = scenes.load_config("wavefront_comparison", 400, 16 / 9)
+    cs, meta = golden_fixtures.load_config("wavefront_comparison", 400, 16 / 9)
     W, H = 400, meta["height"]
     assert H == 225
     bg = (0.70, 0.80, 1.00)

@@ -18,11 +18,12 @@ def _engines():
 
 def _scene(name):
     from path_tracer_python_b200 import scenes
+    import golden_fixtures
     if name == "heightfield":
         cs, meta = scenes.heightfield_scene(img_width=960)
         return cs, meta, meta["background"], meta["max_depth"]
     width, bg = (400, (0.7, 0.8, 1.0)) if name == "wavefront_comparison" else (1920, (0, 0, 0))
-    cs, meta = scenes.load_config(name, width, 16 / 9)
+    cs, meta = golden_fixtures.load_config(name, width, 16 / 9)
     meta["width"] = width
     return cs, meta, bg, 50
 
@@ -65,7 +66,8 @@ def test_fast_image_matches_strict_within_mc_error():
     borderline decisions) against the spread of two strict seeds."""
     strict, fast = _engines()
     from path_tracer_python_b200 import scenes
-    cs, meta = scenes.load_config("vol2_final_scene", 480, 16 / 9)
+    import golden_fixtures
+    cs, meta = golden_fixtures.load_config("vol2_final_scene", 480, 16 / 9)
     W, H, spp = 480, meta["height"], 256
     imgs = {}
     for key, e, seed in (("s1", strict, 1), ("s2", strict, 2), ("f1", fast, 1)):

@@ -14,15 +14,16 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 _WORKER = r'''
 import os, sys
-sys.path.insert(0, %(repo)r)
+sys.path.insert(0, %(repo)r); sys.path.insert(0, os.path.join(%(repo)r, "tests"))
 import numpy as np, torch, torch.distributed as dist
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(rank)
 dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
 from path_tracer_python_b200 import scenes
+import golden_fixtures
 from path_tracer_python_b200.engine import Engine
 from path_tracer_python_b200.distributed import sample_slice, reduce_accum, interleaved_window, gather_rows
-cs, meta = scenes.load_config("vol2_final_scene", 480, 16 / 9)
+cs, meta = golden_fixtures.load_config("vol2_final_scene", 480, 16 / 9)
 W, H, spp, seed = 480, meta["height"], 64, 5
 e = Engine(rank)
 e.set_scene(cs); e.set_camera(meta["camera"], (0, 0, 0), 50)

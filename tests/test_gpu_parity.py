@@ -21,7 +21,8 @@ def engine():
 
 def _setup(engine, name):
     from path_tracer_python_b200 import scenes
-    cs, meta, out = scenes.load_fixture(name)
+    import golden_fixtures
+    cs, meta, out = golden_fixtures.load_fixture(name)
     engine.set_scene(cs)
     engine.set_camera(meta["camera"], meta["background"], meta["max_depth"])
     return cs, meta, out

@@ -13,9 +13,10 @@ pytestmark = pytest.mark.gpu
 
 def _renderer(name="wavefront_comparison", width=48, aspect=16 / 9, spp=4, **kw):
     from path_tracer_python_b200 import scenes
+    import golden_fixtures
     from path_tracer_python_b200.renderer_factory import RendererFactory
     from path_tracer_python_b200.scene import camera, point3, vec3
-    cs, meta = scenes.load_config(name, width, aspect)
+    cs, meta = golden_fixtures.load_config(name, width, aspect)
     cam = camera()
     cam.aspect_ratio, cam.img_width, cam.samples_per_pixel = aspect, width, spp
     c = scenes._CAMERAS[name]
@@ -28,7 +29,8 @@ def test_render_call_matches_reference_golden(tmp_path):
     """RendererFactory.create('taichi', ...) -> set knobs -> render(): the reference's call sequence
     (src/scenes.py:1504-1514) reproduces the reference's accumulation buffer bit for bit."""
     from path_tracer_python_b200 import scenes
-    _, gmeta, out = scenes.load_fixture("wavefront_comparison")
+    import golden_fixtures
+    _, gmeta, out = golden_fixtures.load_fixture("wavefront_comparison")
     path = str(tmp_path / "mega.png")
     r, cs, meta = _renderer(spp=gmeta["spp"], seed=gmeta["rng_seed"], path=path)
     r.background_color = gmeta["background"]
@@ -69,9 +71,10 @@ def test_full_resolution_properties():
     """Config 2 at full size (1920x1080): determinism, sample-range and row-range composition
     (the multi-GPU splits) are bit-exact; megakernel and wavefront agree statistically."""
     from path_tracer_python_b200 import scenes
+    import golden_fixtures
     from path_tracer_python_b200.engine import Engine
     e = Engine(0)
-    cs, meta = scenes.load_config("vol2_final_scene", 1920, 16 / 9)
+    cs, meta = golden_fixtures.load_config("vol2_final_scene", 1920, 16 / 9)
     e.set_scene(cs)
     e.set_camera(meta["camera"], (0, 0, 0), 50)
     W, H = 1920, meta["height"]
@@ -98,6 +101,7 @@ def test_full_resolution_properties():
 def test_edge_cases_empty_single_and_ragged():
     from path_tracer_python_b200.engine import Engine
     from path_tracer_python_b200 import scenes, bvh
+    import golden_fixtures
     e = Engine(0)
     cam, h = scenes.camera_vectors((0, 0, 5), (0, 0, 0), (0, 1, 0), 40, 37, 37 / 13)   # ragged 37x13: not a tile multiple
     # empty scene: every path returns the background
@@ -137,9 +141,10 @@ def test_counters_match_oracle_semantics(oracle_mod):
     """paths/bounces/rays are traversal-order independent and must equal the oracle's exactly;
     box tests differ (different visiting order) but stay within 2x of the reference-order count."""
     from path_tracer_python_b200 import scenes
+    import golden_fixtures
     from path_tracer_python_b200.engine import Engine
     O = oracle_mod
-    cs, meta, _ = scenes.load_fixture("vol2_final_scene")
+    cs, meta, _ = golden_fixtures.load_fixture("vol2_final_scene")
     e = Engine(0)
     e.set_scene(cs); e.set_camera(meta["camera"], meta["background"], meta["max_depth"])
     e.enable_counters(True); e.counters(reset=True)
@@ -157,8 +162,9 @@ def test_results_do_not_depend_on_tuning_options(scene_name):
     size, number of full waves, fused leading waves, material sort) change how the work is laid out
     on the machine, never the result: every combination reproduces the reference bit for bit."""
     from path_tracer_python_b200 import scenes
+    import golden_fixtures
     from path_tracer_python_b200.engine import Engine
-    cs, meta, out = scenes.load_fixture(scene_name)
+    cs, meta, out = golden_fixtures.load_fixture(scene_name)
     e = Engine(0)
     e.set_scene(cs)
     e.set_camera(meta["camera"], meta["background"], meta["max_depth"])
@@ -194,8 +200,9 @@ def test_stage_timing_reports_every_launch():
     """pt_enable_stage_timing / pt_get_stage_times: one record per kernel launch of the last wavefront
     call, in launch order, and switching it on does not change the image."""
     from path_tracer_python_b200 import scenes
+    import golden_fixtures
     from path_tracer_python_b200.engine import Engine
-    cs, meta, out = scenes.load_fixture("feature_zoo")
+    cs, meta, out = golden_fixtures.load_fixture("feature_zoo")
     e = Engine(0)
     e.set_scene(cs)
     e.set_camera(meta["camera"], meta["background"], meta["max_depth"])
@@ -222,9 +229,10 @@ def test_origin_relative_nodes_follow_camera_and_scene_changes():
     context: moving the camera or swapping the scene must rebuild it.  A context that renders camera A,
     then camera B, then another scene, gives the same images as fresh contexts do."""
     from path_tracer_python_b200 import scenes
+    import golden_fixtures
     from path_tracer_python_b200.engine import Engine
-    cs, meta, _ = scenes.load_fixture("vol2_final_scene")
-    cs2, meta2, _ = scenes.load_fixture("cornell_smoke")
+    cs, meta, _ = golden_fixtures.load_fixture("vol2_final_scene")
+    cs2, meta2, _ = golden_fixtures.load_fixture("cornell_smoke")
     assert not meta["camera"]["cam_defocus_angle"] > 0          # the relative path is actually taken
     W, H, seed = meta["width"], meta["height"], meta["rng_seed"]
     cam_b = dict(meta["camera"])
@@ -263,9 +271,10 @@ def test_full_size_window_bit_exact_vs_oracle(oracle_mod, mode):
     a row range of the full frame, with the wavefront's defaults -- tiles, origin-relative primary
     nodes, 32 samples in flight)."""
     from path_tracer_python_b200 import scenes
+    import golden_fixtures
     from path_tracer_python_b200.engine import Engine
     O = oracle_mod
-    cs, meta = scenes.load_config("vol2_final_scene", 1920, 16 / 9)
+    cs, meta = golden_fixtures.load_config("vol2_final_scene", 1920, 16 / 9)
     W, H, y0, y1, spp, seed = 1920, meta["height"], 500, 564, 4, 2024
     e = Engine(0)
     e.set_scene(cs)
@@ -285,12 +294,13 @@ def test_one_context_many_scenes_with_batch_overlap():
     the two-stream batch schedule and the per-call origin-relative node copy are exercised across
     scene / camera / workspace changes): every image equals the reference's."""
     from path_tracer_python_b200 import scenes
+    import golden_fixtures
     from path_tracer_python_b200.engine import Engine
     e = Engine(0)
     e.wavefront_samples_in_flight = 2
     for _ in range(2):
         for name in GOLDEN_SCENES:
-            cs, meta, out = scenes.load_fixture(name)
+            cs, meta, out = golden_fixtures.load_fixture(name)
             e.set_scene(cs)
             e.set_camera(meta["camera"], meta["background"], meta["max_depth"])
             acc = e.new_accum(meta["width"], meta["height"])
@@ -304,10 +314,11 @@ def test_interleaved_row_windows_compose_to_the_full_frame(mode):
     each, pt_set_row_interleave) into one buffer -- the union is bit-identical to the full-frame render.
     270 rows / 8-row blocks = 33.75 blocks: the last block sticks out of the image (rows skipped)."""
     from path_tracer_python_b200 import scenes
+    import golden_fixtures
     from path_tracer_python_b200.distributed import interleaved_window
     from path_tracer_python_b200.engine import Engine
     e = Engine(0)
-    cs, meta = scenes.load_config("vol2_final_scene", 480, 16 / 9)
+    cs, meta = golden_fixtures.load_config("vol2_final_scene", 480, 16 / 9)
     e.set_scene(cs)
     e.set_camera(meta["camera"], (0, 0, 0), 50)
     W, H, spp, seed = 480, meta["height"], 8, 3

@@ -5,12 +5,13 @@ import pytest
 
 from conftest import GOLDEN_SCENES
 from path_tracer_python_b200 import scenes
+import golden_fixtures
 
 
 @pytest.fixture(scope="module", params=GOLDEN_SCENES)
 def case(request, oracle_mod):
     O = oracle_mod
-    cs, meta, out = scenes.load_fixture(request.param)
+    cs, meta, out = golden_fixtures.load_fixture(request.param)
     S = O.OracleScene(cs)
     cam = O.make_camera(meta["camera"], meta["background"], meta["max_depth"])
     return O, S, cam, meta, out

@@ -6,6 +6,7 @@ import pytest
 
 from conftest import GOLDEN_SCENES
 from path_tracer_python_b200 import _lib, scenes
+import golden_fixtures
 
 
 def _pack(cs):
@@ -20,7 +21,7 @@ def _pack(cs):
 
 @pytest.mark.parametrize("name", GOLDEN_SCENES)
 def test_pack_covers_every_primitive_once(name):
-    cs, meta, _ = scenes.load_fixture(name)
+    cs, meta, _ = golden_fixtures.load_fixture(name)
     info, blob = _pack(cs)
     n_leaf = int((cs["bvh_prim_idx"] >= 0).sum())
     assert info.num_inner == len(cs["bvh_prim_idx"]) - n_leaf
@@ -52,7 +53,7 @@ def test_pack_covers_every_primitive_once(name):
 
 
 def test_vol2_materials_deduplicate():
-    cs, _, _ = scenes.load_fixture("vol2_final_scene")
+    cs, _, _ = golden_fixtures.load_fixture("vol2_final_scene")
     info, blob = _pack(cs)
     assert info.num_spheres == 1007 and info.num_quads == 2401 and info.num_inner == 3407
     assert info.num_materials == 10          # 3408 primitives share 10 distinct materials
@@ -85,7 +86,7 @@ def test_malformed_scenes_are_rejected_not_dereferenced():
     """`compiled_scene=` is public API.  A missing key or a short per-primitive array
     raises in HostScene; index ranges the Python side cannot see are rejected by the C packer with
     PT_ERR_INVALID_ARG (never a NULL / out-of-bounds dereference)."""
-    cs, _, _ = scenes.load_fixture("wavefront_comparison")
+    cs, _, _ = golden_fixtures.load_fixture("wavefront_comparison")
     for drop in ("sphere_material_type", "sphere_is_constant_medium", "bvh_prim_type", "bvh_left_child"):
         bad = {k: v for k, v in cs.items() if k != drop}
         with pytest.raises(_lib.B200PTError, match=drop):
@@ -111,7 +112,7 @@ def test_malformed_scenes_are_rejected_not_dereferenced():
     hs = _lib.HostScene(dict(cs, sphere_material_type=mt))
     assert L.pt_pack_scene_info(C.byref(hs.c), C.byref(_lib.PtPackedInfo())) == -1
     # an image-textured Lambertian whose image index points past the image table
-    z, _, _ = scenes.load_fixture("feature_zoo")
+    z, _, _ = golden_fixtures.load_fixture("feature_zoo")
     idx = z["sphere_texture_image_idx"].copy()
     idx[z["sphere_texture_type"] == 2] = 5
     hs = _lib.HostScene(dict(z, sphere_texture_image_idx=idx))

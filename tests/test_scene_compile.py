@@ -124,3 +124,40 @@ def test_against_reference_compiler(name):
                     ("cam_delta_v", "delta_v"), ("cam_defocus_disk_u", "defocus_disk_u")):
         v = getattr(c2, attr)
         assert np.array_equal(rc[k], np.array([v.x, v.y, v.z])), k
+
+
+@pytest.mark.parametrize("name", ["vol2_final_scene", "wavefront_comparison"])
+def test_own_scene_scripts_reproduce_the_reference_scenes(name):
+    """scenes.vol2_final_scene / wavefront_comparison (own classes, own compiler, native SAH builder -- what
+    bench.py renders) against the golden fixture = the arrays the reference's own scene script + compiler made
+    for seed 1234: the same primitives with the same materials (as multisets: the reference's bvh_node sorts
+    its objects, the container here does not, so indices differ) and bit-identical Perlin tables."""
+    import golden_fixtures
+    from path_tracer_python_b200 import scenes
+    world, cam = getattr(scenes, name)()
+    cs = scenes.compile_world(world)
+    g, meta, _ = golden_fixtures.load_fixture(name)
+
+    def rows(d, prefix, geo_keys):
+        n = len(np.atleast_2d(d[geo_keys[0]]))
+        cols = [np.asarray(d[k], np.float64).reshape(n, -1) for k in geo_keys]
+        cols += [np.asarray(d[f"{prefix}_{k}"], np.float64).reshape(n, -1) for k in (
+            "material_type", "material_albedo", "material_fuzz", "material_ir", "material_emit_color", "texture_type",
+            "texture_scale", "texture_color1", "texture_color2", "texture_image_idx", "is_constant_medium", "medium_density",
+            "medium_albedo")]
+        a = np.concatenate(cols, axis=1)
+        return a[np.lexsort(a.T[::-1])]
+
+    assert np.array_equal(rows(cs, "sphere", ["sphere_data"]), rows(g, "sphere", ["sphere_data"]))
+    if len(g["quad_Q"]):
+        qk = ["quad_Q", "quad_u", "quad_v", "quad_normal", "quad_D", "quad_w"]
+        assert np.array_equal(rows(cs, "quad", qk), rows(g, "quad", qk))
+    assert len(cs["quad_Q"]) == len(g["quad_Q"]) and len(cs["triangle_v0"]) == len(g["triangle_v0"])
+    for k in ("perlin_randvec", "perlin_perm_x", "perlin_perm_y", "perlin_perm_z"):
+        assert np.array_equal(cs[k], g[k]), k
+    assert int(cs["num_images"]) == int(g["num_images"])
+    if int(g["num_images"]):
+        assert np.array_equal(cs["image_0"], g["image_0"])
+    assert len(cs["bvh_prim_idx"]) == len(g["bvh_prim_idx"])               # 2 * primitives - 1 nodes
+    cam.initialize()
+    assert (cam.img_width, cam.img_height) == ((1920, 1080) if name == "vol2_final_scene" else (400, 225))

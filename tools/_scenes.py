@@ -1,7 +1,9 @@
 """Scene selection shared by the development tools: SCENE = a `scenes.load_config` name (default
 vol2_final_scene), `cornell4` (BASELINE config 4) or `heightfield` (config 3).  Returns (cs, meta, W)."""
-import os
+import os, sys
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))   # golden_fixtures
 from path_tracer_python_b200 import scenes
+import golden_fixtures
 
 
 def load(W=None):
@@ -21,7 +23,7 @@ def load(W=None):
         cs, meta = scenes.heightfield_scene()
         return cs, meta, meta["width"]
     W = W or int(os.environ.get("W", 1920))
-    cs, meta = scenes.load_config(name, W, 16 / 9)
+    cs, meta = golden_fixtures.load_config(name, W, 16 / 9)
     meta.setdefault("background", (0, 0, 0)); meta.setdefault("max_depth", 50)
     meta["background"] = (0, 0, 0)
     return cs, meta, W

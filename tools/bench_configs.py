@@ -2,9 +2,11 @@
 Prints one JSON line per measurement; run on one GPU."""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))   # golden_fixtures
 import torch
 from path_tracer_python_b200.engine import Engine, algorithmic_bytes
 from path_tracer_python_b200 import scenes, scene_compiler as SC, bvh
+import golden_fixtures
 
 e = Engine(0)
 
@@ -30,9 +32,9 @@ def render_line(tag, cs, meta, spp, seed=1234, flight=None):
     print(json.dumps(out), flush=True)
 
 # config 1: wavefront_comparison 400x225 x 16 spp
-cs, meta = scenes.load_config("wavefront_comparison", 400, 16 / 9); meta["background"] = (0.7, 0.8, 1.0); meta["max_depth"] = 50
+cs, meta = golden_fixtures.load_config("wavefront_comparison", 400, 16 / 9); meta["background"] = (0.7, 0.8, 1.0); meta["max_depth"] = 50
 render_line("1: wavefront_comparison 400x225 16spp", cs, meta, 16)
-render_line("1b: wavefront_comparison 1920x1080 64spp", *scenes.load_config("wavefront_comparison", 1920, 16 / 9), 64)
+render_line("1b: wavefront_comparison 1920x1080 64spp", *golden_fixtures.load_config("wavefront_comparison", 1920, 16 / 9), 64)
 
 # config 3: 1 M triangles, primary rays + 8-bounce paths
 t0 = time.time(); cs, meta = scenes.heightfield_scene(); build = time.time() - t0
@@ -57,4 +59,4 @@ meta = {"width": 1024, "height": cam.img_height, "background": (0, 0, 0), "max_d
 render_line("4: Cornell+medium+glass+SSS-as-Lambert 1024x1024 64spp (of 4096)", cs, meta, 64)
 
 # config 5 (single GPU share): vol2_final_scene 3840x2160, 32 spp
-render_line("5: vol2_final_scene 3840x2160 32spp (1-GPU share of 1024)", *scenes.load_config("vol2_final_scene", 3840, 16 / 9), 32)
+render_line("5: vol2_final_scene 3840x2160 32spp (1-GPU share of 1024)", *golden_fixtures.load_config("vol2_final_scene", 3840, 16 / 9), 32)

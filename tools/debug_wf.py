@@ -1,13 +1,15 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))   # golden_fixtures
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
 import numpy as np, torch
 from path_tracer_python_b200.engine import Engine
 from path_tracer_python_b200 import scenes
+import golden_fixtures
 import oracle as O
 name = sys.argv[1] if len(sys.argv) > 1 else "wavefront_comparison"
 e = Engine(0)
-cs, meta, out = scenes.load_fixture(name)
+cs, meta, out = golden_fixtures.load_fixture(name)
 e.set_scene(cs); e.set_camera(meta["camera"], meta["background"], meta["max_depth"])
 W, H, spp, seed = meta["width"], meta["height"], meta["spp"], meta["rng_seed"]
 S = O.OracleScene(cs); cam = O.make_camera(meta["camera"], meta["background"], meta["max_depth"])

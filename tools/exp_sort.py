@@ -3,12 +3,14 @@ Builds wave-1-like rays (cosine-weighted bounces off the primary hits of config 
 first-hit kernel on them in different orders (development aid; not bit-exact shading)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))   # golden_fixtures
 import torch
 from path_tracer_python_b200.engine import Engine
 from path_tracer_python_b200 import scenes
+import golden_fixtures
 W = 1920
 e = Engine(0)
-cs, meta = scenes.load_config("vol2_final_scene", W, 16 / 9)
+cs, meta = golden_fixtures.load_config("vol2_final_scene", W, 16 / 9)
 e.set_scene(cs); e.set_camera(meta["camera"], (0, 0, 0), 50)
 H = meta["height"]
 g = torch.Generator(device="cuda").manual_seed(1)

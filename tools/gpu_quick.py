@@ -1,16 +1,18 @@
 """Quick GPU sanity + timing (development aid)."""
 import sys, time, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))   # golden_fixtures
 import torch
 from path_tracer_python_b200.engine import Engine, algorithmic_bytes
 from path_tracer_python_b200 import scenes
+import golden_fixtures
 
 W = int(os.environ.get("W", 1920)); SPP = int(os.environ.get("SPP", 16))
 e = Engine(0)
 for k in ("smem_nodes", "block_threads"):
     if k.upper() in os.environ:
         e.set_option(k, int(os.environ[k.upper()]))
-cs, meta = scenes.load_config("vol2_final_scene", W, 16 / 9)
+cs, meta = golden_fixtures.load_config("vol2_final_scene", W, 16 / 9)
 info = e.set_scene(cs)
 print("inner nodes", info.num_inner, "materials", info.num_materials, "depth", info.max_depth_tree, "bytes", info.total_bytes)
 e.set_camera(meta["camera"], (0, 0, 0), 50)

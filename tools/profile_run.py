@@ -2,16 +2,18 @@
 the wavefront pipeline, on config 2 (vol2_final_scene 1920x1080) at SPP samples (default 4)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))   # golden_fixtures
 import torch
 from path_tracer_python_b200.engine import Engine
 from path_tracer_python_b200 import scenes
+import golden_fixtures
 
 W = int(os.environ.get("W", 1920)); SPP = int(os.environ.get("SPP", 4)); MODES = os.environ.get("MODES", "megakernel,wavefront").split(",")
 e = Engine(0)
 for k in ("smem_nodes", "block_threads"):
     if k.upper() in os.environ:
         e.set_option(k, int(os.environ[k.upper()]))
-cs, meta = scenes.load_config("vol2_final_scene", W, 16 / 9)
+cs, meta = golden_fixtures.load_config("vol2_final_scene", W, 16 / 9)
 e.set_scene(cs); e.set_camera(meta["camera"], (0, 0, 0), 50)
 H = meta["height"]
 for mode in MODES:

@@ -3,9 +3,11 @@ batches per call -- the stress sequence that exposed the device-allocation probl
 DESIGN.md section 5.2 (development aid).    python tools/repro_overlap.py vol2 hf vol2 cornell"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))   # golden_fixtures
 import torch
 from path_tracer_python_b200.engine import Engine
 from path_tracer_python_b200 import scenes, scene_compiler as SC, bvh
+import golden_fixtures
 e = Engine(0)
 for k, v in [kv.split("=") for kv in os.environ.get("OPTS", "").split(",") if kv]:
     e.set_option(k, int(v))
@@ -20,7 +22,7 @@ def cornell():
 order = sys.argv[1:] or ["vol2", "cornell"]
 for name in order:
     if name == "vol2":
-        cs, meta = scenes.load_config("vol2_final_scene", 1920, 16 / 9)
+        cs, meta = golden_fixtures.load_config("vol2_final_scene", 1920, 16 / 9)
     elif name == "hf":
         cs, meta = scenes.heightfield_scene()
     else:

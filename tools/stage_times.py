@@ -2,9 +2,11 @@
     python tools/stage_times.py            env: SPP (default 32), W, FLIGHT (samples per batch), PT_LIB_PATH, OPTS=k=v,..."""
 import os, sys, collections
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))   # golden_fixtures
 import torch
 from path_tracer_python_b200.engine import Engine
 from path_tracer_python_b200 import scenes
+import golden_fixtures
 W = int(os.environ.get("W", 1920)); SPP = int(os.environ.get("SPP", 32))
 e = Engine(0)
 if os.environ.get("SCENE") == "cornell4":        # BASELINE config 4: Cornell + medium + glass + SSS-as-Lambert, 1024^2
@@ -20,7 +22,7 @@ elif os.environ.get("SCENE") == "heightfield":  # BASELINE config 3: 1 M triangl
     cs, meta = scenes.heightfield_scene()
     W = meta["width"]
 else:
-    cs, meta = scenes.load_config(os.environ.get("SCENE", "vol2_final_scene"), W, 16 / 9)
+    cs, meta = golden_fixtures.load_config(os.environ.get("SCENE", "vol2_final_scene"), W, 16 / 9)
 e.set_scene(cs); e.set_camera(meta["camera"], meta.get("background", (0, 0, 0)), meta.get("max_depth", 50))
 H = meta["height"]
 for k, v in [kv.split("=") for kv in os.environ.get("OPTS", "").split(",") if kv]:

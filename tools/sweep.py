@@ -1,12 +1,14 @@
 """Tuning sweep (development aid): megakernel throughput on config 2 vs burst_num / smem_nodes / block size."""
 import os, sys, itertools
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))   # golden_fixtures
 import torch
 from path_tracer_python_b200.engine import Engine
 from path_tracer_python_b200 import scenes
+import golden_fixtures
 W = int(os.environ.get("W", 1920)); SPP = int(os.environ.get("SPP", 32))
 e = Engine(0)
-cs, meta = scenes.load_config("vol2_final_scene", W, 16 / 9)
+cs, meta = golden_fixtures.load_config("vol2_final_scene", W, 16 / 9)
 e.set_scene(cs); e.set_camera(meta["camera"], (0, 0, 0), 50)
 H = meta["height"]
 acc = e.new_accum(W, H)
