@@ -213,6 +213,13 @@ int pt_tonemap(PtContext* ctx, const float* accum, int n_floats, int sample_coun
 int pt_enable_counters(PtContext* ctx, int enable);
 int pt_get_counters(PtContext* ctx, PtCounters* out, int reset);
 
+/* ---- debug-bounds build (libb200pt_dbg.so, -DPT_DEBUG_BOUNDS=1): the kernels check every node / primitive /
+ *      material / texel / queue / bin / slab / stack index before use and record the first violation.  Returns it
+ *      (check code << 24 | source line of pt_device.cuh / b200pt.cu; 0 = none) and clears it; always 0 in the
+ *      product builds, whose kernels carry no checks.  Synchronises the device.  (No reference counterpart:
+ *      Taichi's debug=True bounds checking, renderer.py:16, is the closest.) */
+int pt_get_debug_error(PtContext* ctx, uint32_t* out_code);
+
 /* ---- per-stage device times of the LAST pt_render_wavefront call (what renderer.py:305-334 prints
  *      as its per-bounce timing): when enabled, every kernel launch of the call is bracketed by CUDA
  *      events on the launching stream.  pt_get_stage_times synchronises the device, writes up to

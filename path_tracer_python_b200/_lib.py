@@ -10,7 +10,9 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PT_LIB_PATH") or os.path.join(_HERE, "libb200pt.so")   # PT_LIB_PATH: A/B builds
 # numerics="fast": the same sources built with -DPT_FAST=1 --fmad=true (build.py); never the parity build
-LIB_PATHS = {"strict": LIB_PATH, "fast": os.environ.get("PT_FAST_LIB_PATH") or os.path.join(_HERE, "libb200pt_fast.so")}
+# numerics="debug": strict numerics with every index checked (-DPT_DEBUG_BOUNDS=1), for the parity suite only
+LIB_PATHS = {"strict": LIB_PATH, "fast": os.environ.get("PT_FAST_LIB_PATH") or os.path.join(_HERE, "libb200pt_fast.so"),
+             "debug": os.path.join(_HERE, "libb200pt_dbg.so")}
 
 PT_MAX_IMAGES = 16
 PRIM_SPHERE, PRIM_TRIANGLE, PRIM_QUAD = 0, 1, 2
@@ -75,7 +77,7 @@ EXPORTS = [
     "pt_last_error", "pt_version", "pt_pack_scene_info", "pt_pack_scene", "pt_bvh_build_sah", "pt_create",
     "pt_destroy", "pt_set_option", "pt_set_row_interleave", "pt_set_scene", "pt_set_camera", "pt_render_megakernel",
     "pt_wavefront_workspace_bytes", "pt_wavefront_workspace_bytes_for", "pt_render_wavefront", "pt_generate_camera_rays", "pt_first_hit",
-    "pt_math_eval", "pt_probe_gather", "pt_tonemap", "pt_enable_counters", "pt_get_counters", "pt_enable_stage_timing", "pt_get_stage_times", "pt_get_stage_counters",
+    "pt_math_eval", "pt_probe_gather", "pt_tonemap", "pt_get_debug_error", "pt_enable_counters", "pt_get_counters", "pt_enable_stage_timing", "pt_get_stage_times", "pt_get_stage_counters",
 ]
 
 _libs = {}
@@ -95,7 +97,7 @@ def lib(numerics: str = "strict") -> C.CDLL:
     if numerics in _libs:
         return _libs[numerics]
     if numerics not in LIB_PATHS:
-        raise B200PTError(f"unknown numerics {numerics!r} (strict | fast)")
+        raise B200PTError(f"unknown numerics {numerics!r} (strict | fast | debug)")
     path = LIB_PATHS[numerics]
     if not os.path.exists(path):
         raise B200PTError(
@@ -128,6 +130,7 @@ def lib(numerics: str = "strict") -> C.CDLL:
     L.pt_probe_gather.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double),
                                   C.c_void_p]
     L.pt_tonemap.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.pt_get_debug_error.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
     L.pt_enable_counters.argtypes = [C.c_void_p, C.c_int]
     L.pt_get_counters.argtypes = [C.c_void_p, C.POINTER(PtCounters), C.c_int]
     L.pt_enable_stage_timing.argtypes = [C.c_void_p, C.c_int]

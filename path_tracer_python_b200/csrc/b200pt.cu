@@ -351,6 +351,7 @@ __global__ void __launch_bounds__(PT_MEGA_THREADS, PT_MEGA_MINB) k_megakernel(co
                              min_active > 0 ? min_active : 1, P.vote_num > 0 ? P.vote_num : 1, lc);
         if (fin) st = LANE_HAVE_RESULT;
     }
+    PT_BOUND(!valid || (pixel >= 0 && pixel < P.W * P.H), PT_DBG_PIXEL);
     if (valid) { ap[0] = acc.x; ap[1] = acc.y; ap[2] = acc.z; }
     if (COUNT) flush_counters(P.counters, lc);
 }
@@ -545,6 +546,7 @@ __global__ void __launch_bounds__(PT_EXT_WARPS * 32, MINB) k_wf_extend(const __g
         int n = res_end - res_next;
         n = n > 32 ? 32 : (n < 0 ? 0 : n);
         if ((int)lane < n) {
+            PT_BOUND(res_next >= 0 && res_next + (int)lane < count, PT_DBG_QUEUE);
             cp_async16(&s_ray[warp][b][lane][0], qa + 2 * (size_t)(res_next + lane));
             cp_async16(&s_ray[warp][b][lane][1], qa + 2 * (size_t)(res_next + lane) + 1);
         }
@@ -582,11 +584,13 @@ __global__ void __launch_bounds__(PT_EXT_WARPS * 32, MINB) k_wf_extend(const __g
                     trav_restart<COUNT>(T, S, t_entry + 0.0001f, 1e10f, lc);
                     st = LANE_TRAVERSING;
                 } else {
+                    PT_BOUND(ray >= 0 && ray < count && count <= P.Q.capacity, PT_DBG_QUEUE);
                     P.Q.hit[ray] = make_float4(T.best_t, __int_as_float(ref), 0.0f, __int_as_float(cls << 8));
                     st = LANE_NEED_PATH;
                 }
             } else {
                 mode = 0;
+                PT_BOUND(ray >= 0 && ray < count && count <= P.Q.capacity, PT_DBG_QUEUE);
                 P.Q.hit[ray] = make_float4(t_entry, __int_as_float(ref_entry), T.best_t,
                                            __int_as_float((T.best_ref != kRefNone ? 1 : 0) | (PT_CLS_MEDIUM << 8)));
                 st = LANE_NEED_PATH;
@@ -787,6 +791,7 @@ __global__ void __launch_bounds__(256) k_wf_bin(const __grid_constant__ WfParams
         for (int r = 0; r < kBinRounds; r++) {
             if (cls[r] >= 0) {
                 const int pos = s_base[cls[r]] + s_cnt[cls[r]][warp] + rank[r];
+                PT_BOUND(pos >= 0 && pos < P.Q.capacity, PT_DBG_BIN);
                 P.Q.bins[(size_t)cls[r] * P.Q.capacity + pos] = (uint32_t)(base + r * 256 + threadIdx.x);
             }
         }
@@ -833,6 +838,7 @@ __global__ void __launch_bounds__(PT_SHADE_THREADS, PT_SHADE_MINB) k_wf_shade(co
 #pragma unroll
                 for (int k = 1; k < kNumBins; k++) b += (j >= prefix[k]) ? 1 : 0;
                 i = (int)P.Q.bins[(size_t)b * P.Q.capacity + (j - prefix[b])];
+                PT_BOUND(j - prefix[b] >= 0 && j - prefix[b] < P.Q.capacity && i >= 0 && i < count, PT_DBG_BIN);
             }
             a = P.Q.ra[cur][2 * (size_t)i]; bq = P.Q.ra[cur][2 * (size_t)i + 1]; c = P.Q.r2[cur][i]; h = P.Q.hit[i];
         }
@@ -842,6 +848,7 @@ __global__ void __launch_bounds__(PT_SHADE_THREADS, PT_SHADE_MINB) k_wf_shade(co
         ptm::Rng rng{0u, 1u};
         if (active) {
             path_id = __float_as_int(c.y);
+            PT_BOUND(path_id >= 0 && path_id < P.N * P.batch, PT_DBG_SLAB);
             const ptm::Rng key = wf_path_key(P, path_id);
             rng.s = __float_as_uint(c.z);
             rng.inc = key.inc;
@@ -856,6 +863,7 @@ __global__ void __launch_bounds__(PT_SHADE_THREADS, PT_SHADE_MINB) k_wf_shade(co
         // lives on its warps hiding each other's memory latency.
         const int pos = warp_agg_append(P.Q.qcount + nxt, 0, emit_next);
         if (emit_next) {
+            PT_BOUND(pos >= 0 && pos < P.Q.capacity, PT_DBG_QUEUE);
             P.Q.ra[nxt][2 * (size_t)pos] = make_float4(no.x, no.y, no.z, nd.x);
             P.Q.ra[nxt][2 * (size_t)pos + 1] = make_float4(nd.y, nd.z, nthr.x, nthr.y);
             P.Q.r2[nxt][pos] = make_float4(nthr.z, __int_as_float(path_id), __uint_as_float(rng.s), __int_as_float(ndepth));
@@ -906,6 +914,7 @@ __global__ void __launch_bounds__(256, KIND == 0 ? 8 : (KIND == 1 ? 4 : 3)) k_wf
 #pragma unroll
             for (int k = 1; k < c_hi - c_lo; k++) b += (j >= prefix[k]) ? 1 : 0;
             const int i = (int)P.Q.bins[(size_t)(c_lo + b) * P.Q.capacity + (j - prefix[b])];
+            PT_BOUND(i >= 0 && i < P.Q.qcount[cur] && P.Q.qcount[cur] <= P.Q.capacity, PT_DBG_BIN);
             const float4 bq = P.Q.ra[cur][2 * (size_t)i + 1], c = P.Q.r2[cur][i];
             const f3 thr = mk3(bq.z, bq.w, c.x);
             path_id = __float_as_int(c.y);
@@ -957,6 +966,7 @@ __global__ void __launch_bounds__(256, KIND == 0 ? 8 : (KIND == 1 ? 4 : 3)) k_wf
         if (KIND != 0) {
             const int pos = warp_agg_append(P.Q.qcount + nxt, 0, emit_next);       // one atomic per warp
             if (emit_next) {
+                PT_BOUND(pos >= 0 && pos < P.Q.capacity, PT_DBG_QUEUE);
                 P.Q.ra[nxt][2 * (size_t)pos] = make_float4(no.x, no.y, no.z, nd.x);
                 P.Q.ra[nxt][2 * (size_t)pos + 1] = make_float4(nd.y, nd.z, nthr.x, nthr.y);
                 P.Q.r2[nxt][pos] = make_float4(nthr.z, __int_as_float(path_id), __uint_as_float(rng.s), __int_as_float(ndepth));
@@ -1056,6 +1066,7 @@ __global__ void __launch_bounds__(PT_PRIMARY_THREADS, PT_PRIMARY_MINB) k_wf_prim
         const int qd = ONE ? 1 : (P.fused_waves & 1);   // the queue wave `fused_waves` reads from
         int pos = warp_agg_append(P.Q.qcount + qd, 0, emit_next);
         if (emit_next) {
+            PT_BOUND(pos >= 0 && pos < P.Q.capacity && id >= 0 && id < P.N * P.batch, PT_DBG_QUEUE);
             const int id2 = id;
             P.Q.ra[qd][2 * (size_t)pos] = make_float4(no.x, no.y, no.z, nd.x);
             P.Q.ra[qd][2 * (size_t)pos + 1] = make_float4(nd.y, nd.z, nthr.x, nthr.y);
@@ -1204,6 +1215,7 @@ __global__ void __launch_bounds__(256, 3) k_wf_tail_vote(const __grid_constant__
             if (st == LANE_NEED_PATH) {
                 const int i = base + __popc(want & ((1u << lane) - 1));
                 if (i < count) {
+                    PT_BOUND(i >= 0 && count <= P.Q.capacity, PT_DBG_QUEUE);
                     const float4 a = P.Q.ra[cur][2 * (size_t)i], bq = P.Q.ra[cur][2 * (size_t)i + 1], c = P.Q.r2[cur][i];
                     thr = mk3(bq.z, bq.w, c.x);
                     path_id = __float_as_int(c.y);
@@ -1243,6 +1255,7 @@ __global__ void __launch_bounds__(256) k_wf_resolve(const __grid_constant__ WfPa
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.N; i += stride) {
         const int pixel = win_pixel(P, i);
         if (pixel >= P.W * P.H) continue;               // interleaved window: row beyond the image
+        PT_BOUND(pixel >= 0, PT_DBG_PIXEL);
         float* ap = P.accum + 3 * (size_t)pixel;
         f3 acc = mk3(ap[0], ap[1], ap[2]);
         for (int s = 0; s < P.batch; s++) {
@@ -1407,6 +1420,8 @@ const char* pt_last_error(void) { return pt_error_slot()->c_str(); }
 const char* pt_version(void) {
 #if PT_FAST
     return "b200pt 0.2 (sm_100a, PT-F32 fast: FMA + approximate reciprocal)";
+#elif PT_DEBUG_BOUNDS
+    return "b200pt 0.2 (sm_100a, PT-F32 strict, debug-bounds build)";
 #else
     return "b200pt 0.2 (sm_100a, PT-F32 strict)";
 #endif
@@ -1549,6 +1564,10 @@ int pt_set_scene(PtContext* ctx, const void* device_blob, const PtPackedInfo* in
         S.image_h[i] = info->image_h[i];
     }
     S.num_inner = info->num_inner;
+    S.n_prims[PT_PRIM_SPHERE] = info->num_spheres;
+    S.n_prims[PT_PRIM_TRIANGLE] = info->num_triangles;
+    S.n_prims[PT_PRIM_QUAD] = info->num_quads;
+    S.num_materials = info->num_materials;
     S.mat_base[PT_PRIM_SPHERE] = 0;
     S.mat_base[PT_PRIM_TRIANGLE] = info->num_spheres;
     S.mat_base[PT_PRIM_QUAD] = info->num_spheres + info->num_triangles;
@@ -2011,6 +2030,23 @@ int pt_probe_gather(PtContext* ctx, const void* buffer, size_t bytes, int patter
     PT_CUDA(cudaGetLastError());
     const double gathered = (double)grid * threads * (double)iters * 4.0 * 64.0;
     *out_gbytes_per_s = gathered / (best_ms * 1e-3) / 1e9;
+    return PT_OK;
+}
+
+int pt_get_debug_error(PtContext* ctx, uint32_t* out_code) {
+    if (!ctx || !out_code) return set_error(PT_ERR_INVALID_ARG, "pt_get_debug_error: NULL argument");
+    *out_code = 0;
+#if PT_DEBUG_BOUNDS
+    PT_CUDA(cudaSetDevice(ctx->device));
+    PT_CUDA(cudaDeviceSynchronize());
+    unsigned int v = 0;
+    PT_CUDA(cudaMemcpyFromSymbol(&v, g_pt_debug_error, sizeof v));
+    *out_code = v;
+    if (v) {
+        const unsigned int zero = 0;
+        PT_CUDA(cudaMemcpyToSymbol(g_pt_debug_error, &zero, sizeof zero));
+    }
+#endif
     return PT_OK;
 }
 

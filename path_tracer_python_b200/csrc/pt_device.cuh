@@ -12,6 +12,24 @@
 #include "pt_math.cuh"
 #include "../../include/b200pt.h"
 
+// ---- debug-bounds build (-DPT_DEBUG_BOUNDS=1 -> libb200pt_dbg.so): every index the kernels form -- node, primitive,
+// material, image texel, queue slot, bin slot, slab slot, stack slot -- is checked before use.  The first violation is
+// recorded in a device word (code << 24 | source line; pt_get_debug_error) and the kernel carries on, so that the
+// word can still be read afterwards.  compute-sanitizer is not available on this GPU pool; tests/test_gpu_debug.py
+// runs the golden suite through this build instead.  The product builds compile the checks away.
+#ifndef PT_DEBUG_BOUNDS
+#define PT_DEBUG_BOUNDS 0
+#endif
+#if PT_DEBUG_BOUNDS
+__device__ unsigned int g_pt_debug_error = 0u;
+__device__ __noinline__ void pt_debug_fail(unsigned code, unsigned line) { atomicCAS(&g_pt_debug_error, 0u, (code << 24) | (line & 0xffffffu)); }
+#define PT_BOUND(cond, code) do { if (!(cond)) pt_debug_fail((code), __LINE__); } while (0)
+#else
+#define PT_BOUND(cond, code) ((void)0)
+#endif
+enum : unsigned { PT_DBG_NODE = 1, PT_DBG_PRIM = 2, PT_DBG_MATERIAL = 3, PT_DBG_STACK = 4, PT_DBG_QUEUE = 5, PT_DBG_BIN = 6,
+                  PT_DBG_SLAB = 7, PT_DBG_TEXEL = 8, PT_DBG_PIXEL = 9 };
+
 namespace pt {
 
 struct f3 {
@@ -54,6 +72,8 @@ struct DScene {
     const uchar4* image[PT_MAX_IMAGES];
     int image_w[PT_MAX_IMAGES], image_h[PT_MAX_IMAGES];
     int num_inner;
+    int n_prims[3];           // spheres, triangles, quads (by PT_PRIM_*)
+    int num_materials;
     int mat_base[3];          // offset of each prim type inside prim_mat
     int has_media;
     // "full" feature mode (moving spheres, subsurface materials); 0 = the reference's Taichi path
@@ -113,6 +133,7 @@ __device__ __forceinline__ f3 sphere_center(const DScene& S, int idx, float4 s, 
 template <bool FULL>
 __device__ __forceinline__ bool hit_sphere_t(const DScene& S, int idx, f3 o, f3 d, float t_min, float t_max, float& t,
                                              float time) {
+    PT_BOUND(idx >= 0 && idx < S.n_prims[PT_PRIM_SPHERE], PT_DBG_PRIM);
     float4 s = __ldg(S.spheres + idx);
     f3 oc = sx::sub(sphere_center<FULL>(S, idx, s, time), o);
     float a = sx::dot(d, d);
@@ -129,6 +150,7 @@ __device__ __forceinline__ bool hit_sphere_t(const DScene& S, int idx, f3 o, f3 
 }
 // kernels.py:251-307
 __device__ __forceinline__ bool hit_triangle_t(const DScene& S, int idx, f3 o, f3 d, float t_min, float t_max, float& t) {
+    PT_BOUND(idx >= 0 && idx < S.n_prims[PT_PRIM_TRIANGLE], PT_DBG_PRIM);
     const float4* p = S.tris + 3 * idx;
     float4 a0 = __ldg(p), a1 = __ldg(p + 1), a2 = __ldg(p + 2);
     f3 v0 = mk3(a0.x, a0.y, a0.z), e1 = mk3(a1.x, a1.y, a1.z), e2 = mk3(a2.x, a2.y, a2.z);
@@ -151,6 +173,7 @@ __device__ __forceinline__ bool hit_triangle_t(const DScene& S, int idx, f3 o, f
 }
 // kernels.py:310-362
 __device__ __forceinline__ bool hit_quad_t(const DScene& S, int idx, f3 o, f3 d, float t_min, float t_max, float& t) {
+    PT_BOUND(idx >= 0 && idx < S.n_prims[PT_PRIM_QUAD], PT_DBG_PRIM);
     const float4* p = S.quads + 4 * idx;
     float4 q0 = __ldg(p);
     f3 n = mk3(q0.x, q0.y, q0.z);
@@ -175,6 +198,7 @@ template <bool FULL = false>
 __device__ __forceinline__ void finalize_hit(const DScene& S, int ref, f3 o, f3 d, float t, f3& p, f3& n,
                                              float time = 0.0f) {
     int type = ref_type(ref), idx = ref_index(ref);
+    PT_BOUND(ref < 0 && ref != kRefNone && type <= 2 && idx < S.n_prims[type], PT_DBG_PRIM);
     p = o + t * d;
     if (type == PT_PRIM_SPHERE) {
         float4 s = __ldg(S.spheres + idx);
@@ -335,6 +359,7 @@ template <class STK>
 __device__ __forceinline__ void trav_push(TravState& T, const STK& stack, StackEntry e) {
 #if PT_STACK_TOP
     if ((int)(unsigned)T.top != kRefNone) {      // cannot overflow: pt_set_scene rejects trees deeper than kStackSize
+        PT_BOUND(T.sp + 1 < kStackSlots, PT_DBG_STACK);
         T.sp++;
         stack.store(T.sp, T.top);
     }
@@ -393,13 +418,14 @@ __device__ __forceinline__ SNodeBase snode_base(const float4* s_node_mem) {
 #endif
 }
 __device__ __forceinline__ void load_node(const float4* __restrict__ nodes, SNodeBase s_nodes, int n_snodes, int cur,
-                                          float4& nx, float4& ny, float4& nz, float4& nc) {
+                                          float4& nx, float4& ny, float4& nz, float4& nc, int n_nodes_dbg = 0) {
 #if PT_SNODES
     const unsigned long long base = cur < n_snodes ? s_nodes : (unsigned long long)nodes;
     const float4* p = reinterpret_cast<const float4*>(base) + 4 * cur;
     nx = p[0]; ny = p[1]; nz = p[2];
     const float2 c2 = *reinterpret_cast<const float2*>(p + 3);
 #else
+    PT_BOUND(cur >= 0 && cur < n_nodes_dbg, PT_DBG_NODE);
     // one IMAD.WIDE: the 64-byte stride applied in 64-bit arithmetic (4 * cur as an int costs a shift first)
     const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const char*>(nodes) + (unsigned long long)(unsigned)cur * 64ull);
     nx = __ldg(p); ny = __ldg(p + 1); nz = __ldg(p + 2);
@@ -430,7 +456,7 @@ __device__ __forceinline__ bool trav_run(TravState& T, const DScene& S, SNodeBas
     while (T.cur != kRefNone) {
         while (T.cur >= 0) {
             float4 nx, ny, nz, nc;
-            load_node(nodes, s_nodes, n_snodes, T.cur, nx, ny, nz, nc);
+            load_node(nodes, s_nodes, n_snodes, T.cur, nx, ny, nz, nc, S.num_inner);
             if (COUNT) lc.box_tests += 2;
             const float best_t = T.best_t;
             float l0x, l1x, l0y, l1y, l0z, l1z, r0x, r1x, r0y, r1y, r0z, r1z;
@@ -520,7 +546,7 @@ __device__ __forceinline__ void trav_run_vote(TravState& T, bool active, bool& d
         if (do_node) {
             if (want_node) {
                 float4 nx, ny, nz, nc;
-                load_node(nodes, s_nodes, n_snodes, cur, nx, ny, nz, nc);
+                load_node(nodes, s_nodes, n_snodes, cur, nx, ny, nz, nc, S.num_inner);
                 if (COUNT) lc.box_tests += 2;
                 const float best_t = T.best_t;
                 float l0x = PT_SLAB(nx.x, o.x, inv.x, noi.x), l1x = PT_SLAB(nx.y, o.x, inv.x, noi.x);
@@ -680,9 +706,11 @@ struct Mat {
     f3 c1, c2;      // Lambert: texture colours; metal: albedo; emissive: emit colour
 };
 __device__ __forceinline__ int mat_id_of(const DScene& S, int ref) {
+    PT_BOUND(ref < 0 && ref != kRefNone && ref_type(ref) <= 2 && ref_index(ref) < S.n_prims[ref_type(ref)], PT_DBG_PRIM);
     return (int)__ldg(S.prim_mat + S.mat_base[ref_type(ref)] + ref_index(ref));
 }
 __device__ __forceinline__ Mat load_mat(const DScene& S, int mid) {
+    PT_BOUND(mid >= 0 && mid < S.num_materials, PT_DBG_MATERIAL);
     float4 m0 = __ldg(S.materials + 3 * mid), m1 = __ldg(S.materials + 3 * mid + 1);
     Mat m;
     m.header = __float_as_int(m0.x);
@@ -722,6 +750,7 @@ __device__ __forceinline__ f3 eval_texture(const DScene& S, const Mat& m, int re
                 int i = (int)(u * (float)iw), j = (int)(v * (float)ih);
                 i = max(0, min(iw - 1, i));
                 j = max(0, min(ih - 1, j));
+                PT_BOUND(img < PT_MAX_IMAGES && S.image[img] != nullptr && i >= 0 && i < iw && j >= 0 && j < ih, PT_DBG_TEXEL);
                 uchar4 t = __ldg(S.image[img] + (size_t)j * iw + i);
                 result = mk3(ptm::fdiv((float)t.x, 255.0f), ptm::fdiv((float)t.y, 255.0f), ptm::fdiv((float)t.z, 255.0f));
             }

@@ -211,6 +211,13 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ statistics
+    def debug_error(self) -> int:
+        """First bounds violation the kernels of the debug build recorded since the last call
+        (check code << 24 | source line; 0 = none).  Always 0 with the product builds."""
+        code = C.c_uint32(0)
+        self._check(self.L.pt_get_debug_error(self.ctx, C.byref(code)), "pt_get_debug_error")
+        return int(code.value)
+
     def enable_counters(self, on: bool = True):
         self._check(self.L.pt_enable_counters(self.ctx, 1 if on else 0), "pt_enable_counters")
 

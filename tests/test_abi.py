@@ -10,10 +10,11 @@ from path_tracer_python_b200 import _lib, build
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.fixture(scope="module", params=["strict", "fast"])
+@pytest.fixture(scope="module", params=["strict", "fast", "debug"])
 def L(request):
-    """Both builds of the library: the strict (parity) one and the fast-numerics variant of the same sources."""
-    build.build_native() if request.param == "strict" else build.build_fast()
+    """All builds of the library: the strict (parity) one, the fast-numerics variant and the debug-bounds variant
+    of the same sources."""
+    {"strict": build.build_native, "fast": build.build_fast, "debug": build.build_debug}[request.param]()
     return _lib.lib(request.param)
 
 
@@ -50,11 +51,13 @@ def test_errors_are_reported_without_a_gpu(L):
     assert one == L.pt_wavefront_workspace_bytes(1920, 1080)
     assert many - one == 31 * n * 168 and 0 < one - n * 168 <= 64 * 1024
     assert b"sm_100a" in L.pt_version() and (b"strict" in L.pt_version()) != (b"fast" in L.pt_version())
+    code = ctypes.c_uint32(7)
+    assert L.pt_get_debug_error(None, ctypes.byref(code)) == -1
 
 
 def test_no_cpu_fallback_when_library_missing(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "_libs", {})
-    monkeypatch.setattr(_lib, "LIB_PATHS", {"strict": str(tmp_path / "nope.so"), "fast": str(tmp_path / "nope_fast.so")})
+    monkeypatch.setattr(_lib, "LIB_PATHS", {"strict": str(tmp_path / "nope.so"), "fast": str(tmp_path / "nope_fast.so")})   # (and no "debug")
     for numerics in ("strict", "fast"):
         with pytest.raises(_lib.B200PTError, match="not built"):
             _lib.lib(numerics)
