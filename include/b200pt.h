@@ -183,6 +183,32 @@ size_t pt_wavefront_workspace_bytes_for(int W, int rows, int samples_in_flight);
 int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int y1, int sample_begin,
                         int sample_count, uint32_t seed, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- stage-level entry points: ONE batch -- `samples` samples of every pixel of the window,
+ *      sample indices sample_base .. -- driven one wavefront kernel at a time, as the reference's host loop drives
+ *      its kernels (renderer.py:305-334): generate, then per bounce extend + shade until no ray is left, then resolve.
+ *      The batch lives in the caller's workspace (>= pt_wavefront_workspace_bytes_for(W, rows, samples)); pt_wf_begin
+ *      binds it to the context.  Queue q = bounce & 1 is the one wave `bounce` reads.
+ *        pt_wf_generate  = generate_camera_rays (kernels.py:1219-1239): camera rays of the batch -> queue 0
+ *        pt_wf_extend    = intersect_rays (:1242-1263) for the rays of queue bounce & 1, plus the exit search of
+ *                          apply_constant_medium (:417-419) for hits on a medium boundary -> hit records
+ *        pt_wf_shade     = shade_miss_rays + reset_next_ray_count + shade_and_scatter (:1266-1399): material binning,
+ *                          radiance contributions, survivors appended (compacted) to the other queue; the reference's
+ *                          swap_ray_buffers copy (:1402-1418) is the role swap of the two queues
+ *        pt_wf_compact   = the host's read of active_ray_count (renderer.py:315): live rays in the queue that wave
+ *                          `bounce` reads (compaction itself is part of pt_wf_shade's append); synchronises `stream`
+ *        pt_wf_read_rays / pt_wf_read_hits = the queue / the hit records as plain device arrays ([n][3] floats, pixel
+ *                          index = fields.ray_pixel_index, prim = (type << 28) | index or -1); any pointer may be NULL
+ *        pt_wf_resolve   = adds the batch's radiance to accum (H*W*3 f32), sample after sample (kernels.py:1280/:1373) */
+int pt_wf_begin(PtContext* ctx, int W, int H, int y0, int y1, int sample_base, int samples, uint32_t seed, void* workspace,
+                size_t workspace_bytes);
+int pt_wf_generate(PtContext* ctx, void* stream);
+int pt_wf_extend(PtContext* ctx, int bounce, void* stream);
+int pt_wf_shade(PtContext* ctx, int bounce, void* stream);
+int pt_wf_compact(PtContext* ctx, int bounce, int* live_rays, void* stream);
+int pt_wf_read_rays(PtContext* ctx, int bounce, int n, float* o, float* d, float* throughput, int32_t* pixel, int32_t* depth, void* stream);
+int pt_wf_read_hits(PtContext* ctx, int n, float* t, int32_t* prim, float* t_exit, void* stream);
+int pt_wf_resolve(PtContext* ctx, float* accum, void* stream);
+
 /* ---- stage-level probes used by the parity tests */
 /* get_ray for one sample of every pixel (kernels.py:176-201, :1219-1239); o,d: device [H*W][3] */
 int pt_generate_camera_rays(PtContext* ctx, int W, int H, uint32_t seed, int sample, float* o, float* d, void* stream);

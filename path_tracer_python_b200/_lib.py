@@ -76,7 +76,8 @@ class PtCounters(C.Structure):
 EXPORTS = [
     "pt_last_error", "pt_version", "pt_pack_scene_info", "pt_pack_scene", "pt_bvh_build_sah", "pt_create",
     "pt_destroy", "pt_set_option", "pt_set_row_interleave", "pt_set_scene", "pt_set_camera", "pt_render_megakernel",
-    "pt_wavefront_workspace_bytes", "pt_wavefront_workspace_bytes_for", "pt_render_wavefront", "pt_generate_camera_rays", "pt_first_hit",
+    "pt_wavefront_workspace_bytes", "pt_wavefront_workspace_bytes_for", "pt_render_wavefront", "pt_wf_begin", "pt_wf_generate", "pt_wf_extend", "pt_wf_shade", "pt_wf_compact",
+    "pt_wf_read_rays", "pt_wf_read_hits", "pt_wf_resolve", "pt_generate_camera_rays", "pt_first_hit",
     "pt_math_eval", "pt_probe_gather", "pt_tonemap", "pt_get_debug_error", "pt_enable_counters", "pt_get_counters", "pt_enable_stage_timing", "pt_get_stage_times", "pt_get_stage_counters",
 ]
 
@@ -122,6 +123,14 @@ def lib(numerics: str = "strict") -> C.CDLL:
                                        C.c_uint32, C.c_void_p]
     L.pt_render_wavefront.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.pt_wf_begin.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_size_t]
+    L.pt_wf_generate.argtypes = [C.c_void_p, C.c_void_p]
+    L.pt_wf_extend.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.pt_wf_shade.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.pt_wf_compact.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p]
+    L.pt_wf_read_rays.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 6
+    L.pt_wf_read_hits.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4
+    L.pt_wf_resolve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.pt_generate_camera_rays.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p,
                                           C.c_void_p]
     L.pt_first_hit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p,

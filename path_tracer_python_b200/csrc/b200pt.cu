@@ -49,6 +49,7 @@ static int set_error(int code, const std::string& msg) {
 #endif
 
 constexpr int kMaxPipes = 4;
+struct WfParams;
 struct PtContext {
     int device = 0;
     bool has_scene = false;
@@ -85,6 +86,7 @@ struct PtContext {
     int row_shift = -1, row_stride = 0;   // pt_set_row_interleave
     int num_sms = 148;
     int max_smem_optin = 0;
+    WfParams* stage_P = nullptr; // pt_wf_begin: the batch bound for the stage-level entry points
     bool count = false;
     DCounters* d_counters = nullptr;
     // stage timing (pt_enable_stage_timing): events around every launch of the last render call
@@ -1249,6 +1251,34 @@ __global__ void __launch_bounds__(256, 3) k_wf_tail_vote(const __grid_constant__
     if (COUNT) flush_counters(P.counters, lc);
 }
 
+// stage-level probes: the queue a wave reads / the hit records a wave wrote, unpacked into plain arrays
+__global__ void __launch_bounds__(256) k_wf_unpack_rays(const __grid_constant__ WfParams P, int cur, int n, float* o, float* d, float* thr,
+                                                        int32_t* pixel, int32_t* depth) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 a = P.Q.ra[cur][2 * (size_t)i], b = P.Q.ra[cur][2 * (size_t)i + 1], c = P.Q.r2[cur][i];
+    if (o) { o[3 * i] = a.x; o[3 * i + 1] = a.y; o[3 * i + 2] = a.z; }
+    if (d) { d[3 * i] = a.w; d[3 * i + 1] = b.x; d[3 * i + 2] = b.y; }
+    if (thr) { thr[3 * i] = b.z; thr[3 * i + 1] = b.w; thr[3 * i + 2] = c.x; }
+    if (pixel) {
+        const int path_id = __float_as_int(c.y);
+        int slot = (int)((float)path_id * P.inv_N);
+        int local = path_id - slot * P.N;
+        if (local < 0) local += P.N; else if (local >= P.N) local -= P.N;
+        pixel[i] = win_pixel(P, local);                 // ray_pixel_index (fields.py:205)
+    }
+    if (depth) depth[i] = __float_as_int(c.w);
+}
+__global__ void __launch_bounds__(256) k_wf_unpack_hits(const __grid_constant__ WfParams P, int n, float* t, int32_t* prim, float* t_exit) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 h = P.Q.hit[i];
+    const int ref = __float_as_int(h.y);
+    if (t) t[i] = h.x;
+    if (prim) prim[i] = ref == kRefNone ? -1 : ((ref_type(ref) << 28) | ref_index(ref));
+    if (t_exit) t_exit[i] = h.z;
+}
+
 // accum[pixel] += slab[0][pixel]; += slab[1][pixel]; ... in sample order (kernels.py:1280/:1373)
 __global__ void __launch_bounds__(256) k_wf_resolve(const __grid_constant__ WfParams P) {
     const int stride = gridDim.x * blockDim.x;
@@ -1414,6 +1444,8 @@ static int set_smem(K kernel, size_t bytes) {
     return PT_OK;
 }
 
+static void wf_stage_free(PtContext* ctx);
+
 extern "C" {
 
 const char* pt_last_error(void) { return pt_error_slot()->c_str(); }
@@ -1456,6 +1488,7 @@ int pt_destroy(PtContext* ctx) {
         if (ctx->aux_stream[i]) cudaStreamDestroy(ctx->aux_stream[i]);
     }
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
+    wf_stage_free(ctx);
     delete ctx;
     return PT_OK;
 }
@@ -1944,6 +1977,164 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
     return PT_OK;
 }
 
+// ---- stage-level entry points: one batch, one of the reference's wavefront kernels per call ----------------
+int pt_wf_begin(PtContext* ctx, int W, int H, int y0, int y1, int sample_base, int samples, uint32_t seed, void* workspace,
+                size_t workspace_bytes) {
+    float dummy;
+    int rc = check_render_args(ctx, &dummy, W, H, y0, y1, samples);
+    if (rc) return rc;
+    const int rows = y1 - y0;
+    const size_t n = (size_t)W * rows;
+    if (samples <= 0 || rows <= 0) return set_error(PT_ERR_INVALID_ARG, "pt_wf_begin: empty batch");
+    if (!workspace || workspace_bytes < pt_wavefront_workspace_bytes_for(W, rows, samples))
+        return set_error(PT_ERR_WORKSPACE, "pt_wf_begin: workspace too small for this many samples in flight");
+    if ((size_t)samples * n > kMaxPathsInFlight || samples > 256) return set_error(PT_ERR_CAPACITY, "pt_wf_begin: batch too large");
+    if (!ctx->stage_P) ctx->stage_P = new WfParams();
+    WfParams& P = *ctx->stage_P;
+    const size_t cap = (size_t)samples * n;
+    char* p = static_cast<char*>(workspace);
+    auto take = [&](size_t bytes) { char* q = p; p += align_up(bytes, 256); return q; };
+    P.S = ctx->scene;
+    P.cam = ctx->cam;
+    for (int q = 0; q < 2; q++) {
+        P.Q.ra[q] = reinterpret_cast<float4*>(take(cap * 32));
+        P.Q.r2[q] = reinterpret_cast<float4*>(take(cap * 16));
+    }
+    P.Q.hit = reinterpret_cast<float4*>(take(cap * 16));
+    P.Q.bins = reinterpret_cast<uint32_t*>(take((size_t)kNumBins * cap * 4));
+    P.Q.slab = reinterpret_cast<float*>(take(cap * 12));
+    int* counters = reinterpret_cast<int*>(take(256));
+    P.Q.qcount = counters;
+    P.Q.bin_count = counters + 8;
+    P.Q.cursor = counters + 32;
+    P.Q.capacity = (int)cap;
+    P.accum = nullptr;
+    P.W = W; P.H = H; P.y0 = y0; P.y1 = y1;
+    P.row_shift = ctx->row_shift; P.row_stride = ctx->row_stride;
+    P.inv_W = 1.0f / (float)W;
+    P.N = (int)n;
+    P.inv_N = 1.0f / (float)n;
+    P.sample_base = sample_base;
+    P.batch = samples;
+    P.seed = seed;
+    P.n_snodes = 0;
+    P.bounce = 0;
+    P.sort = 1;
+    P.burst_num = ctx->wf_burst_num;
+    P.vote_num = ctx->wf_vote_num;
+    P.fused_waves = 0;
+    P.tile = ctx->wf_tile;
+    P.counters = ctx->d_counters;
+    return PT_OK;
+}
+
+static int wf_stage_params(PtContext* ctx, WfParams** P, const char* who) {
+    if (!ctx) return set_error(PT_ERR_INVALID_ARG, std::string(who) + ": NULL context");
+    if (!ctx->stage_P) return set_error(PT_ERR_NO_SCENE, std::string(who) + ": no batch bound (pt_wf_begin)");
+    if (!ctx->has_scene || !ctx->has_camera) return set_error(PT_ERR_NO_SCENE, std::string(who) + ": scene or camera not set");
+    PT_CUDA(cudaSetDevice(ctx->device));
+    ctx->stage_P->S = ctx->scene;         // the scene / camera as they are now
+    ctx->stage_P->cam = ctx->cam;
+    *P = ctx->stage_P;
+    return PT_OK;
+}
+
+int pt_wf_generate(PtContext* ctx, void* stream) {
+    WfParams* P;
+    int rc = wf_stage_params(ctx, &P, "pt_wf_generate");
+    if (rc) return rc;
+    const long long total = (long long)P->N * P->batch;
+    int grid = (int)((total + 255) / 256);
+    if (grid > ctx->num_sms * 8) grid = ctx->num_sms * 8;
+    P->bounce = 0;
+    k_wf_generate<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(*P);
+    PT_CUDA(cudaGetLastError());
+    return PT_OK;
+}
+
+int pt_wf_extend(PtContext* ctx, int bounce, void* stream) {
+    WfParams* P;
+    int rc = wf_stage_params(ctx, &P, "pt_wf_extend");
+    if (rc) return rc;
+    if (bounce < 0) return set_error(PT_ERR_INVALID_ARG, "pt_wf_extend: negative bounce");
+    P->bounce = bounce;
+    const bool full = ctx->scene.full_features != 0;
+    void (*k)(const WfParams) = ctx->count ? (full ? k_wf_extend<true, true, 4> : k_wf_extend<true, false, 4>)
+                                           : (full ? k_wf_extend<false, true, 5> : k_wf_extend<false, false, 5>);
+    const long long total = (long long)P->N * P->batch;
+    const int grid_full = (int)((total + PT_EXT_WARPS * 32 - 1) / (PT_EXT_WARPS * 32));
+    const int grid_persist = ctx->num_sms * ctx->wf_blocks_per_sm;
+    k<<<grid_persist < grid_full ? grid_persist : grid_full, PT_EXT_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(*P);
+    PT_CUDA(cudaGetLastError());
+    return PT_OK;
+}
+
+int pt_wf_shade(PtContext* ctx, int bounce, void* stream) {
+    WfParams* P;
+    int rc = wf_stage_params(ctx, &P, "pt_wf_shade");
+    if (rc) return rc;
+    if (bounce < 0) return set_error(PT_ERR_INVALID_ARG, "pt_wf_shade: negative bounce");
+    P->bounce = bounce;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long total = (long long)P->N * P->batch;
+    int grid = (int)((total + 255) / 256);
+    const int grid_wide = ctx->num_sms * 8 < grid ? ctx->num_sms * 8 : grid;
+    k_wf_bin<<<grid_wide, 256, 0, st>>>(*P);
+    if (ctx->scene.full_features) k_wf_shade<true><<<grid_wide, PT_SHADE_THREADS, 0, st>>>(*P);
+    else k_wf_shade<false><<<grid_wide, PT_SHADE_THREADS, 0, st>>>(*P);
+    PT_CUDA(cudaGetLastError());
+    return PT_OK;
+}
+
+int pt_wf_compact(PtContext* ctx, int bounce, int* live_rays, void* stream) {
+    WfParams* P;
+    int rc = wf_stage_params(ctx, &P, "pt_wf_compact");
+    if (rc) return rc;
+    if (!live_rays || bounce < 0) return set_error(PT_ERR_INVALID_ARG, "pt_wf_compact: bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int v = 0;
+    PT_CUDA(cudaMemcpyAsync(&v, P->Q.qcount + (bounce & 1), sizeof v, cudaMemcpyDeviceToHost, st));
+    PT_CUDA(cudaStreamSynchronize(st));
+    *live_rays = v;
+    return PT_OK;
+}
+
+int pt_wf_read_rays(PtContext* ctx, int bounce, int n, float* o, float* d, float* throughput, int32_t* pixel, int32_t* depth, void* stream) {
+    WfParams* P;
+    int rc = wf_stage_params(ctx, &P, "pt_wf_read_rays");
+    if (rc) return rc;
+    if (n < 0 || n > P->Q.capacity || bounce < 0) return set_error(PT_ERR_INVALID_ARG, "pt_wf_read_rays: bad count / bounce");
+    if (n == 0) return PT_OK;
+    k_wf_unpack_rays<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(*P, bounce & 1, n, o, d, throughput, pixel, depth);
+    PT_CUDA(cudaGetLastError());
+    return PT_OK;
+}
+
+int pt_wf_read_hits(PtContext* ctx, int n, float* t, int32_t* prim, float* t_exit, void* stream) {
+    WfParams* P;
+    int rc = wf_stage_params(ctx, &P, "pt_wf_read_hits");
+    if (rc) return rc;
+    if (n < 0 || n > P->Q.capacity) return set_error(PT_ERR_INVALID_ARG, "pt_wf_read_hits: bad count");
+    if (n == 0) return PT_OK;
+    k_wf_unpack_hits<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(*P, n, t, prim, t_exit);
+    PT_CUDA(cudaGetLastError());
+    return PT_OK;
+}
+
+int pt_wf_resolve(PtContext* ctx, float* accum, void* stream) {
+    WfParams* P;
+    int rc = wf_stage_params(ctx, &P, "pt_wf_resolve");
+    if (rc) return rc;
+    if (!accum) return set_error(PT_ERR_INVALID_ARG, "pt_wf_resolve: NULL accumulation buffer");
+    WfParams R = *P;
+    R.accum = accum;
+    int grid = (R.N + 255) / 256;
+    if (grid > ctx->num_sms * 8) grid = ctx->num_sms * 8;
+    k_wf_resolve<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(R);
+    PT_CUDA(cudaGetLastError());
+    return PT_OK;
+}
+
 int pt_generate_camera_rays(PtContext* ctx, int W, int H, uint32_t seed, int sample, float* o, float* d, void* stream) {
     if (!ctx || !o || !d) return set_error(PT_ERR_INVALID_ARG, "pt_generate_camera_rays: NULL argument");
     if (!ctx->has_camera) return set_error(PT_ERR_NO_SCENE, "pt_generate_camera_rays: camera not set");
@@ -2116,3 +2307,8 @@ int pt_get_stage_times(PtContext* ctx, PtStageTime* out, int max_entries, int* n
 }
 
 }  // extern "C"
+
+static void wf_stage_free(PtContext* ctx) {
+    delete ctx->stage_P;
+    ctx->stage_P = nullptr;
+}

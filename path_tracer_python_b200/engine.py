@@ -158,6 +158,61 @@ class Engine:
                                              C.c_void_p(self._workspace.data_ptr()), C.c_size_t(need),
                                              self._stream_ptr()), "pt_render_wavefront")
 
+    # ------------------------------------------------------------------ wavefront, one stage at a time
+    def wf_begin(self, W: int, H: int, sample_base: int, samples: int, seed: int = 0, y0: int = 0, y1: int | None = None):
+        """Bind one batch (`samples` samples of every pixel of rows [y0, y1)) for the stage-level calls below --
+        the reference's wavefront kernels one at a time, in the order its host loop launches them
+        (renderer.py:305-334): wf_generate, then per bounce wf_extend + wf_shade until wf_compact says no ray
+        is left, then wf_resolve."""
+        y1 = H if y1 is None else y1
+        need = int(self.L.pt_wavefront_workspace_bytes_for(W, y1 - y0, samples))
+        if getattr(self, "_stage_ws", None) is None or self._stage_ws.numel() < need:
+            self._stage_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        self._stage_paths = W * (y1 - y0) * samples
+        self._check(self.L.pt_wf_begin(self.ctx, W, H, y0, y1, int(sample_base), int(samples), C.c_uint32(seed & 0xFFFFFFFF),
+                                       C.c_void_p(self._stage_ws.data_ptr()), C.c_size_t(need)), "pt_wf_begin")
+
+    def wf_generate(self):
+        with torch.cuda.device(self.device):
+            self._check(self.L.pt_wf_generate(self.ctx, self._stream_ptr()), "pt_wf_generate")
+
+    def wf_extend(self, bounce: int):
+        with torch.cuda.device(self.device):
+            self._check(self.L.pt_wf_extend(self.ctx, int(bounce), self._stream_ptr()), "pt_wf_extend")
+
+    def wf_shade(self, bounce: int):
+        with torch.cuda.device(self.device):
+            self._check(self.L.pt_wf_shade(self.ctx, int(bounce), self._stream_ptr()), "pt_wf_shade")
+
+    def wf_compact(self, bounce: int) -> int:
+        """Live rays in the queue wave `bounce` reads (synchronises; the reference's active_ray_count read-back)."""
+        n = C.c_int(0)
+        with torch.cuda.device(self.device):
+            self._check(self.L.pt_wf_compact(self.ctx, int(bounce), C.byref(n), self._stream_ptr()), "pt_wf_compact")
+        return int(n.value)
+
+    def wf_read_rays(self, bounce: int, n: int) -> dict:
+        f = lambda: torch.empty((n, 3), dtype=torch.float32, device=self.device)
+        out = {"o": f(), "d": f(), "throughput": f(), "pixel": torch.empty(n, dtype=torch.int32, device=self.device),
+               "depth": torch.empty(n, dtype=torch.int32, device=self.device)}
+        with torch.cuda.device(self.device):
+            self._check(self.L.pt_wf_read_rays(self.ctx, int(bounce), int(n), *[C.c_void_p(out[k].data_ptr()) for k in
+                                               ("o", "d", "throughput", "pixel", "depth")], self._stream_ptr()), "pt_wf_read_rays")
+        return out
+
+    def wf_read_hits(self, n: int) -> dict:
+        out = {"t": torch.empty(n, dtype=torch.float32, device=self.device), "prim": torch.empty(n, dtype=torch.int32, device=self.device),
+               "t_exit": torch.empty(n, dtype=torch.float32, device=self.device)}
+        with torch.cuda.device(self.device):
+            self._check(self.L.pt_wf_read_hits(self.ctx, int(n), *[C.c_void_p(out[k].data_ptr()) for k in ("t", "prim", "t_exit")],
+                                               self._stream_ptr()), "pt_wf_read_hits")
+        return out
+
+    def wf_resolve(self, accum: torch.Tensor):
+        assert accum.is_cuda and accum.dtype == torch.float32 and accum.is_contiguous()
+        with torch.cuda.device(self.device):
+            self._check(self.L.pt_wf_resolve(self.ctx, C.c_void_p(accum.data_ptr()), self._stream_ptr()), "pt_wf_resolve")
+
     # ------------------------------------------------------------------ probes
     def generate_camera_rays(self, W: int, H: int, seed: int = 0, sample: int = 0):
         o = torch.empty((H * W, 3), dtype=torch.float32, device=self.device)
