@@ -369,7 +369,7 @@ def main():
     extras = not args.no_extras
     modes = {args.mode: value}
     numerics_modes = {args.numerics: value}
-    nccl_check = config5 = primary = None
+    nccl_check = config5 = primary = tile_split = None
     if extras:
         # ---- the other architecture, for the record (BASELINE config 2 is "megakernel vs wavefront")
         other_mode = "megakernel" if args.mode == "wavefront" else "wavefront"
@@ -395,6 +395,44 @@ def main():
                           "allclose_rtol_1e-5": bool(torch.allclose(reduced, alone, rtol=1e-5, atol=1e-5 * float(alone.abs().mean())))}
             del alone
         barrier()
+
+        # ---- N > 1: the other sharding -- interleaved 8-row blocks per rank (one render call each), gather instead
+        #      of reduce: each rank ships only its own 1/N of the frame and nothing is summed
+        if group is not None and strong:
+            from path_tracer_python_b200.distributed import gather_rows, interleaved_window
+            ty0, ty1, tstride = interleaved_window(H, rank, world, 8)
+
+            def tile_step():
+                r._accum.zero_()
+                eng.set_row_interleave(8, tstride)
+                render(r._accum, 0, spp_total, SEED, y0=ty0, y1=ty1)
+                eng.set_row_interleave(0)
+                gather_rows(r._accum, H, group=group, block=8, dst=0)
+            tile_step()
+            barrier()
+            tev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            flush.fill_(7)
+            r._accum.zero_()
+            tev[0].record()
+            eng.set_row_interleave(8, tstride)
+            render(r._accum, 0, spp_total, SEED, y0=ty0, y1=ty1)
+            eng.set_row_interleave(0)
+            tev[1].record()
+            gather_rows(r._accum, H, group=group, block=8, dst=0)
+            tev[2].record()
+            barrier()
+            tile_ms = gmax(tev[0].elapsed_time(tev[2]))
+            tile_split = {"what": "interleaved 8-row blocks per rank (pt_set_row_interleave, one call), gather onto rank 0",
+                          "value": paths_per_step / (tile_ms * 1e-3) / 1e6, "unit": "Mpaths/s", "ms": tile_ms, "steps": 1,
+                          "rank_render_ms": gather_list(tev[0].elapsed_time(tev[1])),
+                          "rank_gather_ms": gather_list(tev[1].elapsed_time(tev[2]))}
+            if rank == 0:
+                alone = eng.new_accum(W, H)
+                render(alone, 0, spp_total, SEED)
+                torch.cuda.synchronize(dev)
+                tile_split["bit_identical_to_single_gpu"] = bool(torch.equal(r._accum, alone))
+                del alone
+            barrier()
 
     # ---- roofline of the dominant kernel (rank 0).  Algorithmic bytes come from the counting instantiation
     #      of the same kernels on the identical (seed, samples) launch; durations are CUDA-event times on
@@ -577,7 +615,7 @@ def main():
             "modes": modes, "numerics_modes": numerics_modes, "primary": primary,
             "ranks": {"render_ms": rank_render_ms, "reduce_ms": rank_reduce_ms,
                       "reduce_bytes": int(r._accum.numel() * 4) if world > 1 else 0, "samples_per_rank": n_samples},
-            "nccl_vs_single_gpu": nccl_check, "config5": config5,
+            "nccl_vs_single_gpu": nccl_check, "tile_split": tile_split, "config5": config5,
         }
         emit(line)
     if group is not None:
