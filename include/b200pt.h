@@ -88,7 +88,7 @@ typedef struct PtHostScene {
  * every section 256-byte aligned. */
 typedef struct PtPackedInfo {
     uint64_t total_bytes;
-    uint64_t off_nodes;      /* num_inner * 64 B : two child boxes + two child refs per node */
+    uint64_t off_nodes;      /* num_inner * node_bytes : the children's boxes + child refs of every inner node */
     uint64_t off_spheres;    /* num_spheres * 16 B */
     uint64_t off_quads;      /* num_quads * 64 B */
     uint64_t off_tris;       /* num_triangles * 48 B */
@@ -103,7 +103,7 @@ typedef struct PtPackedInfo {
     int32_t has_media;       /* any is_medium flag set */
     uint64_t off_sphere_motion; /* num_spheres * 16 B, present iff full_features */
     int32_t full_features;
-    int32_t reserved_;
+    int32_t node_bytes;      /* bytes per packed node: 64 (two children per node) or 128 (the 4-wide build, -DPT_WIDE=1) */
 } PtPackedInfo;
 
 /* Camera + render settings: what _upload_camera writes (renderer.py:230-247; fields.py:159-172) */

@@ -12,7 +12,8 @@ LIB_PATH = os.environ.get("PT_LIB_PATH") or os.path.join(_HERE, "libb200pt.so") 
 # numerics="fast": the same sources built with -DPT_FAST=1 --fmad=true (build.py); never the parity build
 # numerics="debug": strict numerics with every index checked (-DPT_DEBUG_BOUNDS=1), for the parity suite only
 LIB_PATHS = {"strict": LIB_PATH, "fast": os.environ.get("PT_FAST_LIB_PATH") or os.path.join(_HERE, "libb200pt_fast.so"),
-             "debug": os.path.join(_HERE, "libb200pt_dbg.so")}
+             "debug": os.path.join(_HERE, "libb200pt_dbg.so"),
+             "wide": os.path.join(_HERE, "libb200pt_wide.so")}     # strict numerics over the 4-wide collapsed BVH (-DPT_WIDE=1)
 
 PT_MAX_IMAGES = 16
 PRIM_SPHERE, PRIM_TRIANGLE, PRIM_QUAD = 0, 1, 2
@@ -47,7 +48,7 @@ class PtPackedInfo(C.Structure):
            ("image_h", C.c_int32 * PT_MAX_IMAGES)]
         + [(n, C.c_int32) for n in ("num_inner", "num_spheres", "num_quads", "num_triangles", "num_materials",
                                     "num_images", "max_depth_tree", "has_media")]
-        + [("off_sphere_motion", C.c_uint64), ("full_features", C.c_int32), ("reserved_", C.c_int32)]
+        + [("off_sphere_motion", C.c_uint64), ("full_features", C.c_int32), ("node_bytes", C.c_int32)]
     )
 
 
@@ -98,7 +99,7 @@ def lib(numerics: str = "strict") -> C.CDLL:
     if numerics in _libs:
         return _libs[numerics]
     if numerics not in LIB_PATHS:
-        raise B200PTError(f"unknown numerics {numerics!r} (strict | fast | debug)")
+        raise B200PTError(f"unknown numerics {numerics!r} (strict | fast | debug | wide)")
     path = LIB_PATHS[numerics]
     if not os.path.exists(path):
         raise B200PTError(

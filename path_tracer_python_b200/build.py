@@ -1,7 +1,7 @@
 """Builds libb200pt.so (strict numerics, the parity build) and libb200pt_fast.so (production numerics)
 in-tree with nvcc for sm_100a (cross-compiles without a GPU).
 
-    python -m path_tracer_python_b200.build [--force] [--verbose] [--only=strict|fast|debug]
+    python -m path_tracer_python_b200.build [--force] [--verbose] [--only=strict|fast|debug|wide]
 
 Flags that matter: ``--fmad=false`` (PT-F32 contract: no FFMA contraction; the fast variant is the same
 sources with ``-DPT_FAST=1 --fmad=true``), ``-lineinfo`` (ncu source page),
@@ -18,6 +18,8 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libb200pt.so")
 FAST_LIB_PATH = os.path.join(HERE, "libb200pt_fast.so")
 FAST_DEFINES = ("PT_FAST=1",)
+WIDE_LIB_PATH = os.path.join(HERE, "libb200pt_wide.so")
+WIDE_DEFINES = ("PT_WIDE=1",)
 DEBUG_LIB_PATH = os.path.join(HERE, "libb200pt_dbg.so")
 DEBUG_DEFINES = ("PT_DEBUG_BOUNDS=1",)
 SOURCES = ["b200pt.cu", "pt_host.cpp"]
@@ -75,6 +77,14 @@ def build_fast(force: bool = False, verbose: bool = False) -> str:
     return build_native(force=True, verbose=verbose, defines=FAST_DEFINES, out=FAST_LIB_PATH)
 
 
+def build_wide(force: bool = False, verbose: bool = False) -> str:
+    """The 4-wide BVH variant (PT_WIDE: the packer collapses the binary tree into 128-byte 4-child nodes).  Same
+    results; measured 5 % slower than the binary layout on config 2, so not the default."""
+    if not force and not needs_build(WIDE_LIB_PATH):
+        return WIDE_LIB_PATH
+    return build_native(force=True, verbose=verbose, defines=WIDE_DEFINES, out=WIDE_LIB_PATH)
+
+
 def build_debug(force: bool = False, verbose: bool = False) -> str:
     """Strict numerics with every node / primitive / queue / bin / slab / stack index checked in the kernels
     (PT_DEBUG_BOUNDS); tests/test_gpu_debug.py runs the golden suite through it."""
@@ -97,3 +107,5 @@ if __name__ == "__main__":
             print(build_fast(force=force, verbose=verbose))
         if not only or only[0] == "debug":
             print(build_debug(force=force, verbose=verbose))
+        if not only or only[0] == "wide":
+            print(build_wide(force=force, verbose=verbose))

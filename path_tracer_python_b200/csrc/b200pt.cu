@@ -381,7 +381,7 @@ struct WfQueues {
     int* cursor;             // dynamic-fetch cursor of k_wf_extend
     int capacity;            // B * N
 };
-constexpr int kNodeBytes = 64;   // one packed inner node (both children's boxes + two references)
+constexpr int kNodeBytes = 16 * kNodeQuads;   // one packed inner node: 64 B (two children) or 128 B (PT_WIDE: four)
 constexpr int kNumBins = 8;  // one bin per shading class (pt_device.cuh PT_CLS_*)
 
 struct WfParams {
@@ -842,7 +842,8 @@ __global__ void __launch_bounds__(PT_SHADE_THREADS, PT_SHADE_MINB) k_wf_shade(co
                 i = (int)P.Q.bins[(size_t)b * P.Q.capacity + (j - prefix[b])];
                 PT_BOUND(j - prefix[b] >= 0 && j - prefix[b] < P.Q.capacity && i >= 0 && i < count, PT_DBG_BIN);
             }
-            a = P.Q.ra[cur][2 * (size_t)i]; bq = P.Q.ra[cur][2 * (size_t)i + 1]; c = P.Q.r2[cur][i]; h = P.Q.hit[i];
+            ld256(P.Q.ra[cur] + 2 * (size_t)i, a, bq);          // the 32-byte ray pair = one sector, one 256-bit load
+            c = P.Q.r2[cur][i]; h = P.Q.hit[i];
         }
         bool emit_next = false;
         f3 no, nd, nthr;
@@ -866,8 +867,7 @@ __global__ void __launch_bounds__(PT_SHADE_THREADS, PT_SHADE_MINB) k_wf_shade(co
         const int pos = warp_agg_append(P.Q.qcount + nxt, 0, emit_next);
         if (emit_next) {
             PT_BOUND(pos >= 0 && pos < P.Q.capacity, PT_DBG_QUEUE);
-            P.Q.ra[nxt][2 * (size_t)pos] = make_float4(no.x, no.y, no.z, nd.x);
-            P.Q.ra[nxt][2 * (size_t)pos + 1] = make_float4(nd.y, nd.z, nthr.x, nthr.y);
+            st256(P.Q.ra[nxt] + 2 * (size_t)pos, make_float4(no.x, no.y, no.z, nd.x), make_float4(nd.y, nd.z, nthr.x, nthr.y));
             P.Q.r2[nxt][pos] = make_float4(nthr.z, __int_as_float(path_id), __uint_as_float(rng.s), __int_as_float(ndepth));
         }
     }
@@ -969,8 +969,7 @@ __global__ void __launch_bounds__(256, KIND == 0 ? 8 : (KIND == 1 ? 4 : 3)) k_wf
             const int pos = warp_agg_append(P.Q.qcount + nxt, 0, emit_next);       // one atomic per warp
             if (emit_next) {
                 PT_BOUND(pos >= 0 && pos < P.Q.capacity, PT_DBG_QUEUE);
-                P.Q.ra[nxt][2 * (size_t)pos] = make_float4(no.x, no.y, no.z, nd.x);
-                P.Q.ra[nxt][2 * (size_t)pos + 1] = make_float4(nd.y, nd.z, nthr.x, nthr.y);
+                st256(P.Q.ra[nxt] + 2 * (size_t)pos, make_float4(no.x, no.y, no.z, nd.x), make_float4(nd.y, nd.z, nthr.x, nthr.y));
                 P.Q.r2[nxt][pos] = make_float4(nthr.z, __int_as_float(path_id), __uint_as_float(rng.s), __int_as_float(ndepth));
             }
         }
@@ -1070,8 +1069,7 @@ __global__ void __launch_bounds__(PT_PRIMARY_THREADS, PT_PRIMARY_MINB) k_wf_prim
         if (emit_next) {
             PT_BOUND(pos >= 0 && pos < P.Q.capacity && id >= 0 && id < P.N * P.batch, PT_DBG_QUEUE);
             const int id2 = id;
-            P.Q.ra[qd][2 * (size_t)pos] = make_float4(no.x, no.y, no.z, nd.x);
-            P.Q.ra[qd][2 * (size_t)pos + 1] = make_float4(nd.y, nd.z, nthr.x, nthr.y);
+            st256(P.Q.ra[qd] + 2 * (size_t)pos, make_float4(no.x, no.y, no.z, nd.x), make_float4(nd.y, nd.z, nthr.x, nthr.y));
             P.Q.r2[qd][pos] = make_float4(nthr.z, __int_as_float(id2), __uint_as_float(rng.s), __int_as_float(ndepth));
         }
     }
@@ -1083,11 +1081,17 @@ __global__ void __launch_bounds__(PT_PRIMARY_THREADS, PT_PRIMARY_MINB) k_wf_prim
 __global__ void __launch_bounds__(256) k_make_rel_nodes(const float4* __restrict__ nodes, float4* __restrict__ rel, int num_inner,
                                                         float ox, float oy, float oz) {
     const int stride = gridDim.x * blockDim.x;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 4 * num_inner; i += stride) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kNodeQuads * num_inner; i += stride) {
         float4 v = nodes[i];
+#if PT_WIDE
+        const int row = i & 7, axis = row >> 1;          // rows 0..5: (min, max) of x, y, z; rows 6, 7: references
+        const float o = axis == 0 ? ox : (axis == 1 ? oy : oz);
+        if (row < 6) v = make_float4(v.x - o, v.y - o, v.z - o, v.w - o);
+#else
         const int row = i & 3;
         const float o = row == 0 ? ox : (row == 1 ? oy : oz);
         if (row < 3) v = make_float4(v.x - o, v.y - o, v.z - o, v.w - o);
+#endif
         rel[i] = v;
     }
 }
@@ -1454,6 +1458,8 @@ const char* pt_version(void) {
     return "b200pt 0.2 (sm_100a, PT-F32 fast: FMA + approximate reciprocal)";
 #elif PT_DEBUG_BOUNDS
     return "b200pt 0.2 (sm_100a, PT-F32 strict, debug-bounds build)";
+#elif PT_WIDE
+    return "b200pt 0.2 (sm_100a, PT-F32 strict, 4-wide BVH)";
 #else
     return "b200pt 0.2 (sm_100a, PT-F32 strict)";
 #endif
@@ -1565,6 +1571,8 @@ int pt_set_scene(PtContext* ctx, const void* device_blob, const PtPackedInfo* in
     // (and has_scene) exactly as they were.
     if (info->max_depth_tree > kStackSize)
         return set_error(PT_ERR_CAPACITY, "pt_set_scene: BVH deeper than the 64-entry traversal stack (kernels.py:649)");
+    if (info->node_bytes != kNodeBytes)
+        return set_error(PT_ERR_INVALID_ARG, "pt_set_scene: the blob was packed for another node layout (node_bytes)");
     if (info->num_inner < 0 || info->num_spheres < 0 || info->num_quads < 0 || info->num_triangles < 0 ||
         info->num_materials < 0 || info->num_images < 0 || info->num_images > PT_MAX_IMAGES)
         return set_error(PT_ERR_INVALID_ARG, "pt_set_scene: bad counts in PtPackedInfo");
@@ -1753,7 +1761,7 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
     // The origin-relative node copy of the primary wave (64 B per inner node) comes out of the caller's
     // workspace too, when that leaves room for at least one sample in flight; it is rebuilt by every
     // call (microseconds), so the context owns no device memory besides its counters.
-    size_t rel_bytes = align_up((size_t)ctx->scene.num_inner * 64, 256);
+    size_t rel_bytes = align_up((size_t)ctx->scene.num_inner * kNodeBytes, 256);
     if (workspace_bytes < kWfFixedBytes + rel_bytes + wf_bytes_per_sample(n)) rel_bytes = 0;
     // samples in flight: as many as the workspace holds (and the 31-bit path id allows)
     const size_t S_cap = (workspace_bytes - kWfFixedBytes - rel_bytes) / wf_bytes_per_sample(n);
@@ -1840,7 +1848,7 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
     bool rel = !PT_FAST && ctx->wf_rel_primary && ctx->wf_fuse_primary == 1 && !(ctx->cam.defocus_angle > 0.0f) &&
                ctx->scene.num_inner > 0 && ctx->cam.max_depth > 0 && !ctx->count && rel_nodes != nullptr;
     if (rel) {
-        int g = (int)(((size_t)ctx->scene.num_inner * 4 + 255) / 256);
+        int g = (int)(((size_t)ctx->scene.num_inner * kNodeQuads + 255) / 256);
         if (g > ctx->num_sms * 8) g = ctx->num_sms * 8;
         k_make_rel_nodes<<<g, 256, 0, static_cast<cudaStream_t>(stream)>>>(ctx->scene.nodes, rel_nodes, ctx->scene.num_inner,
                                                                           ctx->cam.center[0], ctx->cam.center[1], ctx->cam.center[2]);

@@ -333,6 +333,12 @@ constexpr int kStackSlots = kStackSize + PT_STACK_TOP;
 // to the lane-interleaved local array touches one 256-byte line per distinct depth in the warp and competes
 // with the node fetches for L1's tag stage (ncu round 1: 262 M local-memory sectors against 397 M global-load
 // sectors per wave-1 launch of k_wf_extend).
+// the entry distance of a stack entry: all of it (binary build) or without the two child-slot bits (wide build)
+#if PT_WIDE
+constexpr unsigned kDistMask = ~3u;
+#else
+constexpr unsigned kDistMask = ~0u;
+#endif
 struct LocalStack {
     StackEntry* p;
     __device__ __forceinline__ StackEntry load(int i) const { return p[i]; }
@@ -376,7 +382,7 @@ __device__ __forceinline__ int trav_pop(TravState& T, const STK& stack) {
     int next = kRefNone;
 #if PT_STACK_TOP
     while ((int)(unsigned)T.top != kRefNone) {
-        const bool take = __uint_as_float((unsigned)(T.top >> 32)) <= T.best_t;
+        const bool take = __uint_as_float((unsigned)(T.top >> 32) & kDistMask) <= T.best_t;
         const int cand = (int)(unsigned)T.top;
         // the old top is consumed above; the barrier keeps the compiler from hoisting the load over
         // those uses, so it can land in T.top's own registers and nothing waits for it here
@@ -389,7 +395,7 @@ __device__ __forceinline__ int trav_pop(TravState& T, const STK& stack) {
     while (T.sp > 0) {
         --T.sp;
         const StackEntry e = stack.load(T.sp);
-        if (__uint_as_float((unsigned)(e >> 32)) <= T.best_t) { next = (int)(unsigned)e; break; }
+        if (__uint_as_float((unsigned)(e >> 32) & kDistMask) <= T.best_t) { next = (int)(unsigned)e; break; }
     }
 #endif
     return next;
@@ -407,6 +413,23 @@ __device__ __forceinline__ int trav_pop(TravState& T, const STK& stack) {
 #ifndef PT_SNODES
 #define PT_SNODES 0
 #endif
+#ifndef PT_LDG256
+#define PT_LDG256 1
+#endif
+// two consecutive float4 (32-byte aligned) through the read-only path in one 256-bit load
+__device__ __forceinline__ void ldg256(const float4* p, float4& a, float4& b) {
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
+// ... and the plain (coherent) 256-bit load / store for queue records that other kernels write
+__device__ __forceinline__ void ld256(const float4* p, float4& a, float4& b) {
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void st256(float4* p, float4 a, float4 b) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+}
 typedef unsigned long long SNodeBase;
 __device__ __forceinline__ SNodeBase snode_base(const float4* s_node_mem) {
 #if PT_SNODES
@@ -428,11 +451,82 @@ __device__ __forceinline__ void load_node(const float4* __restrict__ nodes, SNod
     PT_BOUND(cur >= 0 && cur < n_nodes_dbg, PT_DBG_NODE);
     // one IMAD.WIDE: the 64-byte stride applied in 64-bit arithmetic (4 * cur as an int costs a shift first)
     const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const char*>(nodes) + (unsigned long long)(unsigned)cur * 64ull);
+#if PT_LDG256
+    // Blackwell's 256-bit global load (LDG.E.256, sm_100+): the 64-byte node in TWO load instructions instead of
+    // four -- half the LSU issue slots and half the L1 tag look-ups of a divergent fetch (every lane its own node)
+    float2 c2;
+    float pad0, pad1;
+    ldg256(p, nx, ny);
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(nz.x), "=f"(nz.y), "=f"(nz.z), "=f"(nz.w), "=f"(c2.x), "=f"(c2.y), "=f"(pad0), "=f"(pad1) : "l"(p + 2));
+#else
     nx = __ldg(p); ny = __ldg(p + 1); nz = __ldg(p + 2);
     const float2 c2 = __ldg(reinterpret_cast<const float2*>(p + 3));
 #endif
+#endif
     nc = make_float4(c2.x, c2.y, 0.0f, 0.0f);
 }
+
+#ifndef PT_WIDE
+#define PT_WIDE 0
+#endif
+#if PT_WIDE
+// ---- the 4-wide node visit (PT_WIDE=1 build): one 128-byte node = four 256-bit loads, four slab tests, the hit
+// children sorted by entry distance with a 5-comparator network on 32-bit keys (entry distance with the child slot in
+// its two lowest mantissa bits; distances are positive, so their bit patterns order like the numbers), the nearest
+// one descended into and the others pushed farthest first.  Returns the next node / leaf reference (or pops).
+constexpr int kNodeQuads = 8;        // float4 per node
+__device__ __forceinline__ unsigned umin2(unsigned a, unsigned b) { return a < b ? a : b; }
+__device__ __forceinline__ unsigned umax2(unsigned a, unsigned b) { return a > b ? a : b; }
+__device__ __forceinline__ int sel4(float4 r, unsigned slot) {
+    const float lo = (slot & 1u) ? r.y : r.x, hi = (slot & 1u) ? r.w : r.z;
+    return __float_as_int((slot & 2u) ? hi : lo);
+}
+template <bool REL, class STK>
+__device__ __forceinline__ int visit_wide(TravState& T, const float4* __restrict__ nodes, int cur, f3 o, f3 inv, f3 noi, float slack,
+                                          float t_min, const STK& stack, int n_nodes_dbg) {
+    PT_BOUND(cur >= 0 && cur < n_nodes_dbg, PT_DBG_NODE);
+    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const char*>(nodes) + (unsigned long long)(unsigned)cur * 128ull);
+    float4 mnx, mxx, mny, mxy, mnz, mxz, refs, pad;
+    ldg256(p, mnx, mxx);
+    ldg256(p + 2, mny, mxy);
+    ldg256(p + 4, mnz, mxz);
+    ldg256(p + 6, refs, pad);
+    const float best_t = T.best_t;
+    unsigned key[4];
+#define PT_WIDE_CHILD(K, C)                                                                                          \
+    {                                                                                                                \
+        float a0, a1, b0, b1, c0, c1;                                                                                \
+        if (REL) {                                                                                                   \
+            a0 = mnx.C * inv.x; a1 = mxx.C * inv.x; b0 = mny.C * inv.y; b1 = mxy.C * inv.y; c0 = mnz.C * inv.z; c1 = mxz.C * inv.z; \
+        } else {                                                                                                     \
+            a0 = PT_SLAB(mnx.C, o.x, inv.x, noi.x); a1 = PT_SLAB(mxx.C, o.x, inv.x, noi.x);                          \
+            b0 = PT_SLAB(mny.C, o.y, inv.y, noi.y); b1 = PT_SLAB(mxy.C, o.y, inv.y, noi.y);                          \
+            c0 = PT_SLAB(mnz.C, o.z, inv.z, noi.z); c1 = PT_SLAB(mxz.C, o.z, inv.z, noi.z);                          \
+        }                                                                                                            \
+        const float tn = fmax3(fminf(a0, a1), fminf(b0, b1), fmaxf(fminf(c0, c1), t_min));                           \
+        const float tf = fmin3(fmaxf(a0, a1), fmaxf(b0, b1), fminf(fmaxf(c0, c1), best_t));                          \
+        key[K] = PT_BOX_HIT(tf, tn, slack) ? ((__float_as_uint(tn) & ~3u) | (unsigned)(K)) : 0xffffffffu;            \
+    }
+    PT_WIDE_CHILD(0, x)
+    PT_WIDE_CHILD(1, y)
+    PT_WIDE_CHILD(2, z)
+    PT_WIDE_CHILD(3, w)
+#undef PT_WIDE_CHILD
+    // sorting network (0,1)(2,3)(0,2)(1,3)(1,2): ascending, misses (0xffffffff) last
+    unsigned a = umin2(key[0], key[1]), b = umax2(key[0], key[1]), c = umin2(key[2], key[3]), d = umax2(key[2], key[3]);
+    const unsigned k0 = umin2(a, c), m1 = umax2(a, c), m2 = umin2(b, d), k3 = umax2(b, d);
+    const unsigned k1 = umin2(m1, m2), k2 = umax2(m1, m2);
+    if (k0 == 0xffffffffu) return trav_pop(T, stack);
+    // farthest first, so that the nearest deferred child is popped first; the key (distance, low bits = slot) rides in the entry
+    if (k3 != 0xffffffffu) trav_push(T, stack, ((StackEntry)k3 << 32) | (StackEntry)(unsigned)sel4(refs, k3 & 3u));
+    if (k2 != 0xffffffffu) trav_push(T, stack, ((StackEntry)k2 << 32) | (StackEntry)(unsigned)sel4(refs, k2 & 3u));
+    if (k1 != 0xffffffffu) trav_push(T, stack, ((StackEntry)k1 << 32) | (StackEntry)(unsigned)sel4(refs, k1 & 3u));
+    return sel4(refs, k0 & 3u);
+}
+#else
+constexpr int kNodeQuads = 4;
+#endif
 
 // Runs the traversal until it finishes (returns true) or, when min_active > 0, until fewer than
 // min_active lanes of the warp are still inside the loop (returns false; call again to resume).
@@ -455,6 +549,11 @@ __device__ __forceinline__ bool trav_run(TravState& T, const DScene& S, SNodeBas
     const float4* const nodes = S.nodes;
     while (T.cur != kRefNone) {
         while (T.cur >= 0) {
+#if PT_WIDE
+            if (COUNT) lc.box_tests += 4;
+            T.cur = visit_wide<REL>(T, nodes, T.cur, o, inv, noi, slack, t_min, stack, S.num_inner);
+            continue;
+#endif
             float4 nx, ny, nz, nc;
             load_node(nodes, s_nodes, n_snodes, T.cur, nx, ny, nz, nc, S.num_inner);
             if (COUNT) lc.box_tests += 2;
@@ -544,6 +643,12 @@ __device__ __forceinline__ void trav_run_vote(TravState& T, bool active, bool& d
         }
         progressed = true;
         if (do_node) {
+#if PT_WIDE
+            if (want_node) {
+                if (COUNT) lc.box_tests += 4;
+                cur = visit_wide<false>(T, nodes, cur, o, inv, noi, slack, t_min, stack, S.num_inner);
+            }
+#else
             if (want_node) {
                 float4 nx, ny, nz, nc;
                 load_node(nodes, s_nodes, n_snodes, cur, nx, ny, nz, nc, S.num_inner);
@@ -574,6 +679,7 @@ __device__ __forceinline__ void trav_run_vote(TravState& T, bool active, bool& d
                     cur = trav_pop(T, stack);
                 }
             }
+#endif
         } else {
             if ((unsigned)cur > (unsigned)kRefNone) {
                 const int type = ref_type(cur), idx = ref_index(cur);

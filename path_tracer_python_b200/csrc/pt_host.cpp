@@ -201,6 +201,84 @@ int validate_scene(const PtHostScene* s) {
     return PT_OK;
 }
 
+#ifndef PT_WIDE
+#define PT_WIDE 0
+#endif
+#if PT_WIDE
+// ---- 4-wide collapse of the reference's binary tree (SURVEY.md section 8f N1 "optionally wide / collapsed 4-ary").
+// A wide node takes a binary inner node's two children and, while it has fewer than four, replaces the inner
+// child with the largest surface area by that child's own two children.  Child boxes are the reference's node
+// boxes, unchanged; skipped intermediate boxes enclose the ones kept, and the slab test is monotone in the box
+// (rounding is monotone), so a ray reaches exactly the leaves whose own boxes it passes -- the same set as in
+// the binary tree: closest-hit t is unchanged, primitive ids up to exact-t ties.
+struct Wide {
+    int kid[4];   // reference node index of each child, -1 = empty slot
+    int n;
+};
+struct Collapsed4 {
+    std::vector<Wide> nodes;         // breadth-first
+    std::vector<int> wide_of;        // reference inner node -> wide index (for the ones that head a wide node)
+    int depth = 0;                   // levels of wide nodes
+};
+inline float box_area(const PtHostScene* s, int ni) {
+    const float dx = s->bvh_bbox_max[3 * ni] - s->bvh_bbox_min[3 * ni], dy = s->bvh_bbox_max[3 * ni + 1] - s->bvh_bbox_min[3 * ni + 1],
+                dz = s->bvh_bbox_max[3 * ni + 2] - s->bvh_bbox_min[3 * ni + 2];
+    return dx * dy + dy * dz + dz * dx;
+}
+int collapse4(const PtHostScene* s, Collapsed4& c) {
+    const int n = s->num_nodes;
+    c.wide_of.assign(n > 0 ? n : 0, -1);
+    if (n == 0) return PT_OK;
+    auto is_leaf = [&](int ni) { return s->bvh_prim_idx[ni] >= 0; };
+    std::vector<int> level{0}, next;
+    if (is_leaf(0)) {                       // a one-primitive scene: one wide node with that leaf
+        c.nodes.push_back(Wide{{0, -1, -1, -1}, 1});
+        c.depth = 1;
+        return PT_OK;
+    }
+    c.wide_of[0] = 0;
+    c.nodes.push_back(Wide{{-1, -1, -1, -1}, 0});
+    while (!level.empty()) {
+        c.depth++;
+        if (c.depth > 4096) { g_host_error = "BVH has a cycle"; return PT_ERR_INVALID_ARG; }
+        next.clear();
+        for (int head : level) {
+            std::vector<int> kids;
+            for (int ch : {s->bvh_left[head], s->bvh_right[head]}) {
+                if (ch < 0) continue;
+                if (ch >= n) { g_host_error = "BVH child index out of range"; return PT_ERR_INVALID_ARG; }
+                kids.push_back(ch);
+            }
+            if (kids.empty()) { g_host_error = "BVH inner node without children"; return PT_ERR_INVALID_ARG; }
+            while (kids.size() < 4) {
+                int best = -1;
+                float best_area = -1.0f;
+                for (size_t k = 0; k < kids.size(); k++)
+                    if (!is_leaf(kids[k]) && box_area(s, kids[k]) > best_area) { best = (int)k; best_area = box_area(s, kids[k]); }
+                if (best < 0) break;
+                const int open = kids[best], l = s->bvh_left[open], r = s->bvh_right[open];
+                if ((l < 0 && r < 0) || l >= n || r >= n) { g_host_error = "BVH inner node with bad children"; return PT_ERR_INVALID_ARG; }
+                kids.erase(kids.begin() + best);
+                if (l >= 0) kids.push_back(l);
+                if (r >= 0) kids.push_back(r);
+            }
+            Wide w{{-1, -1, -1, -1}, (int)kids.size()};
+            for (size_t k = 0; k < kids.size(); k++) {
+                w.kid[k] = kids[k];
+                if (!is_leaf(kids[k])) {
+                    c.wide_of[kids[k]] = (int)c.nodes.size();
+                    c.nodes.push_back(Wide{{-1, -1, -1, -1}, 0});
+                    next.push_back(kids[k]);
+                }
+            }
+            c.nodes[c.wide_of[head]] = w;
+        }
+        level.swap(next);
+    }
+    return PT_OK;
+}
+#endif
+
 }  // namespace
 
 extern "C" {
@@ -218,22 +296,37 @@ int pt_pack_scene_info(const PtHostScene* s, PtPackedInfo* info) {
     memset(info, 0, sizeof *info);
     int rc = validate_scene(s);
     if (rc) return rc;
+#if PT_WIDE
+    Collapsed4 c;
+    rc = collapse4(s, c);
+    if (rc) return rc;
+    MatTable mt;
+    build_materials(s, mt);
+    info->num_inner = (int)c.nodes.size();
+    info->node_bytes = 128;
+#else
     Collapsed c;
     rc = collapse(s, c);
     if (rc) return rc;
     MatTable mt;
     build_materials(s, mt);
     info->num_inner = c.root_is_leaf ? 1 : (int)c.order.size();
+    info->node_bytes = 64;
+#endif
     info->num_spheres = s->num_spheres;
     info->num_quads = s->num_quads;
     info->num_triangles = s->num_triangles;
     info->num_materials = (int)mt.recs.size();
     info->num_images = s->num_images;
+#if PT_WIDE
+    info->max_depth_tree = c.depth > 0 ? 3 * c.depth + 1 : 0;     // stack slots a 4-wide traversal can need (3 deferred children per level)
+#else
     info->max_depth_tree = c.depth;
+#endif
     info->has_media = mt.has_media;
     uint64_t off = 0;
     auto section = [&](uint64_t bytes) { uint64_t o = off; off = align_up(off + bytes, 256); return o; };
-    info->off_nodes = section((uint64_t)info->num_inner * 64);
+    info->off_nodes = section((uint64_t)info->num_inner * (uint64_t)info->node_bytes);
     info->off_spheres = section((uint64_t)s->num_spheres * 16);
     info->off_quads = section((uint64_t)s->num_quads * 64);
     info->off_tris = section((uint64_t)s->num_triangles * 48);
@@ -262,6 +355,37 @@ int pt_pack_scene(const PtHostScene* s, const PtPackedInfo* info, void* host_blo
     int rc = validate_scene(s);
     if (rc) return rc;
     memset(base, 0, info->total_bytes);
+#if PT_WIDE
+    // ---- nodes, 128 B: (min.x of the 4 children)(max.x)(min.y)(max.y)(min.z)(max.z)(4 child refs)(unused).
+    //      An empty slot holds a box no ray can pass (a point at 1e30) and the "none" reference.
+    {
+        Collapsed4 c;
+        rc = collapse4(s, c);
+        if (rc) return rc;
+        if ((int)c.nodes.size() != info->num_inner) { g_host_error = "pt_pack_scene: info does not match scene"; return PT_ERR_INVALID_ARG; }
+        float* nodes = reinterpret_cast<float*>(base + info->off_nodes);
+        for (size_t w = 0; w < c.nodes.size(); w++) {
+            float* p = nodes + 32 * w;
+            for (int k = 0; k < 4; k++) {
+                const int ni = c.nodes[w].kid[k];
+                int ref = kRefNone;
+                for (int a = 0; a < 3; a++) {
+                    p[8 * a + k] = ni < 0 ? 1e30f : s->bvh_bbox_min[3 * ni + a];
+                    p[8 * a + 4 + k] = ni < 0 ? 1e30f : s->bvh_bbox_max[3 * ni + a];
+                }
+                if (ni >= 0) {
+                    if (s->bvh_prim_idx[ni] >= 0) {
+                        const int pt = s->bvh_prim_type[ni], pi = s->bvh_prim_idx[ni];
+                        ref = leaf_ref(pt, pi, shading_class(s->mat[pt], pi));
+                    } else {
+                        ref = c.wide_of[ni];
+                    }
+                }
+                memcpy(p + 24 + k, &ref, 4);
+            }
+        }
+    }
+#else
     Collapsed c;
     rc = collapse(s, c);
     if (rc) return rc;
@@ -295,6 +419,7 @@ int pt_pack_scene(const PtHostScene* s, const PtPackedInfo* info, void* host_blo
     } else {
         for (size_t k = 0; k < c.order.size(); k++) write_node((int)k, s->bvh_left[c.order[k]], s->bvh_right[c.order[k]]);
     }
+#endif
 
     // ---- primitives
     if (s->num_spheres) memcpy(base + info->off_spheres, s->sphere_data, (size_t)s->num_spheres * 16);

@@ -145,7 +145,7 @@ class Engine:
                 b *= self.wavefront_pipelines
         else:
             b = max(1, min(self.wavefront_samples_in_flight, sample_count))
-        extra = 64 * int(self.info.num_inner) + 256 if self.info is not None else 0     # origin-relative node copy
+        extra = int(self.info.node_bytes) * int(self.info.num_inner) + 256 if self.info is not None else 0     # origin-relative node copy
         need = int(self.L.pt_wavefront_workspace_bytes_for(W, y1 - y0, b)) + extra
         while b > 1 and need > self.max_workspace_bytes:
             b -= 1

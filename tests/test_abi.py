@@ -10,11 +10,11 @@ from path_tracer_python_b200 import _lib, build
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.fixture(scope="module", params=["strict", "fast", "debug"])
+@pytest.fixture(scope="module", params=["strict", "fast", "debug", "wide"])
 def L(request):
     """All builds of the library: the strict (parity) one, the fast-numerics variant and the debug-bounds variant
     of the same sources."""
-    {"strict": build.build_native, "fast": build.build_fast, "debug": build.build_debug}[request.param]()
+    {"strict": build.build_native, "fast": build.build_fast, "debug": build.build_debug, "wide": build.build_wide}[request.param]()
     return _lib.lib(request.param)
 
 
