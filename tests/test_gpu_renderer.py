@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 import torch
 
+import golden_fixtures
 from conftest import GOLDEN_SCENES
 
 pytestmark = pytest.mark.gpu
@@ -335,3 +336,63 @@ def test_interleaved_row_windows_compose_to_the_full_frame(mode):
         assert torch.equal(tiles, full), (block, world)
     with pytest.raises(Exception, match="power of two"):
         e.set_row_interleave(6, 12)
+
+
+def test_progressive_preview_never_stalls_and_shows_finished_frames(monkeypatch):
+    """The output step after the hot path: render(enable_preview=True) tonemaps on the device and
+    copies the 8-bit frame to pinned memory on a side stream (renderer._preview_frame_async); the window -- a stub
+    here, there is no display on the box -- receives only completed frames, each equal to buffer_to_image of the
+    accumulation buffer after some whole number of samples, in increasing order, and the final image is unaffected."""
+    from path_tracer_python_b200 import preview
+
+    shown = []
+
+    class StubPreview:
+        def __init__(self, w, h, title=""):
+            self.size = (w, h)
+
+        def start(self, update_interval_ms=50):
+            pass
+
+        def update_image(self, img):
+            shown.append(np.array(img, copy=True))
+
+        def process_events(self):
+            torch.cuda.synchronize()          # "the GUI took a while": lets the side-stream copy finish
+
+        def finish(self):
+            pass
+
+    monkeypatch.setattr(preview, "LivePreview", StubPreview)
+    _, gmeta, out = golden_fixtures.load_fixture("wavefront_comparison")
+    spp = 6
+    r, cs, meta = _renderer(spp=spp, seed=gmeta["rng_seed"])
+    r.background_color = gmeta["background"]
+    r.render(enable_preview=True)                      # one sample per launch, a preview frame after each
+    final = r.accum_numpy()
+    # reference frames: the accumulation buffer after k samples, tonemapped like preview.py:117-132
+    e = r.engine
+    frames = []
+    acc = e.new_accum(r.cam.img_width, r.cam.img_height)
+    for k in range(spp):
+        e.render_megakernel(acc, k, 1, gmeta["rng_seed"])
+        frames.append(preview.buffer_to_image(acc.cpu().numpy(), k + 1))
+    assert np.array_equal(final, acc.cpu().numpy())
+    assert len(r.sample_times) == spp and 1 <= len(shown) <= spp
+    last = -1
+    for img in shown:
+        match = [k for k, f in enumerate(frames) if np.array_equal(f, img)]
+        assert match, "a preview frame that is not the tonemap of any whole-sample state"
+        assert match[0] > last - 1
+        last = match[0]
+    # the async path itself: nothing ready on the first call, the first frame on a later one
+    r2, _, _ = _renderer(spp=2, seed=1)
+    r2.engine.render_megakernel(r2._accum, 0, 1, 1)
+    r2.current_sample = 1
+    want = preview.buffer_to_image(r2.accum_numpy(), 1)
+    assert r2._preview_frame_async() is None
+    torch.cuda.synchronize()
+    r2.engine.render_megakernel(r2._accum, 1, 1, 1)
+    r2.current_sample = 2
+    got = r2._preview_frame_async()
+    assert got is not None and np.array_equal(got, want)
