@@ -56,7 +56,7 @@ v = lambda a: [a.x, a.y, a.z]
 meta = {"width": 1024, "height": cam.img_height, "background": (0, 0, 0), "max_depth": 50,
         "camera": {"cam_center": v(cam.center), "cam_pixel00": v(cam.pixel00_loc), "cam_delta_u": v(cam.delta_u), "cam_delta_v": v(cam.delta_v),
                    "cam_defocus_disk_u": v(cam.defocus_disk_u), "cam_defocus_disk_v": v(cam.defocus_disk_v), "cam_defocus_angle": 0.0}}
-render_line("4: Cornell+medium+glass+SSS-as-Lambert 1024x1024 64spp (of 4096)", cs, meta, 64)
+render_line("4: Cornell+medium+glass+SSS-as-Lambert 1024x1024 4096spp (the full BASELINE config)", cs, meta, 4096)
 
-# config 5 (single GPU share): vol2_final_scene 3840x2160, 32 spp
-render_line("5: vol2_final_scene 3840x2160 32spp (1-GPU share of 1024)", *golden_fixtures.load_config("vol2_final_scene", 3840, 16 / 9), 32)
+# config 5 (one GPU's share at N = 8): vol2_final_scene 3840x2160, 128 spp -- bench.py times the whole 1024 spp at every N
+render_line("5: vol2_final_scene 3840x2160 128spp (the 1/8 share of 1024)", *golden_fixtures.load_config("vol2_final_scene", 3840, 16 / 9), 128)

@@ -28,13 +28,10 @@ for r in rows[1:]:
     unit = r[ix["Metric Unit"]]
     d["m"][r[ix["Metric Name"]]] = float(r[ix["Metric Value"]].replace(",", "")) * scale.get(unit, 1)
 ids = sorted(launches)
-# the measured call = the launches after the last burst of warm-up: find the last k_wf_reset that is followed by the most launches
+# profile_run.py makes 2 one-sample warm-up calls (one batch = one k_wf_reset each), then the measured call of SPP
+# samples (one reset per batch, however many batches the engine splits it into): count from the third reset on
 resets = [i for i in ids if "k_wf_reset" in launches[i]["kernel"]]
-first = resets[-1] if resets else ids[0]
-# a multi-batch call has several resets: walk back while the previous reset belongs to the same call (SPP > batch)
-n_batches = max(1, -(-spp // 32))
-if len(resets) >= n_batches:
-    first = resets[-n_batches]
+first = resets[2] if len(resets) > 2 else (resets[-1] if resets else ids[0])
 per = {}
 for i in ids:
     if i < first:

@@ -13,6 +13,10 @@ e = Engine(0)
 for k in ("smem_nodes", "block_threads"):
     if k.upper() in os.environ:
         e.set_option(k, int(os.environ[k.upper()]))
+for k, v in [kv.split("=") for kv in os.environ.get("OPTS", "").split(",") if kv]:     # e.g. OPTS=wf_overlap=0: one pipeline, one batch
+    e.set_option(k, int(v))
+if os.environ.get("FLIGHT"):
+    e.wavefront_samples_in_flight = int(os.environ["FLIGHT"])
 cs, meta = golden_fixtures.load_config("vol2_final_scene", W, 16 / 9)
 e.set_scene(cs); e.set_camera(meta["camera"], (0, 0, 0), 50)
 H = meta["height"]
