@@ -80,8 +80,11 @@ typedef struct PtHostScene {
     int32_t image_w[PT_MAX_IMAGES], image_h[PT_MAX_IMAGES];
     /* "full" feature mode -- what the Taichi path dropped but src/core renders: */
     const float* sphere_motion;                                 /* [n][3] centre(1)-centre(0) (core/sphere.py:22-36) or NULL */
-    int32_t full_features;                                      /* 0 = taichi_compat; 1 = moving spheres + material types 5/6
-                                                                 * (subsurface_simple / _volumetric, core/material.py:144-276) */
+    int32_t full_features;                                      /* bit field; 0 = taichi_compat.  Bit 0: moving spheres + material
+                                                                 * types 5/6 (subsurface_simple / _volumetric, core/material.py:
+                                                                 * 144-276).  Bit 1: next-event estimation at Lambertian hits
+                                                                 * (the technique docs/optimizations.md:53 claims and
+                                                                 * docs/__optimizations.md:7-10 lists as missing) */
 } PtHostScene;
 
 /* Layout of the packed device blob.  Offsets are bytes from blob start,
@@ -104,6 +107,9 @@ typedef struct PtPackedInfo {
     uint64_t off_sphere_motion; /* num_spheres * 16 B, present iff full_features */
     int32_t full_features;
     int32_t node_bytes;      /* bytes per packed node: 64 (two children per node) or 128 (the 4-wide build, -DPT_WIDE=1) */
+    uint64_t off_lights;     /* num_lights * 32 B: (leaf ref, area, emit.rg)(emit.b, -, -, -) per emissive primitive */
+    int32_t num_lights;
+    float nee_r2;            /* squared switch-over distance of the next-event estimator: 0.25 * mean emitter area */
 } PtPackedInfo;
 
 /* Camera + render settings: what _upload_camera writes (renderer.py:230-247; fields.py:159-172) */

@@ -122,11 +122,21 @@ struct Hit {
     int prim_type, prim_idx;
 };
 
+/* next-event estimation (full_features bit 1): one record per emissive primitive that is not a medium boundary */
+struct OLight {
+    int prim_type, prim_idx;
+    float area;
+    V3 emit;
+};
+
 struct Ctx {
     const OScene* sc;
     const OCamera* cam;
     OCounters cnt;
     float time = 0.0f;   /* shutter time of the path being traced (full-feature mode) */
+    const OLight* lights = nullptr;
+    int n_lights = 0;
+    float nee_r2 = 0.0f;   /* squared switch-over distance between light sampling and the scattered ray (nee_direct) */
 };
 
 /* centre of sphere idx at the current path's time: Ray.at(time) = origin + time * direction
@@ -604,6 +614,106 @@ MediumResult apply_constant_medium(Ctx& c, int prim_type, int prim_idx, V3 o, V3
     return r;
 }
 
+/* ---- next-event estimation (features "nee"; no counterpart in the reference's code -- its docs claim it,
+ * docs/optimizations.md:53, and list it as missing, docs/__optimizations.md:7-10).  This is the CPU twin of
+ * pt_device.cuh nee_direct(), operation for operation: at a Lambertian hit one emitter is chosen uniformly, a point
+ * on it is sampled uniformly by area and its radiance added if the shadow ray reaches it,
+ *     L = albedo/pi * Le * cos_s * cos_l / dist^2 * (area * n_lights) * T,
+ * where the shadow ray follows the reference's constant-medium semantics (kernels.py:365-450, :1100-1119): a medium
+ * boundary is a transmittance exp(-density * length inside), "inside" ends at the next hit of any primitive and the
+ * ray continues beyond it; an exit search that finds nothing makes the boundary an (opaque) surface. */
+void build_lights(const OScene* sc, std::vector<OLight>& out) {
+    const int counts[3] = {sc->num_spheres, sc->num_triangles, sc->num_quads};
+    for (int pt = 0; pt < 3; pt++) {
+        const OMaterials& m = sc->mat[pt];
+        for (int i = 0; i < counts[pt]; i++) {
+            if (m.material_type[i] != 3 || m.is_medium[i] > 0) continue;
+            const float* e = m.emit + 3 * i;
+            if (!(e[0] > 0.0f || e[1] > 0.0f || e[2] > 0.0f)) continue;
+            double area = 0.0;
+            if (pt == 0) {
+                const double r = sc->sphere_data[4 * i + 3];
+                area = 4.0 * 3.14159265358979323846 * r * r;
+            } else {
+                const float* a = pt == 2 ? sc->quad_u + 3 * i : sc->tri_edge1 + 3 * i;
+                const float* b = pt == 2 ? sc->quad_v + 3 * i : sc->tri_edge2 + 3 * i;
+                const double cx = (double)a[1] * b[2] - (double)a[2] * b[1], cy = (double)a[2] * b[0] - (double)a[0] * b[2],
+                             cz = (double)a[0] * b[1] - (double)a[1] * b[0];
+                area = sqrt(cx * cx + cy * cy + cz * cz) * (pt == 2 ? 1.0 : 0.5);
+            }
+            if (!(area > 0.0)) continue;
+            out.push_back(OLight{pt, i, (float)area, v3(e[0], e[1], e[2])});
+        }
+    }
+}
+inline bool nee_on(const Ctx& c) { return (c.sc->full_features & 2) != 0 && c.n_lights > 0; }
+/* 0.25 * mean emitter area: (vertex, emitter point) pairs farther apart than its square root are estimated by light
+ * sampling, closer ones by the cosine-sampled ray hitting the emitter -- a partition of unity, so each pair is counted
+ * exactly once (area sampling has unbounded variance for an emitter that is close) */
+float nee_switch_r2(const std::vector<OLight>& lights) {
+    double sum = 0.0;
+    for (const OLight& l : lights) sum += (double)l.area;
+    return lights.empty() ? 0.0f : (float)(0.25 * (sum / (double)lights.size()));
+}
+
+V3 nee_direct(Ctx& c, V3 hp, V3 n_s, V3 albedo, Rng& rng) {
+    const OScene* sc = c.sc;
+    const V3 zero = v3(0, 0, 0);
+    int li = (int)(rng.next() * (float)c.n_lights);
+    li = li < c.n_lights ? li : c.n_lights - 1;
+    const OLight& L = c.lights[li];
+    V3 y, nl;
+    if (L.prim_type == 0) {
+        V3 dirn = random_unit_vector(rng);
+        y = sphere_center(c, L.prim_idx) + sc->sphere_data[4 * L.prim_idx + 3] * dirn;
+        nl = dirn;
+    } else if (L.prim_type == 2) {
+        float a = rng.next(), b = rng.next();
+        y = (ld3(sc->quad_Q + 3 * L.prim_idx) + a * ld3(sc->quad_u + 3 * L.prim_idx)) + b * ld3(sc->quad_v + 3 * L.prim_idx);
+        nl = ld3(sc->quad_normal + 3 * L.prim_idx);
+    } else {
+        float r1 = rng.next(), r2 = rng.next();
+        if (r1 + r2 > 1.0f) { r1 = 1.0f - r1; r2 = 1.0f - r2; }
+        y = (ld3(sc->tri_v0 + 3 * L.prim_idx) + r1 * ld3(sc->tri_edge1 + 3 * L.prim_idx)) + r2 * ld3(sc->tri_edge2 + 3 * L.prim_idx);
+        nl = ld3(sc->tri_normal + 3 * L.prim_idx);
+    }
+    V3 dv = y - hp;
+    float dist2 = dot(dv, dv);
+    if (!(dist2 > 1e-12f)) return zero;
+    const bool close = !(dist2 >= c.nee_r2);   /* close pairs belong to the scattered ray, unless a medium lies between */
+    bool crossed = false;
+    float dist = sqrtf(dist2);
+    V3 wi = dv / dist;
+    float cos_s = dot(n_s, wi), cos_l = fabsf(dot(nl, wi));
+    if (!(cos_s > 0.0f) || !(cos_l > 0.0f)) return zero;
+    const float t_end = dist * 0.9999f;
+    const float len = sqrtf(dot(wi, wi));
+    float trans = 1.0f, t_cur = 0.001f;
+    OCounters saved = c.cnt;                                   /* shadow rays are not counted (nor are they on the device) */
+    for (int seg = 0; seg < 16; seg++) {
+        if (!(t_cur < t_end)) break;
+        Hit h = traverse_bvh(c, hp, wi, t_cur, t_end);
+        if (!h.hit) break;
+        if (!(sc->mat[h.prim_type].is_medium[h.prim_idx] > 0)) { c.cnt = saved; return zero; }
+        Hit e = traverse_bvh(c, hp, wi, h.t + 0.0001f, 1e10f);
+        if (!e.hit) { c.cnt = saved; return zero; }
+        crossed = true;
+        float density = sc->mat[h.prim_type].medium_density[h.prim_idx];
+        float t1 = fmax2(h.t, 0.001f), t2 = fmin2(e.t, t_end);
+        if (t1 < t2) trans = trans * o_expf(-(density * ((t2 - t1) * len)));
+        /* the "inside" interval reaches the emitter itself: a ray that passes such an interval continues BEYOND its closing
+         * surface (kernels.py:1108), i.e. it never sees this point of the emitter (a sphere is then seen from inside, at
+         * its far side -- the pair this loop reaches when the sampled point lies there) */
+        if (!(e.t < t_end)) { c.cnt = saved; return zero; }
+        t_cur = e.t + 0.001f / len;
+        if (seg == 15) { c.cnt = saved; return zero; }
+    }
+    c.cnt = saved;
+    if (close && !crossed) return zero;
+    float geom = (((cos_s * cos_l) * L.area) * (float)c.n_lights) / (3.14159265358979f * dist2);
+    return (albedo * L.emit) * (geom * trans);
+}
+
 /* kernels.py:1024-1170 */
 V3 trace_ray(Ctx& c, V3 ray_origin, V3 ray_dir, Rng& rng) {
     const OScene* sc = c.sc;
@@ -612,12 +722,15 @@ V3 trace_ray(Ctx& c, V3 ray_origin, V3 ray_dir, Rng& rng) {
     V3 throughput = v3(1, 1, 1);
     V3 cur_o = ray_origin;
     V3 cur_d = normalized(ray_dir);
+    const bool nee = nee_on(c);
+    int prev_nee = 0;   /* 1: the last scatter was a Lambertian vertex with next-event estimation; 2: ... and the ray has
+                         * passed through a medium since (pairs across a medium always belong to the light sampler) */
     for (int depth = 0; depth < max_depth; depth++) {
         c.cnt.bounces++;
         Hit h = traverse_bvh(c, cur_o, cur_d, 0.001f, 1e10f);
         if (h.hit) {
             int is_cm = sc->mat[h.prim_type].is_medium[h.prim_idx];
-            bool scattered = false;
+            bool scattered = false, did_nee = false, surface = false;
             V3 scatter_dir = v3(0, 0, 0), attenuation = v3(1, 1, 1);
             bool volume_passthrough = false;
             V3 hit_point = h.p, normal = h.n;
@@ -635,15 +748,21 @@ V3 trace_ray(Ctx& c, V3 ray_origin, V3 ray_dir, Rng& rng) {
                     float epsilon_t = 0.001f / ray_length;
                     cur_o = cur_o + cur_d * (mr.t_exit + epsilon_t);
                 } else {
-                    V3 emit = emitted(sc, h.prim_type, h.prim_idx);
-                    color = color + throughput * emit;
-                    scattered = scatter(sc, cur_d, hit_point, normal, h.prim_type, h.prim_idx, rng, &scatter_dir, &attenuation, &hit_point);
+                    surface = true;
                 }
             } else {
+                surface = true;
+            }
+            if (surface) {
+                if (nee && sc->mat[h.prim_type].material_type[h.prim_idx] == 0) {
+                    color = color + throughput * nee_direct(c, hit_point, normal, eval_texture(sc, h.prim_type, h.prim_idx, hit_point), rng);
+                    did_nee = true;
+                }
                 V3 emit = emitted(sc, h.prim_type, h.prim_idx);
-                color = color + throughput * emit;
+                if (prev_nee == 0 || (prev_nee == 1 && (h.t * h.t) * dot(cur_d, cur_d) < c.nee_r2)) color = color + throughput * emit;
                 scattered = scatter(sc, cur_d, hit_point, normal, h.prim_type, h.prim_idx, rng, &scatter_dir, &attenuation, &hit_point);
             }
+            if (nee) prev_nee = volume_passthrough ? (prev_nee != 0 ? 2 : 0) : (did_nee ? 1 : 0);
             if (scattered) {
                 cur_o = hit_point;     /* = the hit point, or the displaced exit point of a subsurface material */
                 cur_d = scatter_dir;
@@ -768,6 +887,8 @@ void o_render_megakernel(const OScene* sc, const OCamera* cam, int W, int H, int
                          int sample_count, uint32_t seed, float* accum, OCounters* counters, int nthreads) {
     OCounters total;
     memset(&total, 0, sizeof total);
+    std::vector<OLight> lights;
+    if (sc->full_features & 2) build_lights(sc, lights);
 #ifdef _OPENMP
     if (nthreads > 0) omp_set_num_threads(nthreads);
 #endif
@@ -776,6 +897,9 @@ void o_render_megakernel(const OScene* sc, const OCamera* cam, int W, int H, int
         Ctx c;
         c.sc = sc;
         c.cam = cam;
+        c.lights = lights.data();
+        c.n_lights = (int)lights.size();
+        c.nee_r2 = nee_switch_r2(lights);
         memset(&c.cnt, 0, sizeof c.cnt);
 #pragma omp for schedule(dynamic, 1)
         for (int py = y0; py < y1; py++)
@@ -811,6 +935,8 @@ void o_render_wavefront(const OScene* sc, const OCamera* cam, int W, int H, int 
     OCounters total;
     memset(&total, 0, sizeof total);
     const int max_depth = cam->max_depth;
+    std::vector<OLight> lights;
+    if (sc->full_features & 2) build_lights(sc, lights);
 #ifdef _OPENMP
     if (nthreads > 0) omp_set_num_threads(nthreads);
 #endif
@@ -819,6 +945,9 @@ void o_render_wavefront(const OScene* sc, const OCamera* cam, int W, int H, int 
         Ctx c;
         c.sc = sc;
         c.cam = cam;
+        c.lights = lights.data();
+        c.n_lights = (int)lights.size();
+        c.nee_r2 = nee_switch_r2(lights);
         memset(&c.cnt, 0, sizeof c.cnt);
 #pragma omp for schedule(dynamic, 1)
         for (int py = y0; py < y1; py++)
@@ -835,20 +964,26 @@ void o_render_wavefront(const OScene* sc, const OCamera* cam, int W, int H, int 
                     V3 thr = v3(1, 1, 1);
                     int depth = 0;
                     bool active = true;
+                    const bool nee = nee_on(c);
+                    int prev_nee = 0;
+                    /* the path's radiance is summed on its own and added to the pixel when the path ends (the device
+                     * keeps it in a per-path slab that k_wf_resolve adds in sample order): with one contribution per
+                     * path -- the reference's estimator -- that is the same sum as adding each event straight away */
+                    V3 pc = v3(0, 0, 0);
                     for (int bounce = 0; bounce < max_depth && active; bounce++) { /* renderer.py:313 */
                         c.cnt.bounces++;
                         /* intersect_rays */
                         Hit h = traverse_bvh(c, ro, rd, 0.001f, 1e10f);
                         if (!h.hit) { /* shade_miss_rays, kernels.py:1266-1280 */
                             V3 add = thr * ld3(cam->bg);
-                            A[0] = A[0] + add.x; A[1] = A[1] + add.y; A[2] = A[2] + add.z;
+                            pc = pc + add;
                             active = false;
                             break;
                         }
                         /* shade_and_scatter, kernels.py:1289-1399 */
                         V3 hit_point = h.p, normal = h.n;
                         int is_cm = sc->mat[h.prim_type].is_medium[h.prim_idx];
-                        bool scattered = false, passthrough = false;
+                        bool scattered = false, passthrough = false, surface = false, did_nee = false;
                         V3 scatter_dir = v3(0, 0, 0), attenuation = v3(1, 1, 1), emit = v3(0, 0, 0);
                         V3 next_o = ro;
                         if (is_cm > 0) {
@@ -863,17 +998,25 @@ void o_render_wavefront(const OScene* sc, const OCamera* cam, int W, int H, int 
                                 next_o = ro + rd * (mr.t_exit + epsilon_t);
                                 passthrough = true; /* re-enqueued with unchanged depth/throughput */
                             } else {
-                                emit = emitted(sc, h.prim_type, h.prim_idx);
-                                scattered = scatter(sc, rd, hit_point, normal, h.prim_type, h.prim_idx, rng, &scatter_dir, &attenuation, &hit_point);
+                                surface = true;
                             }
                         } else {
+                            surface = true;
+                        }
+                        if (surface) {
+                            if (nee && sc->mat[h.prim_type].material_type[h.prim_idx] == 0) {
+                                V3 add = thr * nee_direct(c, hit_point, normal, eval_texture(sc, h.prim_type, h.prim_idx, hit_point), rng);
+                                pc = pc + add;
+                                did_nee = true;
+                            }
                             emit = emitted(sc, h.prim_type, h.prim_idx);
                             scattered = scatter(sc, rd, hit_point, normal, h.prim_type, h.prim_idx, rng, &scatter_dir, &attenuation, &hit_point);
                         }
-                        if (emit.x > 0.0f || emit.y > 0.0f || emit.z > 0.0f) {
+                        if ((emit.x > 0.0f || emit.y > 0.0f || emit.z > 0.0f) && (prev_nee == 0 || (prev_nee == 1 && (h.t * h.t) * dot(rd, rd) < c.nee_r2))) {
                             V3 add = thr * emit;
-                            A[0] = A[0] + add.x; A[1] = A[1] + add.y; A[2] = A[2] + add.z;
+                            pc = pc + add;
                         }
+                        if (nee) prev_nee = passthrough ? (prev_nee != 0 ? 2 : 0) : (did_nee ? 1 : 0);
                         active = false;
                         if (passthrough) {
                             ro = next_o;
@@ -899,6 +1042,7 @@ void o_render_wavefront(const OScene* sc, const OCamera* cam, int W, int H, int 
                             }
                         }
                     }
+                    A[0] = A[0] + pc.x; A[1] = A[1] + pc.y; A[2] = A[2] + pc.z;
                 }
             }
 #pragma omp critical

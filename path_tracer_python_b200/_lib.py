@@ -48,7 +48,8 @@ class PtPackedInfo(C.Structure):
            ("image_h", C.c_int32 * PT_MAX_IMAGES)]
         + [(n, C.c_int32) for n in ("num_inner", "num_spheres", "num_quads", "num_triangles", "num_materials",
                                     "num_images", "max_depth_tree", "has_media")]
-        + [("off_sphere_motion", C.c_uint64), ("full_features", C.c_int32), ("node_bytes", C.c_int32)]
+        + [("off_sphere_motion", C.c_uint64), ("full_features", C.c_int32), ("node_bytes", C.c_int32),
+           ("off_lights", C.c_uint64), ("num_lights", C.c_int32), ("nee_r2", C.c_float)]
     )
 
 

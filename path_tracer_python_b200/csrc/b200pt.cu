@@ -210,6 +210,8 @@ __global__ void __launch_bounds__(PT_MEGA_THREADS, PT_MEGA_MINB) k_megakernel(co
     ptm::Rng rng{0u, 1u};
     float time = 0.0f;       // shutter time of the current path (full feature mode)
     int depth = 0;
+    int prev_nee = 0;        // features "nee": 1 = the last scatter was a Lambertian vertex with next-event estimation,
+                             // 2 = ... and the ray has passed through a medium since (nee_direct, pt_device.cuh)
     int mode = 0;            // 0: closest-hit search, 1: medium-exit search (kernels.py:417)
     float t_entry = 0.0f;
     int ref_entry = kRefNone;
@@ -269,12 +271,19 @@ __global__ void __launch_bounds__(PT_MEGA_THREADS, PT_MEGA_MINB) k_megakernel(co
                     do_shade = true;
                 }
             }
+            bool did_nee = false;
             if (do_shade) {
                 f3 n, emit;
                 finalize_hit<FULL>(S, sref, o, d, stt, hp, n, time);
+                if (FULL && nee_on(S) && mat_type(m.header) == 0) {       // direct light at a Lambertian vertex, before its scatter draws
+                    col = col + thr * nee_direct<FULL>(S, hp, n, eval_texture(S, m, sref, hp), rng, time);
+                    did_nee = true;
+                }
                 scattered = shade_surface<FULL>(S, m, sref, d, hp, n, rng, emit, sdir, atten);
-                col = col + thr * emit;                     // kernels.py:1116/1124
+                // kernels.py:1116/1124; after a vertex with next-event estimation only the close pairs are taken from here
+                if (!(FULL && prev_nee != 0) || (prev_nee == 1 && (stt * stt) * dot(d, d) < S.nee_r2)) col = col + thr * emit;
             }
+            if (FULL && !restart) prev_nee = passthrough ? (prev_nee != 0 ? 2 : 0) : (did_nee ? 1 : 0);
             if (!restart) {
                 if (!end_path) {
                     if (scattered) {
@@ -322,6 +331,7 @@ __global__ void __launch_bounds__(PT_MEGA_THREADS, PT_MEGA_MINB) k_megakernel(co
                 thr = mk3(1.0f, 1.0f, 1.0f);
                 col = mk3(0.0f, 0.0f, 0.0f);
                 depth = 0;
+                prev_nee = 0;
                 mode = 0;
                 if (COUNT) { lc.paths++; lc.bounces++; }
                 T.o = o;
@@ -685,14 +695,21 @@ template <bool FULL>
 __device__ __forceinline__ bool wf_shade_one(const DScene& S, f3 bg, int max_depth, float* sp, f3 o, f3 d, f3 thr,
                                              int depth, ptm::Rng& rng, float t, int ref, float t_exit_hit, bool exit_hit,
                                              f3& no, f3& nd, f3& nthr, int& ndepth, float time = 0.0f) {
+    // features "nee" (FULL instantiations only): bits 29-30 of the depth word carry the path's next-event-estimation state
+    // (nee_direct, pt_device.cuh) -- an emitter hit now may already have been counted at the previous vertex.  A path
+    // then contributes at several vertices, so its slab entry is accumulated (+=) instead of written once.
+    const bool nee = FULL && nee_on(S);
+    const int prev_nee = nee ? ((depth >> 29) & 3) : 0;
+    if (nee) depth &= 0x1fffffff;
     if (ref == kRefNone) {                           // shade_miss_rays, kernels.py:1266-1280
         f3 add = thr * bg;
-        sp[0] = 0.0f + add.x; sp[1] = 0.0f + add.y; sp[2] = 0.0f + add.z;     // == slab + add, see above
+        const f3 base = nee ? mk3(sp[0], sp[1], sp[2]) : mk3(0.0f, 0.0f, 0.0f);
+        sp[0] = base.x + add.x; sp[1] = base.y + add.y; sp[2] = base.z + add.z;     // == slab + add, see above
         return false;
     }
     const int mid = mat_id_of(S, ref);               // shade_and_scatter, kernels.py:1289-1399
     Mat m = load_mat(S, mid);
-    bool scattered = false, do_shade = true, emit_next = false;
+    bool scattered = false, do_shade = true, emit_next = false, did_nee = false;
     f3 hp, sdir, atten, emit = mk3(0.0f, 0.0f, 0.0f);
     if (mat_is_medium(m.header)) {
         const float4 m2 = __ldg(S.materials + 3 * mid + 2);
@@ -708,7 +725,7 @@ __device__ __forceinline__ bool wf_shade_one(const DScene& S, f3 bg, int max_dep
             no = o + d * (t_exit + eps_t);
             nd = d;
             nthr = thr;
-            ndepth = depth;
+            ndepth = depth | (prev_nee != 0 ? (2 << 29) : 0);           // passed through a medium since the NEE vertex
             emit_next = true;
             do_shade = false;
         }
@@ -716,11 +733,17 @@ __device__ __forceinline__ bool wf_shade_one(const DScene& S, f3 bg, int max_dep
     if (do_shade) {
         f3 n;
         finalize_hit<FULL>(S, ref, o, d, t, hp, n, time);
+        if (nee && mat_type(m.header) == 0) {        // direct light at a Lambertian vertex, before its scatter draws
+            const f3 add = thr * nee_direct<FULL>(S, hp, n, eval_texture(S, m, ref, hp), rng, time);
+            sp[0] = sp[0] + add.x; sp[1] = sp[1] + add.y; sp[2] = sp[2] + add.z;
+            did_nee = true;
+        }
         scattered = shade_surface<FULL>(S, m, ref, d, hp, n, rng, emit, sdir, atten);
     }
-    if (emit.x > 0.0f || emit.y > 0.0f || emit.z > 0.0f) {      // kernels.py:1368-1375
+    // kernels.py:1368-1375; after a vertex with next-event estimation only the close pairs are taken from here
+    if ((emit.x > 0.0f || emit.y > 0.0f || emit.z > 0.0f) && (prev_nee == 0 || (prev_nee == 1 && (t * t) * dot(d, d) < S.nee_r2))) {
         f3 add = thr * emit;
-        if (scattered) {                             // no such material today: keep the general form
+        if (scattered || nee) {                      // no scattering emitter today: keep the general form
             sp[0] = sp[0] + add.x; sp[1] = sp[1] + add.y; sp[2] = sp[2] + add.z;
         } else {
             sp[0] = 0.0f + add.x; sp[1] = 0.0f + add.y; sp[2] = 0.0f + add.z;
@@ -737,7 +760,7 @@ __device__ __forceinline__ bool wf_shade_one(const DScene& S, f3 bg, int max_dep
                 else new_thr = vdiv(new_thr, survival);
             }
             if (cont) {
-                no = hp; nd = sdir; nthr = new_thr; ndepth = new_depth;
+                no = hp; nd = sdir; nthr = new_thr; ndepth = new_depth | (did_nee ? (1 << 29) : 0);
                 emit_next = true;
             }
         }
@@ -1271,7 +1294,7 @@ __global__ void __launch_bounds__(256) k_wf_unpack_rays(const __grid_constant__ 
         if (local < 0) local += P.N; else if (local >= P.N) local -= P.N;
         pixel[i] = win_pixel(P, local);                 // ray_pixel_index (fields.py:205)
     }
-    if (depth) depth[i] = __float_as_int(c.w);
+    if (depth) depth[i] = __float_as_int(c.w) & 0x1fffffff;          // (bits 29-30: the next-event-estimation state of features "nee")
 }
 __global__ void __launch_bounds__(256) k_wf_unpack_hits(const __grid_constant__ WfParams P, int n, float* t, int32_t* prim, float* t_exit) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1583,7 +1606,8 @@ int pt_set_scene(PtContext* ctx, const void* device_blob, const PtPackedInfo* in
               inside(info->off_quads, (uint64_t)info->num_quads * 64) && inside(info->off_tris, (uint64_t)info->num_triangles * 48) &&
               inside(info->off_prim_mat, n_prims * 4) && inside(info->off_materials, (uint64_t)info->num_materials * 48) &&
               inside(info->off_perlin, 256 * 16 + 768) &&
-              (!info->full_features || inside(info->off_sphere_motion, (uint64_t)info->num_spheres * 16));
+              (!info->full_features || inside(info->off_sphere_motion, (uint64_t)info->num_spheres * 16)) &&
+              info->num_lights >= 0 && inside(info->off_lights, (uint64_t)info->num_lights * 32);
     for (int i = 0; i < info->num_images && ok; i++)
         ok = info->image_w[i] > 0 && info->image_h[i] > 0 && inside(info->off_images, info->image_off[i]) &&
              inside(info->off_images + info->image_off[i], (uint64_t)info->image_w[i] * info->image_h[i] * 4);
@@ -1615,6 +1639,9 @@ int pt_set_scene(PtContext* ctx, const void* device_blob, const PtPackedInfo* in
     S.has_media = info->has_media;
     S.full_features = info->full_features;
     S.sphere_motion = reinterpret_cast<const float4*>(base + info->off_sphere_motion);
+    S.lights = reinterpret_cast<const float4*>(base + info->off_lights);
+    S.n_lights = info->num_lights;
+    S.nee_r2 = info->nee_r2;
     ctx->scene = S;
     ctx->info = *info;
     ctx->has_scene = true;
@@ -1837,7 +1864,7 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
     void (*k_extend)(const WfParams) = nullptr;
     void (*k_tail)(const WfParams) = nullptr;
     void (*k_shade)(const WfParams) = full ? k_wf_shade<true> : k_wf_shade<false>;
-    const bool split = ctx->wf_shade_split && ctx->wavefront_sort && !ctx->dbg_shade_smem;
+    const bool split = ctx->wf_shade_split && ctx->wavefront_sort && !ctx->dbg_shade_smem && !(ctx->scene.full_features & 2);
     void (*k_shade_cls[3])(const WfParams) = {full ? k_wf_shade_cls<true, 0> : k_wf_shade_cls<false, 0>,
                                               full ? k_wf_shade_cls<true, 1> : k_wf_shade_cls<false, 1>,
                                               full ? k_wf_shade_cls<true, 2> : k_wf_shade_cls<false, 2>};
@@ -1845,7 +1872,8 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
     // camera rays without defocus all start at the camera centre: the fused primary wave then tests
     // origin-relative node boxes (one subtraction less per box coordinate).  Only when that kernel
     // runs wave 0 alone -- later waves start elsewhere.
-    bool rel = !PT_FAST && ctx->wf_rel_primary && ctx->wf_fuse_primary == 1 && !(ctx->cam.defocus_angle > 0.0f) &&
+    // (not with next-event estimation: its shadow rays start at the hit points and need the plain node boxes)
+    bool rel = !PT_FAST && !(ctx->scene.full_features & 2) && ctx->wf_rel_primary && ctx->wf_fuse_primary == 1 && !(ctx->cam.defocus_angle > 0.0f) &&
                ctx->scene.num_inner > 0 && ctx->cam.max_depth > 0 && !ctx->count && rel_nodes != nullptr;
     if (rel) {
         int g = (int)(((size_t)ctx->scene.num_inner * kNodeQuads + 255) / 256);

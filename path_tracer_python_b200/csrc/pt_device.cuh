@@ -78,7 +78,11 @@ struct DScene {
     int has_media;
     // "full" feature mode (moving spheres, subsurface materials); 0 = the reference's Taichi path
     const float4* sphere_motion;   // centre(1) - centre(0) per sphere
-    int full_features;
+    int full_features;             // bit 0: motion blur + subsurface; bit 1: next-event estimation
+    // next-event estimation (features "nee"): one record per emissive primitive, (leaf ref, area, emit.rg)(emit.b, -, -, -)
+    const float4* lights;
+    int n_lights;
+    float nee_r2;                  // squared switch-over distance between the two sampling strategies (nee_direct)
 };
 
 struct DCounters {
@@ -990,5 +994,92 @@ __device__ __forceinline__ bool shade_surface(const DScene& S, const Mat& m, int
     }
     return false;
 }
+
+// ---- next-event estimation (features="nee"; only in the FULL kernel instantiations).
+// At a Lambertian hit one emitter is chosen uniformly, a point on it is sampled uniformly by area, and its radiance is
+// added if the shadow ray reaches it:  L = albedo/pi * Le * cos_s * cos_l / dist^2 * (area * n_lights) * T.
+// cos_s is taken against the SAME normal the cosine-weighted scatter uses (spheres: outward, never flipped,
+// kernels.py:246), emitters emit from both faces (kernels.py:904-906).  The shadow ray follows the reference's
+// constant-medium semantics so that both estimators have the same expectation: a medium boundary is not an occluder
+// but a transmittance exp(-density * length inside), "inside" ends at the next hit of ANY primitive
+// (kernels.py:417-419), and the ray then continues beyond that hit (kernels.py:1100-1110); an exit search that finds
+// nothing makes the boundary a surface (kernels.py:1111-1119), i.e. opaque here.
+// Area sampling is a poor strategy for an emitter that is close (a ceiling point 1 unit above the Cornell light sees
+// area * n / (pi * dist^2) ~ 4000): the two strategies that can produce a (vertex, emitter point) pair -- this one and
+// the cosine-sampled next ray hitting the emitter -- are therefore combined with a partition of unity on their distance:
+// pairs farther apart than sqrt(nee_r2) (= half the side of the mean emitter) are taken from here, closer ones from the
+// scattered ray (the caller keeps a per-path flag and counts a directly hit emitter after such a vertex only when it is
+// closer than that).  Pairs whose connecting segment crosses a medium interval always belong to this strategy (after a
+// pass-through the scattered ray restarts from a new origin and no longer knows its distance to the vertex).  Every
+// pair is counted exactly once either way, so the estimator stays unbiased.  Path state (2 bits): 0 = the last
+// scatter had no next-event estimation, 1 = it had, 2 = it had and the ray has since passed through a medium.
+template <bool FULL>
+__device__ f3 nee_direct(const DScene& S, f3 hp, f3 n_s, f3 albedo, ptm::Rng& rng, float time) {
+    const f3 zero = mk3(0.0f, 0.0f, 0.0f);
+    int li = (int)(ptm::rng_next(rng) * (float)S.n_lights);
+    li = li < S.n_lights ? li : S.n_lights - 1;
+    const float4 L0 = __ldg(S.lights + 2 * li), L1 = __ldg(S.lights + 2 * li + 1);
+    const int lref = __float_as_int(L0.x);
+    const int type = ref_type(lref), idx = ref_index(lref);
+    f3 y, nl;
+    if (type == PT_PRIM_SPHERE) {
+        const float4 sp = __ldg(S.spheres + idx);
+        const f3 dirn = random_unit_vector(rng);
+        y = sphere_center<FULL>(S, idx, sp, time) + sp.w * dirn;
+        nl = dirn;
+    } else if (type == PT_PRIM_QUAD) {
+        const float4* p = S.quads + 4 * idx;
+        const float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2), q3 = __ldg(p + 3);
+        const float a = ptm::rng_next(rng), b = ptm::rng_next(rng);
+        y = (mk3(q1.x, q1.y, q1.z) + a * mk3(q2.x, q2.y, q2.z)) + b * mk3(q3.x, q3.y, q3.z);
+        nl = mk3(q0.x, q0.y, q0.z);
+    } else {
+        const float4* p = S.tris + 3 * idx;
+        const float4 a0 = __ldg(p), a1 = __ldg(p + 1), a2 = __ldg(p + 2);
+        float r1 = ptm::rng_next(rng), r2 = ptm::rng_next(rng);
+        if (r1 + r2 > 1.0f) { r1 = 1.0f - r1; r2 = 1.0f - r2; }
+        y = (mk3(a0.x, a0.y, a0.z) + r1 * mk3(a1.x, a1.y, a1.z)) + r2 * mk3(a2.x, a2.y, a2.z);
+        nl = mk3(a0.w, a1.w, a2.w);
+    }
+    const f3 dv = y - hp;
+    const float dist2 = dot(dv, dv);
+    if (!(dist2 > 1e-12f)) return zero;
+    const bool close = !(dist2 >= S.nee_r2);                  // close pairs belong to the scattered ray, unless a medium lies between
+    bool crossed = false;
+    const float dist = ptm::fsqrt(dist2);
+    const f3 wi = vdiv(dv, dist);
+    const float cos_s = dot(n_s, wi), cos_l = fabsf(dot(nl, wi));
+    if (!(cos_s > 0.0f) || !(cos_l > 0.0f)) return zero;
+    const float t_end = dist * 0.9999f;                       // stop short of the emitter itself
+    const float len = ptm::fsqrt(dot(wi, wi));
+    float trans = 1.0f, t_cur = 0.001f;
+    LocalCounters lc;
+    for (int seg = 0; seg < 16; seg++) {
+        if (!(t_cur < t_end)) break;
+        float t;
+        int ref;
+        traverse<false, FULL>(S, 0ull, 0, hp, wi, t_cur, t_end, t, ref, lc, time);
+        if (ref == kRefNone) break;                           // nothing in the way
+        if (!ref_is_medium(ref)) return zero;                 // occluded
+        float t_exit;
+        int eref;
+        traverse<false, FULL>(S, 0ull, 0, hp, wi, t + 0.0001f, 1e10f, t_exit, eref, lc, time);
+        if (eref == kRefNone) return zero;                    // boundary acts as a surface (fallback branch)
+        crossed = true;
+        const float4 m2 = __ldg(S.materials + 3 * mat_id_of(S, ref) + 2);     // (density, medium albedo)
+        const float t1 = max2(t, 0.001f), t2 = min2(t_exit, t_end);
+        if (t1 < t2) trans = trans * ptm::exp_c(-(m2.x * ((t2 - t1) * len)));
+        // the "inside" interval reaches the emitter itself: a ray that passes such an interval continues BEYOND its closing
+        // surface (kernels.py:1108), i.e. it never sees this point of the emitter (a sphere is then seen from inside, at
+        // its far side -- the pair this loop reaches when the sampled point lies there)
+        if (!(t_exit < t_end)) return zero;
+        t_cur = t_exit + ptm::fdiv(0.001f, len);
+        if (seg == 15) return zero;                           // pathological nesting: give up (unbiasedness is not at stake in practice)
+    }
+    if (close && !crossed) return zero;
+    const float geom = ptm::fdiv(((cos_s * cos_l) * L0.y) * (float)S.n_lights, 3.14159265358979f * dist2);
+    return (albedo * mk3(L0.z, L0.w, L1.x)) * (geom * trans);
+}
+__device__ __forceinline__ bool nee_on(const DScene& S) { return (S.full_features & 2) != 0 && S.n_lights > 0; }
 
 }  // namespace pt

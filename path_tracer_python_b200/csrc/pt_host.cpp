@@ -201,6 +201,38 @@ int validate_scene(const PtHostScene* s) {
     return PT_OK;
 }
 
+// ---- light table for next-event estimation: every emissive primitive that is not a medium boundary, with the
+// area its sampler needs (quad |u x v|, sphere 4 pi r^2, triangle |e1 x e2| / 2: double arithmetic on the float32
+// inputs, narrowed once -- oracle.cpp computes them the same way).  Order: spheres, triangles, quads, by index.
+struct LightRec {
+    int ref;
+    float area, emit[3];
+};
+void build_lights(const PtHostScene* s, std::vector<LightRec>& out) {
+    const int counts[3] = {s->num_spheres, s->num_triangles, s->num_quads};
+    for (int pt = 0; pt < 3; pt++) {
+        const PtHostMaterials& m = s->mat[pt];
+        for (int i = 0; i < counts[pt]; i++) {
+            if (m.material_type[i] != 3 || m.is_medium[i] > 0) continue;
+            const float* e = m.emit + 3 * i;
+            if (!(e[0] > 0.0f || e[1] > 0.0f || e[2] > 0.0f)) continue;
+            double area = 0.0;
+            if (pt == PT_PRIM_SPHERE) {
+                const double r = s->sphere_data[4 * i + 3];
+                area = 4.0 * 3.14159265358979323846 * r * r;
+            } else {
+                const float* a = pt == PT_PRIM_QUAD ? s->quad_u + 3 * i : s->tri_edge1 + 3 * i;
+                const float* b = pt == PT_PRIM_QUAD ? s->quad_v + 3 * i : s->tri_edge2 + 3 * i;
+                const double cx = (double)a[1] * b[2] - (double)a[2] * b[1], cy = (double)a[2] * b[0] - (double)a[0] * b[2],
+                             cz = (double)a[0] * b[1] - (double)a[1] * b[0];
+                area = std::sqrt(cx * cx + cy * cy + cz * cz) * (pt == PT_PRIM_QUAD ? 1.0 : 0.5);
+            }
+            if (!(area > 0.0)) continue;
+            out.push_back(LightRec{leaf_ref(pt, i, shading_class(m, i)), (float)area, {e[0], e[1], e[2]}});
+        }
+    }
+}
+
 #ifndef PT_WIDE
 #define PT_WIDE 0
 #endif
@@ -333,8 +365,17 @@ int pt_pack_scene_info(const PtHostScene* s, PtPackedInfo* info) {
     info->off_prim_mat = section((uint64_t)mt.ids.size() * 4);
     info->off_materials = section((uint64_t)mt.recs.size() * 48);
     info->off_perlin = section(256 * 16 + 768);
-    info->full_features = s->full_features ? 1 : 0;
+    info->full_features = s->full_features & 3;
     info->off_sphere_motion = info->full_features ? section((uint64_t)s->num_spheres * 16) : 0;
+    {
+        std::vector<LightRec> lights;
+        if (info->full_features & 2) build_lights(s, lights);
+        info->num_lights = (int)lights.size();
+        info->off_lights = section((uint64_t)lights.size() * 32);
+        double sum = 0.0;
+        for (const LightRec& l : lights) sum += (double)l.area;
+        info->nee_r2 = lights.empty() ? 0.0f : (float)(0.25 * (sum / (double)lights.size()));
+    }
     info->off_images = off;
     uint64_t ioff = 0;
     for (int i = 0; i < s->num_images; i++) {
@@ -440,6 +481,17 @@ int pt_pack_scene(const PtHostScene* s, const PtPackedInfo* info, void* host_blo
         t[8] = e2[0]; t[9] = e2[1]; t[10] = e2[2]; t[11] = n[2];
     }
 
+    if (info->num_lights > 0) {
+        std::vector<LightRec> lights;
+        build_lights(s, lights);
+        if ((int)lights.size() != info->num_lights) { g_host_error = "pt_pack_scene: info does not match scene"; return PT_ERR_INVALID_ARG; }
+        float* lp = reinterpret_cast<float*>(base + info->off_lights);
+        for (size_t i = 0; i < lights.size(); i++) {
+            memcpy(lp + 8 * i, &lights[i].ref, 4);
+            lp[8 * i + 1] = lights[i].area;
+            lp[8 * i + 2] = lights[i].emit[0]; lp[8 * i + 3] = lights[i].emit[1]; lp[8 * i + 4] = lights[i].emit[2];
+        }
+    }
     if (info->full_features && s->sphere_motion) {
         float* mo = reinterpret_cast<float*>(base + info->off_sphere_motion);
         for (int i = 0; i < s->num_spheres; i++) { mo[4 * i] = s->sphere_motion[3 * i]; mo[4 * i + 1] = s->sphere_motion[3 * i + 1]; mo[4 * i + 2] = s->sphere_motion[3 * i + 2]; }

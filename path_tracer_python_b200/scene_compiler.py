@@ -214,12 +214,15 @@ def compile_scene(world, features: str = "taichi_compat") -> dict:
     """world -> CompiledScene dict (geometry, materials, image textures; no BVH, no Perlin).
 
     features="taichi_compat" (default) reproduces the reference's Taichi path exactly: sphere
-    motion baked at time 0, subsurface materials -> grey Lambertian.  features="full" additionally
+    motion baked at time 0, subsurface materials -> grey Lambertian.  "nee" / "full+nee" add next-event
+    estimation at Lambertian hits (same expected image, less noise; the technique the reference's docs list
+    as missing, docs/__optimizations.md:7-10).  features="full" additionally
     exports what only the reference's pure-Python tracer renders: `sphere_motion` (centre(1) -
     centre(0), core/sphere.py:22-36) and the two subsurface materials (core/material.py:144-276)."""
-    if features not in ("taichi_compat", "full"):
-        raise ValueError("features must be 'taichi_compat' or 'full'")
-    full = features == "full"
+    if features not in ("taichi_compat", "full", "nee", "full+nee"):
+        raise ValueError("features must be 'taichi_compat', 'full', 'nee' or 'full+nee'")
+    full = features in ("full", "full+nee")
+    nee = features in ("nee", "full+nee")
     image_registry, image_list = build_image_registry(world)
     medium_registry = build_medium_registry(world)
     spheres, quads, triangles = extract_primitives(world)
@@ -291,6 +294,11 @@ def compile_scene(world, features: str = "taichi_compat") -> dict:
             mo[i] = (c1.x - c0.x, c1.y - c0.y, c1.z - c0.z)
         cs["sphere_motion"] = mo
         cs["full_features"] = 1
+    if nee:
+        # next-event estimation at Lambertian hits (bit 1 of the feature word); the kernels' feature-mode
+        # instantiations always read the motion table, so a compat-material scene gets one of zeros
+        cs.setdefault("sphere_motion", np.zeros((len(spheres), 3), np.float32))
+        cs["full_features"] = int(cs.get("full_features", 0)) | 2
     cs["num_images"] = len(image_list)
     for i, tex in enumerate(image_list):
         cs[f"image_{i}"] = image_to_u8(tex)
