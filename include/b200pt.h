@@ -118,6 +118,9 @@ typedef struct PtCamera {
     float defocus_angle;
     float background[3];
     int32_t max_depth;
+    int32_t jitter;          /* sub-pixel offset of get_ray (kernels.py:183-184): 0 = two draws of the path's random stream, as the
+                              * reference; 1 = the sample's point of a per-pixel XOR-scrambled Sobol' (0,2)-sequence (low-discrepancy
+                              * sampling, docs/__optimizations.md:7-10): same expected image, better-stratified pixel footprints */
 } PtCamera;
 
 typedef struct PtCounters {

@@ -71,6 +71,7 @@ typedef struct {
     float defocus_angle;
     float bg[3];
     int32_t max_depth;
+    int32_t jitter;      /* 0: random sub-pixel offsets (kernels.py:183-184); 1: scrambled Sobol' (0,2) points */
 } OCamera;
 
 typedef struct {
@@ -235,9 +236,16 @@ float perlin_turb(const OScene* sc, V3 p, int depth) {
 }
 
 /* kernels.py:176-201 */
-void get_ray(const OCamera* cam, int px, int py, Rng& rng, V3* o, V3* d) {
-    float offset_x = rng.next() - 0.5f;
-    float offset_y = rng.next() - 0.5f;
+void get_ray(const OCamera* cam, int px, int py, Rng& rng, V3* o, V3* d, uint32_t seed, uint32_t pixel, uint32_t sample) {
+    float offset_x, offset_y;
+    if (cam->jitter == 1) {
+        o_ld_jitter(seed, pixel, sample, &offset_x, &offset_y);
+        offset_x = offset_x - 0.5f;
+        offset_y = offset_y - 0.5f;
+    } else {
+        offset_x = rng.next() - 0.5f;
+        offset_y = rng.next() - 0.5f;
+    }
     V3 pixel_sample = (ld3(cam->pixel00) + ((float)px + offset_x) * ld3(cam->delta_u)) +
                       ((float)py + offset_y) * ld3(cam->delta_v);
     V3 origin = ld3(cam->center);
@@ -815,6 +823,10 @@ uint64_t o_rng_seed_state(uint32_t seed, uint32_t pixel, uint32_t sample) {
     ORng r = o_rng_seed(seed, pixel, sample);
     return ((uint64_t)r.inc << 32) | r.s;
 }
+/* low-discrepancy pixel jitter: the first n sample points of one pixel, (x, y) pairs in [0, 1) */
+void o_ld_jitter_points(uint32_t seed, uint32_t pixel, int n, float* out) {
+    for (int i = 0; i < n; i++) o_ld_jitter(seed, pixel, (uint32_t)i, out + 2 * i, out + 2 * i + 1);
+}
 /* batch form for the stream-uniqueness tests: states of n (pixel, sample) keys */
 void o_rng_seed_states(uint32_t seed, int64_t n, const uint32_t* pixels, const uint32_t* samples, uint64_t* out) {
 #pragma omp parallel for schedule(static)
@@ -843,7 +855,7 @@ void o_generate_camera_rays(const OCamera* cam, int W, int H, uint32_t seed, int
             int idx = py * W + px;
             Rng rng{o_rng_seed(seed, (uint32_t)idx, (uint32_t)sample)};
             V3 o, d;
-            get_ray(cam, px, py, rng, &o, &d);
+            get_ray(cam, px, py, rng, &o, &d, seed, (uint32_t)idx, (uint32_t)sample);
             out_o[3 * idx] = o.x; out_o[3 * idx + 1] = o.y; out_o[3 * idx + 2] = o.z;
             out_d[3 * idx] = d.x; out_d[3 * idx + 1] = d.y; out_d[3 * idx + 2] = d.z;
             if (out_rng) out_rng[idx] = rng.s.s;
@@ -910,7 +922,7 @@ void o_render_megakernel(const OScene* sc, const OCamera* cam, int W, int H, int
                     Rng rng{o_rng_seed(seed, (uint32_t)idx, (uint32_t)s)};
                     c.time = sc->full_features ? o_path_time(rng.s) : 0.0f;
                     V3 o, d;
-                    get_ray(cam, px, py, rng, &o, &d);
+                    get_ray(cam, px, py, rng, &o, &d, seed, (uint32_t)idx, (uint32_t)s);
                     V3 col = trace_ray(c, o, d, rng);
                     acc = acc + col;
                     c.cnt.paths++;
@@ -960,7 +972,7 @@ void o_render_wavefront(const OScene* sc, const OCamera* cam, int W, int H, int 
                     c.time = sc->full_features ? o_path_time(rng.s) : 0.0f;
                     /* generate_camera_rays: direction NOT normalised (kernels.py:1229-1233) */
                     V3 ro, rd;
-                    get_ray(cam, px, py, rng, &ro, &rd);
+                    get_ray(cam, px, py, rng, &ro, &rd, seed, (uint32_t)idx, (uint32_t)s);
                     V3 thr = v3(1, 1, 1);
                     int depth = 0;
                     bool active = true;

@@ -39,7 +39,7 @@ class OScene(C.Structure):
 class OCamera(C.Structure):
     _fields_ = [("center", C.c_float * 3), ("pixel00", C.c_float * 3), ("delta_u", C.c_float * 3),
                 ("delta_v", C.c_float * 3), ("disk_u", C.c_float * 3), ("disk_v", C.c_float * 3),
-                ("defocus_angle", C.c_float), ("bg", C.c_float * 3), ("max_depth", C.c_int32)]
+                ("defocus_angle", C.c_float), ("bg", C.c_float * 3), ("max_depth", C.c_int32), ("jitter", C.c_int32)]
 
 
 class OCounters(C.Structure):
@@ -167,7 +167,7 @@ class OracleScene:
         self.c = s
 
 
-def make_camera(cam: dict, bg=(0.7, 0.8, 1.0), max_depth=50) -> OCamera:
+def make_camera(cam: dict, bg=(0.7, 0.8, 1.0), max_depth=50, jitter: str = "random") -> OCamera:
     """cam: dict with cam_center/... (float64, as uploaded by renderer.py:230-247 -> f32)."""
     c = OCamera()
     for src, dst in (("cam_center", "center"), ("cam_pixel00", "pixel00"), ("cam_delta_u", "delta_u"),
@@ -178,6 +178,7 @@ def make_camera(cam: dict, bg=(0.7, 0.8, 1.0), max_depth=50) -> OCamera:
     c.defocus_angle = float(np.float32(cam["cam_defocus_angle"]))
     c.bg[:] = [float(np.float32(x)) for x in bg]
     c.max_depth = int(max_depth)
+    c.jitter = {"random": 0, "sobol": 1}[jitter]
     return c
 
 
@@ -242,6 +243,13 @@ def rng_draw(state: int, n: int):
     out = np.empty(n, np.float32)
     lib().o_rng_draw(C.byref(st), C.c_int(n), out.ctypes.data_as(C.c_void_p))
     return out, int(st.value)
+
+
+def ld_jitter_points(seed, pixel, n):
+    """The first n points of a pixel's scrambled Sobol' (0,2)-sequence: (n, 2) float32 in [0, 1)."""
+    out = np.empty((n, 2), np.float32)
+    lib().o_ld_jitter_points(C.c_uint32(seed), C.c_uint32(pixel), C.c_int(n), out.ctypes.data_as(C.c_void_p))
+    return out
 
 
 def rng_seed_states(seed, pixels, samples):

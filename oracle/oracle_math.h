@@ -212,6 +212,25 @@ static inline ORng o_rng_seed(uint32_t seed, uint32_t pixel_index, uint32_t samp
 static inline float o_path_time(ORng key) {
     return (float)(o_mix32(key.s ^ 0x7157a3d1u ^ (key.inc * 0x9e3779b9u)) >> 8) * 5.9604644775390625e-8f;
 }
+/* low-discrepancy pixel jitter (OCamera.jitter = 1): point `sample` of the Sobol' (0,2)-sequence, XOR-scrambled per pixel */
+static inline uint32_t o_bitrev32(uint32_t v) {
+    v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
+    v = ((v >> 2) & 0x33333333u) | ((v & 0x33333333u) << 2);
+    v = ((v >> 4) & 0x0f0f0f0fu) | ((v & 0x0f0f0f0fu) << 4);
+    v = ((v >> 8) & 0x00ff00ffu) | ((v & 0x00ff00ffu) << 8);
+    return (v >> 16) | (v << 16);
+}
+static inline uint32_t o_sobol2(uint32_t i) {
+    uint32_t r = 0u, v;
+    for (v = 0x80000000u; i; i >>= 1, v ^= v >> 1)
+        if (i & 1u) r ^= v;
+    return r;
+}
+static inline void o_ld_jitter(uint32_t seed, uint32_t pixel, uint32_t sample, float* jx, float* jy) {
+    uint32_t sx = o_mix32(pixel ^ o_mix32(seed ^ 0x68bc21ebu)), sy = o_mix32(sx ^ 0x02e5be93u);
+    *jx = (float)((o_bitrev32(sample) ^ sx) >> 8) * 5.9604644775390625e-8f;
+    *jy = (float)((o_sobol2(sample) ^ sy) >> 8) * 5.9604644775390625e-8f;
+}
 static inline float o_rng_next(ORng* r) {
     r->s += r->inc;
     return (float)(o_mix32(r->s) >> 8) * 5.9604644775390625e-8f; /* 2^-24, exact */

@@ -56,7 +56,8 @@ class PtPackedInfo(C.Structure):
 class PtCamera(C.Structure):
     _fields_ = [("center", C.c_float * 3), ("pixel00", C.c_float * 3), ("delta_u", C.c_float * 3),
                 ("delta_v", C.c_float * 3), ("defocus_disk_u", C.c_float * 3), ("defocus_disk_v", C.c_float * 3),
-                ("defocus_angle", C.c_float), ("background", C.c_float * 3), ("max_depth", C.c_int32)]
+                ("defocus_angle", C.c_float), ("background", C.c_float * 3), ("max_depth", C.c_int32),
+                ("jitter", C.c_int32)]
 
 
 class PtStageTime(C.Structure):
@@ -258,7 +259,10 @@ class HostScene:
         self.input_bytes = int(sum(a.nbytes for a in self._keep))
 
 
-def make_camera(cam: dict, background=(0.7, 0.8, 1.0), max_depth=50) -> PtCamera:
+JITTER = {"random": 0, "sobol": 1}
+
+
+def make_camera(cam: dict, background=(0.7, 0.8, 1.0), max_depth=50, jitter: str = "random") -> PtCamera:
     """The float64 -> float32 narrowing of _upload_camera (reference renderer.py:230-247)."""
     c = PtCamera()
     for src, dst in (("cam_center", "center"), ("cam_pixel00", "pixel00"), ("cam_delta_u", "delta_u"),
@@ -269,4 +273,7 @@ def make_camera(cam: dict, background=(0.7, 0.8, 1.0), max_depth=50) -> PtCamera
     c.defocus_angle = float(np.float32(cam["cam_defocus_angle"]))
     c.background[:] = [float(np.float32(x)) for x in background]
     c.max_depth = int(max_depth)
+    if jitter not in JITTER:
+        raise B200PTError(f"jitter must be one of {sorted(JITTER)}")
+    c.jitter = JITTER[jitter]
     return c

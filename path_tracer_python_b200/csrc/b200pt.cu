@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(PT_MEGA_THREADS, PT_MEGA_MINB) k_megakernel(co
                 rng = ptm::rng_seed(P.seed, (uint32_t)pixel, (uint32_t)s);
                 time = FULL ? ptm::path_time(rng) : 0.0f;
                 f3 o, d;
-                get_ray(P.cam, px, py, rng, o, d);
+                get_ray(P.cam, px, py, rng, o, d, P.seed, (uint32_t)pixel, (uint32_t)s);
                 d = normalized(d);                          // kernels.py:1042
                 thr = mk3(1.0f, 1.0f, 1.0f);
                 col = mk3(0.0f, 0.0f, 0.0f);
@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ WfP
         const int py = pixel / P.W, px = pixel - py * P.W;
         ptm::Rng rng = ptm::rng_seed(P.seed, (uint32_t)pixel, (uint32_t)(P.sample_base + slot));
         f3 o, d;
-        get_ray(P.cam, px, py, rng, o, d);                  // NOT normalised, kernels.py:1229-1233
+        get_ray(P.cam, px, py, rng, o, d, P.seed, (uint32_t)pixel, (uint32_t)(P.sample_base + slot));     // NOT normalised, kernels.py:1229-1233
         P.Q.ra[0][2 * (size_t)id] = make_float4(o.x, o.y, o.z, d.x);
         P.Q.ra[0][2 * (size_t)id + 1] = make_float4(d.y, d.z, 1.0f, 1.0f);
         P.Q.r2[0][id] = make_float4(1.0f, __int_as_float(id), __uint_as_float(rng.s), __int_as_float(0));
@@ -1068,7 +1068,7 @@ __global__ void __launch_bounds__(PT_PRIMARY_THREADS, PT_PRIMARY_MINB) k_wf_prim
             rng = ptm::rng_seed(P.seed, (uint32_t)pixel, (uint32_t)(P.sample_base + slot));
             const float time = FULL ? ptm::path_time(rng) : 0.0f;
             f3 o, d;
-            get_ray(P.cam, px, py, rng, o, d);                  // NOT normalised, kernels.py:1229-1233
+            get_ray(P.cam, px, py, rng, o, d, P.seed, (uint32_t)pixel, (uint32_t)(P.sample_base + slot));  // NOT normalised, kernels.py:1229-1233
             float* sp = P.Q.slab + 3 * (size_t)id;
             sp[0] = 0.0f; sp[1] = 0.0f; sp[2] = 0.0f;
             if (COUNT) lc.paths++;
@@ -1332,7 +1332,7 @@ __global__ void k_generate_rays(PtCamera cam, int W, int H, uint32_t seed, int s
     int py = i / W, px = i - py * W;
     ptm::Rng rng = ptm::rng_seed(seed, (uint32_t)i, (uint32_t)sample);
     f3 o, d;
-    get_ray(cam, px, py, rng, o, d);
+    get_ray(cam, px, py, rng, o, d, seed, (uint32_t)i, (uint32_t)sample);
     o_out[3 * i] = o.x; o_out[3 * i + 1] = o.y; o_out[3 * i + 2] = o.z;
     d_out[3 * i] = d.x; d_out[3 * i + 1] = d.y; d_out[3 * i + 2] = d.z;
 }
@@ -1650,6 +1650,7 @@ int pt_set_scene(PtContext* ctx, const void* device_blob, const PtPackedInfo* in
 
 int pt_set_camera(PtContext* ctx, const PtCamera* cam) {
     if (!ctx || !cam) return set_error(PT_ERR_INVALID_ARG, "pt_set_camera: NULL argument");
+    if (cam->jitter != 0 && cam->jitter != 1) return set_error(PT_ERR_INVALID_ARG, "pt_set_camera: jitter must be 0 (random) or 1 (Sobol' (0,2))");
     ctx->cam = *cam;
     ctx->has_camera = true;
     return PT_OK;

@@ -755,9 +755,17 @@ __device__ __forceinline__ f3 random_cosine_direction(f3 normal, ptm::Rng& rng) 
 }
 
 // ---- camera (kernels.py:176-201)
-__device__ __forceinline__ void get_ray(const PtCamera& cam, int px, int py, ptm::Rng& rng, f3& o, f3& d) {
-    float ox = ptm::rng_next(rng) - 0.5f;
-    float oy = ptm::rng_next(rng) - 0.5f;
+__device__ __forceinline__ void get_ray(const PtCamera& cam, int px, int py, ptm::Rng& rng, f3& o, f3& d,
+                                        uint32_t seed, uint32_t pixel, uint32_t sample) {
+    float ox, oy;
+    if (cam.jitter == 1) {                      // low-discrepancy sub-pixel offsets; the random stream is left for the bounces
+        ptm::ld_jitter(seed, pixel, sample, ox, oy);
+        ox = ox - 0.5f;
+        oy = oy - 0.5f;
+    } else {
+        ox = ptm::rng_next(rng) - 0.5f;
+        oy = ptm::rng_next(rng) - 0.5f;
+    }
     f3 p00 = mk3(cam.pixel00[0], cam.pixel00[1], cam.pixel00[2]);
     f3 du = mk3(cam.delta_u[0], cam.delta_u[1], cam.delta_u[2]);
     f3 dv = mk3(cam.delta_v[0], cam.delta_v[1], cam.delta_v[2]);

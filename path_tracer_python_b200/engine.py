@@ -114,8 +114,10 @@ class Engine:
             self._upload_done.record()
         return nbytes
 
-    def set_camera(self, cam: dict | PtCamera, background=(0.7, 0.8, 1.0), max_depth=50):
-        pc = cam if isinstance(cam, PtCamera) else make_camera(cam, background, max_depth)
+    def set_camera(self, cam: dict | PtCamera, background=(0.7, 0.8, 1.0), max_depth=50, jitter: str = "random"):
+        """jitter: "random" = the sub-pixel offset is two draws of the path's random stream (the reference);
+        "sobol" = low-discrepancy offsets, the sample's point of a per-pixel scrambled (0,2)-sequence."""
+        pc = cam if isinstance(cam, PtCamera) else make_camera(cam, background, max_depth, jitter)
         self._check(self.L.pt_set_camera(self.ctx, C.byref(pc)), "pt_set_camera")
         self.camera = pc
 

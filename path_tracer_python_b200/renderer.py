@@ -39,7 +39,7 @@ class TaichiRenderer:
     def __init__(self, world, cam, img_path: str, *, seed: int = 0, device: int | None = None,
                  spp_per_launch: int | None = None, process_group=None, compiled_scene: dict | None = None,
                  quiet: bool = False, features: str = "taichi_compat", numerics: str = "strict",
-                 reduce_dst: int | None = None):
+                 reduce_dst: int | None = None, jitter: str = "random"):
         self.timing = {k: 0.0 for k in ("taichi_init", "scene_compile", "bvh_compile", "bvh_flatten", "camera_upload",
                                         "gpu_upload", "kernel_warmup", "total_setup")}
         self.sample_times = []
@@ -56,6 +56,7 @@ class TaichiRenderer:
         self.seed = int(seed)
         self.spp_per_launch = spp_per_launch
         self.process_group = process_group
+        self.jitter = jitter                 # "random" (the reference's sub-pixel offsets) or "sobol" (low-discrepancy)
         self.reduce_dst = reduce_dst         # None: every rank gets the summed frame (all-reduce); r: only rank r (reduce)
 
         t0 = time.time()
@@ -96,7 +97,7 @@ class TaichiRenderer:
 
     def _upload_camera(self):
         """Camera vectors, background and max_depth (reference renderer.py:230-247)."""
-        self.engine.set_camera(self._camera_dict(), _color_tuple(self.background_color), int(self.max_depth))
+        self.engine.set_camera(self._camera_dict(), _color_tuple(self.background_color), int(self.max_depth), self.jitter)
 
     # ------------------------------------------------------------------ render loops
     def _sample_range(self):

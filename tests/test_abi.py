@@ -33,8 +33,8 @@ def test_header_symbols_exported(L):
 
 
 def test_struct_sizes_match_header(L):
-    # PtCamera: 6*3 floats + angle + 3 bg + max_depth; PtCounters: 7 u64
-    assert ctypes.sizeof(_lib.PtCamera) == 4 * (18 + 1 + 3 + 1)
+    # PtCamera: 6*3 floats + angle + 3 bg + max_depth + jitter; PtCounters: 7 u64
+    assert ctypes.sizeof(_lib.PtCamera) == 4 * (18 + 1 + 3 + 1 + 1)
     assert ctypes.sizeof(_lib.PtCounters) == 56
     assert ctypes.sizeof(_lib.PtHostMaterials) == 13 * 8
 
