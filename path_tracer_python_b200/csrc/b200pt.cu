@@ -226,6 +226,7 @@ __global__ void __launch_bounds__(PT_MEGA_THREADS, PT_MEGA_MINB) k_megakernel(co
     for (;;) {
         // ---- (a) lanes whose traversal finished: medium logic / shading / Russian roulette
         if (st == LANE_HAVE_RESULT) {
+            if (mode == 0) trav_finish<FULL>(T, S);         // equal-t hits: the primitive the reference would have kept
             const f3 o = T.o, d = T.d;
             const float t = T.best_t;
             const int ref = T.best_ref;
@@ -389,6 +390,8 @@ struct WfQueues {
     float* slab;             // [B][N][3] radiance contribution of each path of the batch
     int* qcount;             // [2] ray counts of the two queues
     int* cursor;             // dynamic-fetch cursor of k_wf_extend
+    int* tie_list;           // [capacity] paths / rays whose closest hit is shared by several primitives (resolve_tie, pt_device.cuh)
+    int* tie_count;          // [2]: [0] the fused primary wave's list, [1] this wave's k_wf_extend list
     int capacity;            // B * N
 };
 constexpr int kNodeBytes = 16 * kNodeQuads;   // one packed inner node: 64 B (two children) or 128 B (PT_WIDE: four)
@@ -467,6 +470,8 @@ __global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ WfP
         P.Q.qcount[1] = 0;
         P.Q.cursor[0] = 0;
         P.Q.cursor[1] = 0;
+        P.Q.tie_count[0] = 0;
+        P.Q.tie_count[1] = 0;
     }
 }
 
@@ -586,6 +591,15 @@ __global__ void __launch_bounds__(PT_EXT_WARPS * 32, MINB) k_wf_extend(const __g
         // ---- finished lanes: second traversal for medium boundaries, else write the hit record
         if (st == LANE_HAVE_RESULT) {
             if (mode == 0) {
+                // equal-t hits (pt_device.cuh resolve_tie): listed for k_wf_fix_ties, which rewrites the record where the
+                // reference would have kept another primitive; the counting instantiation resolves in place
+                if (COUNT) {
+                    trav_finish<FULL>(T, S);
+                } else if (trav_take_tie(T)) {
+                    const int k = atomicAdd(P.Q.tie_count + 1, 1);
+                    PT_BOUND(k >= 0 && k < P.Q.capacity, PT_DBG_QUEUE);
+                    P.Q.tie_list[k] = ray;
+                }
                 const int ref = T.best_ref;
                 // shading class of the hit = its material bin (0 = miss)
                 const int cls = ref != kRefNone ? ref_class(ref) : 0;
@@ -654,11 +668,49 @@ __global__ void __launch_bounds__(PT_EXT_WARPS * 32, MINB) k_wf_extend(const __g
     if (COUNT) flush_counters(P.counters, lc);
 }
 
+// Equal-t hits of a wave, resolved with every lane busy (pt_device.cuh resolve_tie).  For each ray k_wf_extend listed:
+// the primitive the reference's visiting order keeps; when that is not the one in the hit record the record is rewritten
+// -- with the exit search if the hit turns INTO a medium boundary, without it if it stops being one.
+template <bool FULL>
+__global__ void __launch_bounds__(128) k_wf_fix_ties(const __grid_constant__ WfParams P) {
+    const DScene& S = P.S;
+    const int cur = P.bounce & 1;
+    const int n = P.Q.tie_count[1];
+    LocalCounters lc;
+    const int stride = gridDim.x * blockDim.x;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        const int ray = P.Q.tie_list[k];
+        PT_BOUND(ray >= 0 && ray < P.Q.qcount[cur] && n <= P.Q.capacity, PT_DBG_QUEUE);
+        const float4 a = P.Q.ra[cur][2 * (size_t)ray], b = P.Q.ra[cur][2 * (size_t)ray + 1];
+        const float4 h = P.Q.hit[ray];
+        const f3 o = mk3(a.x, a.y, a.z), d = mk3(a.w, b.x, b.y);
+        const float time = FULL ? wf_path_time<FULL>(P, __float_as_int(P.Q.r2[cur][ray].y)) : 0.0f;
+        f3 inv;
+        ptm::inv_dir3(d.x, d.y, d.z, inv.x, inv.y, inv.z);
+        const int old_ref = __float_as_int(h.y);
+        const int ref = resolve_tie<FULL>(S, o, d, inv, 0.001f, h.x, time);
+        if (ref == kRefNone || ref == old_ref) continue;
+        const int cls = ref_class(ref);
+        if (cls != PT_CLS_MEDIUM) {
+            P.Q.hit[ray] = make_float4(h.x, __int_as_float(ref), 0.0f, __int_as_float(cls << 8));
+        } else if (ref_class(old_ref) == PT_CLS_MEDIUM) {
+            P.Q.hit[ray] = make_float4(h.x, __int_as_float(ref), h.z, h.w);       // same entry point: same exit search
+        } else {
+            float t_exit;
+            int eref;
+            traverse<false, FULL>(S, (SNodeBase)0, 0, o, d, h.x + 0.0001f, 1e10f, t_exit, eref, lc, time);
+            P.Q.hit[ray] = make_float4(h.x, __int_as_float(ref), t_exit, __int_as_float((eref != kRefNone ? 1 : 0) | (PT_CLS_MEDIUM << 8)));
+        }
+    }
+}
+
 // Closest hit of a ray and, when that hit is a constant-medium boundary, the exit search behind it
 // (kernels.py:417-419) -- as ONE traversal loop run up to twice, so that the kernels that inline it
 // (k_wf_primary, k_wf_tail) carry one copy of the traversal code, not two (instruction cache).
-template <bool COUNT, bool FULL, bool REL = false>
-__device__ __forceinline__ void closest_hit_and_exit(const DScene& S, SNodeBase s_nodes, int n_snodes, f3 o, f3 d, float time,
+// DEFER: an exact-t tie is not resolved here -- the function returns true at once and the caller hands the path to a
+// launch that does (k_wf_primary<..., TIES>).
+template <bool COUNT, bool FULL, bool REL = false, bool DEFER = false>
+__device__ __forceinline__ bool closest_hit_and_exit(const DScene& S, SNodeBase s_nodes, int n_snodes, f3 o, f3 d, float time,
                                                      float& t, int& ref, float& t_exit, int& eref, LocalCounters& lc) {
     StackEntry stack_mem[kStackSlots];
     const LocalStack stack{stack_mem};
@@ -673,6 +725,8 @@ __device__ __forceinline__ void closest_hit_and_exit(const DScene& S, SNodeBase 
         if (pass) trav_restart<COUNT>(T, S, t_min, 1e10f, lc);
         trav_run<COUNT, FULL, REL>(T, S, s_nodes, n_snodes, stack, 0, lc);
         if (pass == 0) {
+            if (DEFER) { if (trav_take_tie(T)) return true; }
+            else trav_finish<FULL>(T, S);               // equal-t hits: the primitive the reference would have kept
             t = T.best_t;
             ref = T.best_ref;
             if (ref == kRefNone || !ref_is_medium(ref)) break;
@@ -682,6 +736,7 @@ __device__ __forceinline__ void closest_hit_and_exit(const DScene& S, SNodeBase 
             eref = T.best_ref;
         }
     }
+    return false;
 }
 
 // One ray of shade_miss_rays + shade_and_scatter (kernels.py:1266-1399): adds the ray's radiance
@@ -835,7 +890,7 @@ __global__ void __launch_bounds__(PT_SHADE_THREADS, PT_SHADE_MINB) k_wf_shade(co
     const DScene& S = P.S;
     const int cur = P.bounce & 1, nxt = cur ^ 1;
     const int count = P.Q.qcount[cur];
-    if (blockIdx.x == 0 && threadIdx.x == 0) P.Q.cursor[0] = 0;       // for the next k_wf_extend
+    if (blockIdx.x == 0 && threadIdx.x == 0) { P.Q.cursor[0] = 0; P.Q.tie_count[1] = 0; }       // for the next k_wf_extend
     if ((long long)blockIdx.x * blockDim.x >= count) return;
     // bin boundaries in shared memory: nine values that would otherwise sit in registers through the
     // whole shading code of this register-bound kernel
@@ -913,7 +968,7 @@ __global__ void __launch_bounds__(256, KIND == 0 ? 8 : (KIND == 1 ? 4 : 3)) k_wf
     constexpr int c_hi = KIND == 0 ? PT_CLS_LAMBERT_SOLID : (KIND == 1 ? PT_CLS_LAMBERT_TEX : kNumBins);
     const DScene& S = P.S;
     const int cur = P.bounce & 1, nxt = cur ^ 1;
-    if (KIND == 0 && blockIdx.x == 0 && threadIdx.x == 0) P.Q.cursor[0] = 0;       // for the next k_wf_extend
+    if (KIND == 0 && blockIdx.x == 0 && threadIdx.x == 0) { P.Q.cursor[0] = 0; P.Q.tie_count[1] = 0; }       // for the next k_wf_extend
     __shared__ int prefix[c_hi - c_lo + 1];       // starts of this kernel's classes within its own run
     if (threadIdx.x == 0) {
         int acc = 0;
@@ -1032,7 +1087,12 @@ __device__ __forceinline__ void tile_local_pixel(int local, int W, int rows, int
 // ONE: exactly one fused wave (the default schedule) -- throughput (1,1,1) and depth 0 are then compile-time
 // constants, the wave loop disappears and with it the Russian-roulette code (depth + 1 < 5) and several
 // registers that were live across the traversal.
-template <bool COUNT, bool FULL, bool REL, bool ONE>
+// Equal-t hits (pt_device.cuh resolve_tie): the ONE instantiation does not resolve them -- it appends the path id to
+// WfQueues.tie_list and goes on; a second, small launch of the TIES instantiation runs exactly those paths from their
+// camera ray again, resolving in place.  A path is keyed by (pixel, sample), not by the launch or lane that runs it, and
+// the order of the queue it lands in is free, so the frame is the same bits.  (The counting instantiation resolves in
+// place: every traversal is counted once.)
+template <bool COUNT, bool FULL, bool REL, bool ONE, bool TIES = false>
 __global__ void __launch_bounds__(PT_PRIMARY_THREADS, PT_PRIMARY_MINB) k_wf_primary(const __grid_constant__ WfParams P) {
     extern __shared__ float4 s_node_mem[];
     const DScene& S = P.S;
@@ -1041,7 +1101,8 @@ __global__ void __launch_bounds__(PT_PRIMARY_THREADS, PT_PRIMARY_MINB) k_wf_prim
     LocalCounters lc;
     const int max_depth = P.cam.max_depth;
     const f3 bg = mk3(P.cam.background[0], P.cam.background[1], P.cam.background[2]);
-    const int total = P.N * P.batch;
+    constexpr bool DEFER = ONE && !COUNT && !TIES && PT_TIE;
+    const int total = TIES ? P.Q.tie_count[0] : P.N * P.batch;
     const int stride = gridDim.x * blockDim.x;
     const int rounds = (total + stride - 1) / stride;
     for (int r = 0; r < rounds; r++) {
@@ -1052,9 +1113,14 @@ __global__ void __launch_bounds__(PT_PRIMARY_THREADS, PT_PRIMARY_MINB) k_wf_prim
         int ndepth = 0;
         ptm::Rng rng{0u, 1u};
         if (j < total) {
-            const int slot = j / P.N;
+            const int jj = TIES ? P.Q.tie_list[j] : j;          // TIES: the listed path ids are (slot, row, column) already
+            const int slot = jj / P.N;
             int px, ly;                                         // column, row within the window
-            if (P.tile) {
+            if (TIES) {
+                const int l = jj - slot * P.N;
+                ly = l / P.W;
+                px = l - ly * P.W;
+            } else if (P.tile) {
                 tile_local_pixel(j - slot * P.N, P.W, P.y1 - P.y0, px, ly);
             } else {
                 const int l = j - slot * P.N;
@@ -1081,7 +1147,13 @@ __global__ void __launch_bounds__(PT_PRIMARY_THREADS, PT_PRIMARY_MINB) k_wf_prim
                 float t, t_exit = 0.0f;
                 int ref, eref = kRefNone;
                 if (COUNT) lc.bounces++;
-                closest_hit_and_exit<COUNT, FULL, REL>(S, s_nodes, P.n_snodes, o, d, time, t, ref, t_exit, eref, lc);
+                if (closest_hit_and_exit<COUNT, FULL, REL, DEFER>(S, s_nodes, P.n_snodes, o, d, time, t, ref, t_exit, eref, lc)) {
+                    const int k = atomicAdd(P.Q.tie_count, 1);      // DEFER only: this path runs again in the TIES launch
+                    PT_BOUND(k >= 0 && k < P.Q.capacity, PT_DBG_QUEUE);
+                    P.Q.tie_list[k] = id;
+                    emit_next = false;
+                    break;
+                }
                 emit_next = wf_shade_one<FULL>(S, bg, max_depth, sp, o, d, thr, depth, rng, t, ref, t_exit, eref != kRefNone,
                                          no, nd, nthr, ndepth, time);
                 o = no; d = nd; thr = nthr; depth = ndepth;
@@ -1122,7 +1194,7 @@ __global__ void __launch_bounds__(256) k_make_rel_nodes(const float4* __restrict
 // zeroes the per-batch counters before k_wf_primary
 __global__ void k_wf_reset(const __grid_constant__ WfParams P) {
     if (threadIdx.x < kNumBins) P.Q.bin_count[threadIdx.x] = 0;
-    if (threadIdx.x == 0) { P.Q.qcount[0] = 0; P.Q.qcount[1] = 0; P.Q.cursor[0] = 0; P.Q.cursor[1] = 0; }   // cursor[1]: k_wf_tail_vote's
+    if (threadIdx.x == 0) { P.Q.qcount[0] = 0; P.Q.qcount[1] = 0; P.Q.cursor[0] = 0; P.Q.cursor[1] = 0; P.Q.tie_count[0] = 0; P.Q.tie_count[1] = 0; }   // cursor[1]: k_wf_tail_vote's
 }
 
 // The tail of a batch: after `P.bounce` full waves only a small fraction of the paths is still
@@ -1202,6 +1274,8 @@ __global__ void __launch_bounds__(256, 3) k_wf_tail_vote(const __grid_constant__
             int ref = T.best_ref;
             bool exit_hit = false;
             if (mode == 0) {
+                trav_finish<FULL>(T, S);                // equal-t hits: the primitive the reference would have kept
+                ref = T.best_ref;
                 if (ref != kRefNone && ref_is_medium(ref)) {          // exit search behind a medium boundary
                     mode = 1;
                     t_entry = t;
@@ -1620,6 +1694,7 @@ int pt_set_scene(PtContext* ctx, const void* device_blob, const PtPackedInfo* in
     S.quads = reinterpret_cast<const float4*>(base + info->off_quads);
     S.tris = reinterpret_cast<const float4*>(base + info->off_tris);
     S.prim_mat = reinterpret_cast<const uint32_t*>(base + info->off_prim_mat);
+    S.nodes_plain = S.nodes;
     S.materials = reinterpret_cast<const float4*>(base + info->off_materials);
     S.perlin_vec = reinterpret_cast<const float4*>(base + info->off_perlin);
     S.perlin_perm = reinterpret_cast<const uint8_t*>(base + info->off_perlin + 256 * 16);
@@ -1765,7 +1840,8 @@ static size_t wf_bytes_per_sample(size_t n) {
            + n * 16        // hit records
            + (size_t)kNumBins * n * 4   // material bins
            + n * 12        // radiance slab
-           + n * 12;       // spare (round 1 kept a second slab here; the size formula is part of the ABI)
+           + n * 4         // tie list (k_wf_fix_ties, k_wf_primary<..., TIES>)
+           + n * 8;        // spare (round 1 kept a second slab here; the size formula is part of the ABI)
 }
 static const size_t kMaxPathsInFlight = 0x78000000;
 static const size_t kWfFixedBytes = 4096 + 32 * 256;   // counter sets + per-section alignment slack
@@ -1835,10 +1911,12 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
         Q.hit = reinterpret_cast<float4*>(take(cap * 16));
         Q.bins = reinterpret_cast<uint32_t*>(take((size_t)kNumBins * cap * 4));
         Q.slab = reinterpret_cast<float*>(take(cap * 12));
+        Q.tie_list = reinterpret_cast<int*>(take(cap * 4));
         int* counters = reinterpret_cast<int*>(take(256));       // 64 ints
         Q.qcount = counters;
         Q.bin_count = counters + 8;
         Q.cursor = counters + 32;
+        Q.tie_count = counters + 40;
         Q.capacity = (int)cap;
     }
     P.Q = sets[0];
@@ -1864,6 +1942,10 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
     void (*k_primary)(const WfParams) = nullptr;
     void (*k_extend)(const WfParams) = nullptr;
     void (*k_tail)(const WfParams) = nullptr;
+    // exact-t ties: the launches that resolve what k_wf_extend / the fused primary wave only listed (not in counting mode)
+    void (*k_fix_ties)(const WfParams) = full ? k_wf_fix_ties<true> : k_wf_fix_ties<false>;
+    void (*k_primary_ties)(const WfParams) = nullptr;
+    const int grid_fix = ctx->num_sms * 2;
     void (*k_shade)(const WfParams) = full ? k_wf_shade<true> : k_wf_shade<false>;
     const bool split = ctx->wf_shade_split && ctx->wavefront_sort && !ctx->dbg_shade_smem && !(ctx->scene.full_features & 2);
     void (*k_shade_cls[3])(const WfParams) = {full ? k_wf_shade_cls<true, 0> : k_wf_shade_cls<false, 0>,
@@ -1890,6 +1972,7 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
         else k_tail = full ? k_wf_tail<true, true> : k_wf_tail<true, false>;
     } else {
         const bool one = ctx->wf_fuse_primary == 1 && ctx->cam.max_depth > 0;   // then fused == 1 below
+        if (one && PT_TIE) k_primary_ties = full ? k_wf_primary<false, true, false, true, true> : k_wf_primary<false, false, false, true, true>;
         if (rel) k_primary = full ? k_wf_primary<false, true, true, true> : k_wf_primary<false, false, true, true>;
         else if (one) k_primary = full ? k_wf_primary<false, true, false, true> : k_wf_primary<false, false, false, true>;
         else k_primary = full ? k_wf_primary<false, true, false, false> : k_wf_primary<false, false, false, false>;
@@ -1901,6 +1984,7 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
         else k_tail = full ? k_wf_tail<false, true> : k_wf_tail<false, false>;
     }
     if ((rc = set_smem(k_primary, smem)) || (rc = set_smem(k_extend, smem)) || (rc = set_smem(k_tail, smem))) return rc;
+    if (k_primary_ties && (rc = set_smem(k_primary_ties, smem))) return rc;
     if (ctx->dbg_shade_smem && (rc = set_smem(k_shade, (size_t)ctx->dbg_shade_smem))) return rc;
     int occ_primary = 1, occ_shade = 1, occ_tail = 1;
     const int bt_primary = ctx->wf_primary_threads;
@@ -1975,6 +2059,7 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
                 WfParams Pp = P;
                 if (rel) Pp.S.nodes = rel_nodes;                           // this launch only
                 k_primary<<<grid_primary, bt_primary, smem, bs>>>(Pp);
+                if (k_primary_ties) k_primary_ties<<<ctx->num_sms, bt_primary, smem, bs>>>(P);      // plain node boxes
             }
             first_wave = P.fused_waves;
         } else {
@@ -1982,7 +2067,11 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
         }
         for (int b = first_wave; b < waves; b++) {        // renderer.py:313; no host read-back of the ray count
             P.bounce = b;
-            { StageScope t(ctx, bs, PT_STAGE_EXTEND, b); k_extend<<<grid_extend, PT_EXT_WARPS * 32, smem, bs>>>(P); }
+            {
+                StageScope t(ctx, bs, PT_STAGE_EXTEND, b);
+                k_extend<<<grid_extend, PT_EXT_WARPS * 32, smem, bs>>>(P);
+                if (!ctx->count && PT_TIE) k_fix_ties<<<grid_fix, 128, 0, bs>>>(P);
+            }
             if (P.sort) { StageScope t(ctx, bs, PT_STAGE_BIN, b); k_wf_bin<<<grid_wide, bt, 0, bs>>>(P); }
             if (split) {
                 for (int k = 0; k < 3; k++) {
@@ -2040,10 +2129,12 @@ int pt_wf_begin(PtContext* ctx, int W, int H, int y0, int y1, int sample_base, i
     P.Q.hit = reinterpret_cast<float4*>(take(cap * 16));
     P.Q.bins = reinterpret_cast<uint32_t*>(take((size_t)kNumBins * cap * 4));
     P.Q.slab = reinterpret_cast<float*>(take(cap * 12));
+    P.Q.tie_list = reinterpret_cast<int*>(take(cap * 4));
     int* counters = reinterpret_cast<int*>(take(256));
     P.Q.qcount = counters;
     P.Q.bin_count = counters + 8;
     P.Q.cursor = counters + 32;
+    P.Q.tie_count = counters + 40;
     P.Q.capacity = (int)cap;
     P.accum = nullptr;
     P.W = W; P.H = H; P.y0 = y0; P.y1 = y1;
@@ -2102,6 +2193,10 @@ int pt_wf_extend(PtContext* ctx, int bounce, void* stream) {
     const int grid_full = (int)((total + PT_EXT_WARPS * 32 - 1) / (PT_EXT_WARPS * 32));
     const int grid_persist = ctx->num_sms * ctx->wf_blocks_per_sm;
     k<<<grid_persist < grid_full ? grid_persist : grid_full, PT_EXT_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(*P);
+    if (!ctx->count && PT_TIE) {
+        if (full) k_wf_fix_ties<true><<<ctx->num_sms * 2, 128, 0, static_cast<cudaStream_t>(stream)>>>(*P);
+        else k_wf_fix_ties<false><<<ctx->num_sms * 2, 128, 0, static_cast<cudaStream_t>(stream)>>>(*P);
+    }
     PT_CUDA(cudaGetLastError());
     return PT_OK;
 }

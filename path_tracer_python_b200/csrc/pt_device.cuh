@@ -57,7 +57,15 @@ __device__ __forceinline__ float min2(float a, float b) { return a < b ? a : b; 
 __device__ __forceinline__ float max2(float a, float b) { return a > b ? a : b; }
 
 // ---- packed scene as the kernels see it (pointers into the caller's device blob)
+#ifndef PT_WIDE
+#define PT_WIDE 0
+#endif
+#ifndef PT_TIE
+#define PT_TIE (!PT_WIDE)   // exact-t ties resolved the reference's way (resolve_tie); the 4-wide variant build keeps its visiting order
+#endif
 constexpr int kRefNone = (int)0x80000000;   // "no child" / "no hit"
+constexpr int kRefTie = 0x40000000;         // set in every leaf reference (primitive index < 2^25).  TravState.best_ref with the
+                                            // bit CLEARED: another primitive was hit at exactly best_t (trav_take_tie)
 constexpr int kStackSize = 64;              // kernels.py:649
 
 struct DScene {
@@ -66,6 +74,7 @@ struct DScene {
     const float4* quads;      // (n.xyz D) (Q.xyz w.x) (u.xyz w.y) (v.xyz w.z)
     const float4* tris;       // (v0.xyz n.x) (e1.xyz n.y) (e2.xyz n.z)
     const uint32_t* prim_mat; // material id per primitive: [spheres | triangles | quads]
+    const float4* nodes_plain; // = nodes, except in the launch that traverses the origin-relative copy (resolve_tie)
     const float4* materials;  // 3 x float4 per unique material
     const float4* perlin_vec; // 256 gradient vectors
     const uint8_t* perlin_perm; // perm_x | perm_y | perm_z (256 each)
@@ -471,9 +480,6 @@ __device__ __forceinline__ void load_node(const float4* __restrict__ nodes, SNod
     nc = make_float4(c2.x, c2.y, 0.0f, 0.0f);
 }
 
-#ifndef PT_WIDE
-#define PT_WIDE 0
-#endif
 #if PT_WIDE
 // ---- the 4-wide node visit (PT_WIDE=1 build): one 128-byte node = four 256-bit loads, four slab tests, the hit
 // children sorted by entry distance with a 5-comparator network on 32-bit keys (entry distance with the child slot in
@@ -600,6 +606,9 @@ __device__ __forceinline__ bool trav_run(TravState& T, const DScene& S, SNodeBas
             if (type == PT_PRIM_SPHERE) { if (COUNT) lc.sphere_tests++; hit = hit_sphere_t<FULL>(S, idx, T.o, T.d, t_min, T.best_t, t, T.time); }
             else if (type == PT_PRIM_QUAD) { if (COUNT) lc.quad_tests++; hit = hit_quad_t(S, idx, T.o, T.d, t_min, T.best_t, t); }
             else { if (COUNT) lc.triangle_tests++; hit = hit_triangle_t(S, idx, T.o, T.d, t_min, T.best_t, t); }
+            // the primitive tests accept t <= best_t; exactly equal: trav_take_tie (kRefNone stays kRefNone).  Two separate
+            // predicated statements: as if / else the compiler routes best_t and best_ref through copies on every path
+            if (PT_TIE && hit && t == T.best_t) T.best_ref &= ~kRefTie;
             if (hit && t < T.best_t) { T.best_t = t; T.best_ref = T.cur; }   // kernels.py:691 (strict)
             T.cur = trav_pop(T, stack);
         }
@@ -692,6 +701,8 @@ __device__ __forceinline__ void trav_run_vote(TravState& T, bool active, bool& d
                 if (type == PT_PRIM_SPHERE) { if (COUNT) lc.sphere_tests++; hit = hit_sphere_t<FULL>(S, idx, T.o, T.d, t_min, T.best_t, t, T.time); }
                 else if (type == PT_PRIM_QUAD) { if (COUNT) lc.quad_tests++; hit = hit_quad_t(S, idx, T.o, T.d, t_min, T.best_t, t); }
                 else { if (COUNT) lc.triangle_tests++; hit = hit_triangle_t(S, idx, T.o, T.d, t_min, T.best_t, t); }
+                // the primitive tests accept t <= best_t; exactly equal: trav_take_tie (kRefNone stays kRefNone)
+                if (PT_TIE && hit && t == T.best_t) T.best_ref &= ~kRefTie;
                 if (hit && t < T.best_t) { T.best_t = t; T.best_ref = cur; }   // kernels.py:691 (strict)
                 cur = trav_pop(T, stack);
             }
@@ -699,6 +710,86 @@ __device__ __forceinline__ void trav_run_vote(TravState& T, bool active, bool& d
     }
     if (active) T.cur = cur;
     done = active && cur == kRefNone;
+}
+
+// ---- equal-t hits.  The reference keeps the FIRST of several primitives hit at exactly the same t (strict
+// `t < closest_t`, kernels.py:691), and it meets them in the order of ITS traversal: at every inner node the child whose
+// box centre projects nearer along the ray first (kernels.py:703-732).  The traversals above meet them in another order
+// (nearest slab entry first, warp votes), so they only note that it happened -- bit kRefTie of best_ref cleared; a closer
+// hit sets a fresh reference and with it the bit again, which matters: 0.8 % of config 2's rays meet two coincident box
+// walls BEHIND the surface they finally stop at, 0.02 % end on a shared hit.  For those, resolve_tie walks the tree the
+// reference's way and returns the first primitive it meets that is hit at exactly t.  Pruning nodes never changes the
+// relative order in which a depth-first walk meets the leaves that remain, so the walk only follows boxes the ray is
+// inside of at the hit itself: slab interval meeting [t (1 - 2^-7), t], a margin five orders of magnitude above the
+// rounding of a slab distance -- a root-to-leaf path or two.
+// Where it runs: measured on config 2, ANY resolve code inside k_wf_extend -- a call or an inlined loop, executed for
+// one ray in 5000 -- slows that kernel by 10 % (register allocation / scheduling of the voting loop around it), while
+// noting costs under 1 %.  So the two kernels that carry the frame defer: k_wf_extend lists the ray (WfQueues.tie_list)
+// for k_wf_fix_ties, the fused primary wave lists the path for a second, small launch of its resolving instantiation.
+// Whole cost on config 2: -1.5 % (note 0.8, the extra launches 0.5, list appends 0.2); megakernel -2.7 %.
+// The kernels that shade in place and are not on the critical path of the frame (k_megakernel, the tails, probes, the
+// counting instantiations) call trav_finish.  Coincident faces of neighbouring boxes and a medium standing on a floor
+// are everyday modelling, and when the tied primitives have different materials the choice shows in the image.
+template <bool FULL>
+__device__ __noinline__ int resolve_tie(const DScene& S, f3 o, f3 d, f3 inv, float t_min, float t, float time) {
+#if PT_WIDE
+    return kRefNone;
+#else
+    int stack[kStackSize];
+    int sp = 0;
+    int cur = S.num_inner > 0 ? 0 : kRefNone;
+    const float t_lo = fmaxf(t_min, t * 0.9921875f);
+    while (cur != kRefNone) {
+        if (cur >= 0) {
+            PT_BOUND(cur < S.num_inner, PT_DBG_NODE);
+            const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const char*>(S.nodes_plain) + (unsigned long long)(unsigned)cur * 64ull);
+            const float4 nx = __ldg(p), ny = __ldg(p + 1), nz = __ldg(p + 2);
+            const float2 c2 = __ldg(reinterpret_cast<const float2*>(p + 3));
+            const int lref = __float_as_int(c2.x), rref = __float_as_int(c2.y);
+            const float l0x = (nx.x - o.x) * inv.x, l1x = (nx.y - o.x) * inv.x, l0y = (ny.x - o.y) * inv.y, l1y = (ny.y - o.y) * inv.y;
+            const float l0z = (nz.x - o.z) * inv.z, l1z = (nz.y - o.z) * inv.z;
+            const float r0x = (nx.z - o.x) * inv.x, r1x = (nx.w - o.x) * inv.x, r0y = (ny.z - o.y) * inv.y, r1y = (ny.w - o.y) * inv.y;
+            const float r0z = (nz.z - o.z) * inv.z, r1z = (nz.w - o.z) * inv.z;
+            const bool hl = fmin3(fmaxf(l0x, l1x), fmaxf(l0y, l1y), fminf(fmaxf(l0z, l1z), t)) >=
+                            fmax3(fminf(l0x, l1x), fminf(l0y, l1y), fmaxf(fminf(l0z, l1z), t_lo));
+            const bool hr = fmin3(fmaxf(r0x, r1x), fmaxf(r0y, r1y), fminf(fmaxf(r0z, r1z), t)) >=
+                            fmax3(fminf(r0x, r1x), fminf(r0y, r1y), fmaxf(fminf(r0z, r1z), t_lo));
+            const f3 lc = mk3((nx.x + nx.y) * 0.5f, (ny.x + ny.y) * 0.5f, (nz.x + nz.y) * 0.5f);
+            const f3 rc = mk3((nx.z + nx.w) * 0.5f, (ny.z + ny.w) * 0.5f, (nz.z + nz.w) * 0.5f);
+            const bool left_first = dot(lc - o, d) < dot(rc - o, d);        // kernels.py:716-721
+            const int first = left_first ? lref : rref, second = left_first ? rref : lref;
+            const bool hf = left_first ? hl : hr, hs = left_first ? hr : hl;
+            if (hf && hs) { if (sp < kStackSize) stack[sp++] = second; cur = first; }
+            else if (hf) cur = first;
+            else if (hs) cur = second;
+            else cur = sp > 0 ? stack[--sp] : kRefNone;
+        } else {
+            const int type = ref_type(cur), idx = ref_index(cur);
+            float tt = 0.0f;
+            bool hit;
+            if (type == PT_PRIM_SPHERE) hit = hit_sphere_t<FULL>(S, idx, o, d, t_min, t, tt, time);
+            else if (type == PT_PRIM_QUAD) hit = hit_quad_t(S, idx, o, d, t_min, t, tt);
+            else hit = hit_triangle_t(S, idx, o, d, t_min, t, tt);
+            if (hit && tt == t) return cur;
+            cur = sp > 0 ? stack[--sp] : kRefNone;
+        }
+    }
+    return kRefNone;
+#endif
+}
+// the tie flag of a finished closest-hit traversal; leaves best_ref a plain reference again
+__device__ __forceinline__ bool trav_take_tie(TravState& T) {
+    const bool tie = PT_TIE && !(T.best_ref & kRefTie) && T.best_ref != kRefNone;
+    if (tie) T.best_ref |= kRefTie;
+    return tie;
+}
+// call when a closest-hit traversal has finished and the primitive id matters (resolves in place)
+template <bool FULL>
+__device__ __forceinline__ void trav_finish(TravState& T, const DScene& S) {
+    if (trav_take_tie(T)) {
+        const int r = resolve_tie<FULL>(S, T.o, T.d, T.inv, T.t_min, T.best_t, T.time);
+        if (r != kRefNone) T.best_ref = r;
+    }
 }
 
 // One-shot traversal (probe / wavefront kernels).
@@ -712,6 +803,7 @@ __device__ __forceinline__ void traverse(const DScene& S, SNodeBase s_nodes, int
     TravState T;
     trav_begin<COUNT>(T, S, o, d, t_min, t_max, lc, time);
     trav_run<COUNT, FULL>(T, S, s_nodes, n_snodes, stack, 0, lc);
+    trav_finish<FULL>(T, S);
     best_t = T.best_t;
     best_ref = T.best_ref;
 }

@@ -21,7 +21,7 @@ constexpr int kRefNone = (int)0x80000000;
 // material tables: 1 emissive, 2 Lambert with a solid colour, 3 Lambert with a checker / image / noise
 // texture, 4 metal, 5 dielectric, 6 constant-medium boundary, 7 everything else (isotropic, subsurface);
 // 0 is reserved for "miss" (pt_device.cuh PT_CLS_*).
-constexpr int kMaxPrimsPerType = 1 << 26;
+constexpr int kMaxPrimsPerType = 1 << 25;   // bit 30 of a leaf reference stays set: the traversal clears it to flag an exact-t tie (kRefTie)
 inline int leaf_ref(int prim_type, int prim_idx, int cls) { return ~((prim_idx << 5) | ((cls & 7) << 2) | prim_type); }
 inline int shading_class(const PtHostMaterials& m, int i) {
     if (m.is_medium[i] > 0) return 6;
@@ -322,7 +322,7 @@ int pt_pack_scene_info(const PtHostScene* s, PtPackedInfo* info) {
     if (!s || !info) { g_host_error = "pt_pack_scene_info: NULL argument"; return PT_ERR_INVALID_ARG; }
     if (s->num_images > PT_MAX_IMAGES) { g_host_error = "too many image textures"; return PT_ERR_CAPACITY; }
     if (s->num_spheres >= kMaxPrimsPerType || s->num_quads >= kMaxPrimsPerType || s->num_triangles >= kMaxPrimsPerType) {
-        g_host_error = "more than 2^26 primitives of one type";
+        g_host_error = "more than 2^25 primitives of one type";
         return PT_ERR_CAPACITY;
     }
     memset(info, 0, sizeof *info);

@@ -16,7 +16,7 @@ def engine():
 
 def test_config3_million_triangles_first_hit_bit_exact(engine, oracle_mod):
     """~1 M triangles: native SAH build, then first-hit parity (bit-exact t / point / normal, ids equal
-    up to exact-t ties between neighbouring triangles) on primary and on incoherent bounce rays."""
+    including exact-t ties between neighbouring triangles, which follow the reference's visiting order) on primary and on incoherent bounce rays."""
     from path_tracer_python_b200 import scenes
     import golden_fixtures
     O = oracle_mod
@@ -46,7 +46,7 @@ def test_config3_million_triangles_first_hit_bit_exact(engine, oracle_mod):
         rp = (ref["prim_type"].astype(np.int64) << 28) | ref["prim_idx"]
         hit = ref["valid"] == 1
         same = gprim[hit] == rp[hit]
-        assert same.mean() > 0.995
+        assert same.all(), f"{np.count_nonzero(~same)} primitive ids differ"      # exact-t ties resolve as in the reference's visiting order
         m = hit.copy(); m[hit] = same
         assert np.array_equal(gp[m], ref["p"][m]) and np.array_equal(gn[m], ref["n"][m])
         assert hit.mean() > 0.3
