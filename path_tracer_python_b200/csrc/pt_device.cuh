@@ -264,6 +264,39 @@ __device__ __forceinline__ float fmin3(float a, float b, float c) {
 #define PT_SLAB(b, o_, inv_, noi_) (((b) - (o_)) * (inv_))
 #define PT_BOX_HIT(tmax, tmin, slack) ((tmax) >= (tmin))
 #endif
+// Blackwell's packed fp32 arithmetic (sub / mul .f32x2 -> FADD2 / FMUL2, sm_100+): two IEEE round-to-nearest
+// operations per issue slot, the scalar operand broadcast by the instruction itself (Rn.F32).  The two planes
+// of one axis of one child box arrive as an aligned register pair out of the 256-bit node load, so the strict
+// slab test's 12 FADD + 12 FMUL per node visit become 6 FADD2 + 6 FMUL2 -- same roundings, same bits
+// (no .ftz: subnormals are kept, as in the scalar code under -ftz=false).
+#ifndef PT_F32X2
+#define PT_F32X2 (!PT_FAST)
+#endif
+__device__ __forceinline__ void slab2(float b0, float b1, float o, float inv, float& r0, float& r1) {
+#if PT_F32X2
+    asm("{\n\t.reg .b64 v, oo, ii;\n\t"
+        "mov.b64 v, {%2, %3};\n\tmov.b64 oo, {%4, %4};\n\tmov.b64 ii, {%5, %5};\n\t"
+        "sub.rn.f32x2 v, v, oo;\n\tmul.rn.f32x2 v, v, ii;\n\t"
+        "mov.b64 {%0, %1}, v;\n\t}"
+        : "=f"(r0), "=f"(r1) : "f"(b0), "f"(b1), "f"(o), "f"(inv));
+#else
+    r0 = (b0 - o) * inv;
+    r1 = (b1 - o) * inv;
+#endif
+}
+// ... and the origin-relative form (boxes with the shared ray origin already subtracted): one FMUL2
+__device__ __forceinline__ void slab2_rel(float b0, float b1, float inv, float& r0, float& r1) {
+#if PT_F32X2
+    asm("{\n\t.reg .b64 v, ii;\n\t"
+        "mov.b64 v, {%2, %3};\n\tmov.b64 ii, {%4, %4};\n\t"
+        "mul.rn.f32x2 v, v, ii;\n\t"
+        "mov.b64 {%0, %1}, v;\n\t}"
+        : "=f"(r0), "=f"(r1) : "f"(b0), "f"(b1), "f"(inv));
+#else
+    r0 = b0 * inv;
+    r1 = b1 * inv;
+#endif
+}
 
 typedef unsigned long long StackEntry;
 #ifndef PT_STACK_TOP
@@ -569,6 +602,15 @@ __device__ __forceinline__ bool trav_run(TravState& T, const DScene& S, SNodeBas
             if (COUNT) lc.box_tests += 2;
             const float best_t = T.best_t;
             float l0x, l1x, l0y, l1y, l0z, l1z, r0x, r1x, r0y, r1y, r0z, r1z;
+#if PT_F32X2
+            if (REL) {
+                slab2_rel(nx.x, nx.y, inv.x, l0x, l1x); slab2_rel(ny.x, ny.y, inv.y, l0y, l1y); slab2_rel(nz.x, nz.y, inv.z, l0z, l1z);
+                slab2_rel(nx.z, nx.w, inv.x, r0x, r1x); slab2_rel(ny.z, ny.w, inv.y, r0y, r1y); slab2_rel(nz.z, nz.w, inv.z, r0z, r1z);
+            } else {
+                slab2(nx.x, nx.y, o.x, inv.x, l0x, l1x); slab2(ny.x, ny.y, o.y, inv.y, l0y, l1y); slab2(nz.x, nz.y, o.z, inv.z, l0z, l1z);
+                slab2(nx.z, nx.w, o.x, inv.x, r0x, r1x); slab2(ny.z, ny.w, o.y, inv.y, r0y, r1y); slab2(nz.z, nz.w, o.z, inv.z, r0z, r1z);
+            }
+#else
             if (REL) {
                 l0x = nx.x * inv.x; l1x = nx.y * inv.x; l0y = ny.x * inv.y; l1y = ny.y * inv.y; l0z = nz.x * inv.z; l1z = nz.y * inv.z;
                 r0x = nx.z * inv.x; r1x = nx.w * inv.x; r0y = ny.z * inv.y; r1y = ny.w * inv.y; r0z = nz.z * inv.z; r1z = nz.w * inv.z;
@@ -580,6 +622,7 @@ __device__ __forceinline__ bool trav_run(TravState& T, const DScene& S, SNodeBas
                 r0y = PT_SLAB(ny.z, o.y, inv.y, noi.y); r1y = PT_SLAB(ny.w, o.y, inv.y, noi.y);
                 r0z = PT_SLAB(nz.z, o.z, inv.z, noi.z); r1z = PT_SLAB(nz.w, o.z, inv.z, noi.z);
             }
+#endif
             float ltmin = fmax3(fminf(l0x, l1x), fminf(l0y, l1y), fmaxf(fminf(l0z, l1z), t_min));
             float ltmax = fmin3(fmaxf(l0x, l1x), fmaxf(l0y, l1y), fminf(fmaxf(l0z, l1z), best_t));
             float rtmin = fmax3(fminf(r0x, r1x), fminf(r0y, r1y), fmaxf(fminf(r0z, r1z), t_min));
@@ -667,6 +710,13 @@ __device__ __forceinline__ void trav_run_vote(TravState& T, bool active, bool& d
                 load_node(nodes, s_nodes, n_snodes, cur, nx, ny, nz, nc, S.num_inner);
                 if (COUNT) lc.box_tests += 2;
                 const float best_t = T.best_t;
+#if PT_F32X2
+                float l0x, l1x, l0y, l1y, l0z, l1z, r0x, r1x, r0y, r1y, r0z, r1z;
+                slab2(nx.x, nx.y, o.x, inv.x, l0x, l1x); slab2(ny.x, ny.y, o.y, inv.y, l0y, l1y); slab2(nz.x, nz.y, o.z, inv.z, l0z, l1z);
+                slab2(nx.z, nx.w, o.x, inv.x, r0x, r1x); slab2(ny.z, ny.w, o.y, inv.y, r0y, r1y); slab2(nz.z, nz.w, o.z, inv.z, r0z, r1z);
+                float ltmin = fmax3(fminf(l0x, l1x), fminf(l0y, l1y), fmaxf(fminf(l0z, l1z), t_min));
+                float ltmax = fmin3(fmaxf(l0x, l1x), fmaxf(l0y, l1y), fminf(fmaxf(l0z, l1z), best_t));
+#else
                 float l0x = PT_SLAB(nx.x, o.x, inv.x, noi.x), l1x = PT_SLAB(nx.y, o.x, inv.x, noi.x);
                 float l0y = PT_SLAB(ny.x, o.y, inv.y, noi.y), l1y = PT_SLAB(ny.y, o.y, inv.y, noi.y);
                 float l0z = PT_SLAB(nz.x, o.z, inv.z, noi.z), l1z = PT_SLAB(nz.y, o.z, inv.z, noi.z);
@@ -675,6 +725,7 @@ __device__ __forceinline__ void trav_run_vote(TravState& T, bool active, bool& d
                 float r0x = PT_SLAB(nx.z, o.x, inv.x, noi.x), r1x = PT_SLAB(nx.w, o.x, inv.x, noi.x);
                 float r0y = PT_SLAB(ny.z, o.y, inv.y, noi.y), r1y = PT_SLAB(ny.w, o.y, inv.y, noi.y);
                 float r0z = PT_SLAB(nz.z, o.z, inv.z, noi.z), r1z = PT_SLAB(nz.w, o.z, inv.z, noi.z);
+#endif
                 float rtmin = fmax3(fminf(r0x, r1x), fminf(r0y, r1y), fmaxf(fminf(r0z, r1z), t_min));
                 float rtmax = fmin3(fmaxf(r0x, r1x), fmaxf(r0y, r1y), fminf(fmaxf(r0z, r1z), best_t));
                 const int lref = __float_as_int(nc.x), rref = __float_as_int(nc.y);
