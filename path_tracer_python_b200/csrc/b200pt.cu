@@ -72,6 +72,7 @@ struct PtContext {
     cudaEvent_t ev_resolve[kMaxPipes] = {}, ev_start = nullptr;
     int wf_tail_vote = 1;    // the tail as a persistent voting state machine (k_wf_tail_vote) instead of one lane per ray
     int wf_rel_primary = 1;  // camera rays without defocus: slab test against origin-relative node boxes
+    int wf_oct_nodes = 1;    // direction-octant variants of the node array (pt_device.cuh trav_root), built per call in the workspace
     int wf_grid_waves = 16;  // static-partition kernels launch this many full waves of resident CTAs
     int dbg_shade_smem = 0;  // experiment knob: dynamic shared memory reserved per k_wf_shade CTA (limits residency)
     int wf_fuse_primary = 1; // wave 0 (camera rays) as one fused kernel
@@ -709,7 +710,7 @@ __global__ void __launch_bounds__(128) k_wf_fix_ties(const __grid_constant__ WfP
 // (k_wf_primary, k_wf_tail) carry one copy of the traversal code, not two (instruction cache).
 // DEFER: an exact-t tie is not resolved here -- the function returns true at once and the caller hands the path to a
 // launch that does (k_wf_primary<..., TIES>).
-template <bool COUNT, bool FULL, bool REL = false, bool DEFER = false>
+template <bool COUNT, bool FULL, bool REL = false, bool DEFER = false, bool OCT = false>
 __device__ __forceinline__ bool closest_hit_and_exit(const DScene& S, SNodeBase s_nodes, int n_snodes, f3 o, f3 d, float time,
                                                      float& t, int& ref, float& t_exit, int& eref, LocalCounters& lc) {
     StackEntry stack_mem[kStackSlots];
@@ -723,7 +724,8 @@ __device__ __forceinline__ bool closest_hit_and_exit(const DScene& S, SNodeBase 
 #pragma unroll 1
     for (int pass = 0; pass < 2; pass++) {
         if (pass) trav_restart<COUNT>(T, S, t_min, 1e10f, lc);
-        trav_run<COUNT, FULL, REL>(T, S, s_nodes, n_snodes, stack, 0, lc);
+        if (OCT) T.cur = trav_root(S, T.inv);       // S.nodes holds the direction-octant variants
+        trav_run<COUNT, FULL, REL, LocalStack, OCT>(T, S, s_nodes, n_snodes, stack, 0, lc);
         if (pass == 0) {
             if (DEFER) { if (trav_take_tie(T)) return true; }
             else trav_finish<FULL>(T, S);               // equal-t hits: the primitive the reference would have kept
@@ -1092,7 +1094,9 @@ __device__ __forceinline__ void tile_local_pixel(int local, int W, int rows, int
 // camera ray again, resolving in place.  A path is keyed by (pixel, sample), not by the launch or lane that runs it, and
 // the order of the queue it lands in is free, so the frame is the same bits.  (The counting instantiation resolves in
 // place: every traversal is counted once.)
-template <bool COUNT, bool FULL, bool REL, bool ONE, bool TIES = false>
+// OCT: the launch traverses the direction-octant variants of the node array (pt_device.cuh trav_root; P.S.nodes and
+// P.S.oct_stride are set for this launch only).
+template <bool COUNT, bool FULL, bool REL, bool ONE, bool TIES = false, bool OCT = false>
 __global__ void __launch_bounds__(PT_PRIMARY_THREADS, PT_PRIMARY_MINB) k_wf_primary(const __grid_constant__ WfParams P) {
     extern __shared__ float4 s_node_mem[];
     const DScene& S = P.S;
@@ -1147,7 +1151,7 @@ __global__ void __launch_bounds__(PT_PRIMARY_THREADS, PT_PRIMARY_MINB) k_wf_prim
                 float t, t_exit = 0.0f;
                 int ref, eref = kRefNone;
                 if (COUNT) lc.bounces++;
-                if (closest_hit_and_exit<COUNT, FULL, REL, DEFER>(S, s_nodes, P.n_snodes, o, d, time, t, ref, t_exit, eref, lc)) {
+                if (closest_hit_and_exit<COUNT, FULL, REL, DEFER, OCT>(S, s_nodes, P.n_snodes, o, d, time, t, ref, t_exit, eref, lc)) {
                     const int k = atomicAdd(P.Q.tie_count, 1);      // DEFER only: this path runs again in the TIES launch
                     PT_BOUND(k >= 0 && k < P.Q.capacity, PT_DBG_QUEUE);
                     P.Q.tie_list[k] = id;
@@ -1190,6 +1194,34 @@ __global__ void __launch_bounds__(256) k_make_rel_nodes(const float4* __restrict
         rel[i] = v;
     }
 }
+
+#if !PT_WIDE
+// The eight direction-octant variants of the node array (trav_root): variant k swaps the (min, max) slots of both child
+// boxes on the axes whose bit is set in k and points its inner references into itself (+ k * num_inner); with `rel`
+// the origin is subtracted as in k_make_rel_nodes.  One thread per (variant, node).
+__global__ void __launch_bounds__(256) k_make_oct_nodes(const float4* __restrict__ nodes, float4* __restrict__ out, int num_inner,
+                                                        int rel, float ox, float oy, float oz) {
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 8 * num_inner; i += stride) {
+        const int k = i / num_inner, j = i - k * num_inner;
+        float4 v[3];
+        const float o[3] = {ox, oy, oz};
+        for (int a = 0; a < 3; a++) {
+            v[a] = nodes[4 * j + a];
+            if (rel) v[a] = make_float4(v[a].x - o[a], v[a].y - o[a], v[a].z - o[a], v[a].w - o[a]);
+            if ((k >> a) & 1) v[a] = make_float4(v[a].y, v[a].x, v[a].w, v[a].z);
+        }
+        float4 r = nodes[4 * j + 3];
+        int lref = __float_as_int(r.x), rref = __float_as_int(r.y);
+        if (lref >= 0) lref += k * num_inner;
+        if (rref >= 0) rref += k * num_inner;
+        r.x = __int_as_float(lref);
+        r.y = __int_as_float(rref);
+        float4* q = out + 4 * (size_t)i;
+        q[0] = v[0]; q[1] = v[1]; q[2] = v[2]; q[3] = r;
+    }
+}
+#endif
 
 // zeroes the per-batch counters before k_wf_primary
 __global__ void k_wf_reset(const __grid_constant__ WfParams P) {
@@ -1624,6 +1656,8 @@ int pt_set_option(PtContext* ctx, const char* name, int64_t value) {
         ctx->wf_tail_vote = value ? 1 : 0;
     } else if (k == "wf_rel_primary") {
         ctx->wf_rel_primary = value ? 1 : 0;
+    } else if (k == "wf_oct_nodes") {
+        ctx->wf_oct_nodes = value ? 1 : 0;
     } else if (k == "wf_grid_waves") {
         if (value < 1 || value > 4096) return set_error(PT_ERR_INVALID_ARG, "wf_grid_waves must be in [1, 4096]");
         ctx->wf_grid_waves = (int)value;
@@ -1866,6 +1900,16 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
     // workspace too, when that leaves room for at least one sample in flight; it is rebuilt by every
     // call (microseconds), so the context owns no device memory besides its counters.
     size_t rel_bytes = align_up((size_t)ctx->scene.num_inner * kNodeBytes, 256);
+    // With room for eight copies (and up to 1 GiB of them), the primary wave traverses the direction-octant variants of
+    // that array (pt_device.cuh trav_root).
+    bool oct = false;
+#if !PT_WIDE && !PT_FAST
+    if (ctx->wf_oct_nodes && ctx->scene.num_inner > 0 && 8 * rel_bytes <= ((size_t)1 << 30) &&
+        workspace_bytes >= kWfFixedBytes + 8 * rel_bytes + wf_bytes_per_sample(n)) {
+        oct = true;
+        rel_bytes *= 8;
+    }
+#endif
     if (workspace_bytes < kWfFixedBytes + rel_bytes + wf_bytes_per_sample(n)) rel_bytes = 0;
     // samples in flight: as many as the workspace holds (and the 31-bit path id allows)
     const size_t S_cap = (workspace_bytes - kWfFixedBytes - rel_bytes) / wf_bytes_per_sample(n);
@@ -1958,6 +2002,19 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
     // (not with next-event estimation: its shadow rays start at the hit points and need the plain node boxes)
     bool rel = !PT_FAST && !(ctx->scene.full_features & 2) && ctx->wf_rel_primary && ctx->wf_fuse_primary == 1 && !(ctx->cam.defocus_angle > 0.0f) &&
                ctx->scene.num_inner > 0 && ctx->cam.max_depth > 0 && !ctx->count && rel_nodes != nullptr;
+    // ... and its direction-octant variants (8 copies, with the origin subtracted when `rel`), same conditions minus the
+    // shared origin: camera rays are coherent in direction with or without defocus
+    oct = oct && !(ctx->scene.full_features & 2) && ctx->wf_fuse_primary == 1 && ctx->scene.num_inner > 0 && ctx->cam.max_depth > 0 &&
+          !ctx->count && rel_nodes != nullptr;
+#if !PT_WIDE
+    if (oct) {
+        int g = (int)(((size_t)ctx->scene.num_inner * 8 + 255) / 256);
+        if (g > ctx->num_sms * 8) g = ctx->num_sms * 8;
+        k_make_oct_nodes<<<g, 256, 0, static_cast<cudaStream_t>(stream)>>>(ctx->scene.nodes, rel_nodes, ctx->scene.num_inner, rel ? 1 : 0,
+                                                                          ctx->cam.center[0], ctx->cam.center[1], ctx->cam.center[2]);
+        PT_CUDA(cudaGetLastError());
+    } else
+#endif
     if (rel) {
         int g = (int)(((size_t)ctx->scene.num_inner * kNodeQuads + 255) / 256);
         if (g > ctx->num_sms * 8) g = ctx->num_sms * 8;
@@ -1973,7 +2030,9 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
     } else {
         const bool one = ctx->wf_fuse_primary == 1 && ctx->cam.max_depth > 0;   // then fused == 1 below
         if (one && PT_TIE) k_primary_ties = full ? k_wf_primary<false, true, false, true, true> : k_wf_primary<false, false, false, true, true>;
-        if (rel) k_primary = full ? k_wf_primary<false, true, true, true> : k_wf_primary<false, false, true, true>;
+        if (oct && rel) k_primary = full ? k_wf_primary<false, true, true, true, false, true> : k_wf_primary<false, false, true, true, false, true>;
+        else if (oct) k_primary = full ? k_wf_primary<false, true, false, true, false, true> : k_wf_primary<false, false, false, true, false, true>;
+        else if (rel) k_primary = full ? k_wf_primary<false, true, true, true> : k_wf_primary<false, false, true, true>;
         else if (one) k_primary = full ? k_wf_primary<false, true, false, true> : k_wf_primary<false, false, false, true>;
         else k_primary = full ? k_wf_primary<false, true, false, false> : k_wf_primary<false, false, false, false>;
         // MINB = resident CTAs per SM the register allocation is capped for (4: 64 regs, 5: 48, 6: 40)
@@ -2057,7 +2116,8 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
             {
                 StageScope t(ctx, bs, PT_STAGE_PRIMARY, 0);
                 WfParams Pp = P;
-                if (rel) Pp.S.nodes = rel_nodes;                           // this launch only
+                if (rel || oct) Pp.S.nodes = rel_nodes;                    // this launch only
+                if (oct) Pp.S.oct_stride = ctx->scene.num_inner;
                 k_primary<<<grid_primary, bt_primary, smem, bs>>>(Pp);
                 if (k_primary_ties) k_primary_ties<<<ctx->num_sms, bt_primary, smem, bs>>>(P);      // plain node boxes
             }

@@ -81,6 +81,8 @@ struct DScene {
     const uchar4* image[PT_MAX_IMAGES];
     int image_w[PT_MAX_IMAGES], image_h[PT_MAX_IMAGES];
     int num_inner;
+    int oct_stride;           // 0: `nodes` is the plain array.  N = num_inner: `nodes` holds 8 direction-octant variants of
+                              // it (variant k at node index k * N, its inner references offset likewise): see trav_root
     int n_prims[3];           // spheres, triangles, quads (by PT_PRIM_*)
     int num_materials;
     int mat_base[3];          // offset of each prim type inside prim_mat
@@ -318,6 +320,22 @@ struct TravState {
     unsigned long long top;   // newest stack entry, held in registers (low word kRefNone = stack empty)
 #endif
 };
+
+// ---- direction-octant node variants.  Variant k of the node array (bit 0 / 1 / 2 of k = the ray runs towards -x / -y / -z)
+// stores the two planes of an axis in the order the ray meets them: (max, min) instead of (min, max) on the axes the ray
+// descends.  The slab distances (b - o) * inv are the same numbers whichever slot they come from, and
+// min(a0, a1) is a0 by construction (fp subtraction and multiplication are monotone), so for a ray that traverses ITS
+// variant the six pair-wise FMNMX of a child box disappear: 8 min/max per node visit instead of 20 -- on the ALU pipe,
+// the most loaded one in the traversal kernels.  A variant is a complete tree (its inner references point into itself),
+// so picking it costs nothing but the root index.  Built per render call in the caller's workspace (k_make_oct_nodes).
+// Measured on config 2: the fused primary wave (coherent camera rays: a warp stays in one or two variants) -19 %;
+// k_wf_extend (incoherent bounce rays: eight times the node footprint in L1) +5.5 %, and a run-time switch between
+// the two forms of the test costs that kernel another 5 % -- so only trav_run<..., OCT> (the primary wave) has it.
+__device__ __forceinline__ int trav_root(const DScene& S, f3 inv) {
+    if (S.num_inner <= 0) return kRefNone;
+    const int k = (inv.x < 0.0f ? 1 : 0) | (inv.y < 0.0f ? 2 : 0) | (inv.z < 0.0f ? 4 : 0);
+    return k * S.oct_stride;
+}
 
 template <bool COUNT>
 __device__ __forceinline__ void trav_begin(TravState& T, const DScene& S, f3 o, f3 d, float t_min, float t_max,
@@ -576,7 +594,7 @@ constexpr int kNodeQuads = 4;
 // REL: S.nodes holds the node boxes with the ray origin already subtracted (every ray of the launch
 // shares that origin: camera rays without defocus; b200pt.cu k_make_rel_nodes).  fl(b - o) is the
 // same single rounding whoever performs it, so the slab test drops its 12 subtractions per node.
-template <bool COUNT, bool FULL = false, bool REL = false, class STK = LocalStack>
+template <bool COUNT, bool FULL = false, bool REL = false, class STK = LocalStack, bool OCT = false>
 __device__ __forceinline__ bool trav_run(TravState& T, const DScene& S, SNodeBase s_nodes, int n_snodes,
                                          const STK& stack, int min_active, LocalCounters& lc) {
     const f3 o = REL ? mk3(0.0f, 0.0f, 0.0f) : T.o;
@@ -598,7 +616,7 @@ __device__ __forceinline__ bool trav_run(TravState& T, const DScene& S, SNodeBas
             continue;
 #endif
             float4 nx, ny, nz, nc;
-            load_node(nodes, s_nodes, n_snodes, T.cur, nx, ny, nz, nc, S.num_inner);
+            load_node(nodes, s_nodes, n_snodes, T.cur, nx, ny, nz, nc, S.num_inner + 7 * S.oct_stride);
             if (COUNT) lc.box_tests += 2;
             const float best_t = T.best_t;
             float l0x, l1x, l0y, l1y, l0z, l1z, r0x, r1x, r0y, r1y, r0z, r1z;
@@ -623,10 +641,16 @@ __device__ __forceinline__ bool trav_run(TravState& T, const DScene& S, SNodeBas
                 r0z = PT_SLAB(nz.z, o.z, inv.z, noi.z); r1z = PT_SLAB(nz.w, o.z, inv.z, noi.z);
             }
 #endif
-            float ltmin = fmax3(fminf(l0x, l1x), fminf(l0y, l1y), fmaxf(fminf(l0z, l1z), t_min));
-            float ltmax = fmin3(fmaxf(l0x, l1x), fmaxf(l0y, l1y), fminf(fmaxf(l0z, l1z), best_t));
-            float rtmin = fmax3(fminf(r0x, r1x), fminf(r0y, r1y), fmaxf(fminf(r0z, r1z), t_min));
-            float rtmax = fmin3(fmaxf(r0x, r1x), fmaxf(r0y, r1y), fminf(fmaxf(r0z, r1z), best_t));
+            float ltmin, ltmax, rtmin, rtmax;
+            if (OCT) {      // slot 0 = the plane the ray meets first (trav_root)
+                ltmin = fmax3(l0x, l0y, fmaxf(l0z, t_min)); ltmax = fmin3(l1x, l1y, fminf(l1z, best_t));
+                rtmin = fmax3(r0x, r0y, fmaxf(r0z, t_min)); rtmax = fmin3(r1x, r1y, fminf(r1z, best_t));
+            } else {
+                ltmin = fmax3(fminf(l0x, l1x), fminf(l0y, l1y), fmaxf(fminf(l0z, l1z), t_min));
+                ltmax = fmin3(fmaxf(l0x, l1x), fmaxf(l0y, l1y), fminf(fmaxf(l0z, l1z), best_t));
+                rtmin = fmax3(fminf(r0x, r1x), fminf(r0y, r1y), fmaxf(fminf(r0z, r1z), t_min));
+                rtmax = fmin3(fmaxf(r0x, r1x), fmaxf(r0y, r1y), fminf(fmaxf(r0z, r1z), best_t));
+            }
             const int lref = __float_as_int(nc.x), rref = __float_as_int(nc.y);
             const bool hl = PT_BOX_HIT(ltmax, ltmin, slack);        // both children always exist (host packer)
             const bool hr = PT_BOX_HIT(rtmax, rtmin, slack);
@@ -707,27 +731,25 @@ __device__ __forceinline__ void trav_run_vote(TravState& T, bool active, bool& d
 #else
             if (want_node) {
                 float4 nx, ny, nz, nc;
-                load_node(nodes, s_nodes, n_snodes, cur, nx, ny, nz, nc, S.num_inner);
+                load_node(nodes, s_nodes, n_snodes, cur, nx, ny, nz, nc, S.num_inner + 7 * S.oct_stride);
                 if (COUNT) lc.box_tests += 2;
                 const float best_t = T.best_t;
 #if PT_F32X2
                 float l0x, l1x, l0y, l1y, l0z, l1z, r0x, r1x, r0y, r1y, r0z, r1z;
                 slab2(nx.x, nx.y, o.x, inv.x, l0x, l1x); slab2(ny.x, ny.y, o.y, inv.y, l0y, l1y); slab2(nz.x, nz.y, o.z, inv.z, l0z, l1z);
                 slab2(nx.z, nx.w, o.x, inv.x, r0x, r1x); slab2(ny.z, ny.w, o.y, inv.y, r0y, r1y); slab2(nz.z, nz.w, o.z, inv.z, r0z, r1z);
-                float ltmin = fmax3(fminf(l0x, l1x), fminf(l0y, l1y), fmaxf(fminf(l0z, l1z), t_min));
-                float ltmax = fmin3(fmaxf(l0x, l1x), fmaxf(l0y, l1y), fminf(fmaxf(l0z, l1z), best_t));
 #else
                 float l0x = PT_SLAB(nx.x, o.x, inv.x, noi.x), l1x = PT_SLAB(nx.y, o.x, inv.x, noi.x);
                 float l0y = PT_SLAB(ny.x, o.y, inv.y, noi.y), l1y = PT_SLAB(ny.y, o.y, inv.y, noi.y);
                 float l0z = PT_SLAB(nz.x, o.z, inv.z, noi.z), l1z = PT_SLAB(nz.y, o.z, inv.z, noi.z);
-                float ltmin = fmax3(fminf(l0x, l1x), fminf(l0y, l1y), fmaxf(fminf(l0z, l1z), t_min));
-                float ltmax = fmin3(fmaxf(l0x, l1x), fmaxf(l0y, l1y), fminf(fmaxf(l0z, l1z), best_t));
                 float r0x = PT_SLAB(nx.z, o.x, inv.x, noi.x), r1x = PT_SLAB(nx.w, o.x, inv.x, noi.x);
                 float r0y = PT_SLAB(ny.z, o.y, inv.y, noi.y), r1y = PT_SLAB(ny.w, o.y, inv.y, noi.y);
                 float r0z = PT_SLAB(nz.z, o.z, inv.z, noi.z), r1z = PT_SLAB(nz.w, o.z, inv.z, noi.z);
 #endif
-                float rtmin = fmax3(fminf(r0x, r1x), fminf(r0y, r1y), fmaxf(fminf(r0z, r1z), t_min));
-                float rtmax = fmin3(fmaxf(r0x, r1x), fmaxf(r0y, r1y), fminf(fmaxf(r0z, r1z), best_t));
+                const float ltmin = fmax3(fminf(l0x, l1x), fminf(l0y, l1y), fmaxf(fminf(l0z, l1z), t_min));
+                const float ltmax = fmin3(fmaxf(l0x, l1x), fmaxf(l0y, l1y), fminf(fmaxf(l0z, l1z), best_t));
+                const float rtmin = fmax3(fminf(r0x, r1x), fminf(r0y, r1y), fmaxf(fminf(r0z, r1z), t_min));
+                const float rtmax = fmin3(fmaxf(r0x, r1x), fmaxf(r0y, r1y), fminf(fmaxf(r0z, r1z), best_t));
                 const int lref = __float_as_int(nc.x), rref = __float_as_int(nc.y);
                 const bool hl = PT_BOX_HIT(ltmax, ltmin, slack);        // both children always exist (host packer)
                 const bool hr = PT_BOX_HIT(rtmax, rtmin, slack);

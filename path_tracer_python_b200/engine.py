@@ -147,7 +147,10 @@ class Engine:
                 b *= self.wavefront_pipelines
         else:
             b = max(1, min(self.wavefront_samples_in_flight, sample_count))
-        extra = int(self.info.node_bytes) * int(self.info.num_inner) + 256 if self.info is not None else 0     # origin-relative node copy
+        # room for the node copy a call builds in the workspace for its primary wave: origin-relative boxes in eight
+        # direction-octant variants (pt_render_wavefront; one copy when the tree is large)
+        nb = int(self.info.node_bytes) * int(self.info.num_inner) if self.info is not None else 0
+        extra = (8 * nb + 2048) if 8 * nb + 2048 <= (1 << 30) else nb + 256
         need = int(self.L.pt_wavefront_workspace_bytes_for(W, y1 - y0, b)) + extra
         while b > 1 and need > self.max_workspace_bytes:
             b -= 1
