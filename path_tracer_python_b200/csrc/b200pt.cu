@@ -1086,6 +1086,7 @@ __device__ __forceinline__ void tile_local_pixel(int local, int W, int rows, int
 // primary rays (kernels.py:1219-1399) in one kernel.  Camera rays are coherent, so nothing is gained
 // by sending them through the queues: the ray is generated in registers, traced, shaded, and only
 // the surviving bounce ray is appended (one atomic per warp) to queue 1, where wave 1 picks it up.
+// (The OCT instantiations hold fewer values across the node visit and run 8 CTAs per SM: 62 registers, +0.4 % on config 2.)
 // ONE: exactly one fused wave (the default schedule) -- throughput (1,1,1) and depth 0 are then compile-time
 // constants, the wave loop disappears and with it the Russian-roulette code (depth + 1 < 5) and several
 // registers that were live across the traversal.
@@ -1097,7 +1098,7 @@ __device__ __forceinline__ void tile_local_pixel(int local, int W, int rows, int
 // OCT: the launch traverses the direction-octant variants of the node array (pt_device.cuh trav_root; P.S.nodes and
 // P.S.oct_stride are set for this launch only).
 template <bool COUNT, bool FULL, bool REL, bool ONE, bool TIES = false, bool OCT = false>
-__global__ void __launch_bounds__(PT_PRIMARY_THREADS, PT_PRIMARY_MINB) k_wf_primary(const __grid_constant__ WfParams P) {
+__global__ void __launch_bounds__(PT_PRIMARY_THREADS, PT_PRIMARY_MINB + (OCT && PT_PRIMARY_MINB == 7 ? 1 : 0)) k_wf_primary(const __grid_constant__ WfParams P) {
     extern __shared__ float4 s_node_mem[];
     const DScene& S = P.S;
     stage_nodes(s_node_mem, S, P.n_snodes);
