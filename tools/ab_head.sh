@@ -1,0 +1,8 @@
+#!/bin/bash
+# A/B of the working tree against a checkout of HEAD in _head/ (its library built from HEAD's sources): interleaved runs of
+# tools/ab.py's child, wavefront and megakernel, same box.   tools/ab_head.sh [reps] [spp]
+REPS=${1:-3}; SPP=${2:-256}
+for i in $(seq $REPS); do
+  echo -n "new:  "; AB_CHILD=1 SPP=$SPP python tools/ab.py
+  echo -n "head: "; (cd _head && AB_CHILD=1 SPP=$SPP python tools/ab.py)
+done
