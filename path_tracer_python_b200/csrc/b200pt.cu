@@ -80,6 +80,7 @@ struct PtContext {
     int wf_blocks_per_sm = 7;
     int wf_extend_minb = PT_FAST ? 6 : 5;  // launch bound of k_wf_extend: the one that compiles to <= 56 registers without spills, so
                                            // that six 192-thread CTAs (36 warps) are resident per SM (strict: 5 -> 56; fast: 6 -> 55, 5 -> 61)
+    int wf_extend_bulk = 0;  // ray staging of k_wf_extend with cp.async.bulk + mbarrier (k_wf_extend<..., BULK>; measured -1 %)
     int wf_tile = 1;
     int wf_shade_split = 0;  // 1: k_wf_shade_cls<KIND> per class run instead of one k_wf_shade for all classes (measured slower:
                              // 5.99 vs 5.12 ms per config-2 batch -- three dependent launches, each with its own ramp and tail,
@@ -501,6 +502,36 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
+// ---- bulk async copy (TMA, UBLKCP): ONE instruction from one lane moves a contiguous block global -> shared and reports
+// its bytes to an mbarrier; the waiting side polls the barrier's phase parity.  k_wf_extend's ray staging as a variant
+// (BULK): the 32 rays a warp stages next are one contiguous kilobyte of the queue, so the 64 LDGSTS of a
+// staging step (two per lane) become one UBLKCP issued by lane 0 plus an expect-tx arrive, and the switch to the other
+// buffer polls that buffer's mbarrier instead of cp.async.wait_group.  Bit-identical; measured on config 2 (tools/ab_head.sh,
+// same box, three rounds): k_wf_extend 12.49 vs 12.25 ms per 32-sample batch, frame 3181 vs 3214 Mpaths/s (-1.0 %) -- the
+// kernel is not short of the issue slots the LDGSTS take, the bulk copy's completion latency is the longer one, and the
+// barrier words plus the phase bits cost a register under the 56-register bound.  Not the default: option "wf_extend_bulk"
+// selects the k_wf_extend<..., BULK = true> instantiations (bit-identical in the options test).
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src), "r"(bytes),
+                   "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "WAIT_%=:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra DONE_%=;\n\t"
+                 "bra WAIT_%=;\n\t"
+                 "DONE_%=:\n\t}"
+                 ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+
 constexpr int kWfReserve = 128;   // ray indices a warp reserves per atomic on the global cursor
 constexpr int kWfWarps = 8;       // warps per CTA of the wavefront kernels (256 threads)
 
@@ -522,10 +553,11 @@ constexpr int kWfWarps = 8;       // warps per CTA of the wavefront kernels (256
 #define PT_EXT_SMEM_SLOTS 4
 #endif
 constexpr int kExtSmemSlots = PT_EXT_SMEM_SLOTS;
-template <bool COUNT, bool FULL, int MINB>
+template <bool COUNT, bool FULL, int MINB, bool BULK = false>
 __global__ void __launch_bounds__(PT_EXT_WARPS * 32, MINB) k_wf_extend(const __grid_constant__ WfParams P) {
     extern __shared__ float4 s_dyn[];
-    __shared__ float4 s_ray[PT_EXT_WARPS][2][32][2];      // (o.xyz d.x)(d.yz ..) of staged rays, 2 KB per warp
+    __shared__ __align__(128) float4 s_ray[PT_EXT_WARPS][2][32][2];      // (o.xyz d.x)(d.yz ..) of staged rays, 2 KB per warp
+    __shared__ __align__(8) unsigned long long s_bar[BULK ? PT_EXT_WARPS : 1][2];   // BULK: one mbarrier per staging buffer
     __shared__ StackEntry s_stack[kExtSmemSlots][PT_EXT_WARPS * 32];
     float4* s_node_mem = s_dyn;
     const DScene& S = P.S;
@@ -563,19 +595,42 @@ __global__ void __launch_bounds__(PT_EXT_WARPS * 32, MINB) k_wf_extend(const __g
         }
         int n = res_end - res_next;
         n = n > 32 ? 32 : (n < 0 ? 0 : n);
-        if ((int)lane < n) {
-            PT_BOUND(res_next >= 0 && res_next + (int)lane < count, PT_DBG_QUEUE);
-            cp_async16(&s_ray[warp][b][lane][0], qa + 2 * (size_t)(res_next + lane));
-            cp_async16(&s_ray[warp][b][lane][1], qa + 2 * (size_t)(res_next + lane) + 1);
+        if (BULK) {
+            __syncwarp();                   // every lane has taken its ray out of buffer b
+            if (lane == 0 && n > 0) {
+                PT_BOUND(res_next >= 0 && res_next + n <= count, PT_DBG_QUEUE);
+                mbar_expect_tx(&s_bar[BULK ? warp : 0][b], (unsigned)n * 32u);
+                bulk_g2s(&s_ray[warp][b][0][0], qa + 2 * (size_t)res_next, (unsigned)n * 32u, &s_bar[BULK ? warp : 0][b]);
+            }
+        } else {
+            if ((int)lane < n) {
+                PT_BOUND(res_next >= 0 && res_next + (int)lane < count, PT_DBG_QUEUE);
+                cp_async16(&s_ray[warp][b][lane][0], qa + 2 * (size_t)(res_next + lane));
+                cp_async16(&s_ray[warp][b][lane][1], qa + 2 * (size_t)(res_next + lane) + 1);
+            }
+            cp_async_commit();
         }
-        cp_async_commit();
         stg_base[b] = res_next;
         stg_n[b] = n;
         res_next += n;
     };
+    unsigned phase = 0;                 // BULK, bit b: the parity buffer b's next completion will have
+    if (BULK) {
+        if (lane == 0) { mbar_init(&s_bar[BULK ? warp : 0][0], 1); mbar_init(&s_bar[BULK ? warp : 0][1], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        __syncwarp();
+    }
+    auto wait_staged = [&](int b) {     // the copy into buffer b has landed (BULK: only called when one was started, stg_n[b] > 0)
+        if (BULK) {
+            mbar_wait(&s_bar[BULK ? warp : 0][b], (phase >> b) & 1u);
+            phase ^= 1u << b;
+        } else {
+            cp_async_wait_all();
+            __syncwarp();
+        }
+    };
     stage(0);
-    cp_async_wait_all();
-    __syncwarp();
+    if (!BULK || stg_n[0] > 0) wait_staged(0);
     stage(1);
 
     TravState T;
@@ -632,8 +687,7 @@ __global__ void __launch_bounds__(PT_EXT_WARPS * 32, MINB) k_wf_extend(const __g
                     if (st == LANE_NEED_PATH) st = LANE_DONE;
                     break;
                 }
-                cp_async_wait_all();
-                __syncwarp();
+                wait_staged(buf ^ 1);
                 buf ^= 1;
                 stg_pos = 0;
                 stage(buf ^ 1);
@@ -1657,6 +1711,8 @@ int pt_set_option(PtContext* ctx, const char* name, int64_t value) {
         ctx->wf_tail_vote = value ? 1 : 0;
     } else if (k == "wf_rel_primary") {
         ctx->wf_rel_primary = value ? 1 : 0;
+    } else if (k == "wf_extend_bulk") {
+        ctx->wf_extend_bulk = value ? 1 : 0;
     } else if (k == "wf_oct_nodes") {
         ctx->wf_oct_nodes = value ? 1 : 0;
     } else if (k == "wf_grid_waves") {
@@ -2037,7 +2093,8 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
         else if (one) k_primary = full ? k_wf_primary<false, true, false, true> : k_wf_primary<false, false, false, true>;
         else k_primary = full ? k_wf_primary<false, true, false, false> : k_wf_primary<false, false, false, false>;
         // MINB = resident CTAs per SM the register allocation is capped for (4: 64 regs, 5: 48, 6: 40)
-        if (ctx->wf_extend_minb >= 6) k_extend = full ? k_wf_extend<false, true, 6> : k_wf_extend<false, false, 6>;
+        if (ctx->wf_extend_bulk) k_extend = full ? k_wf_extend<false, true, 6, true> : k_wf_extend<false, false, 6, true>;
+        else if (ctx->wf_extend_minb >= 6) k_extend = full ? k_wf_extend<false, true, 6> : k_wf_extend<false, false, 6>;
         else if (ctx->wf_extend_minb == 5) k_extend = full ? k_wf_extend<false, true, 5> : k_wf_extend<false, false, 5>;
         else k_extend = full ? k_wf_extend<false, true, 4> : k_wf_extend<false, false, 4>;
         if (ctx->wf_tail_vote) k_tail = full ? k_wf_tail_vote<false, true> : k_wf_tail_vote<false, false>;
