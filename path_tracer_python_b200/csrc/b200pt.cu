@@ -80,6 +80,7 @@ struct PtContext {
     int wf_blocks_per_sm = 7;
     int wf_extend_minb = PT_FAST ? 6 : 5;  // launch bound of k_wf_extend: the one that compiles to <= 56 registers without spills, so
                                            // that six 192-thread CTAs (36 warps) are resident per SM (strict: 5 -> 56; fast: 6 -> 55, 5 -> 61)
+    int wf_extend_carveout = -1;   // preferred shared-memory carveout of k_wf_extend in percent of the SM's 228 KB (-1: the driver's choice)
     int wf_extend_bulk = 0;  // ray staging of k_wf_extend with cp.async.bulk + mbarrier (k_wf_extend<..., BULK>; measured -1 %)
     int wf_tile = 1;
     int wf_shade_split = 0;  // 1: k_wf_shade_cls<KIND> per class run instead of one k_wf_shade for all classes (measured slower:
@@ -1711,6 +1712,9 @@ int pt_set_option(PtContext* ctx, const char* name, int64_t value) {
         ctx->wf_tail_vote = value ? 1 : 0;
     } else if (k == "wf_rel_primary") {
         ctx->wf_rel_primary = value ? 1 : 0;
+    } else if (k == "wf_extend_carveout") {
+        if (value < -1 || value > 100) return set_error(PT_ERR_INVALID_ARG, "wf_extend_carveout must be -1 or a percentage");
+        ctx->wf_extend_carveout = (int)value;
     } else if (k == "wf_extend_bulk") {
         ctx->wf_extend_bulk = value ? 1 : 0;
     } else if (k == "wf_oct_nodes") {
@@ -2101,6 +2105,7 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
         else k_tail = full ? k_wf_tail<false, true> : k_wf_tail<false, false>;
     }
     if ((rc = set_smem(k_primary, smem)) || (rc = set_smem(k_extend, smem)) || (rc = set_smem(k_tail, smem))) return rc;
+    PT_CUDA(cudaFuncSetAttribute(k_extend, cudaFuncAttributePreferredSharedMemoryCarveout, ctx->wf_extend_carveout));
     if (k_primary_ties && (rc = set_smem(k_primary_ties, smem))) return rc;
     if (ctx->dbg_shade_smem && (rc = set_smem(k_shade, (size_t)ctx->dbg_shade_smem))) return rc;
     int occ_primary = 1, occ_shade = 1, occ_tail = 1;
