@@ -158,7 +158,14 @@ int pt_destroy(PtContext* ctx);
  *   n lanes want to, else it tests primitives; 0 = while-while order), "sync_samples",
  *   "wf_blocks_per_sm", "wf_extend_minb" (4/5/6: register cap of k_wf_extend), "wf_waves" (full waves
  *   before the tail kernel), "wf_fuse_primary" (leading waves run inside k_wf_primary), "wf_tile"
- *   (8x4 pixel tiles in the primary wave), "wavefront_sort" (material binning, 0/1) */
+ *   (8x4 pixel tiles in the primary wave), "wavefront_sort" (material binning, 0/1),
+ *   "wf_overlap" / "wf_pipelines" (1..4 batches of a call in flight on context-owned streams; default 2),
+ *   "wf_primary_threads", "wf_grid_waves" (grid size of the statically split kernels in waves of resident CTAs),
+ *   "wf_tail_vote" (the tail as a persistent voting kernel), "wf_rel_primary" / "wf_oct_nodes" (origin-relative boxes /
+ *   direction-octant variants of the node array for the primary wave, built per call in the workspace),
+ *   "wf_shade_split" (one shade kernel per class run), "wf_extend_bulk" (ray staging of k_wf_extend with
+ *   cp.async.bulk + mbarrier instead of cp.async), "wf_extend_carveout" (its preferred shared-memory carveout in
+ *   percent, -1 = driver's choice) */
 int pt_set_option(PtContext* ctx, const char* name, int64_t value);
 
 /* `device_blob` (device, info->total_bytes) stays owned by the caller and must outlive its use. */
