@@ -163,7 +163,8 @@ int pt_destroy(PtContext* ctx);
  *   "wf_primary_threads", "wf_grid_waves" (grid size of the statically split kernels in waves of resident CTAs),
  *   "wf_tail_vote" (the tail as a persistent voting kernel), "wf_rel_primary" / "wf_oct_nodes" (origin-relative boxes /
  *   direction-octant variants of the node array for the primary wave, built per call in the workspace),
- *   "wf_shade_split" (one shade kernel per class run), "wf_extend_bulk" (ray staging of k_wf_extend with
+ *   "wf_shade_split" (one shade kernel per class run), "wf_shade_stage" (k_wf_shade collects its survivors per warp in
+ *   shared memory and appends two rounds with one atomic on the queue counter; default 1), "wf_extend_bulk" (ray staging of k_wf_extend with
  *   cp.async.bulk + mbarrier instead of cp.async), "wf_extend_carveout" (its preferred shared-memory carveout in
  *   percent, -1 = driver's choice) */
 int pt_set_option(PtContext* ctx, const char* name, int64_t value);

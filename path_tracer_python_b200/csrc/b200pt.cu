@@ -74,6 +74,7 @@ struct PtContext {
     int wf_rel_primary = 1;  // camera rays without defocus: slab test against origin-relative node boxes
     int wf_oct_nodes = 1;    // direction-octant variants of the node array (pt_device.cuh trav_root), built per call in the workspace
     int wf_grid_waves = 16;  // static-partition kernels launch this many full waves of resident CTAs
+    int wf_shade_stage = 1;  // k_wf_shade<FULL, kShadeStage>: survivors staged per warp in shared memory, one queue-counter atomic per ~4 rounds
     int dbg_shade_smem = 0;  // experiment knob: dynamic shared memory reserved per k_wf_shade CTA (limits residency)
     int wf_fuse_primary = 1; // wave 0 (camera rays) as one fused kernel
     int wf_burst_num = 20;
@@ -942,8 +943,21 @@ __global__ void __launch_bounds__(256) k_wf_bin(const __grid_constant__ WfParams
 #define PT_SHADE_THREADS 256
 #define PT_SHADE_MINB 3
 #endif
-template <bool FULL>
+// STAGE > 0: survivors are collected per warp in shared memory (room for STAGE rounds of 32) and appended in one go --
+// one atomic on the queue counter per ~STAGE rounds instead of one per round, and the queue is written in whole
+// 128-byte lines.  Why it matters: the append counter is ONE address, the L2 serialises atomics on it (measured: an
+// extra returning atomic per warp and round on a neighbouring word DOUBLES the kernel's time, wave after wave --
+// ~1.15 ns per atomic), and with one atomic per 32 rays that ceiling, not HBM, is what k_wf_shade ran into.
+#ifndef PT_SHADE_STAGE
+#define PT_SHADE_STAGE 2     // 2 / 3 / 4 rounds: k_wf_shade 3.80 / 3.78 / 3.80 ms per config-2 batch (4.98 unstaged) -- with half the atomics the
+                             // counter is no longer the limit; 24 KB of shared memory per CTA instead of 48
+#endif
+// (The same staging for the survivors of the fused primary wave: k_wf_primary 4.07 vs 3.84 ms -- that kernel is issue-bound,
+// two million atomics in 3.8 ms are below the counter's ceiling, and the staging code costs it issue slots.)
+constexpr int kShadeStage = PT_SHADE_STAGE;
+template <bool FULL, int STAGE = 0>
 __global__ void __launch_bounds__(PT_SHADE_THREADS, PT_SHADE_MINB) k_wf_shade(const __grid_constant__ WfParams P) {
+    extern __shared__ float4 s_stage[];       // STAGE: [warps][STAGE * 32][2] ray pairs, then [warps][STAGE * 32] third planes
     const DScene& S = P.S;
     const int cur = P.bounce & 1, nxt = cur ^ 1;
     const int count = P.Q.qcount[cur];
@@ -964,6 +978,25 @@ __global__ void __launch_bounds__(PT_SHADE_THREADS, PT_SHADE_MINB) k_wf_shade(co
     const f3 bg = mk3(P.cam.background[0], P.cam.background[1], P.cam.background[2]);
     const int stride = gridDim.x * blockDim.x;
     const int rounds = (count + stride - 1) / stride;
+    constexpr int kSlots = STAGE > 0 ? STAGE * 32 : 1;
+    constexpr int kWarpsPerCta = PT_SHADE_THREADS / 32;
+    const unsigned lane = threadIdx.x & 31;
+    float4* const s_ab = s_stage + (size_t)(threadIdx.x >> 5) * kSlots * 2;
+    float4* const s_c = s_stage + (size_t)kWarpsPerCta * kSlots * 2 + (size_t)(threadIdx.x >> 5) * kSlots;
+    int fill = 0;                       // STAGE: rays in this warp's buffer (warp-uniform)
+    auto flush = [&]() {                // STAGE: append the buffer to the next queue -- one atomic, coalesced line writes
+        __syncwarp();
+        int base = 0;
+        if (lane == 0) base = atomicAdd(P.Q.qcount + nxt, fill);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        PT_BOUND(base >= 0 && base + fill <= P.Q.capacity, PT_DBG_QUEUE);
+        float4* ga = P.Q.ra[nxt] + 2 * (size_t)base;
+        float4* gc = P.Q.r2[nxt] + (size_t)base;
+        for (int i = lane; i < 2 * fill; i += 32) ga[i] = s_ab[i];
+        for (int i = lane; i < fill; i += 32) gc[i] = s_c[i];
+        __syncwarp();
+        fill = 0;
+    };
     for (int r = 0; r < rounds; r++) {
         const int j = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
         const bool active = j < count;
@@ -999,13 +1032,26 @@ __global__ void __launch_bounds__(PT_SHADE_THREADS, PT_SHADE_MINB) k_wf_shade(co
         // further, one atomic per CTA through shared memory and two barriers, measured slower
         // (shade 5.11 vs 4.88 ms per batch): the barriers couple the warps of a CTA, and this kernel
         // lives on its warps hiding each other's memory latency.
-        const int pos = warp_agg_append(P.Q.qcount + nxt, 0, emit_next);
-        if (emit_next) {
-            PT_BOUND(pos >= 0 && pos < P.Q.capacity, PT_DBG_QUEUE);
-            st256(P.Q.ra[nxt] + 2 * (size_t)pos, make_float4(no.x, no.y, no.z, nd.x), make_float4(nd.y, nd.z, nthr.x, nthr.y));
-            P.Q.r2[nxt][pos] = make_float4(nthr.z, __int_as_float(path_id), __uint_as_float(rng.s), __int_as_float(ndepth));
+        if (STAGE > 0) {
+            const unsigned m = __ballot_sync(0xffffffffu, emit_next);
+            if (emit_next) {
+                const int slot = fill + __popc(m & ((1u << lane) - 1));
+                s_ab[2 * slot] = make_float4(no.x, no.y, no.z, nd.x);
+                s_ab[2 * slot + 1] = make_float4(nd.y, nd.z, nthr.x, nthr.y);
+                s_c[slot] = make_float4(nthr.z, __int_as_float(path_id), __uint_as_float(rng.s), __int_as_float(ndepth));
+            }
+            fill += __popc(m);
+            if (fill > kSlots - 32) flush();
+        } else {
+            const int pos = warp_agg_append(P.Q.qcount + nxt, 0, emit_next);
+            if (emit_next) {
+                PT_BOUND(pos >= 0 && pos < P.Q.capacity, PT_DBG_QUEUE);
+                st256(P.Q.ra[nxt] + 2 * (size_t)pos, make_float4(no.x, no.y, no.z, nd.x), make_float4(nd.y, nd.z, nthr.x, nthr.y));
+                P.Q.r2[nxt][pos] = make_float4(nthr.z, __int_as_float(path_id), __uint_as_float(rng.s), __int_as_float(ndepth));
+            }
         }
     }
+    if (STAGE > 0 && fill > 0) flush();
 }
 
 // The same work split by shading class: the bins are class-sorted, so each of three kernels owns a
@@ -1165,6 +1211,7 @@ __global__ void __launch_bounds__(PT_PRIMARY_THREADS, PT_PRIMARY_MINB + (OCT && 
     const int total = TIES ? P.Q.tie_count[0] : P.N * P.batch;
     const int stride = gridDim.x * blockDim.x;
     const int rounds = (total + stride - 1) / stride;
+    const int qd = ONE ? 1 : (P.fused_waves & 1);   // the queue wave `fused_waves` reads from
     for (int r = 0; r < rounds; r++) {
         const int j = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
         int id = j;
@@ -1219,7 +1266,6 @@ __global__ void __launch_bounds__(PT_PRIMARY_THREADS, PT_PRIMARY_MINB + (OCT && 
                 o = no; d = nd; thr = nthr; depth = ndepth;
             }
         }
-        const int qd = ONE ? 1 : (P.fused_waves & 1);   // the queue wave `fused_waves` reads from
         int pos = warp_agg_append(P.Q.qcount + qd, 0, emit_next);
         if (emit_next) {
             PT_BOUND(pos >= 0 && pos < P.Q.capacity && id >= 0 && id < P.N * P.batch, PT_DBG_QUEUE);
@@ -1722,6 +1768,8 @@ int pt_set_option(PtContext* ctx, const char* name, int64_t value) {
     } else if (k == "wf_grid_waves") {
         if (value < 1 || value > 4096) return set_error(PT_ERR_INVALID_ARG, "wf_grid_waves must be in [1, 4096]");
         ctx->wf_grid_waves = (int)value;
+    } else if (k == "wf_shade_stage") {
+        ctx->wf_shade_stage = value ? 1 : 0;
     } else if (k == "dbg_shade_smem") {
         if (value < 0 || value > 200 * 1024) return set_error(PT_ERR_INVALID_ARG, "dbg_shade_smem must be in [0, 200 KiB]");
         ctx->dbg_shade_smem = (int)value;
@@ -2052,6 +2100,12 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
     void (*k_primary_ties)(const WfParams) = nullptr;
     const int grid_fix = ctx->num_sms * 2;
     void (*k_shade)(const WfParams) = full ? k_wf_shade<true> : k_wf_shade<false>;
+    size_t shade_smem = (size_t)ctx->dbg_shade_smem;
+    if (ctx->wf_shade_stage) {
+        k_shade = full ? k_wf_shade<true, kShadeStage> : k_wf_shade<false, kShadeStage>;
+        const size_t need = (size_t)(PT_SHADE_THREADS / 32) * kShadeStage * 32 * 48;
+        if (shade_smem < need) shade_smem = need;
+    }
     const bool split = ctx->wf_shade_split && ctx->wavefront_sort && !ctx->dbg_shade_smem && !(ctx->scene.full_features & 2);
     void (*k_shade_cls[3])(const WfParams) = {full ? k_wf_shade_cls<true, 0> : k_wf_shade_cls<false, 0>,
                                               full ? k_wf_shade_cls<true, 1> : k_wf_shade_cls<false, 1>,
@@ -2107,12 +2161,12 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
     if ((rc = set_smem(k_primary, smem)) || (rc = set_smem(k_extend, smem)) || (rc = set_smem(k_tail, smem))) return rc;
     PT_CUDA(cudaFuncSetAttribute(k_extend, cudaFuncAttributePreferredSharedMemoryCarveout, ctx->wf_extend_carveout));
     if (k_primary_ties && (rc = set_smem(k_primary_ties, smem))) return rc;
-    if (ctx->dbg_shade_smem && (rc = set_smem(k_shade, (size_t)ctx->dbg_shade_smem))) return rc;
+    if (shade_smem && (rc = set_smem(k_shade, shade_smem))) return rc;
     int occ_primary = 1, occ_shade = 1, occ_tail = 1;
     const int bt_primary = ctx->wf_primary_threads;
     PT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_primary, k_primary, bt_primary, smem));
     const int bt_shade = PT_SHADE_THREADS;
-    PT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_shade, k_shade, bt_shade, (size_t)ctx->dbg_shade_smem));
+    PT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_shade, k_shade, bt_shade, shade_smem));
     PT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_tail, k_tail, bt, smem));
     for (int k = 0; k < 3; k++) {
         PT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cls[k], k_shade_cls[k], 256, 0));
@@ -2204,7 +2258,7 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
                 }
             } else {
                 StageScope t(ctx, bs, PT_STAGE_SHADE, b);
-                k_shade<<<grid_shade, bt_shade, ctx->dbg_shade_smem, bs>>>(P);
+                k_shade<<<grid_shade, bt_shade, shade_smem, bs>>>(P);
             }
         }
         if (waves < max_depth) {                          // whatever is still alive: finish in one launch

@@ -186,11 +186,13 @@ def test_results_do_not_depend_on_tuning_options(scene_name):
                dict(wf_overlap=1, wf_waves=5), dict(wf_overlap=1, wf_fuse_primary=2, wf_waves=5),
                dict(wf_shade_split=0), dict(wf_shade_split=0, wf_waves=3, wf_overlap=0), dict(wf_shade_split=1, wf_fuse_primary=0, wf_waves=4),
                dict(wf_oct_nodes=0), dict(wf_oct_nodes=0, wf_rel_primary=0), dict(wf_oct_nodes=1, wf_rel_primary=0, wf_waves=3),
-               dict(wf_extend_bulk=1), dict(wf_extend_bulk=1, wf_fuse_primary=0, wf_waves=50, wf_overlap=0)]
+               dict(wf_extend_bulk=1), dict(wf_extend_bulk=1, wf_fuse_primary=0, wf_waves=50, wf_overlap=0),
+               dict(wf_shade_stage=0), dict(wf_shade_stage=0, wf_shade_split=0), dict(wf_shade_stage=1, wf_shade_split=0, wf_overlap=0, wf_waves=3),
+               dict(wf_shade_stage=1, wf_shade_split=0, wavefront_sort=0, wf_fuse_primary=0, wf_waves=50), dict(wf_extend_carveout=30)]
     for o in wf_opts:
         for k, v in dict(dict(wf_waves=12, wf_fuse_primary=1, wavefront_sort=1, wf_burst_num=20, wf_vote_num=16, wf_blocks_per_sm=6,
                               smem_nodes=-1, wf_tile=1, wf_extend_minb=4, wf_grid_waves=16, wf_rel_primary=1, wf_tail_vote=1, wf_overlap=1,
-                              wf_shade_split=1, wf_oct_nodes=1, wf_extend_bulk=0), **o).items():
+                              wf_shade_split=1, wf_oct_nodes=1, wf_extend_bulk=0, wf_shade_stage=1, wf_extend_carveout=-1), **o).items():
             e.set_option(k, v)
         for flight in (1, 3, 32):
             e.wavefront_samples_in_flight = flight
