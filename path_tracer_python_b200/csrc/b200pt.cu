@@ -79,8 +79,9 @@ struct PtContext {
     int wf_fuse_primary = 1; // wave 0 (camera rays) as one fused kernel
     int wf_burst_num = 20;
     int wf_blocks_per_sm = 7;
-    int wf_extend_minb = PT_FAST ? 6 : 5;  // launch bound of k_wf_extend: the one that compiles to <= 56 registers without spills, so
-                                           // that six 192-thread CTAs (36 warps) are resident per SM (strict: 5 -> 56; fast: 6 -> 55, 5 -> 61)
+    int wf_extend_minb = PT_FAST_SLAB ? 6 : 5;  // launch bound of k_wf_extend: the one that compiles to <= 56 registers without spills, so
+                                           // that six 192-thread CTAs (36 warps) are resident per SM (5 -> 56 in both numerics; with the FMA
+                                           // slab test, PT_FAST_SLAB: 6 -> 55, 5 -> 61)
     int wf_extend_carveout = -1;   // preferred shared-memory carveout of k_wf_extend in percent of the SM's 228 KB (-1: the driver's choice)
     int wf_extend_bulk = 0;  // ray staging of k_wf_extend with cp.async.bulk + mbarrier (k_wf_extend<..., BULK>; measured -1 %)
     int wf_tile = 1;
@@ -1686,7 +1687,8 @@ extern "C" {
 const char* pt_last_error(void) { return pt_error_slot()->c_str(); }
 const char* pt_version(void) {
 #if PT_FAST
-    return "b200pt 0.2 (sm_100a, PT-F32 fast: FMA + approximate reciprocal)";
+    return PT_FAST_SLAB ? "b200pt 0.2 (sm_100a, PT-F32 fast: FMA slab test, FMA + approximate reciprocal)"
+                        : "b200pt 0.2 (sm_100a, PT-F32 fast: FMA + approximate reciprocal around the strict intersection tests)";
 #elif PT_DEBUG_BOUNDS
     return "b200pt 0.2 (sm_100a, PT-F32 strict, debug-bounds build)";
 #elif PT_WIDE
@@ -2012,7 +2014,7 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
     // With room for eight copies (and up to 1 GiB of them), the primary wave traverses the direction-octant variants of
     // that array (pt_device.cuh trav_root).
     bool oct = false;
-#if !PT_WIDE && !PT_FAST
+#if !PT_WIDE       // (fast numerics: fma(b, inv, noi) is monotone in b like (b - o) * inv, so the variants hold there too)
     if (ctx->wf_oct_nodes && ctx->scene.num_inner > 0 && 8 * rel_bytes <= ((size_t)1 << 30) &&
         workspace_bytes >= kWfFixedBytes + 8 * rel_bytes + wf_bytes_per_sample(n)) {
         oct = true;
@@ -2115,7 +2117,7 @@ int pt_render_wavefront(PtContext* ctx, float* accum, int W, int H, int y0, int 
     // origin-relative node boxes (one subtraction less per box coordinate).  Only when that kernel
     // runs wave 0 alone -- later waves start elsewhere.
     // (not with next-event estimation: its shadow rays start at the hit points and need the plain node boxes)
-    bool rel = !PT_FAST && !(ctx->scene.full_features & 2) && ctx->wf_rel_primary && ctx->wf_fuse_primary == 1 && !(ctx->cam.defocus_angle > 0.0f) &&
+    bool rel = !PT_FAST_SLAB && !(ctx->scene.full_features & 2) && ctx->wf_rel_primary && ctx->wf_fuse_primary == 1 && !(ctx->cam.defocus_angle > 0.0f) &&
                ctx->scene.num_inner > 0 && ctx->cam.max_depth > 0 && !ctx->count && rel_nodes != nullptr;
     // ... and its direction-octant variants (8 copies, with the origin subtracted when `rel`), same conditions minus the
     // shared origin: camera rays are coherent in direction with or without defocus

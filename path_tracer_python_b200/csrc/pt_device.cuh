@@ -253,9 +253,20 @@ __device__ __forceinline__ float fmin3(float a, float b, float c) {
     return d;
 }
 
+// PT_FAST_SLAB=1: the FMA form of the slab test (one FMA per plane against -(o * inv), conservative box test) -- what
+// the fast-numerics build used until it was measured against the strict test in the same build (config 2, same box):
+// wavefront 3105 vs 3287 Mpaths/s, megakernel 2345 vs 2468.  Packed, the strict test is 6 FADD2 + 6 FMUL2 per node
+// visit against 6 FFMA2 + 2 FFMA, and it needs four registers less per ray (no -(o * inv), no slack) in kernels
+// that sit on their register cap; with the strict boxes the primary wave also gets the origin-relative node copy.
+// So the fast build (PT_FAST=1) now keeps the strict box test too -- its first hits ARE the strict build's -- and is
+// "fast" in everything else: FMA contraction, approximate reciprocal / division / square root.  -DPT_FAST_SLAB=1
+// rebuilds the FMA variant.
+#ifndef PT_FAST_SLAB
+#define PT_FAST_SLAB 0
+#endif
 // One plane of the slab test, hit_aabb_optimized (kernels.py:609-614): (b - o) * inv, two roundings
 // (strict) -- or one FFMA against the precomputed -(o * inv) in the fast-numerics build.
-#if PT_FAST
+#if PT_FAST_SLAB
 #define PT_SLAB(b, o_, inv_, noi_) __fmaf_rn((b), (inv_), (noi_))
 // fl(b * inv - fl(o * inv)) is off by up to eps * (|o * inv| + |t|) from the exact plane distance, which for a
 // ray that starts far from a thin box (|o * inv| >> thickness * inv) is enough to make the box vanish.  The
@@ -271,19 +282,27 @@ __device__ __forceinline__ float fmin3(float a, float b, float c) {
 // of one axis of one child box arrive as an aligned register pair out of the 256-bit node load, so the strict
 // slab test's 12 FADD + 12 FMUL per node visit become 6 FADD2 + 6 FMUL2 -- same roundings, same bits
 // (no .ftz: subnormals are kept, as in the scalar code under -ftz=false).
+// The fast-numerics build packs its one-FFMA plane test the same way: fma.rn.f32x2 (FFMA2) against the broadcast
+// reciprocal direction and -(o * inv).
 #ifndef PT_F32X2
-#define PT_F32X2 (!PT_FAST)
+#define PT_F32X2 1
 #endif
-__device__ __forceinline__ void slab2(float b0, float b1, float o, float inv, float& r0, float& r1) {
-#if PT_F32X2
+__device__ __forceinline__ void slab2(float b0, float b1, float o, float inv, float noi, float& r0, float& r1) {
+#if PT_F32X2 && PT_FAST_SLAB
+    asm("{\n\t.reg .b64 v, ii, nn;\n\t"
+        "mov.b64 v, {%2, %3};\n\tmov.b64 ii, {%4, %4};\n\tmov.b64 nn, {%5, %5};\n\t"
+        "fma.rn.f32x2 v, v, ii, nn;\n\t"
+        "mov.b64 {%0, %1}, v;\n\t}"
+        : "=f"(r0), "=f"(r1) : "f"(b0), "f"(b1), "f"(inv), "f"(noi));
+#elif PT_F32X2
     asm("{\n\t.reg .b64 v, oo, ii;\n\t"
         "mov.b64 v, {%2, %3};\n\tmov.b64 oo, {%4, %4};\n\tmov.b64 ii, {%5, %5};\n\t"
         "sub.rn.f32x2 v, v, oo;\n\tmul.rn.f32x2 v, v, ii;\n\t"
         "mov.b64 {%0, %1}, v;\n\t}"
         : "=f"(r0), "=f"(r1) : "f"(b0), "f"(b1), "f"(o), "f"(inv));
 #else
-    r0 = (b0 - o) * inv;
-    r1 = (b1 - o) * inv;
+    r0 = PT_SLAB(b0, o, inv, noi);
+    r1 = PT_SLAB(b1, o, inv, noi);
 #endif
 }
 // ... and the origin-relative form (boxes with the shared ray origin already subtracted): one FMUL2
@@ -307,7 +326,7 @@ typedef unsigned long long StackEntry;
 
 struct TravState {
     f3 o, d, inv;
-#if PT_FAST
+#if PT_FAST_SLAB
     f3 noi;              // -(o * inv): the slab test is fma(b, inv, noi) per plane (fast numerics only)
     float slack;         // 2^-21 * max |o * inv| (PT_BOX_HIT)
 #endif
@@ -344,7 +363,7 @@ __device__ __forceinline__ void trav_begin(TravState& T, const DScene& S, f3 o, 
     T.d = d;
     T.time = time;
     ptm::inv_dir3(d.x, d.y, d.z, T.inv.x, T.inv.y, T.inv.z);
-#if PT_FAST
+#if PT_FAST_SLAB
     T.noi = mk3(-(o.x * T.inv.x), -(o.y * T.inv.y), -(o.z * T.inv.z));
     T.slack = 4.76837158e-7f * fmaxf(fmaxf(fabsf(T.noi.x), fabsf(T.noi.y)), fabsf(T.noi.z));
 #endif
@@ -599,7 +618,7 @@ __device__ __forceinline__ bool trav_run(TravState& T, const DScene& S, SNodeBas
                                          const STK& stack, int min_active, LocalCounters& lc) {
     const f3 o = REL ? mk3(0.0f, 0.0f, 0.0f) : T.o;
     const f3 inv = T.inv;
-#if PT_FAST
+#if PT_FAST_SLAB
     const f3 noi = T.noi;
     const float slack = T.slack;
 #else
@@ -625,8 +644,8 @@ __device__ __forceinline__ bool trav_run(TravState& T, const DScene& S, SNodeBas
                 slab2_rel(nx.x, nx.y, inv.x, l0x, l1x); slab2_rel(ny.x, ny.y, inv.y, l0y, l1y); slab2_rel(nz.x, nz.y, inv.z, l0z, l1z);
                 slab2_rel(nx.z, nx.w, inv.x, r0x, r1x); slab2_rel(ny.z, ny.w, inv.y, r0y, r1y); slab2_rel(nz.z, nz.w, inv.z, r0z, r1z);
             } else {
-                slab2(nx.x, nx.y, o.x, inv.x, l0x, l1x); slab2(ny.x, ny.y, o.y, inv.y, l0y, l1y); slab2(nz.x, nz.y, o.z, inv.z, l0z, l1z);
-                slab2(nx.z, nx.w, o.x, inv.x, r0x, r1x); slab2(ny.z, ny.w, o.y, inv.y, r0y, r1y); slab2(nz.z, nz.w, o.z, inv.z, r0z, r1z);
+                slab2(nx.x, nx.y, o.x, inv.x, noi.x, l0x, l1x); slab2(ny.x, ny.y, o.y, inv.y, noi.y, l0y, l1y); slab2(nz.x, nz.y, o.z, inv.z, noi.z, l0z, l1z);
+                slab2(nx.z, nx.w, o.x, inv.x, noi.x, r0x, r1x); slab2(ny.z, ny.w, o.y, inv.y, noi.y, r0y, r1y); slab2(nz.z, nz.w, o.z, inv.z, noi.z, r0z, r1z);
             }
 #else
             if (REL) {
@@ -697,7 +716,7 @@ __device__ __forceinline__ void trav_run_vote(TravState& T, bool active, bool& d
                                               SNodeBase s_nodes, int n_snodes, const STK& stack,
                                               int min_active, int vote_num, LocalCounters& lc) {
     const f3 o = T.o, inv = T.inv;
-#if PT_FAST
+#if PT_FAST_SLAB
     const f3 noi = T.noi;
     const float slack = T.slack;
 #else
@@ -736,8 +755,8 @@ __device__ __forceinline__ void trav_run_vote(TravState& T, bool active, bool& d
                 const float best_t = T.best_t;
 #if PT_F32X2
                 float l0x, l1x, l0y, l1y, l0z, l1z, r0x, r1x, r0y, r1y, r0z, r1z;
-                slab2(nx.x, nx.y, o.x, inv.x, l0x, l1x); slab2(ny.x, ny.y, o.y, inv.y, l0y, l1y); slab2(nz.x, nz.y, o.z, inv.z, l0z, l1z);
-                slab2(nx.z, nx.w, o.x, inv.x, r0x, r1x); slab2(ny.z, ny.w, o.y, inv.y, r0y, r1y); slab2(nz.z, nz.w, o.z, inv.z, r0z, r1z);
+                slab2(nx.x, nx.y, o.x, inv.x, noi.x, l0x, l1x); slab2(ny.x, ny.y, o.y, inv.y, noi.y, l0y, l1y); slab2(nz.x, nz.y, o.z, inv.z, noi.z, l0z, l1z);
+                slab2(nx.z, nx.w, o.x, inv.x, noi.x, r0x, r1x); slab2(ny.z, ny.w, o.y, inv.y, noi.y, r0y, r1y); slab2(nz.z, nz.w, o.z, inv.z, noi.z, r0z, r1z);
 #else
                 float l0x = PT_SLAB(nx.x, o.x, inv.x, noi.x), l1x = PT_SLAB(nx.y, o.x, inv.x, noi.x);
                 float l0y = PT_SLAB(ny.x, o.y, inv.y, noi.y), l1y = PT_SLAB(ny.y, o.y, inv.y, noi.y);
