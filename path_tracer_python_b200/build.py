@@ -71,7 +71,8 @@ def build_native(force: bool = False, verbose: bool = False, defines=(), out: st
 
 
 def build_fast(force: bool = False, verbose: bool = False) -> str:
-    """The production-numerics variant (PT_FAST: FMA slab test, approximate reciprocals) next to the strict library."""
+    """The production-numerics variant (PT_FAST: FMA contraction and approximate reciprocals around the strict
+    intersection tests) next to the strict library."""
     if not force and not needs_build(FAST_LIB_PATH):
         return FAST_LIB_PATH
     return build_native(force=True, verbose=verbose, defines=FAST_DEFINES, out=FAST_LIB_PATH)

@@ -22,8 +22,8 @@ def _require_cuda():
 class Engine:
     def __init__(self, device: int | None = None, numerics: str = "strict"):
         """numerics: "strict" = the PT-F32 contract (bit-exact against the reference's kernels; the parity
-        build) or "fast" = the production build of the same sources (FMA contraction, FFMA slab test,
-        approximate reciprocal / division / square root; first hits within 1e-5 relative of strict)."""
+        build) or "fast" = the production build of the same sources (FMA contraction and approximate reciprocal /
+        division / square root around the strict intersection tests; first hits equal to strict's)."""
         _require_cuda()
         self.numerics = numerics
         self.L = _lib.lib(numerics)
