@@ -1688,7 +1688,7 @@ const char* pt_last_error(void) { return pt_error_slot()->c_str(); }
 const char* pt_version(void) {
 #if PT_FAST
     return PT_FAST_SLAB ? "b200pt 0.2 (sm_100a, PT-F32 fast: FMA slab test, FMA + approximate reciprocal)"
-                        : "b200pt 0.2 (sm_100a, PT-F32 fast: FMA + approximate reciprocal around the strict intersection tests)";
+                        : "b200pt 0.2 (sm_100a, PT-F32 fast: FMA + approximate reciprocal around the exactly rounded intersection tests)";
 #elif PT_DEBUG_BOUNDS
     return "b200pt 0.2 (sm_100a, PT-F32 strict, debug-bounds build)";
 #elif PT_WIDE
