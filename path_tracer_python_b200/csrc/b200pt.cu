@@ -64,7 +64,7 @@ struct PtContext {
     int sync_samples = 0;
     int vote_num = 12;       // megakernel: descend when >= 12 lanes want to (tools/sweep.py, config 2)
     int wf_vote_num = 16;    // the same threshold for k_wf_extend (tools/sweep_wf.py)
-    int wf_waves = 8;        // full waves per batch before the tail kernel takes over (tools/sweep_wf.py)
+    int wf_waves = 9;        // full waves per batch before the tail kernel takes over (config 2, final build: 8 / 9 / 10 waves = 3209 / 3225 / 3221 Mpaths/s)
     int wf_primary_threads = PT_PRIMARY_THREADS;   // CTA size of k_wf_primary (<= its launch bound)
     int wf_overlap = 1;      // two pipelines: consecutive batches on two streams with their own queue sets (pt_render_wavefront)
     int wf_pipelines = 2;    // batches in flight at once when wf_overlap is on (each with its own stream and queue set)
